@@ -1,0 +1,292 @@
+/*
+ * polar_oracle.c -- CPU restatement of PARTNER's point -> polar-grid front end.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under partner_b200/ may import, link or
+ * execute this file.  Legitimate users: tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs, where it is the checker or
+ * the timed CPU baseline -- never the product path.
+ *
+ * Parity status: PINNED.  tests/golden/make_golden.py imports the reference's
+ * own numba / torch functions from /root/reference in the build container and
+ * freezes their outputs under tests/golden/*.npz; tests/test_oracle_golden.py
+ * checks every function below against those vectors (bit-exact for all
+ * integer / gather outputs, 1e-5 for the float reductions).
+ *
+ * Every function cites the reference file:line it follows (paths relative to
+ * the reference checkout).  Plain C99, scalar, single threaded, compiled with
+ * -ffp-contract=off so that each float operation is rounded separately, as
+ * numpy / numba / eager torch do.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------- */
+/* phi = arctan2(y, x)  (det3d/datasets/pipelines/utils.py:41)                */
+/*                                                                           */
+/* numpy's float32 arctan2 is a vendor SIMD routine (<= 3.4 ulp, differs from */
+/* glibc and from CUDA), so it cannot be a bit-exact target.  The front end   */
+/* therefore DEFINES phi by this fixed sequence of IEEE-754 binary32          */
+/* operations (div, mul, fma, add; max error 1.66 ulp, measured <= 4 ulp from */
+/* numpy on 2e7 points).  Only correctly rounded primitives are used, so the  */
+/* CUDA kernel reproduces it bit for bit.                                     */
+/* ------------------------------------------------------------------------- */
+static const float PO_ATAN_C[9] = {
+    -0x1.55553ep-2f, 0x1.9991fep-3f, -0x1.2421b4p-3f, 0x1.c099fap-4f, -0x1.583482p-4f,
+    0x1.dac9b4p-5f,  -0x1.fed102p-6f, 0x1.65a5f8p-7f,  -0x1.d62f3cp-10f};
+
+float po_atan2f(float y, float x)
+{
+    if (x != x || y != y) return NAN;
+    float ax = fabsf(x), ay = fabsf(y);
+    float mx = ax > ay ? ax : ay;
+    float mn = ax > ay ? ay : ax;
+    float a = mn / mx;
+    if (mx == 0.0f) a = 0.0f;
+    if (isinf(mn)) a = 1.0f;
+    float s = a * a;
+    float p = PO_ATAN_C[8];
+    for (int i = 7; i >= 0; --i) p = fmaf(p, s, PO_ATAN_C[i]);
+    float r = fmaf(a * s, p, a);
+    if (ay > ax) r = (0x1.921fb6p+0f - r) + (-0x1.777a5cp-25f);  /* pi/2 = hi + lo */
+    if (signbit(x)) r = (0x1.921fb6p+1f - r) + (-0x1.777a5cp-24f); /* pi   = hi + lo */
+    return copysignf(r, y);
+}
+
+/* ------------------------------------------------------------------------- */
+/* transform_points -- det3d/datasets/pipelines/utils.py:34-47                */
+/* rho = sqrt(x**2 + y**2) : four separately rounded f32 ops (utils.py:40).   */
+/* cylinder: [rho, phi, z, x, y, feat3..]   (utils.py:42-44)                  */
+/* cuboid  : [x, y, z, feat3.., rho, phi]   (utils.py:45-47)                  */
+/* ------------------------------------------------------------------------- */
+void po_transform_points(const float *in, int64_t n, int c_in, int cylinder, float *out)
+{
+    const int c = c_in + 2;
+    for (int64_t i = 0; i < n; ++i) {
+        const float *p = in + i * c_in;
+        float *q = out + i * c;
+        float xx = p[0] * p[0];
+        float yy = p[1] * p[1];
+        float rho = sqrtf(xx + yy);
+        float phi = po_atan2f(p[1], p[0]);
+        if (cylinder) {
+            q[0] = rho; q[1] = phi; q[2] = p[2]; q[3] = p[0]; q[4] = p[1];
+            for (int k = 3; k < c_in; ++k) q[k + 2] = p[k];
+        } else {
+            for (int k = 0; k < c_in; ++k) q[k] = p[k];
+            q[c_in] = rho; q[c_in + 1] = phi;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* grid_size -- det3d/core/input/voxel_generator.py:10-11 and                 */
+/* det3d/ops/point_cloud/point_cloud_ops.py:27-31: (hi - lo) / vs in f32,     */
+/* np.round (half to even), xyz order.                                        */
+/* ------------------------------------------------------------------------- */
+void po_grid_size(const float *voxel_size, const float *range, int32_t *grid)
+{
+    for (int j = 0; j < 3; ++j) {
+        float g = (range[3 + j] - range[j]) / voxel_size[j];
+        grid[j] = (int32_t)rintf(g);
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* points_to_voxel(reverse_index=True) -- point_cloud_ops.py:146-224 wrapping */
+/* _points_to_voxel_reverse_kernel :7-72.                                     */
+/*                                                                           */
+/* Caller provides voxels[max_voxels*T*C], coors[max_voxels*3],               */
+/* num_points[max_voxels]; they are cleared here exactly as the reference     */
+/* allocates them zeroed (:185-190).  The dense coor_to_voxelidx map          */
+/* (nz*ny*nx int32 = -1, :186) is allocated and filled per call, as the       */
+/* reference does -- that cost is part of the reference path.                 */
+/* pc_grid_ind [n,3] and density [nz,ny,nx] may be NULL (return_* = False).   */
+/* Returns voxel_num, or -1 if the map allocation fails.                      */
+/*                                                                           */
+/* NaN coordinates are undefined behaviour in the reference (the int32 cast   */
+/* of NaN indexes out of bounds); here, as in the CUDA build, a NaN bin is    */
+/* treated as below range (dropped, grid index clamped to 0).                 */
+/* ------------------------------------------------------------------------- */
+int64_t po_points_to_voxel(const float *points, int64_t n, int c,
+                           const float *voxel_size, const float *range,
+                           int max_points, int max_voxels,
+                           float *voxels, int32_t *coors, int32_t *num_points,
+                           int32_t *pc_grid_ind, int32_t *density)
+{
+    int32_t grid[3];
+    po_grid_size(voxel_size, range, grid);
+    const int64_t nx = grid[0], ny = grid[1], nz = grid[2];
+    const int64_t cells = nx * ny * nz;
+    int32_t *map = (int32_t *)malloc((size_t)cells * sizeof(int32_t));
+    if (!map) return -1;
+    for (int64_t k = 0; k < cells; ++k) map[k] = -1;                    /* :186 */
+    memset(num_points, 0, (size_t)max_voxels * sizeof(int32_t));        /* :185 */
+    memset(voxels, 0, (size_t)max_voxels * max_points * c * sizeof(float)); /* :187 */
+    memset(coors, 0, (size_t)max_voxels * 3 * sizeof(int32_t));         /* :190 */
+    if (pc_grid_ind) memset(pc_grid_ind, 0, (size_t)n * 3 * sizeof(int32_t)); /* :36 */
+    if (density) memset(density, 0, (size_t)cells * sizeof(int32_t));   /* :40 */
+
+    int32_t coor[3] = {0, 0, 0};   /* persists across iterations, like :32 */
+    int64_t voxel_num = 0;
+    const int want_ind = pc_grid_ind != NULL;
+    for (int64_t i = 0; i < n; ++i) {                                   /* :42 */
+        int failed = 0;
+        for (int j = 0; j < 3; ++j) {
+            float cf = floorf((points[i * c + j] - range[j]) / voxel_size[j]); /* :45 */
+            int32_t ci;
+            if (cf != cf) { failed = 1; if (!want_ind) break; ci = 0; }
+            else if (cf < 0.0f || cf >= (float)grid[j]) {               /* :46 */
+                failed = 1;
+                if (!want_ind) break;                                   /* :51 */
+                ci = cf < 0.0f ? 0 : grid[j] - 1;                       /* :49 */
+            } else ci = (int32_t)cf;
+            coor[2 - j] = ci;                                           /* :52 */
+        }
+        if (want_ind) {                                                 /* :53-54 */
+            pc_grid_ind[i * 3 + 0] = coor[0];
+            pc_grid_ind[i * 3 + 1] = coor[1];
+            pc_grid_ind[i * 3 + 2] = coor[2];
+        }
+        if (failed) continue;                                           /* :55-56 */
+        int64_t cell = ((int64_t)coor[0] * ny + coor[1]) * nx + coor[2];
+        int32_t vid = map[cell];                                        /* :57 */
+        if (vid == -1) {
+            vid = (int32_t)voxel_num;
+            if (voxel_num >= max_voxels) continue;                      /* :60-61 */
+            voxel_num += 1;
+            map[cell] = vid;
+            coors[vid * 3 + 0] = coor[0];
+            coors[vid * 3 + 1] = coor[1];
+            coors[vid * 3 + 2] = coor[2];
+        }
+        int32_t num = num_points[vid];
+        if (num < max_points) {                                         /* :66-68 */
+            memcpy(voxels + ((int64_t)vid * max_points + num) * c, points + i * c,
+                   (size_t)c * sizeof(float));
+            num_points[vid] = num + 1;
+        }
+        if (density) density[cell] += 1;                                /* :70-71 */
+    }
+    free(map);
+    return voxel_num;
+}
+
+/* ------------------------------------------------------------------------- */
+/* VoxelFeatureExtractorV3.forward -- det3d/models/readers/voxel_encoder.py   */
+/* :15-22: sum over the T slots (zero padding included) / num_points.         */
+/* ------------------------------------------------------------------------- */
+void po_vfe_mean(const float *voxels, const int32_t *num_points, int64_t m, int t, int c,
+                 float *out)
+{
+    for (int64_t v = 0; v < m; ++v) {
+        float nf = (float)num_points[v];
+        for (int k = 0; k < c; ++k) {
+            float s = 0.0f;
+            for (int j = 0; j < t; ++j) s += voxels[(v * t + j) * c + k];
+            out[v * c + k] = s / nf;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* PillarFeatureNet.forward (eval) -- det3d/models/readers/pillar_encoder.py  */
+/* :131-169 with PFNLayer.forward_static :49-61.                              */
+/*                                                                           */
+/* n_layers PFN layers; layer l has weight W_l [units_l, in_l] (nn.Linear,    */
+/* no bias, :41), BatchNorm1d running stats + affine (eval: (x-mu)*invstd*g+b */
+/* with invstd = 1/sqrt(var+eps)), ReLU, max over ALL T slots -- padded slots */
+/* included (:55), which is the reference's behaviour.  Non-last layers       */
+/* output cat([x, repeat(x_max)]) (:59-61).  units[l] is the Linear's output  */
+/* width (already halved for non-last layers, :34-36).                        */
+/* coors is [m,4] (b,z,y,x).  out is [m, units[n_layers-1]].                  */
+/* vx, vy, x_off, y_off are the f32 images of the Python doubles (:123-126).  */
+/* ------------------------------------------------------------------------- */
+void po_pfn_forward(const float *voxels, const int32_t *num_points, const int32_t *coors,
+                    int64_t m, int t, int c, int with_distance,
+                    float vx, float vy, float x_off, float y_off,
+                    int n_layers, const int32_t *units,
+                    const float *const *weight, const float *const *bn_mean,
+                    const float *const *bn_var, const float *const *bn_gamma,
+                    const float *const *bn_beta, float eps, float *out)
+{
+    const int c0 = c + 5 + (with_distance ? 1 : 0);
+    int max_w = c0;
+    for (int l = 0; l < n_layers; ++l) if (2 * units[l] > max_w) max_w = 2 * units[l];
+    float *cur = (float *)malloc((size_t)t * max_w * sizeof(float));
+    float *nxt = (float *)malloc((size_t)t * max_w * sizeof(float));
+    float *xmax = (float *)malloc((size_t)max_w * sizeof(float));
+    for (int64_t v = 0; v < m; ++v) {
+        const float *f = voxels + v * t * c;
+        const float nf = (float)num_points[v];
+        float mean[3];
+        for (int k = 0; k < 3; ++k) {                                   /* :137-139 */
+            float s = 0.0f;
+            for (int j = 0; j < t; ++j) s += f[j * c + k];
+            mean[k] = s / nf;
+        }
+        const float cx = (float)coors[v * 4 + 3] * vx + x_off;          /* :146-147 */
+        const float cy = (float)coors[v * 4 + 2] * vy + y_off;          /* :149-150 */
+        for (int j = 0; j < t; ++j) {
+            float *row = cur + j * c0;
+            const float *p = f + j * c;
+            for (int k = 0; k < c; ++k) row[k] = p[k];
+            for (int k = 0; k < 3; ++k) row[c + k] = p[k] - mean[k];    /* :140 */
+            row[c + 3] = p[0] - cx;
+            row[c + 4] = p[1] - cy;
+            if (with_distance)                                          /* :155 */
+                row[c + 5] = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+            const float mask = j < num_points[v] ? 1.0f : 0.0f;         /* :161-164 */
+            for (int k = 0; k < c0; ++k) row[k] *= mask;
+        }
+        int in_w = c0;
+        for (int l = 0; l < n_layers; ++l) {
+            const int u = units[l];
+            const int last = l == n_layers - 1;
+            const int out_w = last ? u : 2 * u;
+            for (int o = 0; o < u; ++o) xmax[o] = -INFINITY;
+            for (int j = 0; j < t; ++j) {
+                for (int o = 0; o < u; ++o) {
+                    float acc = 0.0f;
+                    const float *w = weight[l] + (size_t)o * in_w;
+                    for (int k = 0; k < in_w; ++k) acc += cur[j * in_w + k] * w[k]; /* :50 */
+                    const float invstd = 1.0f / sqrtf(bn_var[l][o] + eps);
+                    float y = (acc - bn_mean[l][o]) * invstd * bn_gamma[l][o] + bn_beta[l][o]; /* :52 */
+                    y = y > 0.0f ? y : 0.0f;                            /* :54 */
+                    if (!last) nxt[j * out_w + o] = y;
+                    if (y > xmax[o]) xmax[o] = y;                       /* :55 */
+                }
+            }
+            if (last) {
+                for (int o = 0; o < u; ++o) out[v * u + o] = xmax[o];   /* :56-57 */
+            } else {
+                for (int j = 0; j < t; ++j)
+                    for (int o = 0; o < u; ++o) nxt[j * out_w + u + o] = xmax[o]; /* :59-60 */
+                float *tmp = cur; cur = nxt; nxt = tmp;
+                in_w = out_w;
+            }
+        }
+    }
+    free(cur); free(nxt); free(xmax);
+}
+
+/* ------------------------------------------------------------------------- */
+/* PointPillarsScatter.forward -- pillar_encoder.py:189-225.                  */
+/* canvas [batch, c, ny, nx] zeroed; canvas[b, :, y*nx + x] = feats[v, :].    */
+/* bev_index (optional, [m] int64) receives the BEV index map y*nx + x (:211).*/
+/* Later duplicates overwrite earlier ones, as index_put_ on CPU does.        */
+/* ------------------------------------------------------------------------- */
+void po_scatter(const float *feats, const int32_t *coors, int64_t m, int c, int batch,
+                int ny, int nx, float *canvas, int64_t *bev_index)
+{
+    const int64_t plane = (int64_t)ny * nx;
+    memset(canvas, 0, (size_t)batch * c * plane * sizeof(float));
+    for (int64_t v = 0; v < m; ++v) {
+        const int b = coors[v * 4 + 0];
+        const int64_t idx = (int64_t)coors[v * 4 + 2] * nx + coors[v * 4 + 3];
+        if (bev_index) bev_index[v] = idx;
+        if (b < 0 || b >= batch) continue;                              /* :207 mask */
+        for (int k = 0; k < c; ++k) canvas[((int64_t)b * c + k) * plane + idx] = feats[v * c + k];
+    }
+}

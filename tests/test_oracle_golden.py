@@ -1,0 +1,107 @@
+"""Pins oracle/ (the C restatement) against vectors produced by the reference itself.
+
+Golden files come from tests/golden/make_golden.py, which runs the reference's numba
+voxelizer / numpy transform / torch reader modules in the build container.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from util import assert_close_fp32, densify, ulp_diff
+
+CASES = sorted(os.path.basename(p)[6:-4] for p in
+               glob.glob(os.path.join(os.path.dirname(__file__), "golden", "voxel_*.npz")))
+
+
+def test_golden_present():
+    assert len(CASES) >= 6
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_points_to_voxel_bit_exact(case, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"voxel_{case}.npz"))
+    vg = oracle.VoxelGenerator(g["voxel_size"], g["range"], int(g["max_points"]), int(g["max_voxels"]))
+    assert np.array_equal(vg.grid_size, g["grid_size"])
+    want_ind = "pc_grid_ind" in g.files
+    want_den = "den_idx" in g.files
+    voxels, coors, num, ind, den = vg.generate(g["polar"], return_pc_grid_ind=want_ind,
+                                               return_density=want_den)
+    assert np.array_equal(coors, g["coors"])
+    assert np.array_equal(num, g["num_points"])
+    assert np.array_equal(voxels, g["voxels"])           # pure gather -> bit exact
+    assert coors.dtype == np.int32 and num.dtype == np.int32 and voxels.dtype == np.float32
+    if want_ind:
+        assert np.array_equal(ind, g["pc_grid_ind"])
+    else:
+        assert ind is None
+    if want_den:
+        assert np.array_equal(den, densify(g["den_idx"], g["den_val"], g["den_shape"]))
+    else:
+        assert den is None
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_transform_then_voxelize_matches_reference_bins(case, golden_dir):
+    """rho is bit-exact; phi is the front end's own fixed-op-sequence atan2 (<= 4 ulp of numpy)."""
+    g = np.load(os.path.join(golden_dir, f"voxel_{case}.npz"))
+    polar = oracle.transform_points(g["cart"], "cylinder")
+    ref = g["polar"]
+    assert np.array_equal(polar[:, 0], ref[:, 0], equal_nan=True)
+    assert np.array_equal(polar[:, 2:], ref[:, 2:], equal_nan=True)
+    assert ulp_diff(polar[:, 1], ref[:, 1]).max() <= 4
+
+
+def test_transform_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "transform.npz"))
+    for shape in ("cylinder", "cuboid"):
+        out = oracle.transform_points(g["cart"], shape)
+        ref = g[shape]
+        phi_col = 1 if shape == "cylinder" else ref.shape[1] - 1
+        other = [k for k in range(ref.shape[1]) if k != phi_col]
+        assert np.array_equal(out[:, other], ref[:, other])
+        assert ulp_diff(out[:, phi_col], ref[:, phi_col]).max() <= 4
+
+
+def test_atan2_special_values():
+    f = oracle.lib().po_atan2f
+    assert f(0.0, 0.0) == 0.0
+    assert f(0.0, -0.0) == np.float32(np.pi)
+    assert f(-0.0, -1.0) == -np.float32(np.pi)
+    assert f(1.0, 0.0) == np.float32(np.pi / 2)
+    assert f(np.inf, np.inf) == np.float32(np.pi / 4)
+    assert f(np.inf, -np.inf) == np.float32(3 * np.pi / 4)
+    assert np.isnan(f(np.nan, 1.0)) and np.isnan(f(1.0, np.nan))
+
+
+def _layers(g, tag):
+    layers = []
+    i = 0
+    while f"{tag}_w{i}" in g.files:
+        layers.append(dict(weight=g[f"{tag}_w{i}"], mean=g[f"{tag}_mean{i}"], var=g[f"{tag}_var{i}"],
+                           gamma=g[f"{tag}_gamma{i}"], beta=g[f"{tag}_beta{i}"]))
+        i += 1
+    return layers
+
+
+def test_vfe_mean_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "readers.npz"))
+    assert_close_fp32(oracle.vfe_mean(g["voxels"], g["num_points"]), g["vfe_mean"], "vfe_mean")
+
+
+@pytest.mark.parametrize("tag,dist", [("pfn64_128", False), ("pfn64", False), ("pfn32_32_64_dist", True)])
+def test_pfn_golden(tag, dist, golden_dir):
+    g = np.load(os.path.join(golden_dir, "readers.npz"))
+    out = oracle.pfn_forward(g["voxels"], g["num_points"], g["coors"], _layers(g, tag),
+                             g["voxel_size"], g["pc_range"], with_distance=dist,
+                             eps=float(g[f"{tag}_eps"]))
+    assert_close_fp32(out, g[f"{tag}_out"], tag)
+
+
+def test_scatter_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "readers.npz"))
+    canvas, idx = oracle.scatter(g["vfe_mean"], g["coors"], 2, [512, 512, 1])
+    assert np.array_equal(idx, g["bev_index"])
+    assert np.array_equal(canvas, densify(g["canvas_idx"], g["canvas_val"], g["canvas_shape"]))
