@@ -1,0 +1,149 @@
+/*
+ * polar_voxel_b200.h -- C ABI of the B200 (sm_100a) polar front end.
+ *
+ * The reference (fudan-zvg/PARTNER, det3d lineage) has no FFI on this path: it
+ * calls numba-compiled Python and eager torch ops directly.  This header is the
+ * boundary a det3d maintainer binds instead (ctypes stub in INTEGRATION.md), in
+ * the style the reference uses for its other native ops: launchers that take
+ * raw device pointers + sizes (det3d/ops/iou3d_nms/src/iou3d_nms.cpp:47-66).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless noted HOST;
+ *   - the library never allocates, frees or synchronises; every launch goes to
+ *     the caller's stream, so every entry point is CUDA-graph capturable;
+ *   - one opaque caller-provided workspace (size from pv_workspace_bytes);
+ *   - return value: PV_OK (0) or a negative PV_ERR_* code.  Conditions only
+ *     detectable on the device (hash table overflow) set a status word that
+ *     pv_read_status() copies back.  Nothing here calls exit().
+ *   - all floating point is IEEE binary32 without contraction, so integer
+ *     outputs are bit-identical to the reference's numba loop on the same input.
+ *
+ * Point rows are float32 [n, c_in].  With is_cartesian != 0 rows are
+ * (x, y, z, feat...) and the kernels apply the cylinder transform of
+ * det3d/datasets/pipelines/utils.py:34-44 on the fly, producing
+ * (rho, phi, z, x, y, feat...) with C = c_in + 2 channels; otherwise rows are
+ * already polar (what VoxelGenerator.generate receives) and C = c_in.
+ */
+#ifndef POLAR_VOXEL_B200_H_
+#define POLAR_VOXEL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *pv_stream_t; /* == cudaStream_t */
+
+#define PV_OK 0
+#define PV_ERR_BAD_CONFIG (-1)    /* non-positive grid / T / V, grid too large        */
+#define PV_ERR_BAD_ARGUMENT (-2)  /* null pointer, channel count out of range, ...    */
+#define PV_ERR_WORKSPACE (-3)     /* workspace smaller than pv_workspace_bytes says    */
+#define PV_ERR_CUDA (-4)          /* a CUDA runtime call failed (cudaGetLastError)     */
+#define PV_ERR_TABLE_FULL (-5)    /* device status: a frame had more points than frame_capacity */
+#define PV_ERR_UNSUPPORTED (-6)   /* layer shape outside what the kernels cover        */
+
+#define PV_MAX_CHANNELS 16        /* C (after the transform) <= 16                     */
+#define PV_MAX_PFN_LAYERS 4
+
+/* Replaces the state of VoxelGenerator (det3d/core/input/voxel_generator.py:6-17):
+ * voxel_size / point_cloud_range already rounded to f32, grid = round((hi-lo)/vs). */
+typedef struct pv_config {
+    float lo[3];        /* range lower bound, (rho, phi, z) order             */
+    float vs[3];        /* voxel size                                         */
+    int32_t grid[3];    /* nx, ny, nz                                         */
+    int32_t max_points; /* T = max_points_in_voxel                            */
+    int32_t max_voxels; /* V = max_voxels per frame                           */
+} pv_config;
+
+/* One PFNLayer (det3d/models/readers/pillar_encoder.py:19-61) in eval mode. */
+typedef struct pv_pfn_layer {
+    const float *weight;   /* linear.weight [units, in_channels], no bias     */
+    const float *bn_mean;  /* norm.running_mean [units]                       */
+    const float *bn_var;   /* norm.running_var  [units]                       */
+    const float *bn_gamma; /* norm.weight       [units]                       */
+    const float *bn_beta;  /* norm.bias         [units]                       */
+    int32_t in_channels;
+    int32_t units;         /* Linear output width (already halved if not last) */
+} pv_pfn_layer;
+
+int pv_version(void);
+const char *pv_error_string(int code);
+
+/* Bytes of workspace for a batch of `batch` frames holding at most
+ * `max_points_total` points, no frame larger than `frame_capacity` points. */
+size_t pv_workspace_bytes(const pv_config *cfg, int64_t max_points_total, int32_t batch,
+                          int64_t frame_capacity);
+
+/* transform_points (det3d/datasets/pipelines/utils.py:34-47).  out is [n, c_in+2]. */
+int pv_transform_points(const float *in, int64_t n, int32_t c_in, int32_t cylinder, float *out,
+                        pv_stream_t stream);
+
+/*
+ * Hard voxelization of a batch of frames: replaces points_to_voxel
+ * (det3d/ops/point_cloud/point_cloud_ops.py:146-224, reverse_index=True) for
+ * every frame plus the batch assembly of collate_kitti
+ * (det3d/torchie/parallel/collate.py:157-164: batch index prepended, frames
+ * concatenated).  Frame f owns points [frame_offsets[f], frame_offsets[f+1]).
+ *
+ * Outputs (rows are in frame order, then first-occurrence order; SM = sum of
+ * per-frame voxel counts <= min(batch * V, n_total)):
+ *   coors        int32 [SM, 4]  (b, z, y, x)                     required
+ *   num_points   int32 [SM]                                       required
+ *   voxel_counts int32 [batch]   M per frame                      required
+ *   voxels       f32   [SM, T, C] zero padded                     or NULL
+ *   mean_feats   f32   [SM, C]   mean over kept points (VFE V3)   or NULL
+ *   pc_grid_ind  int32 [n_total, 3] clamped (z, y, x)             or NULL
+ *   density      int32 [batch, nz, ny, nx] un-capped counts of kept voxels, or NULL
+ * Output buffers must have capacity for min(batch * V, n_total) rows.
+ */
+int pv_voxelize(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
+                int32_t batch, int64_t n_total, int32_t c_in, int32_t is_cartesian,
+                int64_t frame_capacity, void *workspace, size_t workspace_bytes,
+                int32_t *coors, int32_t *num_points, int32_t *voxel_counts, float *voxels,
+                float *mean_feats, int32_t *pc_grid_ind, int32_t *density, pv_stream_t stream);
+
+/* Fused front end for pillar grids (nz == 1): pv_voxelize (mean_feats) followed by the
+ * scatter of PointPillarsScatter (pillar_encoder.py:189-225) into canvas
+ * f32 [batch, C, ny, nx]; every canvas element is written exactly once. */
+int pv_forward_mean_canvas(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
+                           int32_t batch, int64_t n_total, int32_t c_in, int32_t is_cartesian,
+                           int64_t frame_capacity, void *workspace, size_t workspace_bytes,
+                           int32_t *coors, int32_t *num_points, int32_t *voxel_counts,
+                           float *mean_feats, float *canvas, pv_stream_t stream);
+
+/* Copies the device status word of the last pv_voxelize on `workspace` to the host
+ * (synchronises `stream`).  Returns PV_OK or PV_ERR_TABLE_FULL / PV_ERR_CUDA. */
+int pv_read_status(const void *workspace, pv_stream_t stream);
+
+/* VoxelFeatureExtractorV3.forward (det3d/models/readers/voxel_encoder.py:15-22):
+ * out[m, c] = sum_t voxels[m, t, c] / num_points[m]. */
+int pv_vfe_mean(const float *voxels, const int32_t *num_points, int64_t m, int32_t t, int32_t c,
+                float *out, pv_stream_t stream);
+
+/* PillarFeatureNet.forward in eval mode (pillar_encoder.py:131-169, PFNLayer :49-61):
+ * decoration (cluster offset, pillar-centre offset, optional distance), padding mask,
+ * n_layers x (Linear, BatchNorm1d eval, ReLU, max over all T slots incl. padding).
+ * voxels [m, t, c], num_points [m], coors [m, 4] (b, z, y, x); out [m, units of last layer].
+ * `layers` is a HOST array. vx, vy, x_off, y_off as computed at pillar_encoder.py:123-126. */
+int pv_pfn_forward(const float *voxels, const int32_t *num_points, const int32_t *coors, int64_t m,
+                   int32_t t, int32_t c, int32_t with_distance, float vx, float vy, float x_off,
+                   float y_off, const pv_pfn_layer *layers, int32_t n_layers, float eps,
+                   float *out, pv_stream_t stream);
+
+/* Bytes of workspace pv_scatter needs (the BEV index map). */
+size_t pv_scatter_workspace_bytes(int32_t batch, int32_t ny, int32_t nx);
+
+/* PointPillarsScatter.forward (pillar_encoder.py:189-225): canvas [batch, c, ny, nx] =
+ * zeros, canvas[b, :, y, x] = feats[v, :] for coors[v] = (b, z, y, x).  Rows whose batch
+ * index is outside [0, batch) are ignored (:207); duplicate cells keep the last row.
+ * bev_index (optional, int64 [m]) receives y * nx + x (:211). */
+int pv_scatter(const float *feats, const int32_t *coors, int64_t m, int32_t c, int32_t batch,
+               int32_t ny, int32_t nx, void *workspace, size_t workspace_bytes, float *canvas,
+               int64_t *bev_index, pv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLAR_VOXEL_B200_H_ */

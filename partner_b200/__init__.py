@@ -1,0 +1,32 @@
+"""partner_b200 -- B200-native (sm_100a) polar front end of fudan-zvg/PARTNER.
+
+Drop-in classes (same names / signatures as the reference):
+    VoxelGenerator                         det3d/core/input/voxel_generator.py
+    VoxelFeatureExtractorV3                det3d/models/readers/voxel_encoder.py
+    PillarFeatureNet, PointPillarsScatter  det3d/models/readers/pillar_encoder.py
+    transform_points                       det3d/datasets/pipelines/utils.py
+and the fused batched path ``PolarFrontEnd``.  All compute runs in hand-written CUDA kernels
+reached through the C ABI of include/polar_voxel_b200.h; importing the package does not need a
+GPU, calling anything does.
+"""
+from . import synth  # noqa: F401
+from ._lib import build, load  # noqa: F401
+from .registry import BACKBONES, READERS, build_from_cfg  # noqa: F401
+from . import readers as _readers  # noqa: F401  (populates READERS / BACKBONES)
+
+
+def __getattr__(name):
+    # torch-dependent modules are imported lazily so `import partner_b200` stays cheap
+    if name in ("VoxelGenerator",):
+        from .voxel_generator import VoxelGenerator
+        return VoxelGenerator
+    if name in ("VoxelFeatureExtractorV3", "PillarFeatureNet", "PointPillarsScatter", "PFNLayer"):
+        from . import readers
+        return getattr(readers, name)
+    if name in ("PolarFrontEnd", "shard_range"):
+        from . import frontend
+        return getattr(frontend, name)
+    if name == "transform_points":
+        from .functional import transform_points
+        return transform_points
+    raise AttributeError(name)

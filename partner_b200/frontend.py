@@ -1,0 +1,118 @@
+"""Fused, batched front end: raw Cartesian sweeps -> voxels -> reader -> BEV canvas on one GPU.
+
+This is the whole hot path of SURVEY.md section 3.4 as one launch sequence per *batch*
+(transform_points + VoxelGenerator.generate per frame + collate + reader + scatter in the
+reference), with device-side voxel counts (no host sync) so it can be replayed as a CUDA graph.
+Frames are independent, so multi-GPU use is plain frame sharding (``shard_range``); there is no
+collective on this path.
+"""
+import numpy as np
+import torch
+
+from . import functional as F
+
+
+def shard_range(n_frames, world_size, rank):
+    """Contiguous block of frames owned by ``rank``."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError("bad rank/world_size")
+    base, rem = divmod(n_frames, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class PolarFrontEnd:
+    """voxelize (+ fused cylinder transform) -> mean VFE -> dense polar BEV canvas.
+
+    Parameters follow the reference's ``voxel_generator`` config dict
+    (det3d/datasets/pipelines/voxelization.py:14-36): range, voxel_size, max_points_in_voxel,
+    max_voxel_num.
+    """
+
+    def __init__(self, voxel_size, point_cloud_range, max_points_in_voxel, max_voxel_num,
+                 cartesian=True, canvas=None, device=None):
+        self.cfg, self.voxel_size, self.point_cloud_range, self.grid_size = F.make_config(
+            voxel_size, point_cloud_range, max_points_in_voxel, max_voxel_num)
+        self.cartesian = bool(cartesian)
+        self.pillar = int(self.grid_size[2]) == 1
+        self.canvas = self.pillar if canvas is None else bool(canvas)
+        if self.canvas and not self.pillar:
+            raise ValueError("a dense BEV canvas needs a pillar grid (nz == 1)")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._graph = None
+        self._static = None
+
+    # ---- device-resident path (what `value` in bench.py times) -----------------------------
+    def forward_device(self, points, frame_offsets, batch, frame_capacity, out=None):
+        """points [N, c_in] f32 CUDA, frame_offsets [batch+1] int32 CUDA -> VoxelBatch (no sync)."""
+        return F.voxelize(self.cfg, points, frame_offsets, batch, frame_capacity, self.cartesian,
+                          want_mean=True, canvas=self.canvas, out=out)
+
+    def capture(self, points, frame_offsets, batch, frame_capacity):
+        """Record the launch sequence on static buffers as a CUDA graph; returns the VoxelBatch
+        the graph writes.  Replay with ``replay()`` after refreshing ``points`` in place."""
+        out = self.forward_device(points, frame_offsets, batch, frame_capacity)   # warm-up + allocation
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward_device(points, frame_offsets, batch, frame_capacity, out=out)
+        self._graph, self._static = g, out
+        return out
+
+    def replay(self):
+        self._graph.replay()
+        return self._static
+
+    # ---- host-buffer path (what `e2e` in bench.py times) ------------------------------------
+    def make_host_io(self, n_total, batch, c_in):
+        """Pinned staging buffers + device mirrors for ``forward_host``."""
+        C = c_in + 2 if self.cartesian else c_in
+        rows = max(1, min(batch * self.cfg.max_voxels, n_total))
+        pin = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt).pin_memory()   # noqa: E731
+        io = dict(
+            h_points=pin(n_total, c_in), h_offsets=pin(batch + 1, dt=torch.int32),
+            d_points=torch.empty((n_total, c_in), dtype=torch.float32, device=self.device),
+            d_offsets=torch.empty((batch + 1,), dtype=torch.int32, device=self.device),
+            h_counts=pin(batch, dt=torch.int32), h_coors=pin(rows, 4, dt=torch.int32),
+            h_num=pin(rows, dt=torch.int32), h_feats=pin(rows, C),
+            h_canvas=pin(batch, C, int(self.grid_size[1]), int(self.grid_size[0])) if self.canvas else None,
+            vb=None, batch=batch, n_total=n_total)
+        return io
+
+    def forward_host(self, io, frame_capacity):
+        """H2D of io['h_points'/'h_offsets'] -> kernels -> D2H of every output.  Returns
+        (sum of voxel counts, bytes copied H2D, bytes copied D2H); outputs land in io['h_*']."""
+        io["d_points"].copy_(io["h_points"], non_blocking=True)
+        io["d_offsets"].copy_(io["h_offsets"], non_blocking=True)
+        vb = self.forward_device(io["d_points"], io["d_offsets"], io["batch"], frame_capacity, out=io["vb"])
+        io["vb"] = vb
+        io["h_counts"].copy_(vb.voxel_counts, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        m = int(io["h_counts"].sum())
+        io["h_coors"][:m].copy_(vb.coors[:m], non_blocking=True)
+        io["h_num"][:m].copy_(vb.num_points[:m], non_blocking=True)
+        io["h_feats"][:m].copy_(vb.mean_feats[:m], non_blocking=True)
+        d2h = io["h_counts"].numel() * 4 + m * (16 + 4 + 4 * vb.mean_feats.shape[1])
+        if self.canvas:
+            io["h_canvas"].copy_(vb.canvas, non_blocking=True)
+            d2h += io["h_canvas"].numel() * 4
+        torch.cuda.current_stream(self.device).synchronize()
+        h2d = io["h_points"].numel() * 4 + io["h_offsets"].numel() * 4
+        return m, h2d, d2h
+
+    # ---- convenience ---------------------------------------------------------------------
+    def __call__(self, frames):
+        """List of float32 numpy frames [N_f, c_in] -> dict of numpy outputs (syncs)."""
+        sizes = [int(f.shape[0]) for f in frames]
+        offsets = np.zeros(len(frames) + 1, dtype=np.int32)
+        np.cumsum(sizes, out=offsets[1:])
+        pts = torch.from_numpy(np.ascontiguousarray(np.concatenate(frames, axis=0), dtype=np.float32)).to(self.device)
+        vb = self.forward_device(pts, torch.from_numpy(offsets).to(self.device), len(frames), max(sizes))
+        counts = vb.voxel_counts.cpu().numpy()
+        F.read_status(vb)
+        m = int(counts.sum())
+        out = dict(coordinates=vb.coors[:m].cpu().numpy(), num_points=vb.num_points[:m].cpu().numpy(),
+                   num_voxels=counts.astype(np.int64), features=vb.mean_feats[:m].cpu().numpy())
+        if self.canvas:
+            out["canvas"] = vb.canvas.cpu().numpy()
+        return out

@@ -1,0 +1,181 @@
+"""Tensor-level wrappers over the C ABI (torch is only the allocator / stream provider).
+
+Every function takes CUDA float32/int32 tensors, validates them the way the reference's native
+ops do (is_cuda / is_contiguous / dtype -- det3d/ops/iou3d_nms/src/iou3d_nms.cpp:14-27, but raising
+instead of exiting), allocates outputs with torch and launches on the current stream.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PvConfig, PvPfnLayer, check, current_stream, ptr
+
+_workspaces = {}
+
+
+def make_config(voxel_size, point_cloud_range, max_points, max_voxels):
+    """VoxelGenerator.__init__ arithmetic (det3d/core/input/voxel_generator.py:6-11)."""
+    rng = np.array(point_cloud_range, dtype=np.float32)
+    vs = np.array(voxel_size, dtype=np.float32)
+    grid = np.round((rng[3:] - rng[:3]) / vs).astype(np.int64)
+    cfg = PvConfig()
+    for j in range(3):
+        cfg.lo[j] = float(rng[j])
+        cfg.vs[j] = float(vs[j])
+        cfg.grid[j] = int(grid[j])
+    cfg.max_points = int(max_points)
+    cfg.max_voxels = int(max_voxels)
+    return cfg, vs, rng, grid
+
+
+def _need(t, dtype, name, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (there is no CPU path)" % name)
+    if t.dtype != dtype:
+        raise ValueError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError("%s must have %d dims" % (name, ndim))
+
+
+def workspace(nbytes, device, tag="main"):
+    """Grow-only byte buffer per (device, tag); the library itself never allocates."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def transform_points(points, voxel_shape="cylinder"):
+    """pv_transform_points: pipelines/utils.py:34-47 on the device."""
+    _need(points, torch.float32, "points", 2)
+    n, c_in = points.shape
+    if c_in < 3:
+        raise ValueError("points need at least x, y, z columns")
+    if voxel_shape not in ("cylinder", "cuboid"):
+        raise ValueError("voxel_shape must be 'cylinder' or 'cuboid'")
+    out = torch.empty((n, c_in + 2), dtype=torch.float32, device=points.device)
+    check(_lib.load().pv_transform_points(ptr(points), n, c_in, 1 if voxel_shape == "cylinder" else 0,
+                                          ptr(out), current_stream(points.device)), "pv_transform_points")
+    return out
+
+
+class VoxelBatch:
+    """Outputs of one batched voxelization, in capacity layout until ``counts`` is read."""
+
+    __slots__ = ("coors", "num_points", "voxel_counts", "voxels", "mean_feats", "pc_grid_ind",
+                 "density", "canvas", "ws", "cfg")
+
+    def total(self):
+        """Sum of per-frame voxel counts (one device->host read)."""
+        return int(self.voxel_counts.sum().item())
+
+
+def voxelize(cfg, points, frame_offsets, batch, frame_capacity, is_cartesian, want_voxels=False,
+             want_mean=False, want_grid_ind=False, want_density=False, canvas=False, out=None):
+    """pv_voxelize / pv_forward_mean_canvas on CUDA tensors.
+
+    points [N, c_in] f32, frame_offsets [batch+1] int32 (device).  Returns a VoxelBatch whose row
+    tensors have capacity min(batch*V, N); rows [0, sum(voxel_counts)) are valid.
+    ``out`` may carry a previous VoxelBatch whose buffers are reused (static-shape serving).
+    """
+    _need(points, torch.float32, "points", 2)
+    _need(frame_offsets, torch.int32, "frame_offsets", 1)
+    if frame_offsets.numel() != batch + 1:
+        raise ValueError("frame_offsets must have batch+1 entries")
+    n, c_in = points.shape
+    C = c_in + 2 if is_cartesian else c_in
+    dev = points.device
+    lib = _lib.load()
+    nbytes = lib.pv_workspace_bytes(cfg, n, batch, frame_capacity)
+    if nbytes == 0:
+        check(-1, "pv_workspace_bytes")
+    ws = workspace(nbytes, dev)
+    rows = max(1, min(batch * cfg.max_voxels, n))
+    T = cfg.max_points
+    r = out if out is not None else VoxelBatch()
+    if out is None:
+        r.coors = torch.empty((rows, 4), dtype=torch.int32, device=dev)
+        r.num_points = torch.empty((rows,), dtype=torch.int32, device=dev)
+        r.voxel_counts = torch.empty((batch,), dtype=torch.int32, device=dev)
+        r.voxels = torch.empty((rows, T, C), dtype=torch.float32, device=dev) if want_voxels else None
+        r.mean_feats = torch.empty((rows, C), dtype=torch.float32, device=dev) if (want_mean or canvas) else None
+        r.pc_grid_ind = torch.empty((n, 3), dtype=torch.int32, device=dev) if want_grid_ind else None
+        r.density = (torch.empty((batch, cfg.grid[2], cfg.grid[1], cfg.grid[0]), dtype=torch.int32, device=dev)
+                     if want_density else None)
+        r.canvas = (torch.empty((batch, C, cfg.grid[1], cfg.grid[0]), dtype=torch.float32, device=dev)
+                    if canvas else None)
+    r.ws = ws
+    r.cfg = cfg
+    st = current_stream(dev)
+    if canvas:
+        check(lib.pv_forward_mean_canvas(cfg, ptr(points), ptr(frame_offsets), batch, n, c_in,
+                                         1 if is_cartesian else 0, frame_capacity, ptr(ws), ws.numel(),
+                                         ptr(r.coors), ptr(r.num_points), ptr(r.voxel_counts),
+                                         ptr(r.mean_feats), ptr(r.canvas), st), "pv_forward_mean_canvas")
+    else:
+        check(lib.pv_voxelize(cfg, ptr(points), ptr(frame_offsets), batch, n, c_in,
+                              1 if is_cartesian else 0, frame_capacity, ptr(ws), ws.numel(),
+                              ptr(r.coors), ptr(r.num_points), ptr(r.voxel_counts), ptr(r.voxels),
+                              ptr(r.mean_feats), ptr(r.pc_grid_ind), ptr(r.density), st), "pv_voxelize")
+    return r
+
+
+def read_status(vb):
+    check(_lib.load().pv_read_status(ptr(vb.ws), current_stream(vb.ws.device)), "device status")
+
+
+def vfe_mean(features, num_voxels):
+    _need(features, torch.float32, "features", 3)
+    _need(num_voxels, torch.int32, "num_voxels", 1)
+    m, t, c = features.shape
+    if num_voxels.numel() != m:
+        raise ValueError("num_voxels must have one entry per voxel")
+    out = torch.empty((m, c), dtype=torch.float32, device=features.device)
+    check(_lib.load().pv_vfe_mean(ptr(features), ptr(num_voxels), m, t, c, ptr(out),
+                                  current_stream(features.device)), "pv_vfe_mean")
+    return out
+
+
+def pfn_forward(features, num_voxels, coors, layers, vx, vy, x_off, y_off, with_distance, eps):
+    """layers: list of (weight [U,K], running_mean, running_var, gamma, beta) CUDA f32 tensors."""
+    _need(features, torch.float32, "features", 3)
+    _need(num_voxels, torch.int32, "num_voxels", 1)
+    _need(coors, torch.int32, "coors", 2)
+    m, t, c = features.shape
+    if coors.shape != (m, 4) or num_voxels.numel() != m:
+        raise ValueError("coors must be [M,4] and num_voxels [M]")
+    arr = (PvPfnLayer * len(layers))()
+    for i, (w, mean, var, gamma, beta) in enumerate(layers):
+        for nm, x in (("weight", w), ("mean", mean), ("var", var), ("gamma", gamma), ("beta", beta)):
+            _need(x, torch.float32, "pfn_layers.%d.%s" % (i, nm))
+        arr[i].weight, arr[i].bn_mean, arr[i].bn_var = w.data_ptr(), mean.data_ptr(), var.data_ptr()
+        arr[i].bn_gamma, arr[i].bn_beta = gamma.data_ptr(), beta.data_ptr()
+        arr[i].units, arr[i].in_channels = w.shape[0], w.shape[1]
+    out = torch.empty((m, layers[-1][0].shape[0]), dtype=torch.float32, device=features.device)
+    check(_lib.load().pv_pfn_forward(ptr(features), ptr(num_voxels), ptr(coors), m, t, c,
+                                     1 if with_distance else 0, vx, vy, x_off, y_off, arr, len(layers),
+                                     eps, ptr(out), current_stream(features.device)), "pv_pfn_forward")
+    return out
+
+
+def scatter(voxel_features, coords, batch_size, ny, nx, want_bev_index=False):
+    _need(voxel_features, torch.float32, "voxel_features", 2)
+    _need(coords, torch.int32, "coords", 2)
+    m, c = voxel_features.shape
+    if coords.shape != (m, 4):
+        raise ValueError("coords must be [M,4] (b,z,y,x)")
+    dev = voxel_features.device
+    lib = _lib.load()
+    nbytes = lib.pv_scatter_workspace_bytes(batch_size, ny, nx)
+    ws = workspace(nbytes, dev, "scatter")
+    canvas = torch.empty((batch_size, c, ny, nx), dtype=torch.float32, device=dev)
+    bev = torch.empty((m,), dtype=torch.int64, device=dev) if want_bev_index else None
+    check(lib.pv_scatter(ptr(voxel_features), ptr(coords), m, c, batch_size, ny, nx, ptr(ws),
+                         ws.numel(), ptr(canvas), ptr(bev), current_stream(dev)), "pv_scatter")
+    return (canvas, bev) if want_bev_index else canvas

@@ -1,0 +1,110 @@
+"""Drop-in reader / scatter modules (inference) backed by the sm_100a kernels.
+
+Same class names, constructor kwargs, forward signatures and state_dict keys as
+det3d/models/readers/voxel_encoder.py:7-22 and det3d/models/readers/pillar_encoder.py:19-225, so
+reference configs (``type="PillarFeatureNet"`` ...) and checkpoints
+(``reader.pfn_layers.{i}.linear.weight``, ``...norm.{weight,bias,running_mean,running_var}``)
+load unchanged.  Forward runs the CUDA kernels; there is no eager-PyTorch or CPU fallback.
+Training-mode batch statistics are a "next" row: forward() in training
+mode raises instead of silently using running statistics.
+"""
+import torch
+from torch import nn
+
+from . import functional as F
+from .registry import BACKBONES, READERS
+
+
+@READERS.register_module
+class VoxelFeatureExtractorV3(nn.Module):
+    def __init__(self, num_input_features=4, norm_cfg=None, name="VoxelFeatureExtractorV3"):
+        super(VoxelFeatureExtractorV3, self).__init__()
+        self.name = name
+        self.num_input_features = num_input_features
+
+    def forward(self, features, num_voxels, coors=None):
+        assert self.num_input_features == features.shape[-1]
+        return F.vfe_mean(features, _as_i32(num_voxels))
+
+
+def _as_i32(t):
+    # the reference collates num_points as int32 (point_cloud_ops.py:185); accept int64 too
+    return t if t.dtype == torch.int32 else t.to(torch.int32)
+
+
+class PFNLayer(nn.Module):
+    """Parameter container matching pillar_encoder.py:19-47 (Linear no-bias + BatchNorm1d)."""
+
+    def __init__(self, in_channels, out_channels, norm_cfg=None, last_layer=False):
+        super().__init__()
+        self.name = "PFNLayer"
+        self.last_vfe = last_layer
+        if not self.last_vfe:
+            out_channels = out_channels // 2
+        self.units = out_channels
+        if norm_cfg is None:
+            norm_cfg = dict(type="BN1d", eps=1e-3, momentum=0.01)
+        self.norm_cfg = norm_cfg
+        cfg = dict(norm_cfg)
+        kind = cfg.pop("type")
+        if kind != "BN1d":
+            raise ValueError("PFNLayer kernels implement BN1d only, got %s" % kind)
+        cfg.pop("requires_grad", None)
+        cfg.setdefault("eps", 1e-5)          # det3d/models/utils/norm.py:113
+        self.linear = nn.Linear(in_channels, self.units, bias=False)
+        self.norm = nn.BatchNorm1d(self.units, **cfg)
+
+
+@READERS.register_module
+class PillarFeatureNet(nn.Module):
+    def __init__(self, num_input_features=4, num_filters=(64,), with_distance=False,
+                 voxel_size=(0.2, 0.2, 4), pc_range=(0, -40, -3, 70.4, 40, 1), norm_cfg=None):
+        super().__init__()
+        self.name = "PillarFeatureNet"
+        assert len(num_filters) > 0
+        self.num_input = num_input_features
+        num_input_features += 5
+        if with_distance:
+            num_input_features += 1
+        self._with_distance = with_distance
+        num_filters = [num_input_features] + list(num_filters)
+        layers = []
+        for i in range(len(num_filters) - 1):
+            layers.append(PFNLayer(num_filters[i], num_filters[i + 1], norm_cfg=norm_cfg,
+                                   last_layer=(i >= len(num_filters) - 2)))
+        self.pfn_layers = nn.ModuleList(layers)
+        # pillar_encoder.py:123-126 -- Python doubles, used as f32 scalars by the kernels
+        self.vx = voxel_size[0]
+        self.vy = voxel_size[1]
+        self.x_offset = self.vx / 2 + pc_range[0]
+        self.y_offset = self.vy / 2 + pc_range[1]
+
+    def forward(self, features, num_voxels, coors):
+        if self.training:
+            raise RuntimeError("PillarFeatureNet (B200 kernels) implements eval-mode BatchNorm only; "
+                               "call .eval() first")
+        eps = {l.norm.eps for l in self.pfn_layers}
+        if len(eps) != 1:
+            raise ValueError("all PFN layers must share one BatchNorm eps")
+        layers = [(l.linear.weight.detach().contiguous(), l.norm.running_mean, l.norm.running_var,
+                   l.norm.weight.detach(), l.norm.bias.detach()) for l in self.pfn_layers]
+        out = F.pfn_forward(features, _as_i32(num_voxels), coors if coors.dtype == torch.int32 else coors.int(),
+                            layers, self.vx, self.vy, self.x_offset, self.y_offset,
+                            self._with_distance, eps.pop())
+        return out.squeeze()                      # pillar_encoder.py:169 (M == 1 collapses)
+
+
+@BACKBONES.register_module
+class PointPillarsScatter(nn.Module):
+    def __init__(self, num_input_features=64, norm_cfg=None, name="PointPillarsScatter", **kwargs):
+        super().__init__()
+        self.name = "PointPillarsScatter"
+        self.nchannels = num_input_features
+
+    def forward(self, voxel_features, coords, batch_size, input_shape):
+        self.nx = int(input_shape[0])
+        self.ny = int(input_shape[1])
+        if voxel_features.dim() == 1:             # the reader's .squeeze() on a single voxel
+            voxel_features = voxel_features.view(1, -1)
+        return F.scatter(voxel_features.contiguous(), coords if coords.dtype == torch.int32 else coords.int(),
+                         int(batch_size), self.ny, self.nx)
