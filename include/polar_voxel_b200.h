@@ -11,7 +11,11 @@
  *   - every pointer is a DEVICE pointer owned by the caller unless noted HOST;
  *   - the library never allocates, frees or synchronises; every launch goes to
  *     the caller's stream, so every entry point is CUDA-graph capturable;
- *   - one opaque caller-provided workspace (size from pv_workspace_bytes);
+ *   - one opaque caller-provided workspace (size from pv_workspace_bytes).  It is
+ *     SELF-CLEANING: pv_workspace_init() prepares it once per (config, capacities);
+ *     every call restores whatever it touched, so steady-state calls issue no
+ *     memset.  Re-run pv_workspace_init after an error or when config, batch or a
+ *     capacity changes;
  *   - return value: PV_OK (0) or a negative PV_ERR_* code.  Conditions only
  *     detectable on the device (hash table overflow) set a status word that
  *     pv_read_status() copies back.  Nothing here calls exit().
@@ -76,6 +80,11 @@ const char *pv_error_string(int code);
 size_t pv_workspace_bytes(const pv_config *cfg, int64_t max_points_total, int32_t batch,
                           int64_t frame_capacity);
 
+/* One-time preparation of a workspace for (cfg, capacities); see "SELF-CLEANING" above. */
+int pv_workspace_init(const pv_config *cfg, int64_t max_points_total, int32_t batch,
+                      int64_t frame_capacity, void *workspace, size_t workspace_bytes,
+                      pv_stream_t stream);
+
 /* transform_points (det3d/datasets/pipelines/utils.py:34-47).  out is [n, c_in+2]. */
 int pv_transform_points(const float *in, int64_t n, int32_t c_in, int32_t cylinder, float *out,
                         pv_stream_t stream);
@@ -97,21 +106,38 @@ int pv_transform_points(const float *in, int64_t n, int32_t c_in, int32_t cylind
  *   pc_grid_ind  int32 [n_total, 3] clamped (z, y, x)             or NULL
  *   density      int32 [batch, nz, ny, nx] un-capped counts of kept voxels, or NULL
  * Output buffers must have capacity for min(batch * V, n_total) rows.
+ * max_points_total / frame_capacity are the CAPACITIES the workspace was initialised with
+ * (n_total <= max_points_total, every frame <= frame_capacity points).
  */
 int pv_voxelize(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
                 int32_t batch, int64_t n_total, int32_t c_in, int32_t is_cartesian,
-                int64_t frame_capacity, void *workspace, size_t workspace_bytes,
-                int32_t *coors, int32_t *num_points, int32_t *voxel_counts, float *voxels,
-                float *mean_feats, int32_t *pc_grid_ind, int32_t *density, pv_stream_t stream);
+                int64_t max_points_total, int64_t frame_capacity, void *workspace,
+                size_t workspace_bytes, int32_t *coors, int32_t *num_points, int32_t *voxel_counts,
+                float *voxels, float *mean_feats, int32_t *pc_grid_ind, int32_t *density,
+                pv_stream_t stream);
 
 /* Fused front end for pillar grids (nz == 1): pv_voxelize (mean_feats) followed by the
  * scatter of PointPillarsScatter (pillar_encoder.py:189-225) into canvas
  * f32 [batch, C, ny, nx]; every canvas element is written exactly once. */
 int pv_forward_mean_canvas(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
                            int32_t batch, int64_t n_total, int32_t c_in, int32_t is_cartesian,
-                           int64_t frame_capacity, void *workspace, size_t workspace_bytes,
-                           int32_t *coors, int32_t *num_points, int32_t *voxel_counts,
-                           float *mean_feats, float *canvas, pv_stream_t stream);
+                           int64_t max_points_total, int64_t frame_capacity, void *workspace,
+                           size_t workspace_bytes, int32_t *coors, int32_t *num_points,
+                           int32_t *voxel_counts, float *mean_feats, float *canvas,
+                           pv_stream_t stream);
+
+/* Measurement aid for bench.py: runs pv_forward_mean_canvas (canvas may be NULL for 3-D grids)
+ * `iters` times with CUDA events recorded on `stream` between the stages and returns the average
+ * milliseconds per stage in stage_ms (HOST, PV_PROFILE_STAGES floats): 0 bin_insert,
+ * 1 rank_scan, 2 fill_lists, 3 emit (+ canvas on direct-map pillar grids), 4 hash-map canvas +
+ * restore (pillar grids beyond the direct-map limit only).  Synchronises. */
+#define PV_PROFILE_STAGES 5
+int pv_profile_mean_canvas(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
+                           int32_t batch, int64_t n_total, int32_t c_in, int32_t is_cartesian,
+                           int64_t max_points_total, int64_t frame_capacity, void *workspace,
+                           size_t workspace_bytes, int32_t *coors, int32_t *num_points,
+                           int32_t *voxel_counts, float *mean_feats, float *canvas,
+                           pv_stream_t stream, int32_t iters, float *stage_ms);
 
 /* Copies the device status word of the last pv_voxelize on `workspace` to the host
  * (synchronises `stream`).  Returns PV_OK or PV_ERR_TABLE_FULL / PV_ERR_CUDA. */

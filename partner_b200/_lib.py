@@ -73,10 +73,13 @@ EXPORTS = {
     "pv_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "pv_workspace_bytes": (SZ, [ctypes.POINTER(PvConfig), I64, I32, I64]),
     "pv_transform_points": (ctypes.c_int, [P, I64, I32, I32, P, P]),
-    "pv_voxelize": (ctypes.c_int, [ctypes.POINTER(PvConfig), P, P, I32, I64, I32, I32, I64, P, SZ,
+    "pv_workspace_init": (ctypes.c_int, [ctypes.POINTER(PvConfig), I64, I32, I64, P, SZ, P]),
+    "pv_voxelize": (ctypes.c_int, [ctypes.POINTER(PvConfig), P, P, I32, I64, I32, I32, I64, I64, P, SZ,
                                    P, P, P, P, P, P, P, P]),
-    "pv_forward_mean_canvas": (ctypes.c_int, [ctypes.POINTER(PvConfig), P, P, I32, I64, I32, I32, I64,
+    "pv_forward_mean_canvas": (ctypes.c_int, [ctypes.POINTER(PvConfig), P, P, I32, I64, I32, I32, I64, I64,
                                               P, SZ, P, P, P, P, P, P]),
+    "pv_profile_mean_canvas": (ctypes.c_int, [ctypes.POINTER(PvConfig), P, P, I32, I64, I32, I32, I64, I64,
+                                              P, SZ, P, P, P, P, P, P, I32, ctypes.POINTER(F32)]),
     "pv_read_status": (ctypes.c_int, [P, P]),
     "pv_vfe_mean": (ctypes.c_int, [P, P, I64, I32, I32, P, P]),
     "pv_pfn_forward": (ctypes.c_int, [P, P, P, I64, I32, I32, I32, F32, F32, F32, F32,

@@ -8,34 +8,42 @@
 #define PV_INF 0xFFFFFFFFu
 #define PV_DENSE_MAX_CELLS (1u << 20)  // grids up to this many cells/frame use a direct map
 
-// One voxel-map entry.  The whole map is reset with a single 0xFF memset:
-//   key = PV_INF (empty), first = PV_INF (ready for atomicMin), cnt = -1 (count - 1), g = PV_INF.
-struct __align__(16) PvEntry {
-    uint32_t key;    // linear cell index inside the frame (hash mode; unused in dense mode)
-    uint32_t first;  // smallest point index that fell into the cell
-    uint32_t cnt;    // number of points in the cell, minus one
-    uint32_t g;      // batch-global first-occurrence rank of the cell
+// One voxel-map entry (one per grid cell in dense mode, one per hash slot otherwise).
+// CLEAN state = all bits set.  The workspace is self-cleaning: k_cell_flags, the only reader,
+// restores every entry it consumes, so no per-call memset is needed (pv_workspace_init once).
+struct __align__(8) PvEntry {
+    uint32_t first;  // smallest point index that fell into the cell        (K1, atomicMin)
+    uint32_t cnt;    // number of points in the cell, minus one             (K1, atomicAdd)
+};
+// Per-cell word written by the scan for the cells occupied in THIS call and read by k_place for
+// points of those cells only, so it never needs cleaning.
+struct __align__(8) PvMeta {
+    uint32_t kg;     // start of the voxel's point list in kept[]; PV_INF = dropped (rank >= V)
+    uint32_t c;      // number of points in the cell
 };
 
-// Workspace carve-up (host computed, passed by value).
+// Workspace carve-up (host computed from CAPACITIES, so it is stable across calls).
 struct PvWs {
-    // --- zeroed every call ---
-    uint32_t *ctrl;           // [0] scan ticket, [1] status bits
-    unsigned long long *frame_scan;  // [B+1] packed exclusive scan at each frame start
+    uint32_t *ctrl;           // [1] status bits
+    uint32_t *counts_raw;     // [B] first-occurrence cells per frame (before the V cap)
     int32_t *base;            // [B+1] first output row of each frame
-    unsigned long long *tile_state;  // [num_tiles] decoupled look-back state
-    // --- set to 0xFF every call ---
-    PvEntry *table;           // [B * capf]
-    uint32_t *kept;           // [n_cap] per-voxel sorted point lists, CSR by vox_koff
-    // --- no init needed ---
+    unsigned long long *tile_agg;    // [max_tiles] per-tile scan aggregates
+    PvEntry *table;           // [B * capf]                              (clean = all ones)
+    uint32_t *keys;           // [B * capf] hash mode: cell index of slot (clean = all ones)
+    uint32_t *kept;           // [n_cap] per-voxel ascending point lists (clean = all ones)
+    PvMeta *meta;             // [B * capf]
     uint32_t *slot;           // [n_cap] map slot of every point (PV_INF = out of range)
-    uint32_t *vox_slot;       // [n_cap] map slot of the voxel with global rank g
-    uint32_t *vox_koff;       // [n_cap] start of that voxel's list in kept[]
+    uint32_t *pv;             // [n_cap] per-point scan word: bit 31 = first point of its cell,
+                              //         bits 30..0 = points in that cell (first points only)
+    uint32_t *pcell;          // [n_cap] hash mode: linear cell index of every point
+    uint32_t *vox_cell;       // [B * fcap] linear cell index of the first-occurrence cell (b, r)
+    uint32_t *vox_kg;         // [B * fcap] its list offset
+    uint32_t *vox_c;          // [B * fcap] its point count
     uint32_t capf;            // map slots per frame (pow2 in hash mode, cells in dense mode)
+    uint32_t fcap;            // frame capacity (points)
     uint32_t dense;           // 1 = direct map
-    uint32_t num_tiles;
-    size_t zero_bytes, ff_bytes, total_bytes;
-    char *zero_begin, *ff_begin;
+    uint32_t max_tiles;
+    size_t total_bytes;
 };
 
 struct PvParams {
@@ -48,23 +56,30 @@ struct PvParams {
     uint32_t n;
     int32_t c_in, cart, C;
     uint32_t cells;
+    uint32_t num_tiles;
     PvWs ws;
     int32_t *coors, *num_points, *voxel_counts, *grid_ind, *density;
     float *voxels, *feats, *canvas;
 };
 
 // ---------------------------------------------------------------------------------------------
-// Scan payload: rank (first points seen) in the high field, kept-point count in the low field.
-// 31 bits each so that a 2-bit look-back flag fits in the same 64-bit word.
+// Scan payload (64 bit): [63:62] look-back flag | [61] segment flag | [60:31] rank | [30:0] ksum.
+// rank = first points seen since the last frame start (segmented by frame), ksum = running sum
+// of min(count, T) over first points (global: offsets into kept[]).
 // ---------------------------------------------------------------------------------------------
-#define PV_FIELD 31
-#define PV_FIELD_MASK ((1ull << PV_FIELD) - 1)
-__device__ __forceinline__ unsigned long long pv_pack(uint32_t rank, uint32_t ksum)
+#define PV_KBITS 31
+#define PV_KMASK ((1ull << PV_KBITS) - 1)
+#define PV_SEG (1ull << 61)
+#define PV_RANK_ONE (1ull << PV_KBITS)
+#define PV_VAL_MASK ((1ull << 62) - 1)
+__device__ __forceinline__ unsigned long long pv_comb(unsigned long long a, unsigned long long b)
 {
-    return ((unsigned long long)rank << PV_FIELD) | ksum;
+    const unsigned long long ks = (a & PV_KMASK) + (b & PV_KMASK);
+    const unsigned long long ah = a & ~PV_KMASK, bh = b & ~PV_KMASK;
+    return ((b & PV_SEG) ? bh : ah + bh) | ks;
 }
-__device__ __forceinline__ uint32_t pv_rank(unsigned long long v) { return (uint32_t)((v >> PV_FIELD) & PV_FIELD_MASK); }
-__device__ __forceinline__ uint32_t pv_ksum(unsigned long long v) { return (uint32_t)(v & PV_FIELD_MASK); }
+__device__ __forceinline__ uint32_t pv_rank(unsigned long long v) { return (uint32_t)((v >> PV_KBITS) & 0x3FFFFFFFull); }
+__device__ __forceinline__ uint32_t pv_ksum(unsigned long long v) { return (uint32_t)(v & PV_KMASK); }
 
 __device__ __forceinline__ uint32_t pv_ld_volatile(const uint32_t *p)
 {
@@ -81,11 +96,6 @@ __device__ __forceinline__ unsigned long long pv_ld_volatile64(const unsigned lo
 __device__ __forceinline__ void pv_st_volatile64(unsigned long long *p, unsigned long long v)
 {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint4 pv_ld_entry(const PvEntry *e)
-{
-    // entries are written by earlier kernels only: plain 128-bit load through L2
-    return __ldcg(reinterpret_cast<const uint4 *>(e));
 }
 
 __device__ __forceinline__ uint32_t pv_hash(uint32_t k)
@@ -142,23 +152,24 @@ __device__ __forceinline__ float pv_rho(float x, float y)
     return __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));
 }
 
-// Channel k of the polar row (rho, phi, z, x, y, feat3..) built from a Cartesian row.
-// `row` points at c_in floats.
-__device__ __forceinline__ void pv_polar_row(const float *__restrict__ row, int c_in, int cart,
-                                             float *__restrict__ out)
+// Loads point i's row and expands it to the C-channel feature row the reference voxelizes:
+// Cartesian input -> (rho, phi, z, x, y, feat3..) (utils.py:42-44); polar input -> as is.
+__device__ __forceinline__ void pv_feature_row(const float *__restrict__ pts, uint32_t i, int c_in,
+                                               int cart, float (&out)[PV_MAX_CHANNELS])
 {
+    const float *row = pts + (size_t)i * c_in;
+    float in[PV_MAX_CHANNELS];
+#pragma unroll
+    for (int k = 0; k < PV_MAX_CHANNELS; ++k) in[k] = (k < c_in) ? __ldg(row + k) : 0.0f;
     if (cart) {
-        const float x = row[0], y = row[1];
-        out[0] = pv_rho(x, y);
-        out[1] = pv_atan2f(y, x);
-        out[2] = row[2];
-        out[3] = x;
-        out[4] = y;
-#pragma unroll 4
-        for (int k = 3; k < c_in; ++k) out[k + 2] = row[k];
+        out[0] = pv_rho(in[0], in[1]);
+        out[1] = pv_atan2f(in[1], in[0]);
+        out[2] = in[2]; out[3] = in[0]; out[4] = in[1];
+#pragma unroll
+        for (int k = 5; k < PV_MAX_CHANNELS; ++k) out[k] = in[k - 2];
     } else {
-#pragma unroll 4
-        for (int k = 0; k < c_in; ++k) out[k] = row[k];
+#pragma unroll
+        for (int k = 0; k < PV_MAX_CHANNELS; ++k) out[k] = in[k];
     }
 }
 

@@ -51,6 +51,39 @@ def workspace(nbytes, device, tag="main"):
     return ws
 
 
+def _bucket(n, quantum=65536):
+    """Capacities are rounded up so that frames of varying size share one initialised workspace."""
+    return max(quantum, (int(n) + quantum - 1) // quantum * quantum)
+
+
+_voxel_ws = {}          # layout key -> initialised workspace tensor (LRU, self-cleaning: see header)
+_VOXEL_WS_KEEP = 6
+
+
+def voxel_workspace(cfg, n_cap, batch, frame_cap, device):
+    """Workspace initialised (pv_workspace_init) for exactly this config + capacities."""
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (dev_index, tuple(cfg.lo), tuple(cfg.vs), tuple(cfg.grid), cfg.max_points, n_cap, batch, frame_cap)
+    ws = _voxel_ws.pop(key, None)
+    if ws is None:
+        lib = _lib.load()
+        nbytes = lib.pv_workspace_bytes(cfg, n_cap, batch, frame_cap)
+        if nbytes == 0:
+            check(-1, "pv_workspace_bytes")
+        while len(_voxel_ws) >= _VOXEL_WS_KEEP:
+            _voxel_ws.pop(next(iter(_voxel_ws)))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        check(lib.pv_workspace_init(cfg, n_cap, batch, frame_cap, ptr(ws), ws.numel(), current_stream(device)),
+              "pv_workspace_init")
+    _voxel_ws[key] = ws       # most recently used last
+    return ws
+
+
+def drop_voxel_workspaces():
+    """Forget every cached workspace (call after a device-side error left one dirty)."""
+    _voxel_ws.clear()
+
+
 def transform_points(points, voxel_shape="cylinder"):
     """pv_transform_points: pipelines/utils.py:34-47 on the device."""
     _need(points, torch.float32, "points", 2)
@@ -69,7 +102,7 @@ class VoxelBatch:
     """Outputs of one batched voxelization, in capacity layout until ``counts`` is read."""
 
     __slots__ = ("coors", "num_points", "voxel_counts", "voxels", "mean_feats", "pc_grid_ind",
-                 "density", "canvas", "ws", "cfg")
+                 "density", "canvas", "ws", "cfg", "n_cap", "f_cap")
 
     def total(self):
         """Sum of per-frame voxel counts (one device->host read)."""
@@ -92,10 +125,9 @@ def voxelize(cfg, points, frame_offsets, batch, frame_capacity, is_cartesian, wa
     C = c_in + 2 if is_cartesian else c_in
     dev = points.device
     lib = _lib.load()
-    nbytes = lib.pv_workspace_bytes(cfg, n, batch, frame_capacity)
-    if nbytes == 0:
-        check(-1, "pv_workspace_bytes")
-    ws = workspace(nbytes, dev)
+    n_cap = _bucket(n)
+    f_cap = min(n_cap, _bucket(frame_capacity))
+    ws = voxel_workspace(cfg, n_cap, batch, f_cap, dev)
     rows = max(1, min(batch * cfg.max_voxels, n))
     T = cfg.max_points
     r = out if out is not None else VoxelBatch()
@@ -112,22 +144,26 @@ def voxelize(cfg, points, frame_offsets, batch, frame_capacity, is_cartesian, wa
                     if canvas else None)
     r.ws = ws
     r.cfg = cfg
+    r.n_cap, r.f_cap = n_cap, f_cap
     st = current_stream(dev)
     if canvas:
         check(lib.pv_forward_mean_canvas(cfg, ptr(points), ptr(frame_offsets), batch, n, c_in,
-                                         1 if is_cartesian else 0, frame_capacity, ptr(ws), ws.numel(),
+                                         1 if is_cartesian else 0, n_cap, f_cap, ptr(ws), ws.numel(),
                                          ptr(r.coors), ptr(r.num_points), ptr(r.voxel_counts),
                                          ptr(r.mean_feats), ptr(r.canvas), st), "pv_forward_mean_canvas")
     else:
         check(lib.pv_voxelize(cfg, ptr(points), ptr(frame_offsets), batch, n, c_in,
-                              1 if is_cartesian else 0, frame_capacity, ptr(ws), ws.numel(),
+                              1 if is_cartesian else 0, n_cap, f_cap, ptr(ws), ws.numel(),
                               ptr(r.coors), ptr(r.num_points), ptr(r.voxel_counts), ptr(r.voxels),
                               ptr(r.mean_feats), ptr(r.pc_grid_ind), ptr(r.density), st), "pv_voxelize")
     return r
 
 
 def read_status(vb):
-    check(_lib.load().pv_read_status(ptr(vb.ws), current_stream(vb.ws.device)), "device status")
+    rc = _lib.load().pv_read_status(ptr(vb.ws), current_stream(vb.ws.device))
+    if rc != 0:
+        drop_voxel_workspaces()      # the failed call left its workspace dirty
+    check(rc, "device status")
 
 
 def vfe_mean(features, num_voxels):
