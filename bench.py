@@ -152,6 +152,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="nusc_pillar_mean_canvas_b8", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--streams", type=int, default=4,
+                    help="independent batches in flight on separate CUDA streams (1 = strictly serial steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -199,14 +201,17 @@ def main():
     cap_all = max(s["cap"] for s in sets)
     in_bytes = sum(s["n"] for s in sets) * c_in * 4
 
-    # ---- device-resident path: one CUDA graph per input set -----------------------------
+    # ---- device-resident path: one CUDA graph per input set, each with its own workspace ------
     runners = []
-    for s in sets:
+    fes = []
+    for k, s in enumerate(sets):
+        fe_s = PolarFrontEnd(g["voxel_size"], g["range"], g["max_points"], g["max_voxels"], cartesian=True,
+                             device=dev, workspace_tag=k)
+        fes.append(fe_s)
         if args.no_graph:
-            out = fe.forward_device(s["d_points"], s["d_off"], per_gpu, cap_all)
-            runners.append((lambda s=s, out=out: fe.forward_device(s["d_points"], s["d_off"], per_gpu, cap_all, out=out), out))
+            out = fe_s.forward_device(s["d_points"], s["d_off"], per_gpu, cap_all)
+            runners.append((lambda s=s, out=out, f=fe_s: f.forward_device(s["d_points"], s["d_off"], per_gpu, cap_all, out=out), out))
         else:
-            fe_s = PolarFrontEnd(g["voxel_size"], g["range"], g["max_points"], g["max_voxels"], cartesian=True, device=dev)
             out = fe_s.capture(s["d_points"], s["d_off"], per_gpu, cap_all)
             runners.append((fe_s.replay, out))
     torch.cuda.synchronize()
@@ -217,45 +222,64 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for w in range(args.warmup):
-        runners[w % N_SETS][0]()
-    barrier()
+    def timed(fn, steps, n_streams):
+        """K steps round-robin over n_streams CUDA streams (independent batches overlap), timed with
+        CUDA events on the current stream, which every side stream forks from and joins into."""
+        cur = torch.cuda.current_stream(dev)
+        streams = [torch.cuda.Stream(dev) for _ in range(n_streams)] if n_streams > 1 else [cur]
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        for st in streams:
+            if st is not cur:
+                st.wait_event(e0)
+        for k in range(steps):
+            with torch.cuda.stream(streams[k % n_streams]):
+                fn(k)
+        for st in streams:
+            if st is not cur:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                cur.wait_event(ev)
+        e1.record(cur)
+        barrier()
+        return e0.elapsed_time(e1)
+
+    n_streams = max(1, min(args.streams, N_SETS))
+    step = lambda k: runners[k % N_SETS][0]()        # noqa: E731
+    timed(step, args.warmup, n_streams)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(args.steps):
-        runners[k % N_SETS][0]()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = timed(step, args.steps, n_streams)
+    ms_single = timed(step, args.steps, 1) if n_streams > 1 else ms_total
     pts_done = sum(sets[k % N_SETS]["n"] for k in range(args.steps))
 
     # ---- end-to-end path: pinned host buffers, H2D + D2H inside the timed region ----------
-    n_max = max(s["n"] for s in sets)
     ios = []
-    for s in sets:
-        io = fe.make_host_io(s["n"], per_gpu, c_in)
+    for s, f in zip(sets, fes):
+        io = f.make_host_io(s["n"], per_gpu, c_in)
         io["h_points"].copy_(s["h_points"])
         io["h_offsets"].copy_(s["h_off"])
         ios.append(io)
-    for w in range(3):
-        fe.forward_host(ios[w % N_SETS], cap_all)
-    barrier()
-    e2e_steps = max(3, min(args.steps, 50))
+    e2e_steps = max(4, min(args.steps, 48))
+    traffic = [0, 0]
+
+    def e2e_step(k):
+        a, b = fes[k % N_SETS].forward_host_async(ios[k % N_SETS], cap_all)
+        traffic[0] += a
+        traffic[1] += b
+    timed(e2e_step, 4, n_streams)
+    traffic = [0, 0]
     t0 = time.perf_counter()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    h2d = d2h = 0
-    for k in range(e2e_steps):
-        _, a, b = fe.forward_host(ios[k % N_SETS], cap_all)
-        h2d += a
-        d2h += b
-    e3.record()
-    barrier()
-    e2e_ms = e2.elapsed_time(e3)
+    e2e_ms = timed(e2e_step, e2e_steps, n_streams)
     e2e_wall = (time.perf_counter() - t0) * 1e3
+    h2d, d2h = traffic
+    # fully synchronous variant (one step at a time, slices copied after reading the counts)
+    t0 = time.perf_counter()
+    for k in range(8):
+        fes[k % N_SETS].forward_host(ios[k % N_SETS], cap_all)
+    e2e_sync_ms = (time.perf_counter() - t0) * 1e3 / 8
     e2e_pts = sum(sets[k % N_SETS]["n"] for k in range(e2e_steps))
     clocks = sampler.stop() if rank == 0 else None
 
@@ -275,13 +299,13 @@ def main():
     torch.cuda.synchronize()
 
     # ---- reduce over ranks: max time, sum of work ------------------------------------------
-    vec = torch.tensor([ms_total, e2e_ms, float(pts_done), float(e2e_pts)], dtype=torch.float64, device=dev)
+    vec = torch.tensor([ms_total, e2e_ms, float(pts_done), float(e2e_pts), ms_single], dtype=torch.float64, device=dev)
     if dist is not None:
         mx = vec.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vec.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms_total, e2e_ms = float(mx[0]), float(mx[1])
+        ms_total, e2e_ms, ms_single = float(mx[0]), float(mx[1]), float(mx[4])
         pts_all, e2e_pts_all = float(sm[2]), float(sm[3])
     else:
         pts_all, e2e_pts_all = float(pts_done), float(e2e_pts)
@@ -314,10 +338,16 @@ def main():
                        "max_points": g["max_points"], "max_voxels": g["max_voxels"],
                        "parallelism": "frame-sharded x%d, no collective" % world,
                        "l2": "%d rotating input sets (%.0f MB) + outputs exceed the 126 MB L2" % (N_SETS, in_bytes / 1e6),
-                       "launch": "eager" if args.no_graph else "cuda-graph replay"},
+                       "launch": "eager" if args.no_graph else "cuda-graph replay",
+                       "streams": n_streams,
+                       "note": "steps are independent batches; with streams > 1 consecutive steps overlap on "
+                               "separate CUDA streams (each with its own workspace); single_stream = strictly serial"},
+            "single_stream": {"value": pts_all / (ms_single * 1e-3) / 1e6, "unit": UNIT,
+                              "ms_per_step": ms_single / args.steps},
             "e2e": {"value": e2e_pts_all / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                     "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
-                    "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": e2e_wall / e2e_steps, "steps": e2e_steps},
+                    "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": e2e_wall / e2e_steps, "steps": e2e_steps,
+                    "streams": n_streams, "synchronous_ms_per_step": e2e_sync_ms},
             "gpu_launches": 6 * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,

@@ -15,23 +15,22 @@ struct __align__(8) PvEntry {
     uint32_t first;  // smallest point index that fell into the cell        (K1, atomicMin)
     uint32_t cnt;    // number of points in the cell, minus one             (K1, atomicAdd)
 };
-// Per-cell word written by the scan for the cells occupied in THIS call and read by k_place for
-// points of those cells only, so it never needs cleaning.
-struct __align__(8) PvMeta {
-    uint32_t kg;     // start of the voxel's point list in kept[]; PV_INF = dropped (rank >= V)
-    uint32_t c;      // number of points in the cell
-};
 
 // Workspace carve-up (host computed from CAPACITIES, so it is stable across calls).
 struct PvWs {
     uint32_t *ctrl;           // [1] status bits
     uint32_t *counts_raw;     // [B] first-occurrence cells per frame (before the V cap)
     int32_t *base;            // [B+1] first output row of each frame
-    unsigned long long *tile_agg;    // [max_tiles] per-tile scan aggregates
+    uint32_t *frame_rank0;    // [B] cells of all earlier frames (global rank at the frame start)
+    uint32_t *cum_tiles;      // [B+1] scan tiles of all earlier frames (tiles never straddle frames)
+    unsigned long long *tile_agg;    // [max_tiles] per-tile sums       rank << 32 | ksum
+    unsigned long long *tile_pre;    // [max_tiles] exclusive prefixes  rank << 32 | ksum
     PvEntry *table;           // [B * capf]                              (clean = all ones)
     uint32_t *keys;           // [B * capf] hash mode: cell index of slot (clean = all ones)
     uint32_t *kept;           // [n_cap] per-voxel ascending point lists (clean = all ones)
-    PvMeta *meta;             // [B * capf]
+    unsigned long long *meta; // [B * capf] per-cell word written by the scan for the cells occupied
+                              //   in THIS call (never needs cleaning):
+                              //   [63:48] arrival cursor | [47:32] min(count, 65535) | [31:0] kg
     uint32_t *slot;           // [n_cap] map slot of every point (PV_INF = out of range)
     uint32_t *pv;             // [n_cap] per-point scan word: bit 31 = first point of its cell,
                               //         bits 30..0 = points in that cell (first points only)

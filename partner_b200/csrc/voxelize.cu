@@ -74,6 +74,14 @@ __global__ void __launch_bounds__(K1_THREADS) k_bin_insert(const __grid_constant
     const uint32_t n_tile = tile_base < p.n ? min((uint32_t)K1_THREADS, p.n - tile_base) : 0u;
     const int c_in = p.c_in;
     if (tid == 0) s_b0 = pv_frame_of(p.offsets, p.B, tile_base);
+    if (blockIdx.x == 0 && tid == 32) {        // scan tiles per frame (tiles never straddle frames)
+        uint32_t acc = 0;
+        for (int b = 0; b < p.B; ++b) {
+            p.ws.cum_tiles[b] = acc;
+            acc += ((uint32_t)(p.offsets[b + 1] - p.offsets[b]) + SCAN_TILE - 1) / SCAN_TILE;
+        }
+        p.ws.cum_tiles[p.B] = acc;
+    }
 
     // ---- stage the tile's rows: coalesced 128-bit loads of the contiguous float range ----
     {
@@ -201,176 +209,230 @@ __global__ void __launch_bounds__(256) k_cell_flags(const __grid_constant__ PvPa
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3 -- frame-segmented scan over pv[]: tile_reduce, then scan_apply
+// K3 -- scan over pv[], in point order, of (is_first, min(count, T)).  Tiles never straddle a
+// frame (tile t of frame b covers TILE consecutive points of that frame), so first-occurrence
+// ranks restart per frame without any segmented arithmetic:
+//   tile_reduce : per-tile sums                          -> tile_agg[t] = rank << 32 | ksum
+//   scan_mid    : one block; exclusive prefixes (rank per frame, ksum global) -> tile_pre[t],
+//                 per-frame voxel counts (capped at V) and output row bases
+//   scan_apply  : per-tile scan; a first point's prefix is its rank r and list offset kg.
 // ---------------------------------------------------------------------------------------------
-struct ScanTile {
-    unsigned long long val[SCAN_ITEMS];
-    unsigned long long excl;     // exclusive prefix of this thread inside the tile
-    unsigned long long total;    // tile aggregate
-    uint32_t w[SCAN_ITEMS];
-};
+struct TileRange { int b; uint32_t lo, hi; };   // frame, [lo, hi) point range; b < 0 = no such tile
 
-// Loads a tile of pv[], marks frame starts, scans it block-wide under pv_comb.
-__device__ __forceinline__ void pv_scan_tile(const PvParams &p, uint32_t tile, uint32_t *s_seg,
-                                             unsigned long long *s_warp, ScanTile &t)
+__device__ __forceinline__ TileRange pv_tile_range(const PvParams &p, uint32_t tile)
 {
-    const uint32_t tid = threadIdx.x;
-    const uint32_t tile_base = tile * SCAN_TILE;
-    const uint32_t i0 = tile_base + tid * SCAN_ITEMS;
-    if (tid < SCAN_TILE / 32) s_seg[tid] = 0;
-    if (i0 + SCAN_ITEMS <= p.n) {
+    // cum_tiles[b] = tiles of frames < b (written by k_bin_insert's block 0)
+    const uint32_t *cum = p.ws.cum_tiles;
+    TileRange t;
+    if (tile >= cum[p.B]) { t.b = -1; t.lo = t.hi = 0; return t; }
+    int lo = 0, hi = p.B;            // cum[lo] <= tile < cum[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (cum[mid] <= tile) lo = mid; else hi = mid;
+    }
+    t.b = lo;
+    t.lo = (uint32_t)p.offsets[lo] + (tile - cum[lo]) * SCAN_TILE;
+    t.hi = min(t.lo + SCAN_TILE, (uint32_t)p.offsets[lo + 1]);
+    return t;
+}
+
+// Loads the tile's pv words and returns this thread's packed (rank << 32 | ksum) items.
+__device__ __forceinline__ unsigned long long pv_load_items(const PvParams &p, const TileRange &t,
+                                                            uint32_t (&w)[SCAN_ITEMS],
+                                                            unsigned long long (&val)[SCAN_ITEMS])
+{
+    const uint32_t i0 = t.lo + threadIdx.x * SCAN_ITEMS;
+    if (i0 + SCAN_ITEMS <= t.hi && ((i0 & 3u) == 0)) {
         const uint4 v0 = __ldcg(reinterpret_cast<const uint4 *>(p.ws.pv + i0));
         const uint4 v1 = __ldcg(reinterpret_cast<const uint4 *>(p.ws.pv + i0 + 4));
-        t.w[0] = v0.x; t.w[1] = v0.y; t.w[2] = v0.z; t.w[3] = v0.w;
-        t.w[4] = v1.x; t.w[5] = v1.y; t.w[6] = v1.z; t.w[7] = v1.w;
+        w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
+        w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
     } else {
 #pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j) t.w[j] = (i0 + j < p.n) ? __ldcg(p.ws.pv + i0 + j) : 0u;
+        for (int j = 0; j < SCAN_ITEMS; ++j) w[j] = (i0 + j < t.hi) ? __ldcg(p.ws.pv + i0 + j) : 0u;
     }
-    __syncthreads();
-    for (int b = tid; b < p.B; b += SCAN_THREADS) {
-        const uint32_t off = (uint32_t)p.offsets[b];
-        if (off >= tile_base && off < tile_base + SCAN_TILE && off < p.n)
-            atomicOr(&s_seg[(off - tile_base) >> 5], 1u << ((off - tile_base) & 31u));
-    }
-    __syncthreads();
-    const uint32_t segbits = (s_seg[(tid * SCAN_ITEMS) >> 5] >> ((tid * SCAN_ITEMS) & 31u)) & 0xFFu;
-    unsigned long long tsum = 0;
+    unsigned long long sum = 0;
 #pragma unroll
     for (int j = 0; j < SCAN_ITEMS; ++j) {
-        const uint32_t L = min(t.w[j] & 0x7FFFFFFFu, (uint32_t)p.T);
-        t.val[j] = ((t.w[j] & PV_FIRST) ? (PV_RANK_ONE | L) : 0ull) | (((segbits >> j) & 1u) ? PV_SEG : 0ull);
-        tsum = pv_comb(tsum, t.val[j]);
+        val[j] = (w[j] & PV_FIRST) ? ((1ull << 32) | min(w[j] & 0x7FFFFFFFu, (uint32_t)p.T)) : 0ull;
+        sum += val[j];
     }
-    const unsigned lane = tid & 31u, warp = tid >> 5;
-    unsigned long long incl = tsum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= (unsigned)d) incl = pv_comb(o, incl);
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    unsigned long long excl = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) excl = 0;
+    return sum;
+}
+
+// Exclusive prefixes over the tile sums (rank and ksum), per-frame voxel counts (capped at V) and
+// output row bases.  Runs in the LAST tile_reduce block to finish (no extra launch).
+__device__ void pv_scan_mid(const PvParams &p, unsigned long long *s_warp /*[SCAN_THREADS/32 + 1]*/)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t *cum = p.ws.cum_tiles;
+    const uint32_t ntiles = cum[p.B];
+    unsigned long long &s_carry = s_warp[SCAN_THREADS / 32];
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    unsigned long long warp_off = 0, total = 0;
+    for (uint32_t base = 0; base < ntiles; base += SCAN_THREADS) {
+        const uint32_t t = base + tid;
+        const unsigned long long v = t < ntiles ? __ldcg(p.ws.tile_agg + t) : 0ull;
+        unsigned long long incl = v;
 #pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-        const unsigned long long x = s_warp[w];
-        if ((unsigned)w < warp) warp_off = pv_comb(warp_off, x);
-        total = pv_comb(total, x);
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (unsigned)d) incl += o;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned long long off = s_carry;
+        for (uint32_t k = 0; k < warp; ++k) off += s_warp[k];
+        if (t < ntiles) p.ws.tile_pre[t] = off + incl - v;
+        __syncthreads();
+        if (tid == SCAN_THREADS - 1) s_carry = off + incl;
+        __syncthreads();
     }
-    t.excl = pv_comb(warp_off, excl);
-    t.total = total;
+    // rank prefix at a frame's first tile = cells of all earlier frames
+    const unsigned long long total = s_carry;
+    for (int b0 = 0; b0 < p.B; b0 += SCAN_THREADS) {
+        const int b = b0 + (int)tid;
+        uint32_t m = 0;
+        if (b < p.B) {
+            const uint32_t t0 = cum[b], t1 = cum[b + 1];
+            const unsigned long long g0 = t0 < ntiles ? p.ws.tile_pre[t0] : total;
+            const unsigned long long g1 = t1 < ntiles ? p.ws.tile_pre[t1] : total;
+            const uint32_t raw = (uint32_t)(g1 >> 32) - (uint32_t)(g0 >> 32);
+            p.ws.frame_rank0[b] = (uint32_t)(g0 >> 32);
+            p.ws.counts_raw[b] = raw;
+            m = min(raw, (uint32_t)p.V);
+            p.voxel_counts[b] = (int32_t)m;
+        }
+        // block-wide exclusive sum of m -> output row bases
+        uint32_t incl = m;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (unsigned)d) incl += o;
+        }
+        __syncthreads();
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t off = (b0 == 0) ? 0u : (uint32_t)p.ws.base[b0];
+        for (uint32_t k = 0; k < warp; ++k) off += (uint32_t)s_warp[k];
+        if (b < p.B) p.ws.base[b + 1] = (int32_t)(off + incl);
+        if (b == 0) p.ws.base[0] = 0;
+        __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_tile_reduce(const __grid_constant__ PvParams p)
 {
-    __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
-    __shared__ uint32_t s_seg[SCAN_TILE / 32];
-    ScanTile t;
-    pv_scan_tile(p, blockIdx.x, s_seg, s_warp, t);
-    if (threadIdx.x == 0) p.ws.tile_agg[blockIdx.x] = t.total;
+    __shared__ unsigned long long s_warp[SCAN_THREADS / 32 + 1];
+    __shared__ uint32_t s_last;
+    const TileRange t = pv_tile_range(p, blockIdx.x);
+    if (t.b >= 0) {
+        uint32_t w[SCAN_ITEMS];
+        unsigned long long val[SCAN_ITEMS];
+        unsigned long long sum = pv_load_items(p, t, w, val);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        if ((threadIdx.x & 31u) == 0) s_warp[threadIdx.x >> 5] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long tot = 0;
+#pragma unroll
+            for (int k = 0; k < SCAN_THREADS / 32; ++k) tot += s_warp[k];
+            p.ws.tile_agg[blockIdx.x] = tot;
+        }
+    }
+    // last block to arrive scans the tile sums (counter restores itself for the next call)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t done = atomicAdd(p.ws.ctrl + 2, 1u);
+        s_last = (done == gridDim.x - 1) ? 1u : 0u;
+        if (s_last) p.ws.ctrl[2] = 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        pv_scan_mid(p, s_warp);
+    }
 }
 
+// meta word of a cell: [63:48] arrival cursor | [47:32] min(count, 65535) | [31:0] kg
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const __grid_constant__ PvParams p)
 {
     __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
-    __shared__ uint32_t s_seg[SCAN_TILE / 32];
-    __shared__ uint32_t s_rank_incl[SCAN_TILE];
-    __shared__ unsigned long long s_red[SCAN_THREADS / 32];
-    const uint32_t tid = threadIdx.x, tile = blockIdx.x;
-    const unsigned lane = tid & 31u, warp = tid >> 5;
-
-    // ordered reduction of the aggregates of all earlier tiles: contiguous chunk per thread,
-    // then an ordered combine across lanes and warps
-    unsigned long long pre = 0;
-    {
-        const uint32_t per = (tile + SCAN_THREADS - 1) / SCAN_THREADS;
-        const uint32_t lo = min(tile, tid * per), hi = min(tile, lo + per);
-        for (uint32_t k = lo; k < hi; ++k) pre = pv_comb(pre, __ldcg(p.ws.tile_agg + k));
+    const TileRange t = pv_tile_range(p, blockIdx.x);
+    if (t.b < 0) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t w[SCAN_ITEMS];
+    unsigned long long val[SCAN_ITEMS];
+    const unsigned long long tsum = pv_load_items(p, t, w, val);
+    unsigned long long incl = tsum;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long o = __shfl_up_sync(0xffffffffu, pre, d);
-            if (lane >= (unsigned)d) pre = pv_comb(o, pre);
-        }
-        if (lane == 31) s_red[warp] = pre;
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (unsigned)d) incl += o;
     }
-    ScanTile t;
-    pv_scan_tile(p, tile, s_seg, s_warp, t);       // contains __syncthreads: s_red is visible after it
-    unsigned long long tile_excl = 0;
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long excl = p.ws.tile_pre[blockIdx.x] - ((unsigned long long)p.ws.frame_rank0[t.b] << 32);
+    for (uint32_t k = 0; k < warp; ++k) excl += s_warp[k];
+    excl += incl - tsum;
+    const uint32_t i0 = t.lo + tid * SCAN_ITEMS;
+    uint32_t sl[SCAN_ITEMS];                               // all slot loads in flight before any use
 #pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; ++w) tile_excl = pv_comb(tile_excl, s_red[w]);
-
-    const uint32_t tile_base = tile * SCAN_TILE;
-    const uint32_t i0 = tile_base + tid * SCAN_ITEMS;
-    unsigned long long excl = pv_comb(tile_excl, t.excl);
+    for (int j = 0; j < SCAN_ITEMS; ++j) sl[j] = val[j] ? __ldcs(p.ws.slot + i0 + j) : 0u;
 #pragma unroll
     for (int j = 0; j < SCAN_ITEMS; ++j) {
-        const unsigned long long after = pv_comb(excl, t.val[j]);
-        s_rank_incl[tid * SCAN_ITEMS + j] = pv_rank(after);
-        if (t.val[j] & PV_RANK_ONE) {
+        if (val[j]) {
             const uint32_t i = i0 + j;
-            const uint32_t r = (t.val[j] & PV_SEG) ? 0u : pv_rank(excl);
-            const uint32_t kg = pv_ksum(excl);
-            const uint32_t c = t.w[j] & 0x7FFFFFFFu;
-            const uint32_t s = p.ws.slot[i];
-            const uint32_t b = s / p.ws.capf;
+            const uint32_t r = (uint32_t)(excl >> 32);
+            const uint32_t kg = (uint32_t)excl;
+            const uint32_t c = w[j] & 0x7FFFFFFFu;
+            const uint32_t s = sl[j];
             const bool keep = r < (uint32_t)p.V;                          // :60-61 max_voxels
-            *reinterpret_cast<uint2 *>(p.ws.meta + s) = make_uint2(keep ? kg : PV_INF, c);
+            p.ws.meta[s] = ((unsigned long long)min(c, 65535u) << 32) | (keep ? kg : PV_INF);
             if (keep) {
                 p.ws.kept[kg] = i;                                        // list element 0 = first point
                 if (r < p.ws.fcap) {
-                    const size_t v = (size_t)b * p.ws.fcap + r;
-                    p.ws.vox_cell[v] = p.ws.dense ? pv_dense_cell(p, s - b * p.ws.capf) : p.ws.pcell[i];
+                    const size_t v = (size_t)t.b * p.ws.fcap + r;
+                    p.ws.vox_cell[v] = p.ws.dense ? pv_dense_cell(p, s - (uint32_t)t.b * p.ws.capf) : p.ws.pcell[i];
                     p.ws.vox_kg[v] = kg;
                     p.ws.vox_c[v] = c;
                 } else atomicOr(p.ws.ctrl + 1, 1u);                       // frame larger than frame_capacity
             }
         }
-        excl = after;
-    }
-    __syncthreads();
-    // cells per frame = inclusive segmented rank at the frame's last point
-    for (int b = tid; b < p.B; b += SCAN_THREADS) {
-        const uint32_t lo = (uint32_t)p.offsets[b], hi = (uint32_t)p.offsets[b + 1];
-        if (hi == lo) { if (tile == 0) p.ws.counts_raw[b] = 0; }
-        else if (hi - 1 >= tile_base && hi - 1 < tile_base + SCAN_TILE)
-            p.ws.counts_raw[b] = s_rank_incl[hi - 1 - tile_base];
+        excl += val[j];
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4 -- per-voxel ascending lists of the T smallest point indices (first points already placed)
+// K4 -- place every other point of a kept voxel in the voxel's list.  One 64-bit atomicAdd on
+// the cell's meta word returns the list offset, the count class and an arrival position:
+//   count <= PV_SORT_MAX : the point goes to its arrival position (k_emit orders the few indices
+//                          in registers), one store;
+//   larger cells         : atomicMin chain; the list converges to the min(count, T) smallest
+//                          indices in ascending order.
 // ---------------------------------------------------------------------------------------------
+#define PV_SORT_MAX 8u
+
 __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PvParams p)
 {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        int32_t acc = 0;   // per-frame voxel counts and output row bases (tiny, serial)
-        for (int b = 0; b < p.B; ++b) {
-            const int32_t m = (int32_t)min(p.ws.counts_raw[b], (uint32_t)p.V);
-            p.ws.base[b] = acc;
-            p.voxel_counts[b] = m;
-            acc += m;
-        }
-        p.ws.base[p.B] = acc;
-    }
+    // one point per thread: the chains below serialise per warp, so warps must stay plentiful
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
     const uint32_t s = __ldcs(p.ws.slot + i);
     const uint32_t w = __ldcs(p.ws.pv + i);
     if (s == PV_INF || (w & PV_FIRST)) return;            // out of range, or already placed by the scan
-    const uint2 m = __ldcg(reinterpret_cast<const uint2 *>(p.ws.meta + s));
-    if (m.x == PV_INF) return;                            // voxel beyond max_voxels: dropped
-    const uint32_t c = m.y;
+    const unsigned long long m = atomicAdd(p.ws.meta + s, 1ull << 48);
+    const uint32_t kg = (uint32_t)m;
+    if (kg == PV_INF) return;                             // voxel beyond max_voxels: dropped
+    const uint32_t c = (uint32_t)(m >> 32) & 0xFFFFu;
+    uint32_t *list = p.ws.kept + kg;
+    if (c <= PV_SORT_MAX && c <= (uint32_t)p.T) { list[1u + (uint32_t)(m >> 48)] = i; return; }
     const uint32_t L = min(c, (uint32_t)p.T);
     if (L < 2) return;
-    uint32_t *list = p.ws.kept + m.x;
-    if (c == 2) { list[1] = i; return; }
-    if (c > (uint32_t)p.T) {
-        // slots only ever decrease: a tail already below i can never admit i
-        if (pv_ld_volatile(list + L - 1) < i) return;
-    }
+    // slots only ever decrease: a tail already below i can never admit i
+    if (c > (uint32_t)p.T && pv_ld_volatile(list + L - 1) < i) return;
     uint32_t x = i;
     for (uint32_t k = 1; k < L; ++k) {
         const uint32_t old = atomicMin(list + k, x);
@@ -380,9 +442,12 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PvParams 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5 -- emit: one thread per kept voxel (b, r)
+// K5 -- emit: one thread per kept voxel (b, r); rows are fetched four at a time.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_emit(const __grid_constant__ PvParams p)
+#define PV_CSWAP(a, b) do { const uint32_t lo_ = min(a, b), hi_ = max(a, b); a = lo_; b = hi_; } while (0)
+
+template <int CT>
+__global__ void __launch_bounds__(256, 4) k_emit(const __grid_constant__ PvParams p)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
@@ -393,40 +458,78 @@ __global__ void __launch_bounds__(256) k_emit(const __grid_constant__ PvParams p
     const uint32_t c = __ldcs(p.ws.vox_c + v);
     const int32_t vid = p.ws.base[b] + (int32_t)r;
     const uint32_t L = min(c, (uint32_t)p.T);
+    uint32_t *list = p.ws.kept + kg;
+    const int C = p.C, c_in = p.c_in;
+
+    // first eight indices into registers; small cells hold them in arrival order -> sort
+    uint32_t e[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) e[k] = (uint32_t)k < L ? __ldcg(list + k) : PV_INF;
+    if (c > 2 && c <= PV_SORT_MAX) {                      // Batcher odd-even merge sort, 19 exchanges
+        PV_CSWAP(e[0], e[1]); PV_CSWAP(e[2], e[3]); PV_CSWAP(e[4], e[5]); PV_CSWAP(e[6], e[7]);
+        PV_CSWAP(e[0], e[2]); PV_CSWAP(e[1], e[3]); PV_CSWAP(e[4], e[6]); PV_CSWAP(e[5], e[7]);
+        PV_CSWAP(e[1], e[2]); PV_CSWAP(e[5], e[6]);
+        PV_CSWAP(e[0], e[4]); PV_CSWAP(e[1], e[5]); PV_CSWAP(e[2], e[6]); PV_CSWAP(e[3], e[7]);
+        PV_CSWAP(e[2], e[4]); PV_CSWAP(e[3], e[5]);
+        PV_CSWAP(e[1], e[2]); PV_CSWAP(e[3], e[4]); PV_CSWAP(e[5], e[6]);
+    }
+    float acc[CT];
+#pragma unroll
+    for (int k = 0; k < CT; ++k) acc[k] = 0.0f;
+    float *vox = p.voxels ? p.voxels + (size_t)vid * p.T * C : nullptr;
+    for (uint32_t j0 = 0; j0 < L; j0 += 4) {
+        uint32_t id[4];
+        if (j0 == 0) { id[0] = e[0]; id[1] = e[1]; id[2] = e[2]; id[3] = e[3]; }
+        else if (j0 == 4) { id[0] = e[4]; id[1] = e[5]; id[2] = e[6]; id[3] = e[7]; }
+        else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) id[q] = j0 + q < L ? __ldcg(list + j0 + q) : PV_INF;
+        }
+        float raw[4][CT];                                 // up to 4 * c_in independent loads in flight
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float *row = p.pts + (size_t)id[q] * c_in;
+#pragma unroll
+            for (int k = 0; k < CT; ++k) raw[q][k] = (id[q] != PV_INF && k < c_in) ? __ldg(row + k) : 0.0f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (id[q] == PV_INF) break;
+            list[j0 + q] = PV_INF;                        // restore the list for the next call
+            float f[CT];
+            if (p.cart) {   // utils.py:42-44: (rho, phi, z, x, y, feat3..)
+                f[0] = pv_rho(raw[q][0], raw[q][1]);
+                f[1] = pv_atan2f(raw[q][1], raw[q][0]);
+                f[2] = raw[q][2]; f[3] = raw[q][0]; f[4] = raw[q][1];
+#pragma unroll
+                for (int k = 5; k < CT; ++k) f[k] = raw[q][k - 2];
+            } else {
+#pragma unroll
+                for (int k = 0; k < CT; ++k) f[k] = raw[q][k];
+            }
+#pragma unroll
+            for (int k = 0; k < CT; ++k) acc[k] = __fadd_rn(acc[k], f[k]);   // index order, like sum(dim=1)
+            if (vox) {
+#pragma unroll
+                for (int k = 0; k < CT; ++k)
+                    if (k < C) vox[(size_t)(j0 + q) * C + k] = f[k];
+            }
+        }
+    }
+    if (vox) {                                                           // zero padding (:187)
+        for (uint32_t e2 = L * C; e2 < (uint32_t)(p.T * C); ++e2) vox[e2] = 0.0f;
+    }
     const uint32_t nx = p.grid[0], ny = p.grid[1];
     const uint32_t x = cell % nx, yz = cell / nx;
     reinterpret_cast<int4 *>(p.coors)[vid] = make_int4(b, (int)(yz / ny), (int)(yz % ny), (int)x);
     p.num_points[vid] = (int32_t)L;
     if (p.density) p.density[(size_t)b * p.cells + cell] = (int32_t)c;   // :70-71 un-capped count
-    uint32_t *list = p.ws.kept + kg;
-    float acc[PV_MAX_CHANNELS];
-#pragma unroll
-    for (int k = 0; k < PV_MAX_CHANNELS; ++k) acc[k] = 0.0f;
-    float *vox = p.voxels ? p.voxels + (size_t)vid * p.T * p.C : nullptr;
-    uint32_t idx_next = list[0];
-    for (uint32_t j = 0; j < L; ++j) {
-        const uint32_t i = idx_next;
-        list[j] = PV_INF;                                 // restore the list for the next call
-        if (j + 1 < L) idx_next = list[j + 1];            // next index in flight while this row is folded
-        float f[PV_MAX_CHANNELS];
-        pv_feature_row(p.pts, i, p.c_in, p.cart, f);
-#pragma unroll
-        for (int k = 0; k < PV_MAX_CHANNELS; ++k) acc[k] = __fadd_rn(acc[k], f[k]);   // slot order, like sum(dim=1)
-        if (vox) {
-#pragma unroll
-            for (int k = 0; k < PV_MAX_CHANNELS; ++k)
-                if (k < p.C) vox[(size_t)j * p.C + k] = f[k];
-        }
-    }
-    if (vox) {                                                           // zero padding (:187)
-        for (uint32_t e = L * p.C; e < (uint32_t)(p.T * p.C); ++e) vox[e] = 0.0f;
-    }
     const float nf = (float)L;
-    float *o = p.feats ? p.feats + (size_t)vid * p.C : nullptr;
-    float *cv = p.canvas ? p.canvas + (size_t)b * p.C * p.cells + cell : nullptr;
+    float *o = p.feats ? p.feats + (size_t)vid * C : nullptr;
+    float *cv = p.canvas ? p.canvas + (size_t)b * C * p.cells + cell : nullptr;
 #pragma unroll
-    for (int k = 0; k < PV_MAX_CHANNELS; ++k) {
-        if (k < p.C) {
+    for (int k = 0; k < CT; ++k) {
+        if (k < C) {
             const float m = __fdiv_rn(acc[k], nf);                      // voxel_encoder.py:18-22
             if (o) o[k] = m;
             if (cv) cv[(size_t)k * p.cells] = m;                        // pillar_encoder.py:211-217
@@ -495,18 +598,21 @@ int pv_make_layout(const pv_config *cfg, int64_t n_cap, int32_t batch, int64_t f
     w->capf = (uint32_t)capf;
     w->fcap = (uint32_t)fcap;
     w->dense = dense ? 1u : 0u;
-    w->max_tiles = (uint32_t)(n_cap / SCAN_TILE + 1);
+    w->max_tiles = (uint32_t)(n_cap / SCAN_TILE + batch + 1);
     char *p0 = (char *)base;
     size_t o = 0;
     const size_t slots = (size_t)capf * batch;
     w->ctrl = (uint32_t *)(p0 + o);                      o = align_up(o + 16 * sizeof(uint32_t), 256);
     w->counts_raw = (uint32_t *)(p0 + o);                o = align_up(o + (size_t)batch * 4, 256);
     w->base = (int32_t *)(p0 + o);                       o = align_up(o + (size_t)(batch + 1) * 4, 256);
+    w->frame_rank0 = (uint32_t *)(p0 + o);               o = align_up(o + (size_t)batch * 4, 256);
+    w->cum_tiles = (uint32_t *)(p0 + o);                 o = align_up(o + (size_t)(batch + 1) * 4, 256);
     w->tile_agg = (unsigned long long *)(p0 + o);        o = align_up(o + (size_t)w->max_tiles * 8, 256);
+    w->tile_pre = (unsigned long long *)(p0 + o);        o = align_up(o + (size_t)w->max_tiles * 8, 256);
     w->table = (PvEntry *)(p0 + o);                      o = align_up(o + slots * sizeof(PvEntry) + 16, 256);
     w->keys = (uint32_t *)(p0 + o);                      if (!dense) o = align_up(o + slots * 4, 256);
     w->kept = (uint32_t *)(p0 + o);                      o = align_up(o + n * 4, 256);
-    w->meta = (PvMeta *)(p0 + o);                        o = align_up(o + slots * sizeof(PvMeta), 256);
+    w->meta = (unsigned long long *)(p0 + o);            o = align_up(o + slots * 8, 256);
     w->slot = (uint32_t *)(p0 + o);                      o = align_up(o + n * 4 + 32, 256);
     w->pv = (uint32_t *)(p0 + o);                        o = align_up(o + n * 4 + 32, 256);
     w->pcell = (uint32_t *)(p0 + o);                     if (!dense) o = align_up(o + n * 4 + 32, 256);
@@ -538,15 +644,23 @@ static int fill_params(PvParams *p, const pv_config *cfg, const float *points,
     p->pts = points; p->offsets = frame_offsets; p->B = batch; p->n = (uint32_t)n_total;
     p->c_in = c_in; p->cart = is_cartesian ? 1 : 0; p->C = C;
     p->cells = (uint32_t)((uint64_t)cfg->grid[0] * cfg->grid[1] * cfg->grid[2]);
-    p->num_tiles = (uint32_t)(n_total / SCAN_TILE + 1);
+    p->num_tiles = (uint32_t)(n_total / SCAN_TILE + batch + 1);
     p->coors = p->num_points = p->voxel_counts = p->grid_ind = p->density = nullptr;
     p->voxels = p->feats = p->canvas = nullptr;
     return PV_OK;
 }
 
+template <int CT>
+static void launch_emit(const PvParams &p, cudaStream_t st)
+{
+    const uint32_t vmax = min((uint32_t)p.V, p.ws.fcap);
+    dim3 grid((vmax + 255) / 256, (unsigned)p.B);
+    k_emit<CT><<<grid, 256, 0, st>>>(p);
+}
+
 // Stage boundaries (for pv_profile_*): ev[k] is recorded BEFORE stage k, ev[PV_STAGES] after the
-// last one.  0 bin_insert (+canvas zero fill), 1 cell_flags, 2 scan (tile_reduce + scan_apply),
-// 3 place, 4 emit (+canvas scatter).
+// last one.  0 bin_insert (+canvas zero fill), 1 cell_flags, 2 scan (tile_reduce incl. the mid scan
+// + scan_apply), 3 place, 4 emit (+canvas scatter).
 #define PV_STAGES 5
 #define PV_MARK(k) do { if (ev && cudaEventRecord(ev[k], st) != cudaSuccess) return PV_ERR_CUDA; } while (0)
 
@@ -558,26 +672,28 @@ static int run_voxelize(PvParams &p, cudaStream_t st, cudaEvent_t *ev = nullptr)
         return PV_ERR_CUDA;
     PV_MARK(0);
     unsigned g1 = (p.n + K1_THREADS - 1) / K1_THREADS;
+    if (g1 < 1) g1 = 1;                                   // block 0 also lays out the scan tiles
     if (p.canvas && g1 < 592) g1 = 592;                   // enough blocks to zero the canvas quickly
-    if (g1 > 0) {
-        if (w.dense) k_bin_insert<true><<<g1, K1_THREADS, 0, st>>>(p);
-        else k_bin_insert<false><<<g1, K1_THREADS, 0, st>>>(p);
-    }
+    if (w.dense) k_bin_insert<true><<<g1, K1_THREADS, 0, st>>>(p);
+    else k_bin_insert<false><<<g1, K1_THREADS, 0, st>>>(p);
     PV_MARK(1);
     {
         const size_t pairs = ((size_t)p.B * w.capf + 1) / 2;
         k_cell_flags<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(p);
     }
     PV_MARK(2);
-    k_tile_reduce<<<p.num_tiles, SCAN_THREADS, 0, st>>>(p);
+    k_tile_reduce<<<p.num_tiles, SCAN_THREADS, 0, st>>>(p);      // its last block also runs the mid scan
     k_scan_apply<<<p.num_tiles, SCAN_THREADS, 0, st>>>(p);
     PV_MARK(3);
-    k_place<<<(p.n + 255) / 256 + (p.n == 0), 256, 0, st>>>(p);
+    if (p.n > 0) k_place<<<(p.n + 255) / 256, 256, 0, st>>>(p);
     PV_MARK(4);
-    {
-        const uint32_t vmax = min((uint32_t)p.V, w.fcap);
-        dim3 grid((vmax + 255) / 256, (unsigned)p.B);
-        k_emit<<<grid, 256, 0, st>>>(p);
+    switch (p.C) {
+    case 3: case 4: case 5: launch_emit<5>(p, st); break;
+    case 6: launch_emit<6>(p, st); break;
+    case 7: launch_emit<7>(p, st); break;
+    case 8: launch_emit<8>(p, st); break;
+    case 9: case 10: launch_emit<10>(p, st); break;
+    default: launch_emit<PV_MAX_CHANNELS>(p, st); break;
     }
     PV_MARK(5);
     return pv_last_cuda_error();

@@ -30,7 +30,7 @@ class PolarFrontEnd:
     """
 
     def __init__(self, voxel_size, point_cloud_range, max_points_in_voxel, max_voxel_num,
-                 cartesian=True, canvas=None, device=None):
+                 cartesian=True, canvas=None, device=None, workspace_tag=0):
         self.cfg, self.voxel_size, self.point_cloud_range, self.grid_size = F.make_config(
             voxel_size, point_cloud_range, max_points_in_voxel, max_voxel_num)
         self.cartesian = bool(cartesian)
@@ -39,6 +39,7 @@ class PolarFrontEnd:
         if self.canvas and not self.pillar:
             raise ValueError("a dense BEV canvas needs a pillar grid (nz == 1)")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.workspace_tag = workspace_tag     # distinct tags -> instances may run on concurrent streams
         self._graph = None
         self._static = None
 
@@ -46,7 +47,7 @@ class PolarFrontEnd:
     def forward_device(self, points, frame_offsets, batch, frame_capacity, out=None):
         """points [N, c_in] f32 CUDA, frame_offsets [batch+1] int32 CUDA -> VoxelBatch (no sync)."""
         return F.voxelize(self.cfg, points, frame_offsets, batch, frame_capacity, self.cartesian,
-                          want_mean=True, canvas=self.canvas, out=out)
+                          want_mean=True, canvas=self.canvas, out=out, ws_tag=self.workspace_tag)
 
     def capture(self, points, frame_offsets, batch, frame_capacity):
         """Record the launch sequence on static buffers as a CUDA graph; returns the VoxelBatch
@@ -99,6 +100,25 @@ class PolarFrontEnd:
         torch.cuda.current_stream(self.device).synchronize()
         h2d = io["h_points"].numel() * 4 + io["h_offsets"].numel() * 4
         return m, h2d, d2h
+
+    def forward_host_async(self, io, frame_capacity):
+        """Like forward_host but without any host synchronisation: H2D, kernels and the D2H of
+        every output buffer at full capacity are enqueued on the current stream, so steps issued
+        on different streams overlap their copies and kernels.  Rows beyond sum(h_counts) are
+        undefined.  Returns (bytes H2D, bytes D2H)."""
+        io["d_points"].copy_(io["h_points"], non_blocking=True)
+        io["d_offsets"].copy_(io["h_offsets"], non_blocking=True)
+        vb = self.forward_device(io["d_points"], io["d_offsets"], io["batch"], frame_capacity, out=io["vb"])
+        io["vb"] = vb
+        io["h_counts"].copy_(vb.voxel_counts, non_blocking=True)
+        io["h_coors"].copy_(vb.coors, non_blocking=True)
+        io["h_num"].copy_(vb.num_points, non_blocking=True)
+        io["h_feats"].copy_(vb.mean_feats, non_blocking=True)
+        d2h = 4 * (io["h_counts"].numel() + io["h_coors"].numel() + io["h_num"].numel() + io["h_feats"].numel())
+        if self.canvas:
+            io["h_canvas"].copy_(vb.canvas, non_blocking=True)
+            d2h += io["h_canvas"].numel() * 4
+        return io["h_points"].numel() * 4 + io["h_offsets"].numel() * 4, d2h
 
     # ---- convenience ---------------------------------------------------------------------
     def __call__(self, frames):

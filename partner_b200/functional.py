@@ -57,13 +57,15 @@ def _bucket(n, quantum=65536):
 
 
 _voxel_ws = {}          # layout key -> initialised workspace tensor (LRU, self-cleaning: see header)
-_VOXEL_WS_KEEP = 6
+_VOXEL_WS_KEEP = 12
 
 
-def voxel_workspace(cfg, n_cap, batch, frame_cap, device):
-    """Workspace initialised (pv_workspace_init) for exactly this config + capacities."""
+def voxel_workspace(cfg, n_cap, batch, frame_cap, device, tag=0):
+    """Workspace initialised (pv_workspace_init) for exactly this config + capacities.
+
+    ``tag`` separates workspaces of callers that run concurrently on different streams."""
     dev_index = device.index if device.index is not None else torch.cuda.current_device()
-    key = (dev_index, tuple(cfg.lo), tuple(cfg.vs), tuple(cfg.grid), cfg.max_points, n_cap, batch, frame_cap)
+    key = (dev_index, tag, tuple(cfg.lo), tuple(cfg.vs), tuple(cfg.grid), cfg.max_points, n_cap, batch, frame_cap)
     ws = _voxel_ws.pop(key, None)
     if ws is None:
         lib = _lib.load()
@@ -110,7 +112,7 @@ class VoxelBatch:
 
 
 def voxelize(cfg, points, frame_offsets, batch, frame_capacity, is_cartesian, want_voxels=False,
-             want_mean=False, want_grid_ind=False, want_density=False, canvas=False, out=None):
+             want_mean=False, want_grid_ind=False, want_density=False, canvas=False, out=None, ws_tag=0):
     """pv_voxelize / pv_forward_mean_canvas on CUDA tensors.
 
     points [N, c_in] f32, frame_offsets [batch+1] int32 (device).  Returns a VoxelBatch whose row
@@ -127,7 +129,7 @@ def voxelize(cfg, points, frame_offsets, batch, frame_capacity, is_cartesian, wa
     lib = _lib.load()
     n_cap = _bucket(n)
     f_cap = min(n_cap, _bucket(frame_capacity))
-    ws = voxel_workspace(cfg, n_cap, batch, f_cap, dev)
+    ws = voxel_workspace(cfg, n_cap, batch, f_cap, dev, ws_tag)
     rows = max(1, min(batch * cfg.max_voxels, n))
     T = cfg.max_points
     r = out if out is not None else VoxelBatch()
