@@ -97,6 +97,29 @@ __device__ __forceinline__ void pv_st_volatile64(unsigned long long *p, unsigned
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// L2 residency control (B200: 126 MB L2).  Point rows are read twice per call -- streamed by
+// k_bin_insert, gathered again by k_emit -- so their first read asks L2 to keep them
+// (evict_last), while write-once outputs are stored evict_first.
+__device__ __forceinline__ unsigned long long pv_policy_evict_last()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 pv_ld_keep(const float4 *p, unsigned long long pol)
+{
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float pv_ld_keep(const float *p, unsigned long long pol)
+{
+    float v;
+    asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 __device__ __forceinline__ uint32_t pv_hash(uint32_t k)
 {
     k ^= k >> 16; k *= 0x85ebca6bu; k ^= k >> 13; k *= 0xc2b2ae35u; k ^= k >> 16;

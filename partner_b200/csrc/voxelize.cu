@@ -88,14 +88,15 @@ __global__ void __launch_bounds__(K1_THREADS) k_bin_insert(const __grid_constant
         const size_t f0 = (size_t)tile_base * c_in;
         const uint32_t nf = n_tile * c_in;
         const float *src = p.pts + f0;
+        const unsigned long long keep = pv_policy_evict_last();   // k_emit gathers these rows again
         if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
             const uint32_t nv = nf >> 2;
             const float4 *src4 = reinterpret_cast<const float4 *>(src);
             float4 *dst4 = reinterpret_cast<float4 *>(s_pts);
-            for (uint32_t k = tid; k < nv; k += K1_THREADS) dst4[k] = __ldcs(src4 + k);
-            for (uint32_t k = (nv << 2) + tid; k < nf; k += K1_THREADS) s_pts[k] = __ldcs(src + k);
+            for (uint32_t k = tid; k < nv; k += K1_THREADS) dst4[k] = pv_ld_keep(src4 + k, keep);
+            for (uint32_t k = (nv << 2) + tid; k < nf; k += K1_THREADS) s_pts[k] = pv_ld_keep(src + k, keep);
         } else {
-            for (uint32_t k = tid; k < nf; k += K1_THREADS) s_pts[k] = __ldcs(src + k);
+            for (uint32_t k = tid; k < nf; k += K1_THREADS) s_pts[k] = pv_ld_keep(src + k, keep);
         }
     }
     // ---- this block's slice of the canvas zero fill (pillar grids; k_emit scatters into it) ----
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_bin_insert(const __grid_constant
         const size_t lo4 = (size_t)blockIdx.x * chunk;
         const size_t hi4 = min(total4, lo4 + chunk);
         float4 *c4 = reinterpret_cast<float4 *>(p.canvas);
-        for (size_t k = lo4 + tid; k < hi4; k += K1_THREADS) c4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (size_t k = lo4 + tid; k < hi4; k += K1_THREADS) __stcs(c4 + k, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     __syncthreads();
 
@@ -521,8 +522,8 @@ __global__ void __launch_bounds__(256, 4) k_emit(const __grid_constant__ PvParam
     }
     const uint32_t nx = p.grid[0], ny = p.grid[1];
     const uint32_t x = cell % nx, yz = cell / nx;
-    reinterpret_cast<int4 *>(p.coors)[vid] = make_int4(b, (int)(yz / ny), (int)(yz % ny), (int)x);
-    p.num_points[vid] = (int32_t)L;
+    __stcs(reinterpret_cast<int4 *>(p.coors) + vid, make_int4(b, (int)(yz / ny), (int)(yz % ny), (int)x));
+    __stcs(p.num_points + vid, (int32_t)L);
     if (p.density) p.density[(size_t)b * p.cells + cell] = (int32_t)c;   // :70-71 un-capped count
     const float nf = (float)L;
     float *o = p.feats ? p.feats + (size_t)vid * C : nullptr;
@@ -531,8 +532,8 @@ __global__ void __launch_bounds__(256, 4) k_emit(const __grid_constant__ PvParam
     for (int k = 0; k < CT; ++k) {
         if (k < C) {
             const float m = __fdiv_rn(acc[k], nf);                      // voxel_encoder.py:18-22
-            if (o) o[k] = m;
-            if (cv) cv[(size_t)k * p.cells] = m;                        // pillar_encoder.py:211-217
+            if (o) __stcs(o + k, m);
+            if (cv) __stcs(cv + (size_t)k * p.cells, m);                // pillar_encoder.py:211-217
         }
     }
 }

@@ -12,13 +12,7 @@ import torch
 from . import functional as F
 
 
-def shard_range(n_frames, world_size, rank):
-    """Contiguous block of frames owned by ``rank``."""
-    if world_size <= 0 or not (0 <= rank < world_size):
-        raise ValueError("bad rank/world_size")
-    base, rem = divmod(n_frames, world_size)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+from .sharding import shard_range  # noqa: F401,E402  (re-exported)
 
 
 class PolarFrontEnd:

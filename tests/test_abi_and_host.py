@@ -1,0 +1,96 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/*.h declares, the
+host-only entry points behave, and the drop-in classes mirror the reference's construction-time
+arithmetic.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from partner_b200 import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "polar_voxel_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pv_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.SO_PATH):
+        pytest.skip("library not built yet (run __graft_entry__.build())")
+    lib = ctypes.CDLL(_lib.SO_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    assert set(names) == set(_lib.EXPORTS), "ctypes binding table and header disagree"
+
+
+def test_host_only_entry_points():
+    lib = _lib.load()
+    assert lib.pv_version() >= 200
+    assert lib.pv_error_string(0) == b"ok"
+    assert b"frame_capacity" in lib.pv_error_string(-5)
+    from partner_b200.functional import make_config
+    cfg, vs, rng, grid = make_config([0.098, 0.0123, 8], [0.3, -3.1488, -5, 50.476, 3.1488, 3], 20, 60000)
+    assert lib.pv_workspace_bytes(cfg, 2_400_000, 8, 300_000) > 0
+    bad = _lib.PvConfig()
+    assert lib.pv_workspace_bytes(bad, 1000, 1, 1000) == 0            # zero grid
+    cfg.max_points = 0
+    assert lib.pv_workspace_bytes(cfg, 1000, 1, 1000) == 0
+    assert lib.pv_scatter_workspace_bytes(2, 512, 512) == 2 * 512 * 512 * 4
+    with pytest.raises(ValueError):
+        _lib.check(-1, "x")
+    with pytest.raises(RuntimeError):
+        _lib.check(-4, "x")
+
+
+@pytest.mark.parametrize("grid", sorted(synth.GRIDS))
+def test_voxel_generator_constructor_arithmetic_matches_reference(grid):
+    """voxel_generator.py:6-17: f32 rounding of size/range, grid = round((hi - lo) / vs)."""
+    from partner_b200 import VoxelGenerator
+    g = synth.GRIDS[grid]
+    vg = VoxelGenerator(g["voxel_size"], g["range"], g["max_points"], g["max_voxels"])
+    ref = oracle.VoxelGenerator(g["voxel_size"], g["range"], g["max_points"], g["max_voxels"])
+    assert np.array_equal(vg.grid_size, ref.grid_size) and vg.grid_size.dtype == np.int64
+    assert np.array_equal(vg.voxel_size, ref.voxel_size) and vg.voxel_size.dtype == np.float32
+    assert np.array_equal(vg.point_cloud_range, ref.point_cloud_range)
+    assert vg.max_num_points_per_voxel == g["max_points"]
+    expect = {"NUSC-PILLAR": (512, 512, 1), "NUSC-CYL": (1024, 1024, 40), "WAYMO-PARTNER": (1152, 2048, 40)}[grid]
+    assert tuple(vg.grid_size) == expect
+
+
+def test_reader_state_dict_keys_match_reference():
+    """Checkpoints saved by the reference load unchanged."""
+    from partner_b200 import PillarFeatureNet
+    net = PillarFeatureNet(7, (64, 128), False, (0.098, 0.0123, 8), (0.3, -3.1488, -5, 50.476, 3.1488, 3))
+    keys = set(net.state_dict())
+    for i, (u, k) in enumerate(((32, 12), (128, 64))):
+        assert tuple(net.pfn_layers[i].linear.weight.shape) == (u, k)
+        for name in ("linear.weight", "norm.weight", "norm.bias", "norm.running_mean", "norm.running_var",
+                     "norm.num_batches_tracked"):
+            assert f"pfn_layers.{i}.{name}" in keys
+    assert net.pfn_layers[0].norm.eps == 1e-3 and net.pfn_layers[0].norm.momentum == 0.01
+    assert abs(net.x_offset - (0.098 / 2 + 0.3)) < 1e-12
+
+
+def test_cpu_tensors_are_rejected_not_silently_processed():
+    import torch
+    from partner_b200 import functional as F
+    with pytest.raises(ValueError):
+        F.vfe_mean(torch.zeros(2, 3, 4), torch.ones(2, dtype=torch.int32))
+    with pytest.raises(ValueError):
+        F.transform_points(torch.zeros(4, 5))
+
+
+def test_synthetic_generator_reproduces_survey_statistics():
+    f = synth.nusc_frame(0)
+    assert f.dtype == np.float32 and f.shape[1] == 5 and 280_000 < f.shape[0] < 300_000
+    w = synth.waymo_frame(0, nsweeps=1)
+    assert w.shape == (169_600, 6)
+    assert synth.waymo_frame(0, nsweeps=1, time_column=False).shape == (169_600, 5)
