@@ -44,6 +44,29 @@ STAGES = ["bin_insert", "cell_flags", "scan", "place", "emit"]
 N_SETS = 4          # rotating input sets so a step never finds its inputs in the 126 MB L2
 
 
+STAGE_KERNELS = {"bin_insert": ("k_bin_insert",), "cell_flags": ("k_cell_flags",), "scan": ("k_tile_reduce", "k_scan_apply"),
+                 "place": ("k_place",), "emit": ("k_emit",)}
+
+
+def ncu_traffic(stage):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the stage's kernels from
+    the newest committed ncu --set full capture under profiles/, or None."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_kernels.json")))
+    if not files:
+        return None, None
+    try:
+        with open(files[-1]) as f:
+            prof = json.load(f)
+        tot = 0.0
+        for k in prof["kernels"]:
+            if any(name in k["kernel"] for name in STAGE_KERNELS[stage]):
+                tot += k.get("dram_traffic_bytes", 0.0)
+        return (tot or None), os.path.relpath(files[-1], ROOT)
+    except Exception:
+        return None, None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -328,6 +351,7 @@ def main():
         dom_ms = live[dom]
         dom_bytes = alg.get(dom, 0.0)
         ach = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_bytes > 0 else None
+        traffic, traffic_src = ncu_traffic(dom)
         result = {
             "metric": METRIC, "value": pts_all / (ms_total * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
@@ -350,7 +374,8 @@ def main():
                     "streams": n_streams, "synchronous_ms_per_step": e2e_sync_ms},
             "gpu_launches": 6 * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                         "frac": (ach / peak) if ach else None, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
                          "stage_ms": live, "stage_ms_sum": float(sum(live.values()))},
             "roofline_path": {"algorithmic_bytes_per_step": path_bytes, "achieved": path_bytes / (step_ms * 1e-3) / 1e9,
