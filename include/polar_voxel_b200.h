@@ -152,11 +152,15 @@ int pv_vfe_mean(const float *voxels, const int32_t *num_points, int64_t m, int32
  * decoration (cluster offset, pillar-centre offset, optional distance), padding mask,
  * n_layers x (Linear, BatchNorm1d eval, ReLU, max over all T slots incl. padding).
  * voxels [m, t, c], num_points [m], coors [m, 4] (b, z, y, x); out [m, units of last layer].
- * `layers` is a HOST array. vx, vy, x_off, y_off as computed at pillar_encoder.py:123-126. */
+ * `layers` is a HOST array. vx, vy, x_off, y_off as computed at pillar_encoder.py:123-126.
+ * Padding slots (t >= num_points) must hold zeros, as points_to_voxel produces them. */
 int pv_pfn_forward(const float *voxels, const int32_t *num_points, const int32_t *coors, int64_t m,
                    int32_t t, int32_t c, int32_t with_distance, float vx, float vy, float x_off,
                    float y_off, const pv_pfn_layer *layers, int32_t n_layers, float eps,
-                   float *out, pv_stream_t stream);
+                   void *workspace, size_t workspace_bytes, float *out, pv_stream_t stream);
+
+/* Scratch bytes pv_pfn_forward needs for m voxels (per-voxel statistics). */
+size_t pv_pfn_workspace_bytes(int64_t m);
 
 /* Bytes of workspace pv_scatter needs (the BEV index map). */
 size_t pv_scatter_workspace_bytes(int32_t batch, int32_t ny, int32_t nx);

@@ -198,6 +198,339 @@ __global__ void __launch_bounds__(PFN_THREADS) k_pfn_simt(const __grid_constant_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// PFN, tiled fp32 kernel.  Persistent 256-thread blocks; each packs whole voxels into tiles of at
+// most 64 useful rows (valid points + one representative padded row per non-full voxel) and runs
+// every layer on the tile out of shared memory:
+//     Linear([x, x_max]) = Wa . x (per row)  +  Wb . x_max (per voxel)
+// so the concatenated activation of pillar_encoder.py:59-61 is never formed.  GEMMs are register
+// tiled: a warp owns 8 rows, a lane owns outputs lane, lane+32, ... (8 x N/32 accumulators),
+// activations are read as broadcast float4 along K, weights conflict-free along N.
+// Epilogue: ATen eval BatchNorm order, ReLU, max over the voxel's rows via shared atomicMax
+// (post-ReLU values are >= 0, so integer order == float order).
+// ---------------------------------------------------------------------------------------------
+#define PT_THREADS 256
+#define PT_ROWS 64           // rows per tile
+#define PT_VOX 32            // voxels per tile (each contributes >= 2 rows, or exactly T)
+#define PT_MAX_IN 24         // decorated input width, padded to a multiple of 4
+#define PT_CHUNK 256         // voxels per dynamically scheduled chunk (rows per voxel vary a lot)
+
+struct PtArgs {
+    const float *voxels; const int32_t *num; const int32_t *coors;
+    long long m; int t, c, with_distance;
+    float vx, vy, x_off, y_off, eps;
+    int n_layers;
+    const float *w[PV_MAX_PFN_LAYERS], *mean[PV_MAX_PFN_LAYERS], *var[PV_MAX_PFN_LAYERS],
+        *gamma[PV_MAX_PFN_LAYERS], *beta[PV_MAX_PFN_LAYERS];
+    int in_w[PV_MAX_PFN_LAYERS], units[PV_MAX_PFN_LAYERS];
+    int wa_off[PV_MAX_PFN_LAYERS], wb_off[PV_MAX_PFN_LAYERS];   // offsets of Wa^T / Wb^T in shared memory
+    int ka[PV_MAX_PFN_LAYERS];                                   // per-row K (padded to 4)
+    int w_total, xs;                                             // xs = activation row stride (floats)
+    const float4 *prep;     // [m][2]: (mean x, mean y, mean z, num) and (pillar centre x, y, -, -)
+    unsigned int *chunk_counter;   // dynamic scheduling: next chunk of PT_CHUNK voxels
+    float *out;
+};
+
+// Per-voxel statistics, fully parallel (one thread per voxel): cluster mean of xyz summed over
+// ALL T slots in slot order / num (pillar_encoder.py:137-139) and the pillar centre (:145-150).
+__global__ void __launch_bounds__(256) k_pfn_prep(const float *__restrict__ voxels, const int32_t *__restrict__ num,
+                                                  const int32_t *__restrict__ coors, long long m, int t, int c,
+                                                  float vx, float vy, float x_off, float y_off,
+                                                  float4 *__restrict__ prep)
+{
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v == 0) *reinterpret_cast<unsigned int *>(prep + 2 * m) = 0u;    // chunk counter of k_pfn_tiled
+    if (v >= m) return;
+    const float *f = voxels + v * t * c;
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    for (int j = 0; j < t; ++j) {
+        sx = __fadd_rn(sx, __ldg(f + j * c));
+        sy = __fadd_rn(sy, __ldg(f + j * c + 1));
+        sz = __fadd_rn(sz, __ldg(f + j * c + 2));
+    }
+    const int n = num[v];
+    const float nf = (float)n;
+    const int4 co = reinterpret_cast<const int4 *>(coors)[v];
+    prep[2 * v] = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __int_as_float(n));
+    prep[2 * v + 1] = make_float4(__fadd_rn(__fmul_rn((float)co.w, vx), x_off),
+                                  __fadd_rn(__fmul_rn((float)co.z, vy), y_off), 0.0f, 0.0f);
+}
+
+// acc[i][j] += sum_k A[row0 + i][k] * Wt[k][J * lane + j]   for the 8 rows of this warp.
+// A rows are read as broadcast float4 along K, the lane's J contiguous weights as one vector.
+template <int J>
+__device__ __forceinline__ void pt_fma_row(float av, const float (&w)[J], float (&acc)[J])
+{
+#pragma unroll
+    for (int j = 0; j < J; ++j) acc[j] = __fmaf_rn(av, w[j], acc[j]);
+}
+
+template <int J>
+__device__ __forceinline__ void pt_load_w(const float *p, float (&w)[J])
+{
+    if (J == 4) { const float4 v = *reinterpret_cast<const float4 *>(p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+    else if (J == 2) { const float2 v = *reinterpret_cast<const float2 *>(p); w[0] = v.x; w[1] = v.y; }
+    else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) w[j] = p[j];
+    }
+}
+
+template <int J>
+__device__ __forceinline__ void pt_gemm(const float *__restrict__ A, int astride, int K, int row0,
+                                        const float *__restrict__ Wt, int N, int lane, float (&acc)[8][J])
+{
+    const float *wp = Wt + J * lane;
+    for (int k4 = 0; k4 < K; k4 += 4) {
+        float4 a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4 *>(A + (row0 + i) * astride + k4);
+        float w[J];
+        pt_load_w<J>(wp + (k4 + 0) * N, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pt_fma_row<J>(a[i].x, w, acc[i]);
+        pt_load_w<J>(wp + (k4 + 1) * N, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pt_fma_row<J>(a[i].y, w, acc[i]);
+        pt_load_w<J>(wp + (k4 + 2) * N, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pt_fma_row<J>(a[i].z, w, acc[i]);
+        pt_load_w<J>(wp + (k4 + 3) * N, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pt_fma_row<J>(a[i].w, w, acc[i]);
+    }
+}
+
+// One layer on the current tile.  xin: [PT_ROWS][xs] per-row input (K = ka), vmax_in: [PT_VOX][128]
+// per-voxel max of the previous layer (layer > 0).  Writes xout (non-last layers) and vmax_out.
+template <int J>
+__device__ __forceinline__ void pt_layer(const PtArgs &a, int l, int n_rows, int n_vox, const float *s_w,
+                                         const float *s_bn, const float *xin, const float *vmax_in,
+                                         float *xout, int *vmax_out, float *s_p, const int *s_row_vox)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = a.units[l];
+    const bool last = l == a.n_layers - 1;
+    const float *bn = s_bn + l * 4 * PFN_MAX_W;
+    // ---- per-voxel part: P[v][o] = Wb . vmax_in[v]  (layers > 0) ----
+    if (l > 0) {
+        const int Kb = a.units[l - 1];
+        const int v0 = warp * 8;
+        if (v0 < n_vox) {
+            float acc[8][J];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < J; ++j) acc[i][j] = 0.0f;
+            pt_gemm<J>(vmax_in, PFN_MAX_W, Kb, v0, s_w + a.wb_off[l], N, lane, acc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < J; ++j) s_p[(v0 + i) * PFN_MAX_W + J * lane + j] = acc[i][j];
+        }
+    }
+    for (int vl = warp; vl < n_vox; vl += PT_THREADS / 32) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) vmax_out[vl * PFN_MAX_W + J * lane + j] = 0;
+    }
+    __syncthreads();
+    // ---- per-row part + epilogue ----
+    const int row0 = warp * 8;
+    if (row0 < n_rows) {
+        float acc[8][J];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < J; ++j) acc[i][j] = 0.0f;
+        pt_gemm<J>(xin, a.xs, a.ka[l], row0, s_w + a.wa_off[l], N, lane, acc);
+        float mu[J], is[J], ga[J], be[J], run[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int o = J * lane + j;
+            mu[j] = bn[o]; is[j] = bn[PFN_MAX_W + o]; ga[j] = bn[2 * PFN_MAX_W + o]; be[j] = bn[3 * PFN_MAX_W + o];
+            run[j] = 0.0f;
+        }
+        int cur = s_row_vox[row0];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = row0 + i;
+            if (r < n_rows) {                              // warp-uniform
+                const int v = s_row_vox[r];
+                if (v != cur) {                            // rows are grouped by voxel: flush the finished run
+#pragma unroll
+                    for (int j = 0; j < J; ++j) { atomicMax(vmax_out + cur * PFN_MAX_W + J * lane + j, __float_as_int(run[j])); run[j] = 0.0f; }
+                    cur = v;
+                }
+                float y[J];
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    float x = acc[i][j];
+                    if (l > 0) x = __fadd_rn(x, s_p[v * PFN_MAX_W + J * lane + j]);
+                    // ATen eval batch norm: (x - mean) * invstd * gamma + beta, then ReLU
+                    y[j] = fmaxf(__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x, mu[j]), is[j]), ga[j]), be[j]), 0.0f);
+                    run[j] = fmaxf(run[j], y[j]);
+                }
+                if (!last) {
+#pragma unroll
+                    for (int j = 0; j < J; ++j) xout[r * a.xs + J * lane + j] = y[j];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) atomicMax(vmax_out + cur * PFN_MAX_W + J * lane + j, __float_as_int(run[j]));
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PT_THREADS, 2) k_pfn_tiled(const __grid_constant__ PtArgs a)
+{
+    extern __shared__ __align__(16) float smem[];
+    float *s_w = smem;                                             // all layers: Wa^T then Wb^T, [k][o]
+    float *s_bn = s_w + a.w_total;                                 // per layer 4 * PFN_MAX_W
+    float *s_xa = s_bn + a.n_layers * 4 * PFN_MAX_W;               // [PT_ROWS][xs]
+    float *s_xb = s_xa + PT_ROWS * a.xs;                           // [PT_ROWS][xs]
+    float *s_va = s_xb + PT_ROWS * a.xs;                           // [PT_VOX][PFN_MAX_W] voxel max (ping)
+    float *s_vb = s_va + PT_VOX * PFN_MAX_W;                       // [PT_VOX][PFN_MAX_W] voxel max (pong)
+    float *s_p = s_vb + PT_VOX * PFN_MAX_W;                        // [PT_VOX][PFN_MAX_W] per-voxel term
+    int *s_row_vox = reinterpret_cast<int *>(s_p + PT_VOX * PFN_MAX_W);   // [PT_ROWS]
+    int *s_row_t = s_row_vox + PT_ROWS;                            // [PT_ROWS]
+    float *s_mean = reinterpret_cast<float *>(s_row_t + PT_ROWS);  // [PT_VOX][8]: mean xyz, n, centre xy
+    int *s_vrows = reinterpret_cast<int *>(s_mean + PT_VOX * 8);   // [PT_VOX + 1] first row of each voxel
+    int *s_vn = s_vrows + PT_VOX + 4;                              // [PT_VOX] valid points per voxel
+    __shared__ int s_nvox, s_nrows;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = a.c, t = a.t;
+    const int c0 = c + 5 + (a.with_distance ? 1 : 0);
+
+    // ---- weights: Linear weight is [U, K]; stored transposed, split into the per-row part
+    // (columns < in_w - units[l-1] for l > 0, all columns for l = 0) and the per-voxel part ----
+    for (int l = 0; l < a.n_layers; ++l) {
+        const int K = a.in_w[l], U = a.units[l];
+        const int Ka = l == 0 ? K : K - a.units[l - 1];
+        for (int e = tid; e < a.ka[l] * U; e += PT_THREADS) {
+            const int k = e / U, o = e - k * U;
+            s_w[a.wa_off[l] + e] = k < Ka ? a.w[l][o * K + k] : 0.0f;
+        }
+        if (l > 0) {
+            const int Kb = a.units[l - 1];
+            for (int e = tid; e < Kb * U; e += PT_THREADS) {
+                const int k = e / U, o = e - k * U;
+                s_w[a.wb_off[l] + e] = a.w[l][o * K + Ka + k];
+            }
+        }
+        for (int o = tid; o < U; o += PT_THREADS) {
+            float *bn = s_bn + l * 4 * PFN_MAX_W;
+            bn[o] = a.mean[l][o];
+            bn[PFN_MAX_W + o] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(a.var[l][o], a.eps)));
+            bn[2 * PFN_MAX_W + o] = a.gamma[l][o];
+            bn[3 * PFN_MAX_W + o] = a.beta[l][o];
+        }
+    }
+    __syncthreads();
+
+    // ---- chunks of PT_CHUNK consecutive voxels, handed out dynamically ----
+    __shared__ unsigned int s_chunk;
+    while (true) {
+    if (tid == 0) s_chunk = atomicAdd(a.chunk_counter, 1u);
+    __syncthreads();
+    long long v_next = (long long)s_chunk * PT_CHUNK;
+    if (v_next >= a.m) break;
+    const long long v_end = min(a.m, v_next + (long long)PT_CHUNK);
+    // packing info is fetched one tile ahead (warp 0: lane i looks at voxel v_next + i)
+    int n_ahead = 0;
+    if (warp == 0 && v_next + lane < v_end) n_ahead = __float_as_int(__ldg(&a.prep[2 * (v_next + lane)].w));
+    while (v_next < v_end) {
+        // pack whole voxels greedily into <= PT_ROWS rows (warp 0)
+        if (warp == 0) {
+            const long long v = v_next + lane;
+            int rows = 0;
+            if (v < v_end) {
+                const int n = min(max(n_ahead, 0), t);
+                rows = n < t ? n + 1 : t;
+            }
+            int incl = rows;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const unsigned fits = __ballot_sync(0xffffffffu, v < v_end && incl <= PT_ROWS);
+            const int nv = __popc(fits);                  // prefix property: fits is a run of low bits
+            if (lane < nv) { s_vrows[lane] = incl - rows; s_vn[lane] = min(max(n_ahead, 0), t); }
+            if (lane == nv - 1) { s_vrows[nv] = incl; s_nrows = incl; }
+            if (lane == 0) s_nvox = nv;
+            // prefetch the packing info of the next tile
+            const long long vn = v_next + nv + lane;
+            n_ahead = vn < v_end ? __float_as_int(__ldg(&a.prep[2 * vn].w)) : 0;
+        }
+        __syncthreads();
+        const int n_vox = s_nvox, n_rows = s_nrows;
+        const long long vbase = v_next;
+        // per-voxel statistics and row maps
+        for (int vl = warp; vl < n_vox; vl += PT_THREADS / 32) {
+            if (lane < 2) {
+                const float4 q = __ldg(&a.prep[2 * (vbase + vl) + lane]);
+                reinterpret_cast<float4 *>(s_mean)[vl * 2 + lane] = q;
+            }
+            const int r0 = s_vrows[vl], r1 = s_vrows[vl + 1];
+            for (int r = r0 + lane; r < r1; r += 32) { s_row_vox[r] = vl; s_row_t[r] = r - r0; }
+        }
+        __syncthreads();
+        // decorated input rows (:140-164): warp per row, lane per column; rows >= n_rows and the
+        // padded representatives are zero
+        for (int r = warp; r < PT_ROWS; r += PT_THREADS / 32) {
+            float val = 0.0f;
+            if (r < n_rows && lane < c0) {
+                const int vl = s_row_vox[r], tt = s_row_t[r];
+                if (tt < s_vn[vl]) {
+                    const float *p = a.voxels + ((vbase + vl) * t + tt) * c;
+                    const int k = lane;
+                    if (k < c) val = __ldg(p + k);
+                    else if (k < c + 3) val = __fsub_rn(__ldg(p + k - c), s_mean[vl * 8 + k - c]);       // :140
+                    else if (k == c + 3) val = __fsub_rn(__ldg(p), s_mean[vl * 8 + 4]);                    // :146-147
+                    else if (k == c + 4) val = __fsub_rn(__ldg(p + 1), s_mean[vl * 8 + 5]);                // :149-150
+                    else {
+                        const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);                      // :155
+                        val = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+                    }
+                }
+            }
+            if (lane < a.ka[0]) s_xa[r * a.xs + lane] = val;
+        }
+        __syncthreads();
+        // ---- layers ----
+        float *xin = s_xa, *xout = s_xb;
+        float *vin = s_va, *vout = s_vb;
+        for (int l = 0; l < a.n_layers; ++l) {
+            switch (a.units[l] >> 5) {
+            case 1: pt_layer<1>(a, l, n_rows, n_vox, s_w, s_bn, xin, vin, xout, reinterpret_cast<int *>(vout), s_p, s_row_vox); break;
+            case 2: pt_layer<2>(a, l, n_rows, n_vox, s_w, s_bn, xin, vin, xout, reinterpret_cast<int *>(vout), s_p, s_row_vox); break;
+            case 3: pt_layer<3>(a, l, n_rows, n_vox, s_w, s_bn, xin, vin, xout, reinterpret_cast<int *>(vout), s_p, s_row_vox); break;
+            default: pt_layer<4>(a, l, n_rows, n_vox, s_w, s_bn, xin, vin, xout, reinterpret_cast<int *>(vout), s_p, s_row_vox); break;
+            }
+            float *tmp = xin; xin = xout; xout = tmp;
+            tmp = vin; vin = vout; vout = tmp;
+        }
+        // ---- output: max of the last layer (vin after the swap) ----
+        const int U = a.units[a.n_layers - 1];
+        for (int vl = warp; vl < n_vox; vl += PT_THREADS / 32) {
+            float *dst = a.out + (vbase + vl) * U;
+            for (int o = lane; o < U; o += 32) __stcs(dst + o, vin[vl * PFN_MAX_W + o]);
+        }
+        __syncthreads();
+        v_next += n_vox;
+    }
+    }
+}
+
+static int pfn_tiled_supported(const pv_pfn_layer *layers, int n_layers, int t)
+{
+    if (t < 2 || t > PT_ROWS) return 0;
+    for (int l = 0; l < n_layers; ++l)
+        if (layers[l].units % 32 != 0 || layers[l].units > PFN_MAX_W) return 0;
+    return 1;
+}
+
 extern "C" {
 
 int pv_vfe_mean(const float *voxels, const int32_t *num_points, int64_t m, int32_t t, int32_t c,
@@ -244,15 +577,56 @@ int pv_scatter(const float *feats, const int32_t *coors, int64_t m, int32_t c, i
     return pv_last_cuda_error();
 }
 
+size_t pv_pfn_workspace_bytes(int64_t m) { return m > 0 ? ((size_t)m * 2 + 1) * sizeof(float4) : 0; }
+
 int pv_pfn_forward(const float *voxels, const int32_t *num_points, const int32_t *coors, int64_t m,
                    int32_t t, int32_t c, int32_t with_distance, float vx, float vy, float x_off,
                    float y_off, const pv_pfn_layer *layers, int32_t n_layers, float eps,
-                   float *out, pv_stream_t stream)
+                   void *workspace, size_t workspace_bytes, float *out, pv_stream_t stream)
 {
     if (m < 0 || t <= 0 || c < 3 || !layers || n_layers <= 0) return PV_ERR_BAD_ARGUMENT;
     if (n_layers > PV_MAX_PFN_LAYERS || t > PFN_MAX_T) return PV_ERR_UNSUPPORTED;
     if (m == 0) return PV_OK;
     if (!voxels || !num_points || !coors || !out) return PV_ERR_BAD_ARGUMENT;
+    if (pfn_tiled_supported(layers, n_layers, t) && c + 5 + (with_distance ? 1 : 0) <= PT_MAX_IN) {
+        PtArgs q;
+        q.voxels = voxels; q.num = num_points; q.coors = coors; q.m = m; q.t = t; q.c = c;
+        q.with_distance = with_distance ? 1 : 0;
+        q.vx = vx; q.vy = vy; q.x_off = x_off; q.y_off = y_off; q.eps = eps; q.n_layers = n_layers; q.out = out;
+        int width = c + 5 + q.with_distance, off = 0, xs = 0;
+        for (int l = 0; l < n_layers; ++l) {
+            const pv_pfn_layer &L = layers[l];
+            if (L.in_channels != width) return PV_ERR_BAD_ARGUMENT;
+            if (!L.weight || !L.bn_mean || !L.bn_var || !L.bn_gamma || !L.bn_beta) return PV_ERR_BAD_ARGUMENT;
+            q.w[l] = L.weight; q.mean[l] = L.bn_mean; q.var[l] = L.bn_var; q.gamma[l] = L.bn_gamma; q.beta[l] = L.bn_beta;
+            q.in_w[l] = L.in_channels; q.units[l] = L.units;
+            const int ka = l == 0 ? L.in_channels : L.in_channels - layers[l - 1].units;   // per-row K
+            q.ka[l] = (ka + 3) & ~3;
+            q.wa_off[l] = off; off += q.ka[l] * L.units;
+            q.wb_off[l] = off; if (l > 0) off += layers[l - 1].units * L.units;
+            if (q.ka[l] > xs) xs = q.ka[l];
+            if (l < n_layers - 1 && L.units > xs) xs = L.units;
+            width = (l == n_layers - 1) ? L.units : 2 * L.units;
+        }
+        q.w_total = (off + 3) & ~3;
+        q.xs = xs + 4;                                      // +4: rows start in different banks
+        const size_t smem = sizeof(float) * ((size_t)q.w_total + (size_t)n_layers * 4 * PFN_MAX_W +
+                                             2 * (size_t)PT_ROWS * q.xs + 3 * (size_t)PT_VOX * PFN_MAX_W + PT_VOX * 8) +
+                            sizeof(int) * (2 * PT_ROWS + 2 * PT_VOX + 8) + 64;
+        if (smem <= 110 * 1024 && workspace && workspace_bytes >= pv_pfn_workspace_bytes(m) &&
+            (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0 && (reinterpret_cast<uintptr_t>(coors) & 15u) == 0) {
+            q.prep = reinterpret_cast<const float4 *>(workspace);
+            q.chunk_counter = reinterpret_cast<unsigned int *>(reinterpret_cast<float4 *>(workspace) + 2 * m);
+            k_pfn_prep<<<(unsigned)((m + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+                voxels, num_points, coors, m, t, c, vx, vy, x_off, y_off, reinterpret_cast<float4 *>(workspace));
+            if (cudaFuncSetAttribute(k_pfn_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return PV_ERR_CUDA;
+            const long long want = (m + PT_CHUNK - 1) / PT_CHUNK;
+            const unsigned grid = (unsigned)(want < 296 ? want : 296);
+            k_pfn_tiled<<<grid, PT_THREADS, smem, (cudaStream_t)stream>>>(q);
+            return pv_last_cuda_error();
+        }
+    }
     PfnArgs a;
     a.voxels = voxels; a.num = num_points; a.coors = coors; a.m = m; a.t = t; a.c = c;
     a.with_distance = with_distance ? 1 : 0;

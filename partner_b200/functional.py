@@ -196,9 +196,11 @@ def pfn_forward(features, num_voxels, coors, layers, vx, vy, x_off, y_off, with_
         arr[i].bn_gamma, arr[i].bn_beta = gamma.data_ptr(), beta.data_ptr()
         arr[i].units, arr[i].in_channels = w.shape[0], w.shape[1]
     out = torch.empty((m, layers[-1][0].shape[0]), dtype=torch.float32, device=features.device)
-    check(_lib.load().pv_pfn_forward(ptr(features), ptr(num_voxels), ptr(coors), m, t, c,
-                                     1 if with_distance else 0, vx, vy, x_off, y_off, arr, len(layers),
-                                     eps, ptr(out), current_stream(features.device)), "pv_pfn_forward")
+    lib = _lib.load()
+    ws = workspace(max(256, lib.pv_pfn_workspace_bytes(m)), features.device, "pfn")
+    check(lib.pv_pfn_forward(ptr(features), ptr(num_voxels), ptr(coors), m, t, c,
+                             1 if with_distance else 0, vx, vy, x_off, y_off, arr, len(layers),
+                             eps, ptr(ws), ws.numel(), ptr(out), current_stream(features.device)), "pv_pfn_forward")
     return out
 
 
