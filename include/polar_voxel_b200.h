@@ -162,6 +162,13 @@ int pv_pfn_forward(const float *voxels, const int32_t *num_points, const int32_t
 /* Scratch bytes pv_pfn_forward needs for m voxels (per-voxel statistics). */
 size_t pv_pfn_workspace_bytes(int64_t m);
 
+/* Tensor-core building block of the PFN linear layers (PFNLayer.linear, pillar_encoder.py:41,50):
+ * d[m, n] = a[m, k] . b[n, k]^T in fp32 via tcgen05.mma.kind::tf32 with the 3xTF32 split
+ * (fp32-accurate), accumulators in TMEM.  n multiple of 16 in [16, 256], k multiple of 8, <= 64.
+ * `variant` must be 0 (bit 0 swaps the descriptor stride roles; bring-up aid). */
+int pv_tc_gemm_tf32x3(const float *a, const float *b, int32_t m, int32_t n, int32_t k, float *d,
+                      int32_t variant, pv_stream_t stream);
+
 /* Bytes of workspace pv_scatter needs (the BEV index map). */
 size_t pv_scatter_workspace_bytes(int32_t batch, int32_t ny, int32_t nx);
 
