@@ -159,8 +159,9 @@ int pv_pfn_forward(const float *voxels, const int32_t *num_points, const int32_t
                    float y_off, const pv_pfn_layer *layers, int32_t n_layers, float eps,
                    void *workspace, size_t workspace_bytes, float *out, pv_stream_t stream);
 
-/* Scratch bytes pv_pfn_forward needs for m voxels (per-voxel statistics). */
-size_t pv_pfn_workspace_bytes(int64_t m);
+/* Scratch bytes pv_pfn_forward needs for m voxels of t slots (per-voxel statistics and, for
+ * two-layer nets whose second layer runs on tcgen05, the layer-0 rows). */
+size_t pv_pfn_workspace_bytes(int64_t m, int32_t t);
 
 /* Tensor-core building block of the PFN linear layers (PFNLayer.linear, pillar_encoder.py:41,50):
  * d[m, n] = a[m, k] . b[n, k]^T in fp32 via tcgen05.mma.kind::tf32 with the 3xTF32 split

@@ -84,7 +84,7 @@ EXPORTS = {
     "pv_vfe_mean": (ctypes.c_int, [P, P, I64, I32, I32, P, P]),
     "pv_pfn_forward": (ctypes.c_int, [P, P, P, I64, I32, I32, I32, F32, F32, F32, F32,
                                       ctypes.POINTER(PvPfnLayer), I32, F32, P, SZ, P, P]),
-    "pv_pfn_workspace_bytes": (SZ, [I64]),
+    "pv_pfn_workspace_bytes": (SZ, [I64, I32]),
     "pv_tc_gemm_tf32x3": (ctypes.c_int, [P, P, I32, I32, I32, P, I32, P]),
     "pv_scatter_workspace_bytes": (SZ, [I32, I32, I32]),
     "pv_scatter": (ctypes.c_int, [P, P, I64, I32, I32, I32, I32, P, SZ, P, P, P]),

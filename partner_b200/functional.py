@@ -197,7 +197,7 @@ def pfn_forward(features, num_voxels, coors, layers, vx, vy, x_off, y_off, with_
         arr[i].units, arr[i].in_channels = w.shape[0], w.shape[1]
     out = torch.empty((m, layers[-1][0].shape[0]), dtype=torch.float32, device=features.device)
     lib = _lib.load()
-    ws = workspace(max(256, lib.pv_pfn_workspace_bytes(m)), features.device, "pfn")
+    ws = workspace(max(256, lib.pv_pfn_workspace_bytes(m, t)), features.device, "pfn")
     check(lib.pv_pfn_forward(ptr(features), ptr(num_voxels), ptr(coors), m, t, c,
                              1 if with_distance else 0, vx, vy, x_off, y_off, arr, len(layers),
                              eps, ptr(ws), ws.numel(), ptr(out), current_stream(features.device)), "pv_pfn_forward")

@@ -53,6 +53,18 @@ def test_pillar_feature_net_matches_reference(g, tag, filters, dist):
     assert_close_fp32(out, g[f"{tag}_out"], tag + " vs reference")
 
 
+@pytest.mark.parametrize("tag,filters", [("pfn64_128", (64, 128))])
+def test_pillar_feature_net_tensor_core_path_matches_reference(g, tag, filters, monkeypatch):
+    """Second layer on tcgen05 (3xTF32, accumulators in TMEM): same 1e-5 gate as the fp32 kernel."""
+    monkeypatch.setenv("PV_PFN_TC", "1")
+    net = _load_pfn(g, tag, filters, False)
+    out = net(_cuda(g["voxels"]), _cuda(g["num_points"]), _cuda(g["coors"])).cpu().numpy()
+    assert_close_fp32(out, g[f"{tag}_out"], tag + " (tcgen05) vs reference")
+    monkeypatch.setenv("PV_PFN_TC", "0")
+    ref = net(_cuda(g["voxels"]), _cuda(g["num_points"]), _cuda(g["coors"])).cpu().numpy()
+    assert_close_fp32(out, ref, "tcgen05 vs fp32 kernel")
+
+
 def test_pfn_training_mode_is_refused(g):
     net = _load_pfn(g, "pfn64", (64,), False).train()
     with pytest.raises(RuntimeError):
