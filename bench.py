@@ -40,12 +40,13 @@ WORKLOADS = {
 }
 METRIC = "polar_voxelize_vfe_scatter_throughput"
 UNIT = "Mpoints/s"
-STAGES = ["bin_insert", "cell_flags", "scan", "place", "emit"]
+STAGES = ["insert", "cells", "scan", "finalize", "heavy"]
 N_SETS = 4          # rotating input sets so a step never finds its inputs in the 126 MB L2
 
 
-STAGE_KERNELS = {"bin_insert": ("k_bin_insert",), "cell_flags": ("k_cell_flags",), "scan": ("k_tile_reduce", "k_scan_apply"),
-                 "place": ("k_place",), "emit": ("k_emit",)}
+STAGE_KERNELS = {"insert": ("kf_insert",), "cells": ("kf_cells",), "scan": ("kf_scan",),
+                 "heavy": ("kf_heavy_points", "kf_heavy_cells"), "finalize": ("kf_finalize",)}
+LAUNCHES_PER_STEP = 6
 
 
 def ncu_traffic(stage):
@@ -341,9 +342,10 @@ def main():
         cells = int(fe.grid_size[0]) * int(fe.grid_size[1])
         # algorithmic bytes per step on one GPU: points read once, every required
         # output written once; map / lists / workspace traffic is NOT counted.
-        # the canvas is zero-filled inside bin_insert and scattered by emit: its bytes count once, in bin_insert
-        alg = {"bin_insert": 4.0 * n_avg * c_in + (4.0 * C * cells * per_gpu if has_canvas else 0.0),
-               "emit": (16 + 4 + 4 * C) * m_avg}
+        # insert reads every point row once; finalize writes every output once (the canvas in cell order,
+        # zeros included)
+        alg = {"insert": 4.0 * n_avg * c_in,
+               "finalize": (16 + 4 + 4 * C) * m_avg + (4.0 * C * cells * per_gpu if has_canvas else 0.0)}
         path_bytes = sum(alg.values())
         step_ms = ms_total / args.steps
         live = {STAGES[i]: float(stage[i]) for i in range(len(STAGES)) if stage[i] > 0}
@@ -372,7 +374,7 @@ def main():
                     "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                     "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": e2e_wall / e2e_steps, "steps": e2e_steps,
                     "streams": n_streams, "synchronous_ms_per_step": e2e_sync_ms},
-            "gpu_launches": 6 * args.steps,
+            "gpu_launches": LAUNCHES_PER_STEP * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": (ach / peak) if ach else None, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,

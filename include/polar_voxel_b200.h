@@ -76,14 +76,15 @@ int pv_version(void);
 const char *pv_error_string(int code);
 
 /* Bytes of workspace for a batch of `batch` frames holding at most
- * `max_points_total` points, no frame larger than `frame_capacity` points. */
+ * `max_points_total` points, no frame larger than `frame_capacity` points, voxelized with at
+ * most `channels` feature channels C (c_in + 2 for Cartesian input, c_in otherwise). */
 size_t pv_workspace_bytes(const pv_config *cfg, int64_t max_points_total, int32_t batch,
-                          int64_t frame_capacity);
+                          int64_t frame_capacity, int32_t channels);
 
 /* One-time preparation of a workspace for (cfg, capacities); see "SELF-CLEANING" above. */
 int pv_workspace_init(const pv_config *cfg, int64_t max_points_total, int32_t batch,
-                      int64_t frame_capacity, void *workspace, size_t workspace_bytes,
-                      pv_stream_t stream);
+                      int64_t frame_capacity, int32_t channels, void *workspace,
+                      size_t workspace_bytes, pv_stream_t stream);
 
 /* transform_points (det3d/datasets/pipelines/utils.py:34-47).  out is [n, c_in+2]. */
 int pv_transform_points(const float *in, int64_t n, int32_t c_in, int32_t cylinder, float *out,
@@ -108,6 +109,12 @@ int pv_transform_points(const float *in, int64_t n, int32_t c_in, int32_t cylind
  * Output buffers must have capacity for min(batch * V, n_total) rows.
  * max_points_total / frame_capacity are the CAPACITIES the workspace was initialised with
  * (n_total <= max_points_total, every frame <= frame_capacity points).
+ *
+ * Two pipelines sit behind this entry point.  With voxels == NULL the call runs LIST-FREE
+ * (fused.cu): per-cell accumulator rows updated with 16-byte fp32 reductions, no per-voxel
+ * point lists; integer outputs are bit-exact, mean_feats is the sum of the same addends in an
+ * unspecified order (relative error ~1e-7, not run-to-run bit-reproducible).  With voxels != NULL
+ * the list-based pipeline (voxelize.cu) runs; its sums are in point-index order and reproducible.
  */
 int pv_voxelize(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
                 int32_t batch, int64_t n_total, int32_t c_in, int32_t is_cartesian,
@@ -128,9 +135,8 @@ int pv_forward_mean_canvas(const pv_config *cfg, const float *points, const int3
 
 /* Measurement aid for bench.py: runs pv_forward_mean_canvas (canvas may be NULL for 3-D grids)
  * `iters` times with CUDA events recorded on `stream` between the stages and returns the average
- * milliseconds per stage in stage_ms (HOST, PV_PROFILE_STAGES floats): 0 bin_insert,
- * 1 rank_scan, 2 fill_lists, 3 emit (+ canvas on direct-map pillar grids), 4 hash-map canvas +
- * restore (pillar grids beyond the direct-map limit only).  Synchronises. */
+ * milliseconds per stage in stage_ms (HOST, PV_PROFILE_STAGES floats): 0 insert, 1 cells,
+ * 2 scan, 3 finalize (+ canvas), 4 heavy cells.  Synchronises. */
 #define PV_PROFILE_STAGES 5
 int pv_profile_mean_canvas(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
                            int32_t batch, int64_t n_total, int32_t c_in, int32_t is_cartesian,

@@ -71,9 +71,9 @@ SZ = ctypes.c_size_t
 EXPORTS = {
     "pv_version": (ctypes.c_int, []),
     "pv_error_string": (ctypes.c_char_p, [ctypes.c_int]),
-    "pv_workspace_bytes": (SZ, [ctypes.POINTER(PvConfig), I64, I32, I64]),
+    "pv_workspace_bytes": (SZ, [ctypes.POINTER(PvConfig), I64, I32, I64, I32]),
     "pv_transform_points": (ctypes.c_int, [P, I64, I32, I32, P, P]),
-    "pv_workspace_init": (ctypes.c_int, [ctypes.POINTER(PvConfig), I64, I32, I64, P, SZ, P]),
+    "pv_workspace_init": (ctypes.c_int, [ctypes.POINTER(PvConfig), I64, I32, I64, I32, P, SZ, P]),
     "pv_voxelize": (ctypes.c_int, [ctypes.POINTER(PvConfig), P, P, I32, I64, I32, I32, I64, I64, P, SZ,
                                    P, P, P, P, P, P, P, P]),
     "pv_forward_mean_canvas": (ctypes.c_int, [ctypes.POINTER(PvConfig), P, P, I32, I64, I32, I32, I64, I64,

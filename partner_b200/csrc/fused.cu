@@ -1,0 +1,745 @@
+// fused.cu -- list-free polar front end (sm_100a): voxelize + mean VFE + BEV canvas without ever
+// materialising per-voxel point lists.
+//
+// Same contract as the list-based pipeline of voxelize.cu (point_cloud_ops.py:7-72 through
+// VoxelGenerator.generate, voxel_encoder.py:15-22, pillar_encoder.py:189-225): voxel order =
+// first-occurrence order, kept points = the T smallest indices of the cell, cells of rank >= V
+// dropped.  Integer outputs are bit-exact; the mean is a sum of the same addends in a different
+// order (fp32 reductions at L2), inside the 1e-5 tolerance of the north star.
+//
+// Measured on B200 (tools/probes/atomics_probe.cu): a scattered 4-byte load, store or reduction
+// costs one LSU slot per lane (~1.3 cycles per lane per SM, ~225 G lane-ops/s per GPU), and a
+// 16-byte vector reduction costs the same as a 4-byte one.  The design therefore minimises
+// SCATTERED OPERATIONS PER POINT:
+//
+//   F1 insert      per point: bin -> cell slot; RED.MIN(first[slot], i) and one 16-byte
+//                  RED.ADD.F32x4 per 4 floats of the row {C feature sums, count}.  Fire-and-forget:
+//                  nothing returns, no thread waits on L2.  Rows staged with one TMA bulk copy per
+//                  tile; consecutive points of one thread that share a cell are merged first.
+//   F2 cells       stream over the map: every occupied cell sets the bit of its first point; cells
+//                  with more than T points are registered as heavy.
+//   F3 scan        popcount scan over the first-point bitmap (N/32 words) -> rank of every first
+//                  point in its frame = first-occurrence rank of its cell; voxel counts, row bases.
+//   F4 heavy       (rare cells, 2-5 % of the points) points of heavy cells insert their index into
+//                  the cell's T-entry list (atomicMin chain -> the T smallest, ascending); one
+//                  warp per heavy cell then re-sums exactly those rows.
+//   F5 finalize    stream over the map again: occupied cell -> rank lookup, mean = sum / min(n, T),
+//                  coors / num_points / features rows; the BEV canvas (and density) is written
+//                  IN CELL ORDER, every element exactly once, zeros included -- no zero fill, no
+//                  scatter; the map is restored to its clean state on the way.
+#include <stdlib.h>
+
+#include "pv_common.cuh"
+
+#define PF_THREADS 256
+#define PF_PPT 4                          // consecutive points per thread in the point passes
+#define PF_TILE (PF_THREADS * PF_PPT)
+#define PF_SCAN_THREADS 1024
+
+// ---------------------------------------------------------------------------------------------
+// small PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pf_red_add_v4(float *p, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pf_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pf_mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void pf_mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pf_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+// TMA bulk copy global -> shared (1-D, 16-byte granules), completion on an mbarrier
+__device__ __forceinline__ void pf_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Hash-mode slot claim (same protocol as voxelize.cu): keys[] = cell, clean = INF.
+__device__ __forceinline__ uint32_t pf_claim(uint32_t *keys, uint32_t mask, uint32_t cell, uint32_t *status)
+{
+    uint32_t h = pv_hash(cell) & mask;
+    for (uint32_t probe = 0; probe <= mask; ++probe) {
+        const uint32_t k = pv_ld_volatile(keys + h);
+        if (k == cell) return h;
+        if (k == PV_INF) {
+            const uint32_t old = atomicCAS(keys + h, PV_INF, cell);
+            if (old == PV_INF || old == cell) return h;
+        }
+        h = (h + 1) & mask;
+    }
+    atomicOr(status, 1u);
+    return PV_INF;
+}
+
+// ---------------------------------------------------------------------------------------------
+// F1 -- insert.  CIN > 0: compile-time row width and transform flag (rows read from shared memory
+// with 128-bit loads); CIN == 0: runtime c_in / cart.  NV = 16-byte reductions per row.
+// ---------------------------------------------------------------------------------------------
+template <bool DENSE, int CIN, bool CART, int NV>
+__global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ PvParams p,
+                                                        const __grid_constant__ PvF f)
+{
+    extern __shared__ __align__(128) float s_pts[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ int s_b0;
+    constexpr int CT = NV * 4;
+    const uint32_t tid = threadIdx.x;
+    const int c_in = CIN ? CIN : p.c_in;
+    const bool cart = CIN ? CART : (p.cart != 0);
+    const int C = p.C;
+    const uint32_t tile_base = blockIdx.x * PF_TILE;
+    const uint32_t n_tile = min((uint32_t)PF_TILE, p.n - tile_base);
+    const uint32_t nf = n_tile * (uint32_t)c_in;
+    const float *src = p.pts + (size_t)tile_base * c_in;
+
+    // ---- stage the tile's rows: one TMA bulk copy (16-byte granules) + a scalar tail ----
+    const bool bulk = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && nf >= 4u;
+    const uint32_t bulk_bytes = bulk ? ((nf * 4u) & ~15u) : 0u;
+    const uint32_t bar = pf_smem_addr(&s_bar);
+    if (tid == 0) {
+        s_b0 = pv_frame_of(p.offsets, p.B, tile_base);
+        if (bulk) {
+            pf_mbar_init(bar, 1);
+            pf_mbar_expect_tx(bar, bulk_bytes);
+            pf_bulk_g2s(pf_smem_addr(s_pts), src, bulk_bytes, bar);
+        }
+    }
+    for (uint32_t k = (bulk_bytes >> 2) + tid; k < nf; k += PF_THREADS) s_pts[k] = __ldg(src + k);
+    __syncthreads();                        // barrier initialised + tail visible
+    if (bulk) pf_mbar_wait(bar, 0);
+
+    const uint32_t t0 = tid * PF_PPT;       // first point of this thread inside the tile
+    float rows[CIN ? PF_PPT * CIN : 1];      // this thread's 4 rows = CIN consecutive 16-byte words
+    if constexpr (CIN > 0) {
+        const float4 *q4 = reinterpret_cast<const float4 *>(s_pts) + tid * CIN;
+#pragma unroll
+        for (int k = 0; k < CIN; ++k) {
+            const float4 v = q4[k];
+            rows[4 * k] = v.x; rows[4 * k + 1] = v.y; rows[4 * k + 2] = v.z; rows[4 * k + 3] = v.w;
+        }
+    }
+
+    int b = s_b0;
+    uint32_t cur_s = PV_INF, cur_i = 0;      // current run of consecutive points in one cell
+    float cur[CT], cur_n = 0.0f;             // its feature sums and point count
+    uint32_t sa_out[PF_PPT];
+    auto flush = [&]() {
+        if (cur_s != PV_INF) {
+            atomicMin(f.first + cur_s, cur_i);
+            float o[CT];                     // the count rides in channel C of the row
+#pragma unroll
+            for (int k = 0; k < CT; ++k) o[k] = k < C ? cur[k] : (k == C ? cur_n : 0.0f);
+            float *row = f.acc + (size_t)cur_s * f.rowf;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) pf_red_add_v4(row + 4 * q, o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        }
+    };
+#pragma unroll
+    for (int j = 0; j < PF_PPT; ++j) {
+        sa_out[j] = PV_INF;
+        const uint32_t i = tile_base + t0 + j;
+        if (t0 + j >= n_tile) continue;
+        float in[CT];                        // the raw row, zero padded
+#pragma unroll
+        for (int k = 0; k < CT; ++k) {
+            if constexpr (CIN > 0) in[k] = k < CIN ? rows[j * CIN + (k < CIN ? k : 0)] : 0.0f;
+            else in[k] = k < c_in ? s_pts[(t0 + j) * c_in + k] : 0.0f;
+        }
+        float v[CT];                         // the feature row the reference voxelizes
+        if (cart) {                          // utils.py:42-44: (rho, phi, z, x, y, feat3..)
+#pragma unroll
+            for (int k = 0; k < CT; ++k) v[k] = k >= 5 ? in[k >= 5 ? k - 2 : 0] : 0.0f;
+            v[0] = pv_rho(in[0], in[1]);
+            if (CT > 1) v[1] = pv_atan2f(in[1], in[0]);
+            if (CT > 2) v[2] = in[2];
+            if (CT > 3) v[3] = in[0];
+            if (CT > 4) v[CT > 4 ? 4 : 0] = in[1];
+        } else {
+#pragma unroll
+            for (int k = 0; k < CT; ++k) v[k] = in[k];
+        }
+        bool ok = true;
+        int ci[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {        // point_cloud_ops.py:45 -- float32 subtract, IEEE divide, floor
+            const float cf = floorf(__fdiv_rn(__fsub_rn(v[a < CT ? a : 0], p.lo[a]), p.vs[a]));
+            int c;
+            if (!(cf >= 0.0f)) { ok = false; c = 0; }                     // below range or NaN
+            else if (cf >= p.gridf[a]) { ok = false; c = p.grid[a] - 1; }
+            else c = (int)cf;
+            ci[a] = c;
+        }
+        if (p.grid_ind) {                    // :46-54 clamped (z, y, x) for every point
+            int32_t *gi = p.grid_ind + (size_t)i * 3;
+            gi[0] = ci[2]; gi[1] = ci[1]; gi[2] = ci[0];
+        }
+        while (b + 1 < p.B && i >= (uint32_t)__ldg(p.offsets + b + 1)) ++b;
+        if (!ok) continue;
+        const uint32_t cell = ((uint32_t)ci[2] * (uint32_t)p.grid[1] + (uint32_t)ci[1]) * (uint32_t)p.grid[0] + (uint32_t)ci[0];
+        uint32_t s, sa;
+        if (DENSE) {
+            s = (uint32_t)b * f.capf + cell;
+            // heavy-bitmap order: phi fastest, so azimuth neighbours share a bitmap word
+            sa = (uint32_t)b * f.capf + ((uint32_t)ci[2] * (uint32_t)p.grid[0] + (uint32_t)ci[0]) * (uint32_t)p.grid[1] + (uint32_t)ci[1];
+        } else {
+            const uint32_t h = pf_claim(f.keys + (size_t)b * f.capf, f.capf - 1, cell, p.ws.ctrl + 1);
+            if (h == PV_INF) continue;       // map full: status bit set
+            s = (uint32_t)b * f.capf + h;
+            sa = s;
+        }
+        sa_out[j] = sa;
+        if (s == cur_s) {
+#pragma unroll
+            for (int k = 0; k < CT; ++k) cur[k] = __fadd_rn(cur[k], v[k]);
+            cur_n += 1.0f;
+        } else {
+            flush();
+            cur_s = s; cur_i = i; cur_n = 1.0f;
+#pragma unroll
+            for (int k = 0; k < CT; ++k) cur[k] = v[k];
+        }
+    }
+    flush();
+    if (t0 + PF_PPT <= n_tile) {
+        *reinterpret_cast<uint4 *>(f.sa + tile_base + t0) = make_uint4(sa_out[0], sa_out[1], sa_out[2], sa_out[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < PF_PPT; ++j)
+            if (t0 + j < n_tile) f.sa[tile_base + t0 + j] = sa_out[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// F2 -- stream over the map: every occupied cell sets the bit of its first point.
+// grid = (slots / 4 / 256, B)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kf_cells(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
+{
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+        *reinterpret_cast<unsigned long long *>(f.ctrl + 4) = 0ull;        // heavy-cell allocator of this call
+    const uint32_t l0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    const int b = blockIdx.y;
+    if (l0 >= f.capf) return;
+    const uint32_t s0 = (uint32_t)b * f.capf + l0;
+    const uint4 fv = __ldcg(reinterpret_cast<const uint4 *>(f.first + s0));
+    if ((fv.x & fv.y & fv.z & fv.w) == PV_INF) return;
+    const uint32_t fi4[4] = {fv.x, fv.y, fv.z, fv.w};
+    const uint32_t off_b = (uint32_t)__ldg(p.offsets + b);
+    uint32_t *bits = f.bits + (size_t)b * f.wcap;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t fi = fi4[j];
+        if (fi == PV_INF) continue;
+        const uint32_t ib = fi - off_b;
+        if (ib >= f.wcap * 32u) { atomicOr(p.ws.ctrl + 1, 1u); continue; }     // frame larger than frame_capacity
+        atomicOr(bits + (ib >> 5), 1u << (ib & 31u));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// F3 -- popcount scan over the first-point bitmap, one block per frame; consumes (zeroes) bits[]
+// and publishes wb[] = {prefix, word}.  The last block to finish computes the output row bases.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PF_SCAN_THREADS) kf_scan(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
+{
+    __shared__ uint32_t s_warp[PF_SCAN_THREADS / 32];
+    __shared__ uint32_t s_carry, s_last;
+    const int b = blockIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t n_b = (uint32_t)(p.offsets[b + 1] - p.offsets[b]);
+    const uint32_t nw = min((n_b + 31u) >> 5, f.wcap);
+    uint32_t *bits = f.bits + (size_t)b * f.wcap;
+    uint2 *wb = f.wb + (size_t)b * f.wcap;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t w0 = 0; w0 < nw; w0 += PF_SCAN_THREADS * 4) {
+        const uint32_t w = w0 + tid * 4u;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (w < nw) v = __ldcg(reinterpret_cast<const uint4 *>(bits + w));   // wcap % 4 == 0: stays in bounds
+        const uint32_t c0 = __popc(v.x), c1 = __popc(v.y), c2 = __popc(v.z), c3 = __popc(v.w);
+        const uint32_t tsum = c0 + c1 + c2 + c3;
+        uint32_t incl = tsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (unsigned)d) incl += o;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t wsum = lane < PF_SCAN_THREADS / 32 ? s_warp[lane] : 0u;     // every warp scans the warp totals
+        uint32_t wincl = wsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, wincl, d);
+            if (lane >= (unsigned)d) wincl += o;
+        }
+        const uint32_t warp_excl = __shfl_sync(0xffffffffu, wincl - wsum, warp);
+        const uint32_t total = __shfl_sync(0xffffffffu, wincl, 31);
+        const uint32_t excl = s_carry + warp_excl + incl - tsum;
+        if (w < nw) {
+            uint4 *dst = reinterpret_cast<uint4 *>(wb + w);
+            dst[0] = make_uint4(excl, v.x, excl + c0, v.y);
+            dst[1] = make_uint4(excl + c0 + c1, v.z, excl + c0 + c1 + c2, v.w);
+            // restore the bitmap; issued after the loaded value was consumed (a store to an address
+            // with a load still in flight stalls the SM's load/store unit for the whole round trip)
+            if (tsum) *reinterpret_cast<uint4 *>(bits + w) = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const uint32_t raw = s_carry;
+        f.counts_raw[b] = raw;
+        p.voxel_counts[b] = (int32_t)min(raw, (uint32_t)p.V);
+        __threadfence();
+        const uint32_t done = atomicAdd(f.ctrl + 3, 1u);
+        s_last = done == gridDim.x - 1 ? 1u : 0u;
+        if (s_last) f.ctrl[3] = 0u;
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {                           // row bases: exclusive sum of the capped counts
+        __threadfence();
+        uint32_t carry = 0;
+        for (int b0 = 0; b0 < p.B; b0 += 32) {
+            const int bb = b0 + (int)lane;
+            const uint32_t m = bb < p.B ? (uint32_t)__ldcg(p.voxel_counts + bb) : 0u;
+            uint32_t incl = m;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (unsigned)d) incl += o;
+            }
+            if (bb < p.B) f.base[bb] = (int32_t)(carry + incl - m);
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) f.base[p.B] = (int32_t)carry;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// F4 -- finalize: stream over the map, one slot per thread.  grid = (slots / 256, B)
+// Cells holding more than T points ("heavy", 2-5 % of the points) get coors / num_points here and
+// are registered for F5, which selects their T smallest point indices and writes their features.
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void pf_ld_row(const float *row, float (&r)[NV * 4])
+{
+    if constexpr (NV == 2) {        // one 256-bit load per 32-byte row
+        asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                     : "l"(row));
+    } else {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(row) + q);
+            r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+        }
+    }
+}
+// Restores a row: zeros, except channel 0 which keeps `keep0` (the heavy-cell id until F5 is done).
+template <int NV>
+__device__ __forceinline__ void pf_st_row_clean(float *row, float keep0)
+{
+    if constexpr (NV == 2) {
+        asm volatile("st.global.v8.f32 [%0], {%1,%2,%2,%2,%2,%2,%2,%2};" ::"l"(row), "f"(keep0), "f"(0.0f) : "memory");
+    } else {
+#pragma unroll
+        for (int q = 0; q < NV; ++q)
+            __stcg(reinterpret_cast<float4 *>(row) + q, make_float4(q == 0 ? keep0 : 0.f, 0.f, 0.f, 0.f));
+    }
+}
+
+template <int NV, bool CANVAS>
+__global__ void __launch_bounds__(256) kf_finalize(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
+{
+    constexpr int CT = NV * 4;
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (l >= f.capf) return;
+    const uint32_t s = (uint32_t)b * f.capf + l;
+    const int C = p.C;
+    const uint32_t fi = __ldcs(f.first + s);
+    float m[CANVAS ? CT : 1];
+    int32_t dens = 0;
+    if (CANVAS) {
+#pragma unroll
+        for (int k = 0; k < CT; ++k) m[k] = 0.0f;
+    }
+    if (fi != PV_INF) {
+        float *rowp = f.acc + (size_t)s * f.rowf;
+        float r[CT];
+        pf_ld_row<NV>(rowp, r);
+        const uint32_t ib = fi - (uint32_t)__ldg(p.offsets + b);
+        const bool fits = ib < f.wcap * 32u;                              // else flagged by kf_cells
+        const uint2 wv = fits ? __ldg(f.wb + (size_t)b * f.wcap + (ib >> 5)) : make_uint2(0xFFFFFFFFu, 0u);
+        uint32_t cell = l;
+        if (!f.dense) cell = __ldcg(f.keys + s);
+        const uint32_t rank = wv.x + __popc(wv.y & ((1u << (ib & 31u)) - 1u));
+        float keep0 = 0.0f;
+        if (fits && rank < (uint32_t)p.V) {                               // :60-61 max_voxels
+            float cntf = 0.0f;
+#pragma unroll
+            for (int k = 0; k < CT; ++k) cntf = k == C ? r[k] : cntf;
+            const uint32_t cnt = (uint32_t)cntf;
+            const uint32_t T = (uint32_t)p.T;
+            const uint32_t L = min(cnt, T);
+            const int32_t vid = __ldg(f.base + b) + (int32_t)rank;
+            const uint32_t nx = p.grid[0], ny = p.grid[1];
+            const uint32_t x = cell % nx, yz = cell / nx;
+            reinterpret_cast<int4 *>(p.coors)[vid] = make_int4(b, (int)(yz / ny), (int)(yz % ny), (int)x);
+            p.num_points[vid] = (int32_t)L;
+            dens = (int32_t)cnt;                                          // :70-71 un-capped count
+            if (cnt > T) {
+                // heavy: the row holds the sum over ALL points; F5 re-sums the T smallest indices
+                const unsigned long long a = atomicAdd(reinterpret_cast<unsigned long long *>(f.ctrl + 4),
+                                                       (1ull << 32) | (unsigned long long)cnt);
+                const uint32_t hid = (uint32_t)(a >> 32), off = (uint32_t)a;
+                if (hid < f.hmax) {
+                    uint4 *hi = f.hinfo + 2 * (size_t)hid;
+                    hi[0] = make_uint4(s, (uint32_t)vid, off, cnt);
+                    hi[1] = make_uint4(cell, (uint32_t)b, 0u, 0u);           // .z = arrival cursor
+                    keep0 = __uint_as_float(hid);
+                    uint32_t hb = s;
+                    if (f.dense) {
+                        const uint32_t y = yz % ny, z = yz / ny;
+                        hb = (uint32_t)b * f.capf + (z * nx + x) * ny + y;
+                    }
+                    atomicOr(f.hbits + (hb >> 5), 1u << (hb & 31u));
+                } else atomicOr(p.ws.ctrl + 1, 1u);
+            } else {
+                const float nf = (float)L;
+                float *o = p.feats ? p.feats + (size_t)vid * C : nullptr;
+#pragma unroll
+                for (int k = 0; k < CT; ++k) {
+                    if (k < C) {
+                        const float mean = __fdiv_rn(r[k], nf);           // voxel_encoder.py:18-22
+                        if (o) o[k] = mean;
+                        if (CANVAS) m[k] = mean;
+                        else if (!f.dense && p.canvas) p.canvas[((size_t)b * C + k) * p.cells + cell] = mean;
+                    }
+                }
+            }
+            if (!f.dense && p.density) p.density[(size_t)b * p.cells + cell] = (int32_t)cnt;
+        }
+        // restore the map -- after the loaded row was consumed (see kf_scan)
+        pf_st_row_clean<NV>(rowp, keep0);
+        f.first[s] = PV_INF;
+        if (!f.dense) f.keys[s] = PV_INF;
+    }
+    if (f.dense && l < p.cells) {
+        // direct map: slot order == cell order, so canvas and density are written here in full,
+        // zeros included: no zero fill, no scatter                        pillar_encoder.py:211-217
+        if (CANVAS) {
+#pragma unroll
+            for (int k = 0; k < CT; ++k)
+                if (k < C) __stcs(p.canvas + ((size_t)b * C + k) * p.cells + l, m[k]);
+        }
+        if (p.density) p.density[(size_t)b * p.cells + l] = dens;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// F5a -- every point of a heavy cell appends its index to the cell's candidate range (one atomic
+// cursor per cell; the range was sized from the exact count).  The bitmap lookup has warp
+// locality (phi-fastest bit order).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PF_THREADS) kf_heavy_points(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
+{
+    if (__ldg(reinterpret_cast<const unsigned long long *>(f.ctrl + 4)) == 0ull) return;   // no heavy cell in this batch
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * PF_PPT;
+    if (i0 >= p.n) return;
+    uint32_t sa[PF_PPT];
+    if (i0 + PF_PPT <= p.n) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(f.sa + i0));
+        sa[0] = v.x; sa[1] = v.y; sa[2] = v.z; sa[3] = v.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < PF_PPT; ++j) sa[j] = i0 + j < p.n ? f.sa[i0 + j] : PV_INF;
+    }
+    uint32_t w[PF_PPT];
+#pragma unroll
+    for (int j = 0; j < PF_PPT; ++j) w[j] = sa[j] != PV_INF ? __ldg(f.hbits + (sa[j] >> 5)) : 0u;
+#pragma unroll
+    for (int j = 0; j < PF_PPT; ++j) {
+        if (!((w[j] >> (sa[j] & 31u)) & 1u)) continue;
+        uint32_t s = sa[j];
+        if (f.dense) {
+            const uint32_t bb = s / f.capf, l = s - bb * f.capf, nx = p.grid[0], ny = p.grid[1];
+            const uint32_t y = l % ny, t = l / ny, x = t % nx, z = t / nx;
+            s = bb * f.capf + (z * ny + y) * nx + x;
+        }
+        const uint32_t hid = __float_as_uint(__ldcg(f.acc + (size_t)s * f.rowf));
+        uint32_t *hi = reinterpret_cast<uint32_t *>(f.hinfo + 2 * (size_t)hid);
+        const uint32_t off = __ldcg(hi + 2);
+        const uint32_t pos = atomicAdd(hi + 6, 1u);
+        f.hlist[off + pos] = i0 + j;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// F5b -- one warp per heavy cell: T rounds of "smallest candidate above the previous pick"
+// (REDUX.MIN across the warp) give the T smallest point indices in ascending order -- exactly the
+// points the reference keeps (point_cloud_ops.py:66); their rows are gathered and summed (fixed
+// tree, deterministic), the mean goes to the feature row and the canvas.
+// ---------------------------------------------------------------------------------------------
+#define PF_CAND_REGS 8
+__global__ void __launch_bounds__(256) kf_heavy_cells(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
+{
+    const unsigned long long alloc = __ldg(reinterpret_cast<const unsigned long long *>(f.ctrl + 4));
+    const uint32_t nh = min((uint32_t)(alloc >> 32), f.hmax);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t T = (uint32_t)p.T;
+    const int C = p.C, c_in = p.c_in;
+    for (uint32_t hid = gw; hid < nh; hid += nwarps) {
+        const uint4 h0 = __ldcg(f.hinfo + 2 * (size_t)hid);
+        const uint4 h1 = __ldcg(f.hinfo + 2 * (size_t)hid + 1);
+        const uint32_t s = h0.x, vid = h0.y, off = h0.z, cnt = h0.w, cell = h1.x, b = h1.y;
+        const uint32_t *cand = f.hlist + off;
+        uint32_t cr[PF_CAND_REGS];
+        const bool in_regs = cnt <= 32u * PF_CAND_REGS;
+#pragma unroll
+        for (int q = 0; q < PF_CAND_REGS; ++q) cr[q] = (in_regs && lane + 32u * q < cnt) ? __ldcg(cand + lane + 32u * q) : PV_INF;
+        float acc[PV_MAX_CHANNELS];
+#pragma unroll
+        for (int k = 0; k < PV_MAX_CHANNELS; ++k) acc[k] = 0.0f;
+        uint32_t lower = 0;                     // candidates below `lower` are already picked
+        for (uint32_t r0 = 0; r0 < T; r0 += 32) {
+            uint32_t mine = PV_INF;             // lane k keeps pick r0 + k
+            const uint32_t rounds = min(32u, T - r0);
+            for (uint32_t r = 0; r < rounds; ++r) {
+                uint32_t best = PV_INF;
+                if (in_regs) {
+#pragma unroll
+                    for (int q = 0; q < PF_CAND_REGS; ++q) best = min(best, cr[q] >= lower ? cr[q] : PV_INF);
+                } else {
+                    for (uint32_t k = lane; k < cnt; k += 32) {
+                        const uint32_t v = __ldcg(cand + k);
+                        best = min(best, v >= lower ? v : PV_INF);
+                    }
+                }
+                best = __reduce_min_sync(0xffffffffu, best);
+                if (lane == r) mine = best;
+                lower = best + 1u;
+            }
+            if (mine != PV_INF) {
+                float row[PV_MAX_CHANNELS];
+                pv_feature_row(p.pts, mine, c_in, p.cart, row);
+#pragma unroll
+                for (int q = 0; q < PV_MAX_CHANNELS; ++q) acc[q] = __fadd_rn(acc[q], row[q]);
+            }
+        }
+        const float nf = (float)T;
+#pragma unroll
+        for (int q = 0; q < PV_MAX_CHANNELS; ++q) {
+            if (q < C) {
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) acc[q] = __fadd_rn(acc[q], __shfl_xor_sync(0xffffffffu, acc[q], d));
+                if (lane == 0) {
+                    const float mean = __fdiv_rn(acc[q], nf);
+                    if (p.feats) p.feats[(size_t)vid * C + q] = mean;
+                    if (p.canvas) p.canvas[((size_t)b * C + q) * p.cells + cell] = mean;
+                }
+            }
+        }
+        if (lane == 0) {
+            f.acc[(size_t)s * f.rowf] = 0.0f;    // the row's last dirty word (held the heavy-cell id)
+            uint32_t hb = s;
+            if (f.dense) {
+                const uint32_t l = s - b * f.capf, nx = p.grid[0], ny = p.grid[1];
+                const uint32_t x = l % nx, t = l / nx, y = t % ny, z = t / ny;
+                hb = b * f.capf + (z * nx + x) * ny + y;
+            }
+            atomicAnd(f.hbits + (hb >> 5), ~(1u << (hb & 31u)));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+static size_t pf_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int pvf_make_layout(const pv_config *cfg, int64_t n_cap, int32_t batch, int64_t frame_capacity,
+                    int32_t max_channels, void *base, PvF *w)
+{
+    int rc = pv_check_config(cfg);
+    if (rc) return rc;
+    if (batch <= 0 || n_cap < 0 || frame_capacity < 0 || n_cap >= (1ll << 30)) return PV_ERR_BAD_ARGUMENT;
+    if (max_channels < 3 || max_channels > PV_MAX_CHANNELS) return PV_ERR_BAD_ARGUMENT;
+    if (frame_capacity > n_cap) frame_capacity = n_cap;
+    const uint64_t cells = (uint64_t)cfg->grid[0] * cfg->grid[1] * cfg->grid[2];
+    const bool dense = cells <= PV_DENSE_MAX_CELLS;
+    uint64_t capf;
+    if (dense) capf = (cells + 3) / 4 * 4;
+    else {
+        const uint64_t want = (uint64_t)frame_capacity + (uint64_t)frame_capacity / 4 + 1;
+        capf = 1024;
+        while (capf < want) capf <<= 1;
+    }
+    if (capf * (uint64_t)batch >= 0xFFFFFF00ull) return PV_ERR_BAD_ARGUMENT;
+    const size_t n = (size_t)(n_cap > 0 ? n_cap : 1);
+    const size_t fcap = (size_t)(frame_capacity > 0 ? frame_capacity : 1);
+    const size_t slots = (size_t)capf * batch;
+    w->capf = (uint32_t)capf;
+    w->dense = dense ? 1u : 0u;
+    w->wcap = (uint32_t)(((fcap + 31) / 32 + 3) / 4 * 4);
+    w->rowf_cap = (uint32_t)((max_channels + 1 + 3) / 4 * 4);
+    w->rowf = w->rowf_cap;
+    w->hmax = (uint32_t)(n / ((size_t)cfg->max_points + 1) + 1);
+    char *p0 = (char *)base;
+    size_t o = 0;
+    // ---- clean = 0 ----
+    w->ctrl = (uint32_t *)(p0 + o);        o = pf_align(o + 16 * 4, 256);
+    w->bits = (uint32_t *)(p0 + o);        o = pf_align(o + (size_t)w->wcap * batch * 4, 256);
+    w->hbits = (uint32_t *)(p0 + o);       o = pf_align(o + (slots / 32 + 2) * 4, 256);
+    w->acc = (float *)(p0 + o);            o = pf_align(o + slots * w->rowf_cap * 4, 256);
+    // ---- clean = all ones ----
+    w->first = (uint32_t *)(p0 + o);       o = pf_align(o + slots * 4 + 16, 256);
+    w->keys = (uint32_t *)(p0 + o);        if (!dense) o = pf_align(o + slots * 4, 256);
+    // ---- no clean state ----
+    w->hlist = (uint32_t *)(p0 + o);       o = pf_align(o + (n + 32) * 4, 256);
+    w->hinfo = (uint4 *)(p0 + o);          o = pf_align(o + (size_t)w->hmax * 32, 256);
+    w->base = (int32_t *)(p0 + o);         o = pf_align(o + (size_t)(batch + 1) * 4, 256);
+    w->counts_raw = (uint32_t *)(p0 + o);  o = pf_align(o + (size_t)batch * 4, 256);
+    w->sa = (uint32_t *)(p0 + o);          o = pf_align(o + n * 4 + 32, 256);
+    w->wb = (uint2 *)(p0 + o);             o = pf_align(o + (size_t)w->wcap * batch * 8, 256);
+    w->total_bytes = o;
+    return PV_OK;
+}
+
+int pvf_init(const PvF &f, int32_t batch, int64_t n_cap, cudaStream_t st)
+{
+    (void)batch; (void)n_cap;
+    const size_t zero_bytes = (size_t)((char *)f.first - (char *)f.ctrl);
+    const size_t ff_bytes = (size_t)((char *)f.hlist - (char *)f.first);
+    if (cudaMemsetAsync(f.ctrl, 0, zero_bytes, st) != cudaSuccess) return PV_ERR_CUDA;
+    if (cudaMemsetAsync(f.first, 0xFF, ff_bytes, st) != cudaSuccess) return PV_ERR_CUDA;
+    return PV_OK;
+}
+
+template <bool DENSE, int CIN, bool CART, int NV>
+static int pf_launch_insert(const PvParams &p, const PvF &f, cudaStream_t st)
+{
+    const unsigned grid = (p.n + PF_TILE - 1) / PF_TILE;
+    const size_t smem = (size_t)PF_TILE * p.c_in * sizeof(float);
+    auto kern = kf_insert<DENSE, CIN, CART, NV>;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return PV_ERR_CUDA;
+    kern<<<grid, PF_THREADS, smem, st>>>(p, f);
+    return PV_OK;
+}
+
+template <bool DENSE>
+static int pf_dispatch_insert(const PvParams &p, const PvF &f, cudaStream_t st)
+{
+    const int nv = (int)f.rowf / 4;
+    if (p.cart && p.c_in == 5) return pf_launch_insert<DENSE, 5, true, 2>(p, f, st);     // nuScenes (x,y,z,i,dt)
+    if (p.cart && p.c_in == 6) return pf_launch_insert<DENSE, 6, true, 3>(p, f, st);     // Waymo (x,y,z,i,e,dt)
+    if (p.cart && p.c_in == 4) return pf_launch_insert<DENSE, 4, true, 2>(p, f, st);
+    if (!p.cart && p.c_in == 7) return pf_launch_insert<DENSE, 7, false, 2>(p, f, st);
+    if (!p.cart && p.c_in == 8) return pf_launch_insert<DENSE, 8, false, 3>(p, f, st);
+    switch (nv) {
+    case 1: return pf_launch_insert<DENSE, 0, false, 1>(p, f, st);
+    case 2: return pf_launch_insert<DENSE, 0, false, 2>(p, f, st);
+    case 3: return pf_launch_insert<DENSE, 0, false, 3>(p, f, st);
+    case 4: return pf_launch_insert<DENSE, 0, false, 4>(p, f, st);
+    default: return pf_launch_insert<DENSE, 0, false, 5>(p, f, st);
+    }
+}
+
+template <bool CANVAS>
+static void pf_launch_finalize(const PvParams &p, const PvF &f, dim3 grid, cudaStream_t st)
+{
+    switch ((int)f.rowf / 4) {
+    case 1: kf_finalize<1, CANVAS><<<grid, 256, 0, st>>>(p, f); break;
+    case 2: kf_finalize<2, CANVAS><<<grid, 256, 0, st>>>(p, f); break;
+    case 3: kf_finalize<3, CANVAS><<<grid, 256, 0, st>>>(p, f); break;
+    case 4: kf_finalize<4, CANVAS><<<grid, 256, 0, st>>>(p, f); break;
+    default: kf_finalize<5, CANVAS><<<grid, 256, 0, st>>>(p, f); break;
+    }
+}
+
+#define PF_MARK(k) do { if (ev && cudaEventRecord(ev[k], st) != cudaSuccess) return PV_ERR_CUDA; } while (0)
+
+// Stage boundaries: 0 insert, 1 cells, 2 scan, 3 finalize, 4 heavy (points + cells).
+int pvf_run(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev)
+{
+    f.rowf = (uint32_t)((p.C + 1 + 3) / 4 * 4);
+    if (f.rowf > f.rowf_cap) return PV_ERR_WORKSPACE;
+    if (!f.dense) {     // hash map: slot order is not cell order, dense outputs need a zero fill first
+        if (p.canvas && cudaMemsetAsync(p.canvas, 0, (size_t)p.B * p.C * p.cells * sizeof(float), st) != cudaSuccess)
+            return PV_ERR_CUDA;
+        if (p.density && cudaMemsetAsync(p.density, 0, (size_t)p.B * p.cells * sizeof(int32_t), st) != cudaSuccess)
+            return PV_ERR_CUDA;
+    }
+    PF_MARK(0);
+    if (p.n > 0) {
+        const int rc = f.dense ? pf_dispatch_insert<true>(p, f, st) : pf_dispatch_insert<false>(p, f, st);
+        if (rc) return rc;
+    }
+    PF_MARK(1);
+    kf_cells<<<dim3((f.capf / 4 + 255) / 256, (unsigned)p.B), 256, 0, st>>>(p, f);
+    PF_MARK(2);
+    kf_scan<<<(unsigned)p.B, PF_SCAN_THREADS, 0, st>>>(p, f);
+    PF_MARK(3);
+    const dim3 fgrid((f.capf + 255) / 256, (unsigned)p.B);
+    if (p.canvas && f.dense) pf_launch_finalize<true>(p, f, fgrid, st);
+    else pf_launch_finalize<false>(p, f, fgrid, st);
+    PF_MARK(4);
+    if (p.n > 0) {
+        kf_heavy_points<<<(p.n + PF_TILE - 1) / PF_TILE, PF_THREADS, 0, st>>>(p, f);
+        kf_heavy_cells<<<296, 256, 0, st>>>(p, f);
+    }
+    PF_MARK(5);
+    return pv_last_cuda_error();
+}
+
+// Debug aid (tests only): runs the insert pass alone and copies first[] / acc[] of the first
+// `slots` map slots to the host; the workspace must be re-initialised afterwards.
+extern "C" int pv_debug_insert(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
+                               int32_t batch, int64_t n_total, int32_t c_in, int32_t is_cartesian,
+                               int64_t max_points_total, int64_t frame_capacity, void *workspace,
+                               int64_t slots, uint32_t *first_host, float *acc_host, int32_t force_generic)
+{
+    PvParams p;
+    PvF f;
+    const int C = is_cartesian ? c_in + 2 : c_in;
+    PvWs w;
+    int rc = pv_make_layout(cfg, max_points_total, batch, frame_capacity, workspace, &w);
+    if (rc) return rc;
+    const size_t off = (w.total_bytes + 255) / 256 * 256;
+    rc = pvf_make_layout(cfg, max_points_total, batch, frame_capacity, C, (char *)workspace + off, &f);
+    if (rc) return rc;
+    for (int j = 0; j < 3; ++j) { p.lo[j] = cfg->lo[j]; p.vs[j] = cfg->vs[j]; p.grid[j] = cfg->grid[j]; p.gridf[j] = (float)cfg->grid[j]; }
+    p.T = cfg->max_points; p.V = cfg->max_voxels; p.pts = points; p.offsets = frame_offsets; p.B = batch;
+    p.n = (uint32_t)n_total; p.c_in = c_in; p.cart = is_cartesian ? 1 : 0; p.C = C;
+    p.cells = (uint32_t)((uint64_t)cfg->grid[0] * cfg->grid[1] * cfg->grid[2]);
+    p.ws = w; p.grid_ind = nullptr;
+    f.rowf = (uint32_t)((C + 1 + 3) / 4 * 4);
+    if (force_generic) {
+        if (f.rowf == 8) rc = f.dense ? pf_launch_insert<true, 0, false, 2>(p, f, 0) : pf_launch_insert<false, 0, false, 2>(p, f, 0);
+        else return PV_ERR_UNSUPPORTED;
+    } else rc = f.dense ? pf_dispatch_insert<true>(p, f, 0) : pf_dispatch_insert<false>(p, f, 0);
+    if (rc) return rc;
+    if (cudaMemcpy(first_host, f.first, (size_t)slots * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return PV_ERR_CUDA;
+    if (cudaMemcpy(acc_host, f.acc, (size_t)slots * f.rowf * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return PV_ERR_CUDA;
+    return PV_OK;
+}

@@ -45,6 +45,30 @@ struct PvWs {
     size_t total_bytes;
 };
 
+// Workspace of the list-free path (fused.cu): per-cell accumulator rows instead of point lists.
+// Self-cleaning like PvWs: every array marked "clean" is back in that state when a call ends.
+struct PvF {
+    uint32_t *ctrl;        // [16] [3] scan ticket, [4..5] heavy allocator: cells << 32 | candidates (clean 0)
+    int32_t *base;         // [B+1] first output row of each frame
+    uint32_t *counts_raw;  // [B] occupied cells per frame before the V cap
+    uint32_t *first;       // [B * capf] smallest point index of the cell                      (clean INF)
+    uint32_t *keys;        // [B * capf] hash mode: linear cell index of the slot              (clean INF)
+    float *acc;            // [B * capf * rowf] per-cell row: C feature sums, then the count   (clean 0)
+    uint32_t *sa;          // [n_cap] per point: heavy-bitmap index of its cell (INF = out of range)
+    uint32_t *bits;        // [B * wcap] bit (i - frame start) set <=> point i is its cell's first point (clean 0)
+    uint2 *wb;             // [B * wcap] {first points before this word in the frame, the word}
+    uint32_t *hbits;       // [B * capf / 32 + 1] bitmap of cells holding more than T points   (clean 0)
+    uint4 *hinfo;          // [2 * hmax] heavy cell h: {slot, output row, candidate offset, count}, {cell, frame, cursor, -}
+    uint32_t *hlist;       // [n_cap + 32] candidate point indices of the heavy cells, one range per cell
+    uint32_t capf;         // slots per frame (dense: cells rounded up to 4; hash: pow2)
+    uint32_t wcap;         // bitmap words per frame (multiple of 4)
+    uint32_t rowf_cap;     // floats per accumulator row the workspace was sized for
+    uint32_t rowf;         // floats per row in THIS call: C + 1 rounded up to 4
+    uint32_t dense;
+    uint32_t hmax;
+    size_t total_bytes;
+};
+
 struct PvParams {
     float lo[3], vs[3], gridf[3];
     int32_t grid[3];
@@ -200,3 +224,8 @@ int pv_check_config(const pv_config *cfg);
 int pv_make_layout(const pv_config *cfg, int64_t n_cap, int32_t batch, int64_t frame_capacity,
                    void *base, PvWs *out);
 int pv_last_cuda_error();
+int pvf_make_layout(const pv_config *cfg, int64_t n_cap, int32_t batch, int64_t frame_capacity,
+                    int32_t max_channels, void *base, PvF *out);
+int pvf_init(const PvF &f, int32_t batch, int64_t n_cap, cudaStream_t st);
+// list-free front end; ev (optional) = PV_PROFILE_STAGES + 1 events recorded at the stage boundaries
+int pvf_run(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev);

@@ -21,6 +21,8 @@
 //
 // Voxel order = first-occurrence order, kept points = the T smallest indices in index order,
 // voxels with rank >= V dropped -- the three order-dependent behaviours of the reference loop.
+#include <stdlib.h>
+
 #include "pv_common.cuh"
 
 #define K1_THREADS 256
@@ -624,7 +626,27 @@ int pv_make_layout(const pv_config *cfg, int64_t n_cap, int32_t batch, int64_t f
     return PV_OK;
 }
 
-static int fill_params(PvParams *p, const pv_config *cfg, const float *points,
+// The caller's workspace holds both layouts back to back: [list-based PvWs | list-free PvF].
+static int make_layouts(const pv_config *cfg, int64_t n_cap, int32_t batch, int64_t frame_capacity,
+                        int32_t max_channels, void *base, PvWs *w, PvF *f, size_t *total)
+{
+    int rc = pv_make_layout(cfg, n_cap, batch, frame_capacity, base, w);
+    if (rc) return rc;
+    const size_t off = align_up(w->total_bytes, 256);
+    rc = pvf_make_layout(cfg, n_cap, batch, frame_capacity, max_channels, (char *)base + off, f);
+    if (rc) return rc;
+    *total = off + f->total_bytes;
+    return PV_OK;
+}
+
+// PV_LISTS=1 forces the list-based pipeline everywhere (A/B measurements, debugging).
+static bool force_lists()
+{
+    static const int v = [] { const char *e = getenv("PV_LISTS"); return (e && e[0] == '1') ? 1 : 0; }();
+    return v != 0;
+}
+
+static int fill_params(PvParams *p, PvF *f, const pv_config *cfg, const float *points,
                        const int32_t *frame_offsets, int32_t batch, int64_t n_total, int32_t c_in,
                        int32_t is_cartesian, int64_t max_points_total, int64_t frame_capacity,
                        void *workspace, size_t workspace_bytes)
@@ -634,9 +656,10 @@ static int fill_params(PvParams *p, const pv_config *cfg, const float *points,
     if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return PV_ERR_BAD_ARGUMENT;
     const int C = is_cartesian ? c_in + 2 : c_in;
     if (c_in < 3 || C > PV_MAX_CHANNELS) return PV_ERR_BAD_ARGUMENT;
-    int rc = pv_make_layout(cfg, max_points_total, batch, frame_capacity, workspace, &p->ws);
+    size_t total = 0;
+    int rc = make_layouts(cfg, max_points_total, batch, frame_capacity, C, workspace, &p->ws, f, &total);
     if (rc) return rc;
-    if (p->ws.total_bytes > workspace_bytes) return PV_ERR_WORKSPACE;
+    if (total > workspace_bytes) return PV_ERR_WORKSPACE;
     for (int j = 0; j < 3; ++j) {
         p->lo[j] = cfg->lo[j]; p->vs[j] = cfg->vs[j]; p->grid[j] = cfg->grid[j];
         p->gridf[j] = (float)cfg->grid[j];
@@ -719,23 +742,29 @@ const char *pv_error_string(int code)
 }
 
 size_t pv_workspace_bytes(const pv_config *cfg, int64_t max_points_total, int32_t batch,
-                          int64_t frame_capacity)
+                          int64_t frame_capacity, int32_t channels)
 {
     PvWs w;
-    if (pv_make_layout(cfg, max_points_total, batch, frame_capacity, nullptr, &w) != PV_OK) return 0;
-    return w.total_bytes;
+    PvF f;
+    size_t total = 0;
+    if (make_layouts(cfg, max_points_total, batch, frame_capacity, channels, nullptr, &w, &f, &total) != PV_OK) return 0;
+    return total;
 }
 
 int pv_workspace_init(const pv_config *cfg, int64_t max_points_total, int32_t batch,
-                      int64_t frame_capacity, void *workspace, size_t workspace_bytes,
-                      pv_stream_t stream)
+                      int64_t frame_capacity, int32_t channels, void *workspace,
+                      size_t workspace_bytes, pv_stream_t stream)
 {
     if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return PV_ERR_BAD_ARGUMENT;
     PvWs w;
-    int rc = pv_make_layout(cfg, max_points_total, batch, frame_capacity, workspace, &w);
+    PvF f;
+    size_t total = 0;
+    int rc = make_layouts(cfg, max_points_total, batch, frame_capacity, channels, workspace, &w, &f, &total);
     if (rc) return rc;
-    if (w.total_bytes > workspace_bytes) return PV_ERR_WORKSPACE;
+    if (total > workspace_bytes) return PV_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    rc = pvf_init(f, batch, max_points_total, st);
+    if (rc) return rc;
     const size_t zero_bytes = (size_t)((char *)w.table - (char *)workspace);
     const size_t ff_bytes = (size_t)((char *)w.meta - (char *)w.table);   // table, keys, kept
     if (cudaMemsetAsync(workspace, 0, zero_bytes, st) != cudaSuccess) return PV_ERR_CUDA;
@@ -760,14 +789,17 @@ int pv_voxelize(const pv_config *cfg, const float *points, const int32_t *frame_
                 pv_stream_t stream)
 {
     PvParams p;
-    int rc = fill_params(&p, cfg, points, frame_offsets, batch, n_total, c_in, is_cartesian,
+    PvF f;
+    int rc = fill_params(&p, &f, cfg, points, frame_offsets, batch, n_total, c_in, is_cartesian,
                          max_points_total, frame_capacity, workspace, workspace_bytes);
     if (rc) return rc;
     if (!coors || !num_points || !voxel_counts) return PV_ERR_BAD_ARGUMENT;
     if ((reinterpret_cast<uintptr_t>(coors) & 15u) != 0) return PV_ERR_BAD_ARGUMENT;
     p.coors = coors; p.num_points = num_points; p.voxel_counts = voxel_counts;
     p.voxels = voxels; p.feats = mean_feats; p.grid_ind = pc_grid_ind; p.density = density;
-    return run_voxelize(p, (cudaStream_t)stream);
+    // the padded [M, T, C] tensor needs per-voxel point lists; everything else runs list-free
+    if (voxels || force_lists()) return run_voxelize(p, (cudaStream_t)stream);
+    return pvf_run(p, f, (cudaStream_t)stream, nullptr);
 }
 
 static int setup_canvas_call(PvParams &p, const pv_config *cfg, int32_t *coors, int32_t *num_points,
@@ -792,13 +824,15 @@ int pv_forward_mean_canvas(const pv_config *cfg, const float *points, const int3
                            pv_stream_t stream)
 {
     PvParams p;
-    int rc = fill_params(&p, cfg, points, frame_offsets, batch, n_total, c_in, is_cartesian,
+    PvF f;
+    int rc = fill_params(&p, &f, cfg, points, frame_offsets, batch, n_total, c_in, is_cartesian,
                          max_points_total, frame_capacity, workspace, workspace_bytes);
     if (rc) return rc;
     if (!canvas) return PV_ERR_BAD_ARGUMENT;
     rc = setup_canvas_call(p, cfg, coors, num_points, voxel_counts, mean_feats, canvas);
     if (rc) return rc;
-    return run_voxelize(p, (cudaStream_t)stream);
+    if (force_lists()) return run_voxelize(p, (cudaStream_t)stream);
+    return pvf_run(p, f, (cudaStream_t)stream, nullptr);
 }
 
 int pv_profile_mean_canvas(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
@@ -809,7 +843,8 @@ int pv_profile_mean_canvas(const pv_config *cfg, const float *points, const int3
                            pv_stream_t stream, int32_t iters, float *stage_ms)
 {
     PvParams p;
-    int rc = fill_params(&p, cfg, points, frame_offsets, batch, n_total, c_in, is_cartesian,
+    PvF f;
+    int rc = fill_params(&p, &f, cfg, points, frame_offsets, batch, n_total, c_in, is_cartesian,
                          max_points_total, frame_capacity, workspace, workspace_bytes);
     if (rc) return rc;
     if (!stage_ms || iters <= 0) return PV_ERR_BAD_ARGUMENT;
@@ -821,7 +856,7 @@ int pv_profile_mean_canvas(const pv_config *cfg, const float *points, const int3
         if (cudaEventCreate(&ev[k]) != cudaSuccess) return PV_ERR_CUDA;
     for (int k = 0; k < PV_STAGES; ++k) stage_ms[k] = 0.0f;
     for (int it = 0; it < iters && rc == PV_OK; ++it) {
-        rc = run_voxelize(p, st, ev);
+        rc = force_lists() ? run_voxelize(p, st, ev) : pvf_run(p, f, st, ev);
         if (rc == PV_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = PV_ERR_CUDA;
         for (int k = 0; k < PV_STAGES && rc == PV_OK; ++k) {
             float ms = 0.0f;

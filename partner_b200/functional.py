@@ -60,22 +60,22 @@ _voxel_ws = {}          # layout key -> initialised workspace tensor (LRU, self-
 _VOXEL_WS_KEEP = 12
 
 
-def voxel_workspace(cfg, n_cap, batch, frame_cap, device, tag=0):
+def voxel_workspace(cfg, n_cap, batch, frame_cap, channels, device, tag=0):
     """Workspace initialised (pv_workspace_init) for exactly this config + capacities.
 
     ``tag`` separates workspaces of callers that run concurrently on different streams."""
     dev_index = device.index if device.index is not None else torch.cuda.current_device()
-    key = (dev_index, tag, tuple(cfg.lo), tuple(cfg.vs), tuple(cfg.grid), cfg.max_points, n_cap, batch, frame_cap)
+    key = (dev_index, tag, tuple(cfg.lo), tuple(cfg.vs), tuple(cfg.grid), cfg.max_points, n_cap, batch, frame_cap, channels)
     ws = _voxel_ws.pop(key, None)
     if ws is None:
         lib = _lib.load()
-        nbytes = lib.pv_workspace_bytes(cfg, n_cap, batch, frame_cap)
+        nbytes = lib.pv_workspace_bytes(cfg, n_cap, batch, frame_cap, channels)
         if nbytes == 0:
             check(-1, "pv_workspace_bytes")
         while len(_voxel_ws) >= _VOXEL_WS_KEEP:
             _voxel_ws.pop(next(iter(_voxel_ws)))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        check(lib.pv_workspace_init(cfg, n_cap, batch, frame_cap, ptr(ws), ws.numel(), current_stream(device)),
+        check(lib.pv_workspace_init(cfg, n_cap, batch, frame_cap, channels, ptr(ws), ws.numel(), current_stream(device)),
               "pv_workspace_init")
     _voxel_ws[key] = ws       # most recently used last
     return ws
@@ -129,7 +129,7 @@ def voxelize(cfg, points, frame_offsets, batch, frame_capacity, is_cartesian, wa
     lib = _lib.load()
     n_cap = _bucket(n)
     f_cap = min(n_cap, _bucket(frame_capacity))
-    ws = voxel_workspace(cfg, n_cap, batch, f_cap, dev, ws_tag)
+    ws = voxel_workspace(cfg, n_cap, batch, f_cap, C, dev, ws_tag)
     rows = max(1, min(batch * cfg.max_voxels, n))
     T = cfg.max_points
     r = out if out is not None else VoxelBatch()

@@ -38,11 +38,11 @@ def test_host_only_entry_points():
     assert b"frame_capacity" in lib.pv_error_string(-5)
     from partner_b200.functional import make_config
     cfg, vs, rng, grid = make_config([0.098, 0.0123, 8], [0.3, -3.1488, -5, 50.476, 3.1488, 3], 20, 60000)
-    assert lib.pv_workspace_bytes(cfg, 2_400_000, 8, 300_000) > 0
+    assert lib.pv_workspace_bytes(cfg, 2_400_000, 8, 300_000, 7) > 0
     bad = _lib.PvConfig()
-    assert lib.pv_workspace_bytes(bad, 1000, 1, 1000) == 0            # zero grid
+    assert lib.pv_workspace_bytes(bad, 1000, 1, 1000, 7) == 0            # zero grid
     cfg.max_points = 0
-    assert lib.pv_workspace_bytes(cfg, 1000, 1, 1000) == 0
+    assert lib.pv_workspace_bytes(cfg, 1000, 1, 1000, 7) == 0
     assert lib.pv_scatter_workspace_bytes(2, 512, 512) == 2 * 512 * 512 * 4
     with pytest.raises(ValueError):
         _lib.check(-1, "x")

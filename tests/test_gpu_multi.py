@@ -31,9 +31,12 @@ def _run_rank(rank, world, port, ok):
                       features=loc["features"], canvas=loc["canvas"]).items()}
         got = gather_outputs(local, hi - lo)
         ref = fe(frames)
-        for k, name in (("coordinates", "coordinates"), ("num_points", "num_points"), ("num_voxels", "num_voxels"),
-                        ("features", "features"), ("canvas", "canvas")):
-            assert np.array_equal(got[k].cpu().numpy(), ref[name]), k
+        for k in ("coordinates", "num_points", "num_voxels"):       # integer outputs: bit-exact
+            assert np.array_equal(got[k].cpu().numpy(), ref[k]), k
+        for k in ("features", "canvas"):                            # fp32 sums in unspecified order
+            a, b = got[k].cpu().numpy(), ref[k]
+            assert a.shape == b.shape, k
+            assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * float(np.abs(b).max())), k
         ok[rank] = 1
     finally:
         dist.destroy_process_group()
