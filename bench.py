@@ -40,13 +40,18 @@ WORKLOADS = {
 }
 METRIC = "polar_voxelize_vfe_scatter_throughput"
 UNIT = "Mpoints/s"
-STAGES = ["insert", "cells", "scan", "finalize", "heavy"]
+# stage names of pv_profile_mean_canvas per pipeline (pv_profile_pipeline: 1 list-based, 2 list-free)
+STAGES_BY_PIPELINE = {1: ["bin_insert", "cell_flags", "scan", "place", "emit"],
+                      2: ["insert", "cells", "scan", "finalize", "heavy"]}
+STAGES = STAGES_BY_PIPELINE[2]
 N_SETS = 4          # rotating input sets so a step never finds its inputs in the 126 MB L2
 
 
 STAGE_KERNELS = {"insert": ("kf_insert",), "cells": ("kf_cells",), "scan": ("kf_scan",),
-                 "heavy": ("kf_heavy_points", "kf_heavy_cells"), "finalize": ("kf_finalize",)}
-LAUNCHES_PER_STEP = 6
+                 "heavy": ("kf_heavy_points", "kf_heavy_cells"), "finalize": ("kf_finalize",),
+                 "bin_insert": ("k_bin_insert",), "cell_flags": ("k_cell_flags",), "place": ("k_place",),
+                 "emit": ("k_emit",)}
+LAUNCHES_PER_STEP = 6      # both pipelines launch six kernels per step
 
 
 def ncu_traffic(stage):
@@ -309,6 +314,8 @@ def main():
 
     # ---- per-stage CUDA-event times (same inputs, rotating) -> dominant kernel roofline ----
     lib = _lib.load()
+    pipeline = lib.pv_profile_pipeline(fe.cfg)
+    STAGES = STAGES_BY_PIPELINE[pipeline]
     stage = np.zeros(len(STAGES), np.float64)
     reps = 5
     for k in range(N_SETS):
@@ -344,8 +351,9 @@ def main():
         # output written once; map / lists / workspace traffic is NOT counted.
         # insert reads every point row once; finalize writes every output once (the canvas in cell order,
         # zeros included)
-        alg = {"insert": 4.0 * n_avg * c_in,
-               "finalize": (16 + 4 + 4 * C) * m_avg + (4.0 * C * cells * per_gpu if has_canvas else 0.0)}
+        out_bytes = (16 + 4 + 4 * C) * m_avg + (4.0 * C * cells * per_gpu if has_canvas else 0.0)
+        alg = ({"insert": 4.0 * n_avg * c_in, "finalize": out_bytes} if pipeline == 2 else
+               {"bin_insert": 4.0 * n_avg * c_in, "emit": out_bytes})
         path_bytes = sum(alg.values())
         step_ms = ms_total / args.steps
         live = {STAGES[i]: float(stage[i]) for i in range(len(STAGES)) if stage[i] > 0}
@@ -365,6 +373,7 @@ def main():
                        "parallelism": "frame-sharded x%d, no collective" % world,
                        "l2": "%d rotating input sets (%.0f MB) + outputs exceed the 126 MB L2" % (N_SETS, in_bytes / 1e6),
                        "launch": "eager" if args.no_graph else "cuda-graph replay",
+                       "pipeline": {1: "list-based (voxelize.cu)", 2: "list-free (fused.cu)"}[pipeline],
                        "streams": n_streams,
                        "note": "steps are independent batches; with streams > 1 consecutive steps overlap on "
                                "separate CUDA streams (each with its own workspace); single_stream = strictly serial"},

@@ -75,6 +75,18 @@ typedef struct pv_pfn_layer {
 int pv_version(void);
 const char *pv_error_string(int code);
 
+/* Process-wide pipeline choice for calls that do not request the padded voxels tensor
+ * (measurement / test aid; the default, 0, is what production uses):
+ *   0 auto       list-free (fused.cu) on direct-map grids (<= 2^20 cells per frame), list-based
+ *                (voxelize.cu) on hash-map grids
+ *   1 lists      list-based everywhere      2 list-free  list-free everywhere
+ * The PV_PIPELINE environment variable sets the initial value.  Not thread-safe. */
+int pv_set_pipeline(int mode);
+
+/* Which pipeline (1 lists, 2 list-free) pv_forward_mean_canvas / pv_profile_mean_canvas run for
+ * this grid under the current setting; names the stages pv_profile_mean_canvas reports. */
+int pv_profile_pipeline(const pv_config *cfg);
+
 /* Bytes of workspace for a batch of `batch` frames holding at most
  * `max_points_total` points, no frame larger than `frame_capacity` points, voxelized with at
  * most `channels` feature channels C (c_in + 2 for Cartesian input, c_in otherwise). */
@@ -135,8 +147,9 @@ int pv_forward_mean_canvas(const pv_config *cfg, const float *points, const int3
 
 /* Measurement aid for bench.py: runs pv_forward_mean_canvas (canvas may be NULL for 3-D grids)
  * `iters` times with CUDA events recorded on `stream` between the stages and returns the average
- * milliseconds per stage in stage_ms (HOST, PV_PROFILE_STAGES floats): 0 insert, 1 cells,
- * 2 scan, 3 finalize (+ canvas), 4 heavy cells.  Synchronises. */
+ * milliseconds per stage in stage_ms (HOST, PV_PROFILE_STAGES floats).  List-free pipeline:
+ * 0 insert, 1 cells, 2 scan, 3 finalize (+ canvas), 4 heavy cells; list-based pipeline:
+ * 0 bin_insert, 1 cell_flags, 2 scan, 3 place, 4 emit (see pv_profile_pipeline).  Synchronises. */
 #define PV_PROFILE_STAGES 5
 int pv_profile_mean_canvas(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
                            int32_t batch, int64_t n_total, int32_t c_in, int32_t is_cartesian,

@@ -71,6 +71,8 @@ SZ = ctypes.c_size_t
 EXPORTS = {
     "pv_version": (ctypes.c_int, []),
     "pv_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "pv_set_pipeline": (ctypes.c_int, [ctypes.c_int]),
+    "pv_profile_pipeline": (ctypes.c_int, [ctypes.POINTER(PvConfig)]),
     "pv_workspace_bytes": (SZ, [ctypes.POINTER(PvConfig), I64, I32, I64, I32]),
     "pv_transform_points": (ctypes.c_int, [P, I64, I32, I32, P, P]),
     "pv_workspace_init": (ctypes.c_int, [ctypes.POINTER(PvConfig), I64, I32, I64, I32, P, SZ, P]),

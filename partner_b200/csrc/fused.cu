@@ -35,6 +35,7 @@
 #define PF_PPT 4                          // consecutive points per thread in the point passes
 #define PF_TILE (PF_THREADS * PF_PPT)
 #define PF_SCAN_THREADS 1024
+#define PF_SCAN_VEC 4                    // 4-word vectors per thread per scan iteration
 
 // ---------------------------------------------------------------------------------------------
 // small PTX helpers
@@ -101,7 +102,8 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
     const uint32_t tid = threadIdx.x;
     const int c_in = CIN ? CIN : p.c_in;
     const bool cart = CIN ? CART : (p.cart != 0);
-    const int C = p.C;
+    constexpr int CS = CIN ? CIN + (CART ? 2 : 0) : 0;      // compile-time channel count (0 = runtime)
+    const int C = CS ? CS : p.C;
     const uint32_t tile_base = blockIdx.x * PF_TILE;
     const uint32_t n_tile = min((uint32_t)PF_TILE, p.n - tile_base);
     const uint32_t nf = n_tile * (uint32_t)c_in;
@@ -135,6 +137,11 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
     }
 
     int b = s_b0;
+    uint32_t next_off = b + 1 < p.B ? (uint32_t)__ldg(p.offsets + b + 1) : PV_INF;
+    const float lo0 = p.lo[0], lo1 = p.lo[1], lo2 = p.lo[2];
+    const float iv0 = p.inv_vs[0], iv1 = p.inv_vs[1], iv2 = p.inv_vs[2];
+    const float g0 = p.gridf[0], g1 = p.gridf[1], g2 = p.gridf[2];
+    const uint32_t nx = (uint32_t)p.grid[0], ny = (uint32_t)p.grid[1];
     uint32_t cur_s = PV_INF, cur_i = 0;      // current run of consecutive points in one cell
     float cur[CT], cur_n = 0.0f;             // its feature sums and point count
     uint32_t sa_out[PF_PPT];
@@ -173,29 +180,36 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < CT; ++k) v[k] = in[k];
         }
-        bool ok = true;
-        int ci[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {        // point_cloud_ops.py:45 -- float32 subtract, IEEE divide, floor
-            const float cf = floorf(__fdiv_rn(__fsub_rn(v[a < CT ? a : 0], p.lo[a]), p.vs[a]));
-            int c;
-            if (!(cf >= 0.0f)) { ok = false; c = 0; }                     // below range or NaN
-            else if (cf >= p.gridf[a]) { ok = false; c = p.grid[a] - 1; }
-            else c = (int)cf;
-            ci[a] = c;
+        // point_cloud_ops.py:45 -- floor of the float32 quotient, via pv_bin's reciprocal fast path;
+        // the three near-integer tests share one branch
+        const float t0f = __fsub_rn(v[0], lo0), t1f = __fsub_rn(v[CT > 1 ? 1 : 0], lo1), t2f = __fsub_rn(v[CT > 2 ? 2 : 0], lo2);
+        const float r0 = __fmul_rn(t0f, iv0), r1 = __fmul_rn(t1f, iv1), r2 = __fmul_rn(t2f, iv2);
+        float c0 = floorf(r0), c1 = floorf(r1), c2 = floorf(r2);
+        const bool n0 = pv_bin_unsure(r0, c0), n1 = pv_bin_unsure(r1, c1), n2 = pv_bin_unsure(r2, c2);
+        if (n0 | n1 | n2) {
+            if (n0) c0 = floorf(__fdiv_rn(t0f, p.vs[0]));
+            if (n1) c1 = floorf(__fdiv_rn(t1f, p.vs[1]));
+            if (n2) c2 = floorf(__fdiv_rn(t2f, p.vs[2]));
         }
-        if (p.grid_ind) {                    // :46-54 clamped (z, y, x) for every point
+        const bool ok = c0 >= 0.0f && c0 < g0 && c1 >= 0.0f && c1 < g1 && c2 >= 0.0f && c2 < g2;   // NaN fails
+        if (p.grid_ind) {                    // :46-54 clamped (z, y, x) for every point (NaN -> 0)
             int32_t *gi = p.grid_ind + (size_t)i * 3;
-            gi[0] = ci[2]; gi[1] = ci[1]; gi[2] = ci[0];
+            gi[0] = (int)fminf(fmaxf(c2, 0.0f), g2 - 1.0f);
+            gi[1] = (int)fminf(fmaxf(c1, 0.0f), g1 - 1.0f);
+            gi[2] = (int)fminf(fmaxf(c0, 0.0f), g0 - 1.0f);
         }
-        while (b + 1 < p.B && i >= (uint32_t)__ldg(p.offsets + b + 1)) ++b;
+        while (i >= next_off) {              // crossed into the next frame (frames may be empty)
+            ++b;
+            next_off = b + 1 < p.B ? (uint32_t)__ldg(p.offsets + b + 1) : PV_INF;
+        }
         if (!ok) continue;
-        const uint32_t cell = ((uint32_t)ci[2] * (uint32_t)p.grid[1] + (uint32_t)ci[1]) * (uint32_t)p.grid[0] + (uint32_t)ci[0];
+        const uint32_t cx = (uint32_t)(int)c0, cy = (uint32_t)(int)c1, cz = (uint32_t)(int)c2;
+        const uint32_t cell = (cz * ny + cy) * nx + cx;
         uint32_t s, sa;
         if (DENSE) {
             s = (uint32_t)b * f.capf + cell;
             // heavy-bitmap order: phi fastest, so azimuth neighbours share a bitmap word
-            sa = (uint32_t)b * f.capf + ((uint32_t)ci[2] * (uint32_t)p.grid[0] + (uint32_t)ci[0]) * (uint32_t)p.grid[1] + (uint32_t)ci[1];
+            sa = (uint32_t)b * f.capf + (cz * nx + cx) * ny + cy;
         } else {
             const uint32_t h = pf_claim(f.keys + (size_t)b * f.capf, f.capf - 1, cell, p.ws.ctrl + 1);
             if (h == PV_INF) continue;       // map full: status bit set
@@ -205,7 +219,8 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
         sa_out[j] = sa;
         if (s == cur_s) {
 #pragma unroll
-            for (int k = 0; k < CT; ++k) cur[k] = __fadd_rn(cur[k], v[k]);
+            for (int k = 0; k < CT; ++k)
+                if (k < C) cur[k] = __fadd_rn(cur[k], v[k]);
             cur_n += 1.0f;
         } else {
             flush();
@@ -267,12 +282,17 @@ __global__ void __launch_bounds__(PF_SCAN_THREADS) kf_scan(const __grid_constant
     uint2 *wb = f.wb + (size_t)b * f.wcap;
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (uint32_t w0 = 0; w0 < nw; w0 += PF_SCAN_THREADS * 4) {
-        const uint32_t w = w0 + tid * 4u;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (w < nw) v = __ldcg(reinterpret_cast<const uint4 *>(bits + w));   // wcap % 4 == 0: stays in bounds
-        const uint32_t c0 = __popc(v.x), c1 = __popc(v.y), c2 = __popc(v.z), c3 = __popc(v.w);
-        const uint32_t tsum = c0 + c1 + c2 + c3;
+    // each thread owns PF_SCAN_VEC consecutive 4-word vectors per iteration: one block scan covers
+    // 16k words (512k points), so a LiDAR frame is a single iteration
+    for (uint32_t w0 = 0; w0 < nw; w0 += PF_SCAN_THREADS * 4 * PF_SCAN_VEC) {
+        const uint32_t wt = w0 + tid * (4u * PF_SCAN_VEC);
+        uint4 v[PF_SCAN_VEC];
+        uint32_t tsum = 0;
+#pragma unroll
+        for (int q = 0; q < PF_SCAN_VEC; ++q) {            // wcap % 4 == 0: a vector never straddles the end
+            v[q] = wt + 4u * q < nw ? __ldcg(reinterpret_cast<const uint4 *>(bits + wt) + q) : make_uint4(0, 0, 0, 0);
+            tsum += __popc(v[q].x) + __popc(v[q].y) + __popc(v[q].z) + __popc(v[q].w);
+        }
         uint32_t incl = tsum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -290,14 +310,19 @@ __global__ void __launch_bounds__(PF_SCAN_THREADS) kf_scan(const __grid_constant
         }
         const uint32_t warp_excl = __shfl_sync(0xffffffffu, wincl - wsum, warp);
         const uint32_t total = __shfl_sync(0xffffffffu, wincl, 31);
-        const uint32_t excl = s_carry + warp_excl + incl - tsum;
-        if (w < nw) {
-            uint4 *dst = reinterpret_cast<uint4 *>(wb + w);
-            dst[0] = make_uint4(excl, v.x, excl + c0, v.y);
-            dst[1] = make_uint4(excl + c0 + c1, v.z, excl + c0 + c1 + c2, v.w);
-            // restore the bitmap; issued after the loaded value was consumed (a store to an address
-            // with a load still in flight stalls the SM's load/store unit for the whole round trip)
-            if (tsum) *reinterpret_cast<uint4 *>(bits + w) = make_uint4(0, 0, 0, 0);
+        uint32_t run = s_carry + warp_excl + incl - tsum;
+#pragma unroll
+        for (int q = 0; q < PF_SCAN_VEC; ++q) {
+            if (wt + 4u * q < nw) {
+                const uint32_t c0 = __popc(v[q].x), c1 = __popc(v[q].y), c2 = __popc(v[q].z), c3 = __popc(v[q].w);
+                uint4 *dst = reinterpret_cast<uint4 *>(wb + wt + 4u * q);
+                dst[0] = make_uint4(run, v[q].x, run + c0, v[q].y);
+                dst[1] = make_uint4(run + c0 + c1, v[q].z, run + c0 + c1 + c2, v[q].w);
+                // restore the bitmap; issued after the loaded value was consumed (a store to an
+                // address with a load still in flight stalls the load/store unit for the round trip)
+                if (c0 + c1 + c2 + c3) reinterpret_cast<uint4 *>(bits + wt)[q] = make_uint4(0, 0, 0, 0);
+                run += c0 + c1 + c2 + c3;
+            }
         }
         __syncthreads();
         if (tid == 0) s_carry += total;
@@ -365,15 +390,27 @@ __device__ __forceinline__ void pf_st_row_clean(float *row, float keep0)
     }
 }
 
-template <int NV, bool CANVAS>
+// ROWMAP (direct map only): grid = (ceil(nx / 256), ny * nz, B), one thread per cell of one grid
+// row -- (z, y, x) come from the block index, no integer division anywhere.  Otherwise
+// grid = (slots / 256, B) over the linear slot index.  CC = compile-time channel count (0 = runtime).
+template <int NV, int CC, bool CANVAS, bool ROWMAP>
 __global__ void __launch_bounds__(256) kf_finalize(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
 {
     constexpr int CT = NV * 4;
-    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (l >= f.capf) return;
+    const int C = CC ? CC : p.C;
+    const int b = ROWMAP ? blockIdx.z : blockIdx.y;
+    const uint32_t nx = p.grid[0], ny = p.grid[1];
+    uint32_t l, x = 0, yz = 0;
+    if (ROWMAP) {
+        x = blockIdx.x * blockDim.x + threadIdx.x;
+        yz = blockIdx.y;
+        if (x >= nx) return;
+        l = yz * nx + x;
+    } else {
+        l = blockIdx.x * blockDim.x + threadIdx.x;
+        if (l >= f.capf) return;
+    }
     const uint32_t s = (uint32_t)b * f.capf + l;
-    const int C = p.C;
     const uint32_t fi = __ldcs(f.first + s);
     float m[CANVAS ? CT : 1];
     int32_t dens = 0;
@@ -389,7 +426,7 @@ __global__ void __launch_bounds__(256) kf_finalize(const __grid_constant__ PvPar
         const bool fits = ib < f.wcap * 32u;                              // else flagged by kf_cells
         const uint2 wv = fits ? __ldg(f.wb + (size_t)b * f.wcap + (ib >> 5)) : make_uint2(0xFFFFFFFFu, 0u);
         uint32_t cell = l;
-        if (!f.dense) cell = __ldcg(f.keys + s);
+        if (!ROWMAP && !f.dense) cell = __ldcg(f.keys + s);
         const uint32_t rank = wv.x + __popc(wv.y & ((1u << (ib & 31u)) - 1u));
         float keep0 = 0.0f;
         if (fits && rank < (uint32_t)p.V) {                               // :60-61 max_voxels
@@ -400,9 +437,11 @@ __global__ void __launch_bounds__(256) kf_finalize(const __grid_constant__ PvPar
             const uint32_t T = (uint32_t)p.T;
             const uint32_t L = min(cnt, T);
             const int32_t vid = __ldg(f.base + b) + (int32_t)rank;
-            const uint32_t nx = p.grid[0], ny = p.grid[1];
-            const uint32_t x = cell % nx, yz = cell / nx;
-            reinterpret_cast<int4 *>(p.coors)[vid] = make_int4(b, (int)(yz / ny), (int)(yz % ny), (int)x);
+            if (!ROWMAP) { x = cell % nx; yz = cell / nx; }
+            uint32_t cy, cz;
+            if (ROWMAP) { cz = blockIdx.y / ny; cy = blockIdx.y - cz * ny; }   // uniform
+            else { cz = yz / ny; cy = yz - cz * ny; }
+            reinterpret_cast<int4 *>(p.coors)[vid] = make_int4(b, (int)cz, (int)cy, (int)x);
             p.num_points[vid] = (int32_t)L;
             dens = (int32_t)cnt;                                          // :70-71 un-capped count
             if (cnt > T) {
@@ -415,23 +454,54 @@ __global__ void __launch_bounds__(256) kf_finalize(const __grid_constant__ PvPar
                     hi[0] = make_uint4(s, (uint32_t)vid, off, cnt);
                     hi[1] = make_uint4(cell, (uint32_t)b, 0u, 0u);           // .z = arrival cursor
                     keep0 = __uint_as_float(hid);
-                    uint32_t hb = s;
-                    if (f.dense) {
-                        const uint32_t y = yz % ny, z = yz / ny;
-                        hb = (uint32_t)b * f.capf + (z * nx + x) * ny + y;
-                    }
+                    const uint32_t hb = f.dense ? (uint32_t)b * f.capf + (cz * nx + x) * ny + cy : s;
                     atomicOr(f.hbits + (hb >> 5), 1u << (hb & 31u));
                 } else atomicOr(p.ws.ctrl + 1, 1u);
             } else {
-                const float nf = (float)L;
-                float *o = p.feats ? p.feats + (size_t)vid * C : nullptr;
+                const float nf = (float)L, inv = __frcp_rn(nf);
+                float mean[CT];
 #pragma unroll
                 for (int k = 0; k < CT; ++k) {
-                    if (k < C) {
-                        const float mean = __fdiv_rn(r[k], nf);           // voxel_encoder.py:18-22
-                        if (o) o[k] = mean;
-                        if (CANVAS) m[k] = mean;
-                        else if (!f.dense && p.canvas) p.canvas[((size_t)b * C + k) * p.cells + cell] = mean;
+                    mean[k] = k < C ? pv_div_count(r[k], nf, inv) : 0.0f; // voxel_encoder.py:18-22
+                    if (CANVAS) m[k] = mean[k];
+                }
+                if (!CANVAS && !f.dense && p.canvas) {
+                    float *cv = p.canvas + (size_t)b * C * p.cells + cell;
+#pragma unroll
+                    for (int k = 0; k < CT; ++k)
+                        if (k < C) cv[(size_t)k * p.cells] = mean[k];
+                }
+                if (p.feats) {
+                    float *o = p.feats + (size_t)vid * C;
+                    if (CT == 8 && C == 7 && (reinterpret_cast<uintptr_t>(p.feats) & 15u) == 0) {
+                        // 28-byte rows: one 16-, one 8- and one 4-byte store, whatever the row's alignment
+                        // (a scattered store costs one load/store-unit slot per lane regardless of width)
+                        float2 *o2; float4 *o4;
+                        switch (vid & 3) {
+                        case 0:
+                            o4 = reinterpret_cast<float4 *>(o); o2 = reinterpret_cast<float2 *>(o + 4);
+                            *o4 = make_float4(mean[0], mean[1], mean[2], mean[3]); *o2 = make_float2(mean[4], mean[5]); o[6] = mean[6 % CT];
+                            break;
+                        case 1:     // row starts 12 bytes past a 16-byte boundary
+                            o2 = reinterpret_cast<float2 *>(o + 5); o4 = reinterpret_cast<float4 *>(o + 1);
+                            o[0] = mean[0]; *o4 = make_float4(mean[1], mean[2], mean[3], mean[4]); *o2 = make_float2(mean[5], mean[6 % CT]);
+                            break;
+                        case 2:     // 8 bytes past
+                            o2 = reinterpret_cast<float2 *>(o); o4 = reinterpret_cast<float4 *>(o + 2);
+                            *o2 = make_float2(mean[0], mean[1]); *o4 = make_float4(mean[2], mean[3], mean[4], mean[5]); o[6] = mean[6 % CT];
+                            break;
+                        default:    // 4 bytes past
+                            o2 = reinterpret_cast<float2 *>(o + 1); o4 = reinterpret_cast<float4 *>(o + 3);
+                            o[0] = mean[0]; *o2 = make_float2(mean[1], mean[2]); *o4 = make_float4(mean[3], mean[4], mean[5], mean[6 % CT]);
+                            break;
+                        }
+                    } else if (CT == 12 && C == 8 && (reinterpret_cast<uintptr_t>(p.feats) & 15u) == 0) {
+                        reinterpret_cast<float4 *>(o)[0] = make_float4(mean[0], mean[1], mean[2], mean[3]);   // 32-byte rows
+                        reinterpret_cast<float4 *>(o)[1] = make_float4(mean[4 % CT], mean[5 % CT], mean[6 % CT], mean[7 % CT]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < CT; ++k)
+                            if (k < C) o[k] = mean[k];
                     }
                 }
             }
@@ -446,9 +516,11 @@ __global__ void __launch_bounds__(256) kf_finalize(const __grid_constant__ PvPar
         // direct map: slot order == cell order, so canvas and density are written here in full,
         // zeros included: no zero fill, no scatter                        pillar_encoder.py:211-217
         if (CANVAS) {
+            float *cv = p.canvas + (size_t)b * C * p.cells + l;
 #pragma unroll
-            for (int k = 0; k < CT; ++k)
-                if (k < C) __stcs(p.canvas + ((size_t)b * C + k) * p.cells + l, m[k]);
+            for (int k = 0; k < CT; ++k) {
+                if (k < C) { __stcs(cv, m[k]); cv += p.cells; }
+            }
         }
         if (p.density) p.density[(size_t)b * p.cells + l] = dens;
     }
@@ -665,15 +737,30 @@ static int pf_dispatch_insert(const PvParams &p, const PvF &f, cudaStream_t st)
     }
 }
 
-template <bool CANVAS>
-static void pf_launch_finalize(const PvParams &p, const PvF &f, dim3 grid, cudaStream_t st)
+template <int NV, int CC>
+static void pf_launch_finalize_nv(const PvParams &p, const PvF &f, cudaStream_t st)
+{
+    const bool canvas = p.canvas && f.dense;
+    const unsigned rows = (unsigned)p.grid[1] * (unsigned)p.grid[2];
+    if (f.dense && rows <= 65535u && p.B <= 65535) {     // one thread per cell of a grid row
+        const dim3 grid(((unsigned)p.grid[0] + 255) / 256, rows, (unsigned)p.B);
+        if (canvas) kf_finalize<NV, CC, true, true><<<grid, 256, 0, st>>>(p, f);
+        else kf_finalize<NV, CC, false, true><<<grid, 256, 0, st>>>(p, f);
+    } else {
+        const dim3 grid((f.capf + 255) / 256, (unsigned)p.B);
+        if (canvas) kf_finalize<NV, CC, true, false><<<grid, 256, 0, st>>>(p, f);
+        else kf_finalize<NV, CC, false, false><<<grid, 256, 0, st>>>(p, f);
+    }
+}
+
+static void pf_launch_finalize(const PvParams &p, const PvF &f, cudaStream_t st)
 {
     switch ((int)f.rowf / 4) {
-    case 1: kf_finalize<1, CANVAS><<<grid, 256, 0, st>>>(p, f); break;
-    case 2: kf_finalize<2, CANVAS><<<grid, 256, 0, st>>>(p, f); break;
-    case 3: kf_finalize<3, CANVAS><<<grid, 256, 0, st>>>(p, f); break;
-    case 4: kf_finalize<4, CANVAS><<<grid, 256, 0, st>>>(p, f); break;
-    default: kf_finalize<5, CANVAS><<<grid, 256, 0, st>>>(p, f); break;
+    case 1: pf_launch_finalize_nv<1, 0>(p, f, st); break;
+    case 2: if (p.C == 7) pf_launch_finalize_nv<2, 7>(p, f, st); else pf_launch_finalize_nv<2, 0>(p, f, st); break;
+    case 3: if (p.C == 8) pf_launch_finalize_nv<3, 8>(p, f, st); else pf_launch_finalize_nv<3, 0>(p, f, st); break;
+    case 4: pf_launch_finalize_nv<4, 0>(p, f, st); break;
+    default: pf_launch_finalize_nv<5, 0>(p, f, st); break;
     }
 }
 
@@ -700,9 +787,7 @@ int pvf_run(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev)
     PF_MARK(2);
     kf_scan<<<(unsigned)p.B, PF_SCAN_THREADS, 0, st>>>(p, f);
     PF_MARK(3);
-    const dim3 fgrid((f.capf + 255) / 256, (unsigned)p.B);
-    if (p.canvas && f.dense) pf_launch_finalize<true>(p, f, fgrid, st);
-    else pf_launch_finalize<false>(p, f, fgrid, st);
+    pf_launch_finalize(p, f, st);
     PF_MARK(4);
     if (p.n > 0) {
         kf_heavy_points<<<(p.n + PF_TILE - 1) / PF_TILE, PF_THREADS, 0, st>>>(p, f);
@@ -710,36 +795,4 @@ int pvf_run(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev)
     }
     PF_MARK(5);
     return pv_last_cuda_error();
-}
-
-// Debug aid (tests only): runs the insert pass alone and copies first[] / acc[] of the first
-// `slots` map slots to the host; the workspace must be re-initialised afterwards.
-extern "C" int pv_debug_insert(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
-                               int32_t batch, int64_t n_total, int32_t c_in, int32_t is_cartesian,
-                               int64_t max_points_total, int64_t frame_capacity, void *workspace,
-                               int64_t slots, uint32_t *first_host, float *acc_host, int32_t force_generic)
-{
-    PvParams p;
-    PvF f;
-    const int C = is_cartesian ? c_in + 2 : c_in;
-    PvWs w;
-    int rc = pv_make_layout(cfg, max_points_total, batch, frame_capacity, workspace, &w);
-    if (rc) return rc;
-    const size_t off = (w.total_bytes + 255) / 256 * 256;
-    rc = pvf_make_layout(cfg, max_points_total, batch, frame_capacity, C, (char *)workspace + off, &f);
-    if (rc) return rc;
-    for (int j = 0; j < 3; ++j) { p.lo[j] = cfg->lo[j]; p.vs[j] = cfg->vs[j]; p.grid[j] = cfg->grid[j]; p.gridf[j] = (float)cfg->grid[j]; }
-    p.T = cfg->max_points; p.V = cfg->max_voxels; p.pts = points; p.offsets = frame_offsets; p.B = batch;
-    p.n = (uint32_t)n_total; p.c_in = c_in; p.cart = is_cartesian ? 1 : 0; p.C = C;
-    p.cells = (uint32_t)((uint64_t)cfg->grid[0] * cfg->grid[1] * cfg->grid[2]);
-    p.ws = w; p.grid_ind = nullptr;
-    f.rowf = (uint32_t)((C + 1 + 3) / 4 * 4);
-    if (force_generic) {
-        if (f.rowf == 8) rc = f.dense ? pf_launch_insert<true, 0, false, 2>(p, f, 0) : pf_launch_insert<false, 0, false, 2>(p, f, 0);
-        else return PV_ERR_UNSUPPORTED;
-    } else rc = f.dense ? pf_dispatch_insert<true>(p, f, 0) : pf_dispatch_insert<false>(p, f, 0);
-    if (rc) return rc;
-    if (cudaMemcpy(first_host, f.first, (size_t)slots * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return PV_ERR_CUDA;
-    if (cudaMemcpy(acc_host, f.acc, (size_t)slots * f.rowf * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return PV_ERR_CUDA;
-    return PV_OK;
 }

@@ -71,6 +71,7 @@ struct PvF {
 
 struct PvParams {
     float lo[3], vs[3], gridf[3];
+    float inv_vs[3];          // fl(1 / vs): fast path of pv_bin
     int32_t grid[3];
     int32_t T, V;
     const float *pts;
@@ -190,6 +191,41 @@ __device__ __forceinline__ float pv_atan2f(float y, float x)
     if (ay > ax) r = __fadd_rn(__fsub_rn(0x1.921fb6p+0f, r), -0x1.777a5cp-25f);
     if (__float_as_int(x) < 0) r = __fadd_rn(__fsub_rn(0x1.921fb6p+1f, r), -0x1.777a5cp-24f);
     return copysignf(r, y);
+}
+
+// floor((q - lo) / vs) exactly as the reference evaluates it (point_cloud_ops.py:45: float32
+// subtract, IEEE divide, floor) without paying for the division: r = t * fl(1/vs) is within
+// 2^-23 relative of the exact quotient, so unless r sits within 1e-6 relative of an integer its
+// floor equals the floor of the correctly rounded quotient; the rare near-integer (and NaN / inf /
+// huge) cases take the IEEE division.
+__device__ __forceinline__ float pv_bin(float q, float lo, float vs, float inv)
+{
+    const float t = __fsub_rn(q, lo);
+    const float r = __fmul_rn(t, inv);
+    const float fr = floorf(r);
+    const float d = __fsub_rn(r, fr);
+    const float thr = __fmul_rn(fmaxf(fabsf(r), 1.0f), 1e-6f);
+    if (!(d > thr && d < __fsub_rn(1.0f, thr))) return floorf(__fdiv_rn(t, vs));
+    return fr;
+}
+
+// The near-integer test of pv_bin on its own (r = t * inv, fr = floorf(r)): true = take the division.
+__device__ __forceinline__ bool pv_bin_unsure(float r, float fr)
+{
+    const float d = __fsub_rn(r, fr);
+    const float thr = __fmul_rn(fmaxf(fabsf(r), 1.0f), 1e-6f);
+    return !(d > thr && d < __fsub_rn(1.0f, thr));
+}
+
+// sum / n for n = 1, 2, 3, ... given inv = 1 / n: one Newton correction of the reciprocal product,
+// i.e. the fast path of the IEEE division (correctly rounded except for a vanishing fraction of
+// operands, where it is 1 ulp off -- far inside the 1e-5 gate); infinities pass through.
+__device__ __forceinline__ float pv_div_count(float s, float n, float inv)
+{
+    const float q = __fmul_rn(s, inv);
+    const float r = __fmaf_rn(-q, n, s);
+    const float q1 = __fmaf_rn(r, inv, q);
+    return fabsf(q) <= 3.0e38f ? q1 : q;
 }
 
 // rho = sqrt(x*x + y*y): four separately rounded ops, as numpy evaluates utils.py:40.

@@ -30,11 +30,12 @@ d_off = torch.from_numpy(off).to(dev)
 out = fe.forward_device(pts, d_off, per_gpu, max(sizes))
 torch.cuda.synchronize()
 lib = _lib.load()
-ms = (ctypes.c_float * len(bench.STAGES))()
+names = bench.STAGES_BY_PIPELINE[lib.pv_profile_pipeline(fe.cfg)]
+ms = (ctypes.c_float * len(names))()
 for _ in range(2):
     F.check(lib.pv_profile_mean_canvas(fe.cfg, ptr(pts), ptr(d_off), per_gpu, int(off[-1]), pts.shape[1], 1,
                                        out.n_cap, out.f_cap, ptr(out.ws), out.ws.numel(), ptr(out.coors),
                                        ptr(out.num_points), ptr(out.voxel_counts), ptr(out.mean_feats),
                                        ptr(out.canvas), current_stream(dev), reps, ms), "profile")
-print("PV_DBG=%s %s: " % (os.environ.get("PV_DBG", "0"), wl) +
-      "  ".join("%s %.1f" % (n, v * 1e3) for n, v in zip(bench.STAGES, ms)) + "  | sum %.1f us" % (sum(ms) * 1e3))
+print("PV_PIPELINE=%s %s: " % (os.environ.get("PV_PIPELINE", "0"), wl) +
+      "  ".join("%s %.1f" % (n, v * 1e3) for n, v in zip(names, ms)) + "  | sum %.1f us" % (sum(ms) * 1e3))
