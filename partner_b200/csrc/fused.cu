@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
     extern __shared__ __align__(128) float s_pts[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ int s_b0;
+    __shared__ uint32_t s_next;
     constexpr int CT = NV * 4;
     const uint32_t tid = threadIdx.x;
     const int c_in = CIN ? CIN : p.c_in;
@@ -113,13 +114,22 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
     const bool bulk = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && nf >= 4u;
     const uint32_t bulk_bytes = bulk ? ((nf * 4u) & ~15u) : 0u;
     const uint32_t bar = pf_smem_addr(&s_bar);
-    if (tid == 0) {
-        s_b0 = pv_frame_of(p.offsets, p.B, tile_base);
-        if (bulk) {
-            pf_mbar_init(bar, 1);
-            pf_mbar_expect_tx(bar, bulk_bytes);
-            pf_bulk_g2s(pf_smem_addr(s_pts), src, bulk_bytes, bar);
+    if (tid == 0 && bulk) {
+        pf_mbar_init(bar, 1);
+        pf_mbar_expect_tx(bar, bulk_bytes);
+        pf_bulk_g2s(pf_smem_addr(s_pts), src, bulk_bytes, bar);
+    }
+    if (tid >= 32 && tid < 64) {             // frame of the tile's first point, while the copy is in flight
+        const uint32_t lane = tid & 31u;
+        int cnt = 0;                         // = #{b >= 1 : offsets[b] <= tile_base}
+        uint32_t nxt = PV_INF;               // smallest offsets[b] > tile_base
+        for (int bb = 1 + (int)lane; bb < p.B; bb += 32) {
+            const uint32_t o = (uint32_t)__ldg(p.offsets + bb);
+            if (o <= tile_base) ++cnt; else nxt = min(nxt, o);
         }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        nxt = __reduce_min_sync(0xffffffffu, nxt);
+        if (lane == 0) { s_b0 = cnt; s_next = nxt; }
     }
     for (uint32_t k = (bulk_bytes >> 2) + tid; k < nf; k += PF_THREADS) s_pts[k] = __ldg(src + k);
     __syncthreads();                        // barrier initialised + tail visible
@@ -137,7 +147,7 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
     }
 
     int b = s_b0;
-    uint32_t next_off = b + 1 < p.B ? (uint32_t)__ldg(p.offsets + b + 1) : PV_INF;
+    uint32_t next_off = s_next;              // first point index of the next non-empty frame boundary
     const float lo0 = p.lo[0], lo1 = p.lo[1], lo2 = p.lo[2];
     const float iv0 = p.inv_vs[0], iv1 = p.inv_vs[1], iv2 = p.inv_vs[2];
     const float g0 = p.gridf[0], g1 = p.gridf[1], g2 = p.gridf[2];
