@@ -174,6 +174,7 @@ def run_reference(args, rank, world):
 
 
 def main():
+    global N_SETS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -184,7 +185,9 @@ def main():
     ap.add_argument("--streams", type=int, default=4,
                     help="independent batches in flight on separate CUDA streams (1 = strictly serial steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sets", type=int, default=4, help="rotating input sets (each with its own workspace/graph)")
     args = ap.parse_args()
+    N_SETS = max(1, args.sets)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

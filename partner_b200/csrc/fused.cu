@@ -400,6 +400,44 @@ __device__ __forceinline__ void pf_st_row_clean(float *row, float keep0)
     }
 }
 
+// One feature row [C] at row vid of a packed [M, C] array.  A scattered store costs one load/store
+// unit slot per lane whatever its width, so 28-byte rows (C = 7) go out as one 16-, one 8- and one
+// 4-byte store chosen by the row's alignment, 32-byte rows (C = 8) as two 16-byte stores.
+template <int CT>
+__device__ __forceinline__ void pf_store_feats(float *feats, int32_t vid, int C, const float (&mean)[CT])
+{
+    float *o = feats + (size_t)vid * C;
+    const bool al16 = (reinterpret_cast<uintptr_t>(feats) & 15u) == 0;
+    if (CT == 8 && C == 7 && al16) {
+        float2 *o2; float4 *o4;
+        switch (vid & 3) {
+        case 0:
+            o4 = reinterpret_cast<float4 *>(o); o2 = reinterpret_cast<float2 *>(o + 4);
+            *o4 = make_float4(mean[0], mean[1], mean[2], mean[3]); *o2 = make_float2(mean[4 % CT], mean[5 % CT]); o[6] = mean[6 % CT];
+            break;
+        case 1:     // row starts 12 bytes past a 16-byte boundary
+            o2 = reinterpret_cast<float2 *>(o + 5); o4 = reinterpret_cast<float4 *>(o + 1);
+            o[0] = mean[0]; *o4 = make_float4(mean[1], mean[2], mean[3], mean[4 % CT]); *o2 = make_float2(mean[5 % CT], mean[6 % CT]);
+            break;
+        case 2:     // 8 bytes past
+            o2 = reinterpret_cast<float2 *>(o); o4 = reinterpret_cast<float4 *>(o + 2);
+            *o2 = make_float2(mean[0], mean[1]); *o4 = make_float4(mean[2], mean[3], mean[4 % CT], mean[5 % CT]); o[6] = mean[6 % CT];
+            break;
+        default:    // 4 bytes past
+            o2 = reinterpret_cast<float2 *>(o + 1); o4 = reinterpret_cast<float4 *>(o + 3);
+            o[0] = mean[0]; *o2 = make_float2(mean[1], mean[2]); *o4 = make_float4(mean[3], mean[4 % CT], mean[5 % CT], mean[6 % CT]);
+            break;
+        }
+    } else if (CT == 12 && C == 8 && al16) {
+        reinterpret_cast<float4 *>(o)[0] = make_float4(mean[0], mean[1], mean[2], mean[3]);
+        reinterpret_cast<float4 *>(o)[1] = make_float4(mean[4 % CT], mean[5 % CT], mean[6 % CT], mean[7 % CT]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < CT; ++k)
+            if (k < C) o[k] = mean[k];
+    }
+}
+
 // ROWMAP (direct map only): grid = (ceil(nx / 256), ny * nz, B), one thread per cell of one grid
 // row -- (z, y, x) come from the block index, no integer division anywhere.  Otherwise
 // grid = (slots / 256, B) over the linear slot index.  CC = compile-time channel count (0 = runtime).
@@ -481,39 +519,7 @@ __global__ void __launch_bounds__(256) kf_finalize(const __grid_constant__ PvPar
                     for (int k = 0; k < CT; ++k)
                         if (k < C) cv[(size_t)k * p.cells] = mean[k];
                 }
-                if (p.feats) {
-                    float *o = p.feats + (size_t)vid * C;
-                    if (CT == 8 && C == 7 && (reinterpret_cast<uintptr_t>(p.feats) & 15u) == 0) {
-                        // 28-byte rows: one 16-, one 8- and one 4-byte store, whatever the row's alignment
-                        // (a scattered store costs one load/store-unit slot per lane regardless of width)
-                        float2 *o2; float4 *o4;
-                        switch (vid & 3) {
-                        case 0:
-                            o4 = reinterpret_cast<float4 *>(o); o2 = reinterpret_cast<float2 *>(o + 4);
-                            *o4 = make_float4(mean[0], mean[1], mean[2], mean[3]); *o2 = make_float2(mean[4], mean[5]); o[6] = mean[6 % CT];
-                            break;
-                        case 1:     // row starts 12 bytes past a 16-byte boundary
-                            o2 = reinterpret_cast<float2 *>(o + 5); o4 = reinterpret_cast<float4 *>(o + 1);
-                            o[0] = mean[0]; *o4 = make_float4(mean[1], mean[2], mean[3], mean[4]); *o2 = make_float2(mean[5], mean[6 % CT]);
-                            break;
-                        case 2:     // 8 bytes past
-                            o2 = reinterpret_cast<float2 *>(o); o4 = reinterpret_cast<float4 *>(o + 2);
-                            *o2 = make_float2(mean[0], mean[1]); *o4 = make_float4(mean[2], mean[3], mean[4], mean[5]); o[6] = mean[6 % CT];
-                            break;
-                        default:    // 4 bytes past
-                            o2 = reinterpret_cast<float2 *>(o + 1); o4 = reinterpret_cast<float4 *>(o + 3);
-                            o[0] = mean[0]; *o2 = make_float2(mean[1], mean[2]); *o4 = make_float4(mean[3], mean[4], mean[5], mean[6 % CT]);
-                            break;
-                        }
-                    } else if (CT == 12 && C == 8 && (reinterpret_cast<uintptr_t>(p.feats) & 15u) == 0) {
-                        reinterpret_cast<float4 *>(o)[0] = make_float4(mean[0], mean[1], mean[2], mean[3]);   // 32-byte rows
-                        reinterpret_cast<float4 *>(o)[1] = make_float4(mean[4 % CT], mean[5 % CT], mean[6 % CT], mean[7 % CT]);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < CT; ++k)
-                            if (k < C) o[k] = mean[k];
-                    }
-                }
+                if (p.feats) pf_store_feats<CT>(p.feats, vid, C, mean);
             }
             if (!f.dense && p.density) p.density[(size_t)b * p.cells + cell] = (int32_t)cnt;
         }

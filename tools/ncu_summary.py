@@ -56,6 +56,9 @@ if os.path.exists(launch_src):
     shutil.copy(launch_src, os.path.join(out_dir, "%s_launches.csv" % tag))
     per = {}
     for r in csv.DictReader(l for l in open(launch_src) if l.startswith('"')):
+        name = r["Kernel Name"].replace("void ", "")
+        if not (name.startswith("kf_") or name.startswith("k_")):
+            continue                      # torch's own setup kernels are not part of the step
         per.setdefault(r["Kernel Name"], []).append(float(r["Metric Value"]) / 1e3)
     tot = sum(statistics.mean(v) for v in per.values())
     shares = {k: {"mean_us": statistics.mean(v), "launches": len(v), "share": statistics.mean(v) / tot} for k, v in per.items()}
