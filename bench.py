@@ -391,7 +391,9 @@ def main():
                          "frac": (ach / peak) if ach else None, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
-                         "stage_ms": live, "stage_ms_sum": float(sum(live.values()))},
+                         "stage_ms": live, "stage_ms_sum": float(sum(live.values())),
+                         "note": "HBM fraction as the contract asks; the path is bound by scattered L2 requests, "
+                                 "not bytes (DESIGN.md 3.1)"},
             "roofline_path": {"algorithmic_bytes_per_step": path_bytes, "achieved": path_bytes / (step_ms * 1e-3) / 1e9,
                               "peak": peak, "unit": "GB/s", "frac": path_bytes / (step_ms * 1e-3) / 1e9 / peak,
                               "frac_of_8000": path_bytes / (step_ms * 1e-3) / 1e9 / 8000.0},
