@@ -158,6 +158,34 @@ int pv_profile_mean_canvas(const pv_config *cfg, const float *points, const int3
                            int32_t *voxel_counts, float *mean_feats, float *canvas,
                            pv_stream_t stream, int32_t iters, float *stage_ms);
 
+/*
+ * Dynamic voxelization of a batch ("dynamic=True" configs of the reference): replaces
+ *   - the grid index of Voxelization.voxelize_dynamic (det3d/datasets/pipelines/voxelization.py:169-172:
+ *     floor(clip((p - lo) / vs, 0, grid - 1)), every point gets a cell, nothing is dropped) and the
+ *     batch-index padding of collate_kitti (torchie/parallel/collate.py:157-164),
+ *   - torch.unique(grid_ind, return_inverse=True, return_counts=True, dim=0) + torch_scatter.scatter_mean
+ *     in DynamicVoxelEncoderV1.forward (det3d/models/readers/voxel_encoder.py:38-44),
+ *   - DynamicPPScatter.forward (det3d/models/readers/pillar_encoder.py:413-432) when canvas != NULL.
+ * Voxels are ordered by (b, z, y, x) as torch.unique sorts them; there is no max_points / max_voxels cap.
+ * Two input modes: grid_ind_in == NULL -> the points are binned here (frame_offsets required, Cartesian
+ * rows are transformed on the fly as in pv_voxelize); grid_ind_in != NULL -> int32 [n, 4] (b, z, y, x)
+ * rows computed by the caller are used as they are (frame_offsets may be NULL; rows outside the grid
+ * set a status bit and get unq_inv = -1).
+ * Outputs (M = sum of voxel_counts <= min(n_total, batch * cells) rows):
+ *   grid_ind_out int32 [n, 4] or NULL      unq      int32 [M, 4] (b, z, y, x)   required
+ *   unq_inv      int32 [n]   or NULL       unq_cnt  int32 [M]  or NULL
+ *   voxel_counts int32 [batch]  required   mean_feats f32 [M, C] or NULL
+ *   canvas       f32 [batch, C, ny, nx] or NULL (pillar grids)
+ * Direct-map grids only (<= 2^20 cells per frame: the pillar grids the dynamic configs use);
+ * PV_ERR_UNSUPPORTED otherwise.  Integer outputs are bit-exact; means as in the list-free pipeline.
+ */
+int pv_dynamic_voxelize(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
+                        const int32_t *grid_ind_in, int32_t batch, int64_t n_total, int32_t c_in,
+                        int32_t is_cartesian, int64_t max_points_total, int64_t frame_capacity,
+                        void *workspace, size_t workspace_bytes, int32_t *grid_ind_out, int32_t *unq,
+                        int32_t *unq_inv, int32_t *unq_cnt, int32_t *voxel_counts, float *mean_feats,
+                        float *canvas, pv_stream_t stream);
+
 /* Copies the device status word of the last pv_voxelize on `workspace` to the host
  * (synchronises `stream`).  Returns PV_OK or PV_ERR_TABLE_FULL / PV_ERR_CUDA. */
 int pv_read_status(const void *workspace, pv_stream_t stream);

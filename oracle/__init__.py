@@ -187,3 +187,34 @@ def scatter(voxel_features, coords, batch_size, input_shape):
     lib().po_scatter(_p(f), _p(co), ctypes.c_int64(m), ctypes.c_int(c), ctypes.c_int(batch_size),
                      ctypes.c_int(ny), ctypes.c_int(nx), _p(canvas), _p(idx))
     return canvas, idx
+
+
+def dynamic_grid_ind(points, voxel_size, point_cloud_range):
+    """voxelize_dynamic, datasets/pipelines/voxelization.py:169-172 -> int32 [N, 3] (z, y, x)."""
+    pts = _f32c(points)
+    n, c = pts.shape
+    vs = np.asarray(voxel_size, dtype=np.float32)
+    rg = np.asarray(point_cloud_range, dtype=np.float32)
+    out = np.empty((n, 3), np.int32)
+    lib().po_dynamic_grid_ind(_p(pts), ctypes.c_int64(n), ctypes.c_int(c), _p(vs), _p(rg), _p(out))
+    return out
+
+
+def dynamic_mean(grid_ind, features):
+    """DynamicVoxelEncoderV1.forward, models/readers/voxel_encoder.py:38-44.
+
+    grid_ind int [N, 4] (b, z, y, x), features f32 [N, C] ->
+    (mean [M, C], unq int32 [M, 4], unq_inv int64 [N], unq_cnt int64 [M])."""
+    gi = np.ascontiguousarray(grid_ind, dtype=np.int32)
+    f = _f32c(features)
+    n, c = f.shape
+    unq = np.empty((max(n, 1), 4), np.int32)
+    inv = np.empty((n,), np.int64)
+    cnt = np.empty((max(n, 1),), np.int64)
+    mean = np.empty((max(n, 1), c), np.float32)
+    L = lib()
+    L.po_dynamic_mean.restype = ctypes.c_int64
+    m = L.po_dynamic_mean(_p(gi), _p(f), ctypes.c_int64(n), ctypes.c_int(c), _p(unq), _p(inv), _p(cnt), _p(mean))
+    if m < 0:
+        raise MemoryError("oracle: allocation failed")
+    return mean[:m], unq[:m], inv, cnt[:m]

@@ -290,3 +290,75 @@ void po_scatter(const float *feats, const int32_t *coors, int64_t m, int c, int 
         for (int k = 0; k < c; ++k) canvas[((int64_t)b * c + k) * plane + idx] = feats[v * c + k];
     }
 }
+
+/* ------------------------------------------------------------------------- */
+/* Dynamic voxelization ("next" row f1 of SURVEY.md section 8)                 */
+/* ------------------------------------------------------------------------- */
+
+/* voxelize_dynamic -- det3d/datasets/pipelines/voxelization.py:169-172:
+ *   pc_grid_ind = floor(clip((points[:, :3] - pc_range[:3]) / voxel_size, 0, grid_size - 1))[:, ::-1]
+ * float32 subtract and divide (numpy), clamp, floor; EVERY point gets a cell (out-of-range points
+ * are clamped into the border cells, nothing is dropped).  NaN is undefined behaviour in the
+ * reference (astype(int) of NaN); here it maps to cell 0 like any value below the range.
+ * out: int32 [n, 3] in (z, y, x) order. */
+void po_dynamic_grid_ind(const float *points, int64_t n, int c, const float *voxel_size,
+                         const float *range, int32_t *out)
+{
+    int32_t grid[3];
+    po_grid_size(voxel_size, range, grid);
+    for (int64_t i = 0; i < n; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            float q = (points[i * c + j] - range[j]) / voxel_size[j];
+            float hi = (float)(grid[j] - 1);
+            if (!(q >= 0.0f)) q = 0.0f;      /* below range or NaN */
+            if (q > hi) q = hi;
+            out[i * 3 + (2 - j)] = (int32_t)floorf(q);
+        }
+    }
+}
+
+typedef struct { int32_t k[4]; int64_t idx; } po_key4;
+static int po_cmp_key4(const void *a, const void *b)
+{
+    const po_key4 *x = (const po_key4 *)a, *y = (const po_key4 *)b;
+    for (int j = 0; j < 4; ++j)
+        if (x->k[j] != y->k[j]) return x->k[j] < y->k[j] ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+
+/* DynamicVoxelEncoderV1.forward -- det3d/models/readers/voxel_encoder.py:38-44:
+ *   unq, unq_inv, unq_cnt = torch.unique(grid_ind, return_inverse=True, return_counts=True, dim=0)
+ *   features = torch_scatter.scatter_mean(features, unq_inv, dim=0)
+ * torch.unique(dim=0) sorts the rows lexicographically, so voxels come out in (b, z, y, x) order;
+ * scatter_mean (third-party torch_scatter, not vendored by the reference; documented semantics):
+ * per-voxel fp32 sum in point order divided by the count.  No max_points / max_voxels caps.
+ * grid_ind int32 [n, 4] (b, z, y, x); returns M; unq [M, 4], inv [n], cnt [M], mean [M, c]. */
+int64_t po_dynamic_mean(const int32_t *grid_ind, const float *feats, int64_t n, int c,
+                        int32_t *unq, int64_t *inv, int64_t *cnt, float *mean)
+{
+    if (n == 0) return 0;
+    po_key4 *keys = (po_key4 *)malloc((size_t)n * sizeof(po_key4));
+    if (!keys) return -1;
+    for (int64_t i = 0; i < n; ++i) {
+        memcpy(keys[i].k, grid_ind + i * 4, 4 * sizeof(int32_t));
+        keys[i].idx = i;
+    }
+    qsort(keys, (size_t)n, sizeof(po_key4), po_cmp_key4);
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (i == 0 || memcmp(keys[i].k, keys[i - 1].k, 4 * sizeof(int32_t)) != 0) {
+            memcpy(unq + m * 4, keys[i].k, 4 * sizeof(int32_t));
+            cnt[m] = 0;
+            ++m;
+        }
+        inv[keys[i].idx] = m - 1;
+        cnt[m - 1] += 1;
+    }
+    free(keys);
+    memset(mean, 0, (size_t)m * c * sizeof(float));
+    for (int64_t i = 0; i < n; ++i)                 /* scatter_sum in point order */
+        for (int k = 0; k < c; ++k) mean[inv[i] * c + k] += feats[i * c + k];
+    for (int64_t v = 0; v < m; ++v)
+        for (int k = 0; k < c; ++k) mean[v * c + k] /= (float)cnt[v];
+    return m;
+}

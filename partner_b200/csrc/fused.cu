@@ -91,7 +91,10 @@ __device__ __forceinline__ uint32_t pf_claim(uint32_t *keys, uint32_t mask, uint
 // F1 -- insert.  CIN > 0: compile-time row width and transform flag (rows read from shared memory
 // with 128-bit loads); CIN == 0: runtime c_in / cart.  NV = 16-byte reductions per row.
 // ---------------------------------------------------------------------------------------------
-template <bool DENSE, int CIN, bool CART, int NV>
+// DYN: dynamic voxelization (voxelization.py:169-172): bins are CLAMPED into the grid instead of
+// range-tested, every point lands in a cell; the cell's bit in the cell-order occupancy bitmap
+// replaces the first-point minimum (voxels are ordered by cell, not by first occurrence).
+template <bool DENSE, int CIN, bool CART, int NV, bool DYN = false>
 __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ PvParams p,
                                                         const __grid_constant__ PvF f)
 {
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
         const uint32_t lane = tid & 31u;
         int cnt = 0;                         // = #{b >= 1 : offsets[b] <= tile_base}
         uint32_t nxt = PV_INF;               // smallest offsets[b] > tile_base
-        for (int bb = 1 + (int)lane; bb < p.B; bb += 32) {
+        for (int bb = 1 + (int)lane; bb < p.B && p.offsets; bb += 32) {   // offsets == NULL: frames come from gi_in
             const uint32_t o = (uint32_t)__ldg(p.offsets + bb);
             if (o <= tile_base) ++cnt; else nxt = min(nxt, o);
         }
@@ -157,7 +160,8 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
     uint32_t sa_out[PF_PPT];
     auto flush = [&]() {
         if (cur_s != PV_INF) {
-            atomicMin(f.first + cur_s, cur_i);
+            if constexpr (DYN) atomicOr(f.bits + (cur_i >> 5), 1u << (cur_i & 31u));   // cur_i = the cell's bit address
+            else atomicMin(f.first + cur_s, cur_i);
             float o[CT];                     // the count rides in channel C of the row
 #pragma unroll
             for (int k = 0; k < CT; ++k) o[k] = k < C ? cur[k] : (k == C ? cur_n : 0.0f);
@@ -201,22 +205,35 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
             if (n1) c1 = floorf(__fdiv_rn(t1f, p.vs[1]));
             if (n2) c2 = floorf(__fdiv_rn(t2f, p.vs[2]));
         }
-        const bool ok = c0 >= 0.0f && c0 < g0 && c1 >= 0.0f && c1 < g1 && c2 >= 0.0f && c2 < g2;   // NaN fails
-        if (p.grid_ind) {                    // :46-54 clamped (z, y, x) for every point (NaN -> 0)
+        bool ok = c0 >= 0.0f && c0 < g0 && c1 >= 0.0f && c1 < g1 && c2 >= 0.0f && c2 < g2;   // NaN fails
+        while (i >= next_off) {              // crossed into the next frame (frames may be empty)
+            ++b;
+            next_off = b + 1 < p.B ? (uint32_t)__ldg(p.offsets + b + 1) : PV_INF;
+        }
+        if constexpr (DYN) {                 // voxelization.py:170: clip(q, 0, grid - 1) before the floor (NaN -> 0)
+            c0 = fminf(fmaxf(c0, 0.0f), g0 - 1.0f); c1 = fminf(fmaxf(c1, 0.0f), g1 - 1.0f); c2 = fminf(fmaxf(c2, 0.0f), g2 - 1.0f);
+            ok = true;
+            if (p.gi_in) {                   // drop-in reader: the caller's (b, z, y, x) rows replace the binning
+                const int4 g = __ldg(reinterpret_cast<const int4 *>(p.gi_in) + i);
+                b = g.x; c2 = (float)g.y; c1 = (float)g.z; c0 = (float)g.w;
+                ok = (unsigned)g.x < (unsigned)p.B && (unsigned)g.y < (unsigned)p.grid[2] && (unsigned)g.z < ny && (unsigned)g.w < nx;
+                if (!ok) atomicOr(p.ws.ctrl + 1, 2u);
+            }
+            if (p.grid_ind) reinterpret_cast<int4 *>(p.grid_ind)[i] = make_int4(b, (int)c2, (int)c1, (int)c0);
+        } else if (p.grid_ind) {             // :46-54 clamped (z, y, x) for every point (NaN -> 0)
             int32_t *gi = p.grid_ind + (size_t)i * 3;
             gi[0] = (int)fminf(fmaxf(c2, 0.0f), g2 - 1.0f);
             gi[1] = (int)fminf(fmaxf(c1, 0.0f), g1 - 1.0f);
             gi[2] = (int)fminf(fmaxf(c0, 0.0f), g0 - 1.0f);
         }
-        while (i >= next_off) {              // crossed into the next frame (frames may be empty)
-            ++b;
-            next_off = b + 1 < p.B ? (uint32_t)__ldg(p.offsets + b + 1) : PV_INF;
-        }
         if (!ok) continue;
         const uint32_t cx = (uint32_t)(int)c0, cy = (uint32_t)(int)c1, cz = (uint32_t)(int)c2;
         const uint32_t cell = (cz * ny + cy) * nx + cx;
         uint32_t s, sa;
-        if (DENSE) {
+        if (DYN) {
+            s = (uint32_t)b * f.capf + cell;
+            sa = (uint32_t)b * (f.wcap * 32u) + cell;            // bit address in the occupancy bitmap
+        } else if (DENSE) {
             s = (uint32_t)b * f.capf + cell;
             // heavy-bitmap order: phi fastest, so azimuth neighbours share a bitmap word
             sa = (uint32_t)b * f.capf + (cz * nx + cx) * ny + cy;
@@ -234,12 +251,13 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
             cur_n += 1.0f;
         } else {
             flush();
-            cur_s = s; cur_i = i; cur_n = 1.0f;
+            cur_s = s; cur_i = DYN ? sa : i; cur_n = 1.0f;
 #pragma unroll
             for (int k = 0; k < CT; ++k) cur[k] = v[k];
         }
     }
     flush();
+    if (DYN && !p.unq_inv) return;           // the per-point map is only needed for the inverse index
     if (t0 + PF_PPT <= n_tile) {
         *reinterpret_cast<uint4 *>(f.sa + tile_base + t0) = make_uint4(sa_out[0], sa_out[1], sa_out[2], sa_out[3]);
     } else {
@@ -286,7 +304,8 @@ __global__ void __launch_bounds__(PF_SCAN_THREADS) kf_scan(const __grid_constant
     __shared__ uint32_t s_carry, s_last;
     const int b = blockIdx.x;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t n_b = (uint32_t)(p.offsets[b + 1] - p.offsets[b]);
+    // static: one bit per point of the frame; dynamic: one bit per cell of the grid
+    const uint32_t n_b = p.dyn ? p.cells : (uint32_t)(p.offsets[b + 1] - p.offsets[b]);
     const uint32_t nw = min((n_b + 31u) >> 5, f.wcap);
     uint32_t *bits = f.bits + (size_t)b * f.wcap;
     uint2 *wb = f.wb + (size_t)b * f.wcap;
@@ -341,7 +360,7 @@ __global__ void __launch_bounds__(PF_SCAN_THREADS) kf_scan(const __grid_constant
     if (tid == 0) {
         const uint32_t raw = s_carry;
         f.counts_raw[b] = raw;
-        p.voxel_counts[b] = (int32_t)min(raw, (uint32_t)p.V);
+        p.voxel_counts[b] = (int32_t)(p.dyn ? raw : min(raw, (uint32_t)p.V));    // no max_voxels cap on the dynamic path
         __threadfence();
         const uint32_t done = atomicAdd(f.ctrl + 3, 1u);
         s_last = done == gridDim.x - 1 ? 1u : 0u;
@@ -660,6 +679,83 @@ __global__ void __launch_bounds__(256) kf_heavy_cells(const __grid_constant__ Pv
 }
 
 // ---------------------------------------------------------------------------------------------
+// Dynamic voxelization: Voxelization.voxelize_dynamic
+// (datasets/pipelines/voxelization.py:169-172) + torch.unique(grid_ind, dim=0) + scatter_mean of
+// DynamicVoxelEncoderV1 (models/readers/voxel_encoder.py:38-44) + DynamicPPScatter
+// (models/readers/pillar_encoder.py:413-432).  No max_points / max_voxels caps, voxels ordered by
+// (b, z, y, x) = cell order, so the rank of a cell is the popcount prefix of the CELL-order
+// occupancy bitmap that kf_insert<DYN> sets: insert -> scan -> finalize, three launches, and the
+// finalize pass writes every per-voxel output in increasing row order.
+// ---------------------------------------------------------------------------------------------
+template <int NV, int CC, bool CANVAS>
+__global__ void __launch_bounds__(256) kf_dyn_finalize(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
+{
+    constexpr int CT = NV * 4;
+    const int C = CC ? CC : p.C;
+    const int b = blockIdx.z;
+    const uint32_t nx = p.grid[0], ny = p.grid[1];
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, yz = blockIdx.y;
+    if (x >= nx) return;
+    const uint32_t l = yz * nx + x;
+    const uint32_t s = (uint32_t)b * f.capf + l;
+    const uint2 wv = __ldg(f.wb + (size_t)b * f.wcap + (l >> 5));
+    float m[CANVAS ? CT : 1];
+    if (CANVAS) {
+#pragma unroll
+        for (int k = 0; k < CT; ++k) m[k] = 0.0f;
+    }
+    if ((wv.y >> (l & 31u)) & 1u) {
+        float *rowp = f.acc + (size_t)s * f.rowf;
+        float r[CT];
+        pf_ld_row<NV>(rowp, r);
+        const uint32_t rank = wv.x + __popc(wv.y & ((1u << (l & 31u)) - 1u));
+        const int32_t vid = __ldg(f.base + b) + (int32_t)rank;
+        float cntf = 0.0f;
+#pragma unroll
+        for (int k = 0; k < CT; ++k) cntf = k == C ? r[k] : cntf;
+        const uint32_t cz = yz / ny, cy = yz - cz * ny;                   // uniform
+        reinterpret_cast<int4 *>(p.coors)[vid] = make_int4(b, (int)cz, (int)cy, (int)x);   // unq row
+        if (p.num_points) p.num_points[vid] = (int32_t)cntf;                               // unq_cnt
+        const float inv = __frcp_rn(cntf);
+        float mean[CT];
+#pragma unroll
+        for (int k = 0; k < CT; ++k) {
+            mean[k] = k < C ? pv_div_count(r[k], cntf, inv) : 0.0f;       // scatter_mean: sum / count
+            if (CANVAS) m[k] = mean[k];
+        }
+        if (p.feats) pf_store_feats<CT>(p.feats, vid, C, mean);
+        pf_st_row_clean<NV>(rowp, 0.0f);                                  // restore the row (after use)
+    }
+    if (CANVAS) {                                                         // DynamicPPScatter, zeros included
+        float *cv = p.canvas + (size_t)b * C * p.cells + l;
+#pragma unroll
+        for (int k = 0; k < CT; ++k)
+            if (k < C) { __stcs(cv, m[k]); cv += p.cells; }
+    }
+}
+
+// unq_inv[i] = row of point i's voxel (torch.unique's return_inverse)
+__global__ void __launch_bounds__(PF_THREADS) kf_dyn_inverse(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
+{
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * PF_PPT;
+    if (i0 >= p.n) return;
+    const uint32_t frame_bits = f.wcap * 32u;
+#pragma unroll
+    for (int j = 0; j < PF_PPT; ++j) {
+        const uint32_t i = i0 + j;
+        if (i >= p.n) break;
+        const uint32_t sa = __ldcs(f.sa + i);
+        int32_t v = -1;                                                   // rejected row of a caller-provided grid_ind
+        if (sa != PV_INF) {
+            const uint2 wv = __ldg(f.wb + (sa >> 5));
+            const uint32_t b = sa / frame_bits;
+            v = __ldg(f.base + b) + (int32_t)(wv.x + __popc(wv.y & ((1u << (sa & 31u)) - 1u)));
+        }
+        p.unq_inv[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
 static size_t pf_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -687,7 +783,9 @@ int pvf_make_layout(const pv_config *cfg, int64_t n_cap, int32_t batch, int64_t 
     const size_t slots = (size_t)capf * batch;
     w->capf = (uint32_t)capf;
     w->dense = dense ? 1u : 0u;
-    w->wcap = (uint32_t)(((fcap + 31) / 32 + 3) / 4 * 4);
+    // bitmap words per frame: one bit per point (static path) or per cell (dynamic path, direct maps)
+    const size_t bit_items = dense && capf > fcap ? (size_t)capf : fcap;
+    w->wcap = (uint32_t)(((bit_items + 31) / 32 + 3) / 4 * 4);
     w->rowf_cap = (uint32_t)((max_channels + 1 + 3) / 4 * 4);
     w->rowf = w->rowf_cap;
     w->hmax = (uint32_t)(n / ((size_t)cfg->max_points + 1) + 1);
@@ -722,12 +820,12 @@ int pvf_init(const PvF &f, int32_t batch, int64_t n_cap, cudaStream_t st)
     return PV_OK;
 }
 
-template <bool DENSE, int CIN, bool CART, int NV>
+template <bool DENSE, int CIN, bool CART, int NV, bool DYN = false>
 static int pf_launch_insert(const PvParams &p, const PvF &f, cudaStream_t st)
 {
     const unsigned grid = (p.n + PF_TILE - 1) / PF_TILE;
     const size_t smem = (size_t)PF_TILE * p.c_in * sizeof(float);
-    auto kern = kf_insert<DENSE, CIN, CART, NV>;
+    auto kern = kf_insert<DENSE, CIN, CART, NV, DYN>;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return PV_ERR_CUDA;
@@ -751,6 +849,49 @@ static int pf_dispatch_insert(const PvParams &p, const PvF &f, cudaStream_t st)
     case 4: return pf_launch_insert<DENSE, 0, false, 4>(p, f, st);
     default: return pf_launch_insert<DENSE, 0, false, 5>(p, f, st);
     }
+}
+
+static int pf_dispatch_insert_dyn(const PvParams &p, const PvF &f, cudaStream_t st)
+{
+    if (p.cart && p.c_in == 5) return pf_launch_insert<true, 5, true, 2, true>(p, f, st);
+    if (!p.cart && p.c_in == 7) return pf_launch_insert<true, 7, false, 2, true>(p, f, st);
+    switch ((int)f.rowf / 4) {
+    case 1: return pf_launch_insert<true, 0, false, 1, true>(p, f, st);
+    case 2: return pf_launch_insert<true, 0, false, 2, true>(p, f, st);
+    case 3: return pf_launch_insert<true, 0, false, 3, true>(p, f, st);
+    case 4: return pf_launch_insert<true, 0, false, 4, true>(p, f, st);
+    default: return pf_launch_insert<true, 0, false, 5, true>(p, f, st);
+    }
+}
+
+template <int NV, int CC>
+static void pf_launch_dyn_finalize(const PvParams &p, const PvF &f, cudaStream_t st)
+{
+    const dim3 grid(((unsigned)p.grid[0] + 255) / 256, (unsigned)p.grid[1] * (unsigned)p.grid[2], (unsigned)p.B);
+    if (p.canvas) kf_dyn_finalize<NV, CC, true><<<grid, 256, 0, st>>>(p, f);
+    else kf_dyn_finalize<NV, CC, false><<<grid, 256, 0, st>>>(p, f);
+}
+
+// Dynamic voxelization launch sequence (direct maps only).
+int pvf_run_dynamic(PvParams &p, PvF &f, cudaStream_t st)
+{
+    f.rowf = (uint32_t)((p.C + 1 + 3) / 4 * 4);
+    if (f.rowf > f.rowf_cap) return PV_ERR_WORKSPACE;
+    if (!f.dense || (unsigned)p.grid[1] * (unsigned)p.grid[2] > 65535u || p.B > 65535) return PV_ERR_UNSUPPORTED;
+    if (p.n > 0) {
+        const int rc = pf_dispatch_insert_dyn(p, f, st);
+        if (rc) return rc;
+    }
+    kf_scan<<<(unsigned)p.B, PF_SCAN_THREADS, 0, st>>>(p, f);
+    switch ((int)f.rowf / 4) {
+    case 1: pf_launch_dyn_finalize<1, 0>(p, f, st); break;
+    case 2: if (p.C == 7) pf_launch_dyn_finalize<2, 7>(p, f, st); else pf_launch_dyn_finalize<2, 0>(p, f, st); break;
+    case 3: pf_launch_dyn_finalize<3, 0>(p, f, st); break;
+    case 4: pf_launch_dyn_finalize<4, 0>(p, f, st); break;
+    default: pf_launch_dyn_finalize<5, 0>(p, f, st); break;
+    }
+    if (p.unq_inv && p.n > 0) kf_dyn_inverse<<<(p.n + PF_TILE - 1) / PF_TILE, PF_THREADS, 0, st>>>(p, f);
+    return pv_last_cuda_error();
 }
 
 template <int NV, int CC>

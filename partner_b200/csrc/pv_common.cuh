@@ -84,6 +84,10 @@ struct PvParams {
     PvWs ws;
     int32_t *coors, *num_points, *voxel_counts, *grid_ind, *density;
     float *voxels, *feats, *canvas;
+    // dynamic voxelization (pv_dynamic_voxelize): coors = unq, num_points = unq_cnt, grid_ind = [N, 4]
+    int32_t dyn;
+    const int32_t *gi_in;     // caller-provided (b, z, y, x) per point, or NULL = bin the points
+    int32_t *unq_inv;         // [N] voxel row of every point, or NULL
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -265,3 +269,4 @@ int pvf_make_layout(const pv_config *cfg, int64_t n_cap, int32_t batch, int64_t 
 int pvf_init(const PvF &f, int32_t batch, int64_t n_cap, cudaStream_t st);
 // list-free front end; ev (optional) = PV_PROFILE_STAGES + 1 events recorded at the stage boundaries
 int pvf_run(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev);
+int pvf_run_dynamic(PvParams &p, PvF &f, cudaStream_t st);

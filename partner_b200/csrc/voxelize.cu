@@ -679,6 +679,7 @@ static int fill_params(PvParams *p, PvF *f, const pv_config *cfg, const float *p
     p->num_tiles = (uint32_t)(n_total / SCAN_TILE + batch + 1);
     p->coors = p->num_points = p->voxel_counts = p->grid_ind = p->density = nullptr;
     p->voxels = p->feats = p->canvas = nullptr;
+    p->dyn = 0; p->gi_in = nullptr; p->unq_inv = nullptr;
     return PV_OK;
 }
 
@@ -892,6 +893,35 @@ int pv_profile_mean_canvas(const pv_config *cfg, const float *points, const int3
     return rc;
 }
 
+int pv_dynamic_voxelize(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
+                        const int32_t *grid_ind_in, int32_t batch, int64_t n_total, int32_t c_in,
+                        int32_t is_cartesian, int64_t max_points_total, int64_t frame_capacity,
+                        void *workspace, size_t workspace_bytes, int32_t *grid_ind_out, int32_t *unq,
+                        int32_t *unq_inv, int32_t *unq_cnt, int32_t *voxel_counts, float *mean_feats,
+                        float *canvas, pv_stream_t stream)
+{
+    PvParams p;
+    PvF f;
+    if (!frame_offsets && !grid_ind_in) return PV_ERR_BAD_ARGUMENT;
+    static const int32_t dummy = 0;       // fill_params only checks for NULL; kernels never read it when gi_in is set
+    int rc = fill_params(&p, &f, cfg, points, frame_offsets ? frame_offsets : &dummy, batch, n_total, c_in,
+                         is_cartesian, max_points_total, frame_capacity, workspace, workspace_bytes);
+    if (rc) return rc;
+    if (!frame_offsets) p.offsets = nullptr;
+    if (!unq || !voxel_counts) return PV_ERR_BAD_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(unq) & 15u) != 0) return PV_ERR_BAD_ARGUMENT;
+    if (grid_ind_in && (reinterpret_cast<uintptr_t>(grid_ind_in) & 15u) != 0) return PV_ERR_BAD_ARGUMENT;
+    if (grid_ind_out && (reinterpret_cast<uintptr_t>(grid_ind_out) & 15u) != 0) return PV_ERR_BAD_ARGUMENT;
+    if (canvas) {
+        if (cfg->grid[2] != 1) return PV_ERR_BAD_CONFIG;
+        if ((reinterpret_cast<uintptr_t>(canvas) & 15u) != 0) return PV_ERR_BAD_ARGUMENT;
+    }
+    p.dyn = 1; p.gi_in = grid_ind_in; p.grid_ind = grid_ind_out;
+    p.coors = unq; p.num_points = unq_cnt; p.unq_inv = unq_inv; p.voxel_counts = voxel_counts;
+    p.feats = mean_feats; p.canvas = canvas;
+    return pvf_run_dynamic(p, f, (cudaStream_t)stream);
+}
+
 int pv_read_status(const void *workspace, pv_stream_t stream)
 {
     if (!workspace) return PV_ERR_BAD_ARGUMENT;
@@ -899,7 +929,8 @@ int pv_read_status(const void *workspace, pv_stream_t stream)
     if (cudaMemcpyAsync(ctrl, workspace, sizeof(ctrl), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess)
         return PV_ERR_CUDA;
     if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return PV_ERR_CUDA;
-    return (ctrl[1] & 1u) ? PV_ERR_TABLE_FULL : PV_OK;
+    if (ctrl[1] & 1u) return PV_ERR_TABLE_FULL;
+    return (ctrl[1] & 2u) ? PV_ERR_BAD_ARGUMENT : PV_OK;     // bit 1: a caller-provided grid_ind row was outside the grid
 }
 
 }  // extern "C"

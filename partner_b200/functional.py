@@ -161,6 +161,57 @@ def voxelize(cfg, points, frame_offsets, batch, frame_capacity, is_cartesian, wa
     return r
 
 
+class DynamicBatch:
+    """Outputs of pv_dynamic_voxelize in capacity layout (rows [0, sum(voxel_counts)) are valid)."""
+
+    __slots__ = ("unq", "unq_inv", "unq_cnt", "voxel_counts", "mean_feats", "grid_ind", "canvas", "ws", "cfg")
+
+    def total(self):
+        return int(self.voxel_counts.sum().item())
+
+
+def dynamic_voxelize(cfg, points, frame_offsets, batch, frame_capacity, is_cartesian=False, grid_ind=None,
+                     want_inverse=True, want_counts=True, want_grid_ind=False, canvas=False, ws_tag=0):
+    """pv_dynamic_voxelize on CUDA tensors: dynamic voxelization + unique + scatter_mean (+ scatter).
+
+    points [N, c_in] f32; either frame_offsets [batch+1] int32 (the points are binned here) or
+    grid_ind [N, 4] int32 (b, z, y, x) computed by the caller.  Returns a DynamicBatch."""
+    _need(points, torch.float32, "points", 2)
+    n, c_in = points.shape
+    if grid_ind is not None:
+        _need(grid_ind, torch.int32, "grid_ind", 2)
+        if grid_ind.shape != (n, 4):
+            raise ValueError("grid_ind must be [N, 4] (b, z, y, x)")
+    else:
+        _need(frame_offsets, torch.int32, "frame_offsets", 1)
+        if frame_offsets.numel() != batch + 1:
+            raise ValueError("frame_offsets must have batch+1 entries")
+    C = c_in + 2 if is_cartesian else c_in
+    dev = points.device
+    lib = _lib.load()
+    n_cap = _bucket(n)
+    f_cap = min(n_cap, _bucket(frame_capacity if frame_capacity else n))
+    ws = voxel_workspace(cfg, n_cap, batch, f_cap, C, dev, ws_tag)
+    cells = cfg.grid[0] * cfg.grid[1] * cfg.grid[2]
+    rows = max(1, min(batch * cells, n))
+    r = DynamicBatch()
+    r.unq = torch.empty((rows, 4), dtype=torch.int32, device=dev)
+    r.unq_inv = torch.empty((n,), dtype=torch.int32, device=dev) if want_inverse else None
+    r.unq_cnt = torch.empty((rows,), dtype=torch.int32, device=dev) if want_counts else None
+    r.voxel_counts = torch.empty((batch,), dtype=torch.int32, device=dev)
+    r.mean_feats = torch.empty((rows, C), dtype=torch.float32, device=dev)
+    r.grid_ind = torch.empty((n, 4), dtype=torch.int32, device=dev) if want_grid_ind else None
+    r.canvas = (torch.empty((batch, C, cfg.grid[1], cfg.grid[0]), dtype=torch.float32, device=dev)
+                if canvas else None)
+    r.ws, r.cfg = ws, cfg
+    check(lib.pv_dynamic_voxelize(cfg, ptr(points), ptr(frame_offsets) if grid_ind is None else ptr(None),
+                                  ptr(grid_ind), batch, n, c_in, 1 if is_cartesian else 0, n_cap, f_cap,
+                                  ptr(ws), ws.numel(), ptr(r.grid_ind), ptr(r.unq), ptr(r.unq_inv), ptr(r.unq_cnt),
+                                  ptr(r.voxel_counts), ptr(r.mean_feats), ptr(r.canvas), current_stream(dev)),
+          "pv_dynamic_voxelize")
+    return r
+
+
 def read_status(vb):
     rc = _lib.load().pv_read_status(ptr(vb.ws), current_stream(vb.ws.device))
     if rc != 0:

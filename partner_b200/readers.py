@@ -108,3 +108,58 @@ class PointPillarsScatter(nn.Module):
             voxel_features = voxel_features.view(1, -1)
         return F.scatter(voxel_features.contiguous(), coords if coords.dtype == torch.int32 else coords.int(),
                          int(batch_size), self.ny, self.nx)
+
+
+@READERS.register_module
+class DynamicVoxelEncoderV1(nn.Module):
+    """det3d/models/readers/voxel_encoder.py:26-44: torch.unique(grid_ind, dim=0) + scatter_mean.
+
+    ``forward(data)`` takes the reference's dict (``data["points"]`` [N, C] f32, ``data["grid_ind"]``
+    [N, 4] (b, z, y, x)) and returns ``(features [M, C], unq [M, 4])`` with voxels in sorted
+    (b, z, y, x) order.  ``grid_size`` = (nx, ny, nz) and ``batch_size`` may be given to avoid the
+    one host read that otherwise sizes the direct map from ``grid_ind.max()``."""
+
+    def __init__(self, num_input_features=7, out_channels=16, name="DynamicVoxelEncoderV1", grid_size=None,
+                 batch_size=None):
+        super().__init__()
+        self.name = name
+        self.num_input_features = num_input_features
+        self.point_density = False
+        self.grid_size = grid_size
+        self.batch_size = batch_size
+
+    def forward(self, data):
+        features = data["points"]
+        grid_ind = data["grid_ind"]
+        r = _dynamic_from_grid_ind(features, grid_ind, self.grid_size, self.batch_size, want_inverse=False)
+        m = r.total()
+        return r.mean_feats[:m], r.unq[:m].to(grid_ind.dtype)
+
+
+def _dynamic_from_grid_ind(features, grid_ind, grid_size, batch_size, want_inverse):
+    gi = grid_ind if grid_ind.dtype == torch.int32 else grid_ind.to(torch.int32)
+    gi = gi.contiguous()
+    if grid_size is None or batch_size is None:
+        mx = gi.max(dim=0).values.tolist() if gi.shape[0] else [0, 0, 0, 0]
+        if batch_size is None:
+            batch_size = mx[0] + 1
+        if grid_size is None:
+            grid_size = (mx[3] + 1, mx[2] + 1, mx[1] + 1)
+    nx, ny, nz = (int(v) for v in grid_size)
+    cfg, _, _, _ = F.make_config([1.0, 1.0, 1.0], [0.0, 0.0, 0.0, float(nx), float(ny), float(nz)], 1, 1)
+    return F.dynamic_voxelize(cfg, features.contiguous(), None, int(batch_size), 0, False, grid_ind=gi,
+                              want_inverse=want_inverse)
+
+
+@BACKBONES.register_module
+class DynamicPPScatter(nn.Module):
+    """det3d/models/readers/pillar_encoder.py:413-432."""
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.name = "DynamicPPScatter"
+
+    def forward(self, voxel_features, unq, batch_size, grid_size):
+        nx, ny = int(grid_size[0]), int(grid_size[1])
+        return F.scatter(voxel_features.contiguous(), unq if unq.dtype == torch.int32 else unq.to(torch.int32),
+                         int(batch_size), ny, nx)

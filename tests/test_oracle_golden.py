@@ -105,3 +105,23 @@ def test_scatter_golden(golden_dir):
     canvas, idx = oracle.scatter(g["vfe_mean"], g["coors"], 2, [512, 512, 1])
     assert np.array_equal(idx, g["bev_index"])
     assert np.array_equal(canvas, densify(g["canvas_idx"], g["canvas_val"], g["canvas_shape"]))
+
+
+# ---- dynamic voxelization: golden from tests/golden/make_golden_dynamic.py ----
+def test_dynamic_grid_ind_and_mean_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "dynamic.npz"))
+    sizes = g["sizes"]
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    gi = []
+    for b in range(len(sizes)):
+        zyx = oracle.dynamic_grid_ind(g["polar"][off[b]:off[b + 1]], g["voxel_size"], g["range"])
+        gi.append(np.pad(zyx, ((0, 0), (1, 0)), constant_values=b))
+    gi = np.concatenate(gi)
+    assert np.array_equal(gi, g["grid_ind"])                         # bit-exact incl. the clamped border points
+    mean, unq, inv, cnt = oracle.dynamic_mean(gi, g["polar"])
+    assert np.array_equal(unq, g["unq"])
+    assert np.array_equal(inv, g["unq_inv"])
+    assert np.array_equal(cnt, g["unq_cnt"])
+    assert_close_fp32(mean, g["features"], "scatter_mean")
+    canvas, _ = oracle.scatter(mean, unq, len(sizes), [512, 512, 1])
+    assert_close_fp32(canvas, densify(g["canvas_idx"], g["canvas_val"], g["canvas_shape"]), "canvas")
