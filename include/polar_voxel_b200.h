@@ -186,6 +186,27 @@ int pv_dynamic_voxelize(const pv_config *cfg, const float *points, const int32_t
                         int32_t *unq_inv, int32_t *unq_cnt, int32_t *voxel_counts, float *mean_feats,
                         float *canvas, pv_stream_t stream);
 
+/*
+ * DynamicPFNet.forward (det3d/models/readers/pillar_encoder.py:262-411; PFNLayer.forward_dynamic :63-71)
+ * on the outputs of pv_dynamic_voxelize: feature decoration (get_cluster :228-238, cell centres
+ * :350-351 through polar2cart / cart2polar :240-260), then n_layers x (Linear without bias, ReLU,
+ * scatter_max over the voxel); non-last layers pass cat([x, x_max[unq_inv]]) on.  No normalisation
+ * (the dynamic forward never calls PFNLayer.norm; only `weight` of pv_pfn_layer is read).
+ *   points [n, c] feature rows; unq [m, 4] (b, z, y, x); unq_inv [n] (-1 = skip); unq_cnt [m];
+ *   voxel_mean [m, c] = scatter_mean of the rows (pv_dynamic_voxelize's mean_feats);
+ *   cylinder != 0: voxel_shape == 'cylinder' (xyz = columns 3, 4, 2; ra = columns 0, 1), else
+ *   'cuboid' (xyz = columns 0..2; ra = the last two columns) -- the reference's configs leave the
+ *   reader at 'cuboid'; flags: bit 0 xyz_cluster, 1 raz_cluster, 2 xy_center, 3 ra_center;
+ *   vx, vy, x_off, y_off as computed at pillar_encoder.py:331-334;  out [m, units of the last layer].
+ * 1 or 2 layers, decorated width <= 32, units multiples of 4 (first <= 64 when a second layer
+ * follows, last <= 128); PV_ERR_UNSUPPORTED otherwise.  `layers` is a HOST array.
+ */
+size_t pv_dynamic_pfn_workspace_bytes(int64_t n, int64_t m);
+int pv_dynamic_pfn(const float *points, const int32_t *unq, const int32_t *unq_inv, const int32_t *unq_cnt,
+                   const float *voxel_mean, int64_t n, int64_t m, int32_t c, int32_t cylinder, int32_t flags,
+                   float vx, float vy, float x_off, float y_off, const pv_pfn_layer *layers, int32_t n_layers,
+                   void *workspace, size_t workspace_bytes, float *out, pv_stream_t stream);
+
 /* Copies the device status word of the last pv_voxelize on `workspace` to the host
  * (synchronises `stream`).  Returns PV_OK or PV_ERR_TABLE_FULL / PV_ERR_CUDA. */
 int pv_read_status(const void *workspace, pv_stream_t stream);

@@ -218,3 +218,28 @@ def dynamic_mean(grid_ind, features):
     if m < 0:
         raise MemoryError("oracle: allocation failed")
     return mean[:m], unq[:m], inv, cnt[:m]
+
+
+def dynamic_pfn(points, unq_inv, unq, weights, voxel_size, pc_range, voxel_shape="cuboid", xyz_cluster=False,
+                raz_cluster=False, xy_center=False, ra_center=False):
+    """DynamicPFNet.forward, models/readers/pillar_encoder.py:338-411 (weights: list of [U, K] f32)."""
+    p = _f32c(points)
+    inv = np.ascontiguousarray(unq_inv, dtype=np.int64)
+    u4 = np.ascontiguousarray(unq, dtype=np.int32)
+    n, c = p.shape
+    m = u4.shape[0]
+    vx, vy = float(voxel_size[0]), float(voxel_size[1])
+    x_off = vx / 2 + float(pc_range[0])
+    y_off = vy / 2 + float(pc_range[1])
+    units = np.array([w.shape[0] for w in weights], np.int32)
+    keep = [_f32c(w) for w in weights]
+    arr = (ctypes.c_void_p * len(keep))(*[w.ctypes.data for w in keep])
+    out = np.empty((m, int(units[-1])), np.float32)
+    flags = (1 if xyz_cluster else 0) | (2 if raz_cluster else 0) | (4 if xy_center else 0) | (8 if ra_center else 0)
+    rc = lib().po_dynamic_pfn(_p(p), _p(inv), _p(u4), ctypes.c_int64(n), ctypes.c_int64(m), ctypes.c_int(c),
+                              ctypes.c_int(1 if voxel_shape != "cuboid" else 0), ctypes.c_int(flags),
+                              ctypes.c_float(vx), ctypes.c_float(vy), ctypes.c_float(x_off), ctypes.c_float(y_off),
+                              ctypes.c_int(len(keep)), _p(units), arr, _p(out))
+    if rc:
+        raise MemoryError("oracle: allocation failed")
+    return out

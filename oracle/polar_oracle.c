@@ -362,3 +362,104 @@ int64_t po_dynamic_mean(const int32_t *grid_ind, const float *feats, int64_t n, 
         for (int k = 0; k < c; ++k) mean[v * c + k] /= (float)cnt[v];
     return m;
 }
+
+/* ------------------------------------------------------------------------- */
+/* DynamicPFNet.forward -- det3d/models/readers/pillar_encoder.py:338-411,    */
+/* PFNLayer.forward_dynamic :63-71, get_cluster :228-238, polar2cart /         */
+/* cart2polar :240-260.                                                        */
+/*                                                                           */
+/* points [n, c]; unq_inv [n] voxel row of every point; unq [m, 4] (b,z,y,x). */
+/* flags: bit0 xyz_cluster, bit1 raz_cluster, bit2 xy_center, bit3 ra_center. */
+/* cylinder != 0: voxel_shape == 'cylinder' (xyz = cols [3,4,2], ra = cols     */
+/* [0,1]); else 'cuboid' (xyz = cols [0,1,2], ra = the last two cols) -- the  */
+/* reference's configs leave the reader at its 'cuboid' default (:269).       */
+/* Decoration order (:347-391): points, xyz - mean(xyz), xyz[:2] - centre,    */
+/* ra(z) - mean, ra - centre.  Layers: Linear (no bias), ReLU -- NO norm in    */
+/* the dynamic forward (:64-65) -- scatter_max over the voxel; non-last        */
+/* layers output cat([x, x_max[unq_inv]]).  scatter_mean / scatter_max are     */
+/* torch_scatter's (third party, not vendored): mean = fp32 sum in point      */
+/* order / count, max = plain maximum.  vx, vy, x_off, y_off: f32 images of   */
+/* the Python doubles (:331-334).  out [m, units[n_layers-1]].                */
+/* ------------------------------------------------------------------------- */
+int po_dynamic_pfn(const float *points, const int64_t *unq_inv, const int32_t *unq, int64_t n,
+                   int64_t m, int c, int cylinder, int flags, float vx, float vy, float x_off,
+                   float y_off, int n_layers, const int32_t *units, const float *const *weight,
+                   float *out)
+{
+    const int xyz_cluster = flags & 1, raz_cluster = flags & 2, xy_center = flags & 4, ra_center = flags & 8;
+    const int xi[3] = {cylinder ? 3 : 0, cylinder ? 4 : 1, 2};
+    const int ri[2] = {cylinder ? 0 : c - 2, cylinder ? 1 : c - 1};
+    int c0 = c + (xyz_cluster ? 3 : 0) + (xy_center ? 2 : 0) + (raz_cluster ? (xyz_cluster ? 2 : 3) : 0) + (ra_center ? 2 : 0);
+    /* per-voxel means of the columns get_cluster needs (scatter_mean: sum in point order / count) */
+    float *mean = (float *)calloc((size_t)m * 5, sizeof(float));    /* x, y, z, r, a */
+    int64_t *cnt = (int64_t *)calloc((size_t)m, sizeof(int64_t));
+    if (!mean || !cnt) return -1;
+    for (int64_t i = 0; i < n; ++i) {
+        const float *p = points + i * c;
+        float *mv = mean + unq_inv[i] * 5;
+        for (int k = 0; k < 3; ++k) mv[k] += p[xi[k]];
+        for (int k = 0; k < 2; ++k) mv[3 + k] += p[ri[k]];
+        cnt[unq_inv[i]] += 1;
+    }
+    for (int64_t v = 0; v < m; ++v)
+        for (int k = 0; k < 5; ++k) mean[v * 5 + k] /= (float)(cnt[v] > 0 ? cnt[v] : 1);
+    int max_w = c0;
+    for (int l = 0; l < n_layers; ++l) if (2 * units[l] > max_w) max_w = 2 * units[l];
+    float *cur = (float *)malloc((size_t)n * max_w * sizeof(float));
+    float *nxt = (float *)malloc((size_t)n * max_w * sizeof(float));
+    float *xmax = (float *)malloc((size_t)m * max_w * sizeof(float));
+    if (!cur || !nxt || !xmax) return -1;
+    for (int64_t i = 0; i < n; ++i) {
+        const float *p = points + i * c;
+        const int64_t v = unq_inv[i];
+        const float *mv = mean + v * 5;
+        float *row = cur + i * c0;
+        int o = 0;
+        for (int k = 0; k < c; ++k) row[o++] = p[k];
+        const float center1 = (float)unq[v * 4 + 3] * vx + x_off;      /* :350 */
+        const float center2 = (float)unq[v * 4 + 2] * vy + y_off;      /* :351 */
+        if (xyz_cluster) for (int k = 0; k < 3; ++k) row[o++] = p[xi[k]] - mv[k];
+        if (xy_center) {
+            float xc = center1, yc = center2;
+            if (cylinder) { xc = center1 * cosf(center2); yc = center1 * sinf(center2); }   /* polar2cart */
+            row[o++] = p[xi[0]] - xc;
+            row[o++] = p[xi[1]] - yc;
+        }
+        if (raz_cluster) {
+            row[o++] = p[ri[0]] - mv[3];
+            row[o++] = p[ri[1]] - mv[4];
+            if (!xyz_cluster) row[o++] = p[2] - mv[2];
+        }
+        if (ra_center) {
+            float rc = center1, ac = center2;
+            if (!cylinder) { rc = sqrtf(center1 * center1 + center2 * center2); ac = atan2f(center2, center1); }  /* cart2polar */
+            row[o++] = p[ri[0]] - rc;
+            row[o++] = p[ri[1]] - ac;
+        }
+    }
+    int in_w = c0;
+    for (int l = 0; l < n_layers; ++l) {
+        const int u = units[l], last = l == n_layers - 1, out_w = last ? u : 2 * u;
+        for (int64_t k = 0; k < m * u; ++k) xmax[k] = -INFINITY;
+        for (int64_t i = 0; i < n; ++i) {
+            for (int o = 0; o < u; ++o) {
+                float acc = 0.0f;
+                const float *w = weight[l] + (size_t)o * in_w;
+                for (int k = 0; k < in_w; ++k) acc += cur[i * in_w + k] * w[k];
+                const float y = acc > 0.0f ? acc : 0.0f;
+                if (!last) nxt[i * out_w + o] = y;
+                float *xm = xmax + unq_inv[i] * u + o;
+                if (y > *xm) *xm = y;
+            }
+        }
+        if (last) memcpy(out, xmax, (size_t)m * u * sizeof(float));
+        else {
+            for (int64_t i = 0; i < n; ++i)
+                for (int o = 0; o < u; ++o) nxt[i * out_w + u + o] = xmax[unq_inv[i] * u + o];
+            float *tmp = cur; cur = nxt; nxt = tmp;
+            in_w = out_w;
+        }
+    }
+    free(mean); free(cnt); free(cur); free(nxt); free(xmax);
+    return 0;
+}

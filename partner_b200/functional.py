@@ -212,6 +212,27 @@ def dynamic_voxelize(cfg, points, frame_offsets, batch, frame_capacity, is_carte
     return r
 
 
+def dynamic_pfn(points, batch, m, weights, vx, vy, x_off, y_off, cylinder, xyz_cluster, raz_cluster, xy_center,
+                ra_center):
+    """pv_dynamic_pfn on a DynamicBatch (`batch`) with `m` valid voxel rows; weights: list of [U, K] CUDA f32."""
+    _need(points, torch.float32, "points", 2)
+    n, c = points.shape
+    arr = (PvPfnLayer * len(weights))()
+    for i, w in enumerate(weights):
+        _need(w, torch.float32, "pfn_layers.%d.linear.weight" % i, 2)
+        arr[i].weight = w.data_ptr()
+        arr[i].units, arr[i].in_channels = w.shape[0], w.shape[1]
+    dev = points.device
+    lib = _lib.load()
+    out = torch.empty((m, weights[-1].shape[0]), dtype=torch.float32, device=dev)
+    ws = workspace(max(256, lib.pv_dynamic_pfn_workspace_bytes(n, m)), dev, "dynpfn")
+    flags = (1 if xyz_cluster else 0) | (2 if raz_cluster else 0) | (4 if xy_center else 0) | (8 if ra_center else 0)
+    check(lib.pv_dynamic_pfn(ptr(points), ptr(batch.unq), ptr(batch.unq_inv), ptr(batch.unq_cnt), ptr(batch.mean_feats),
+                             n, m, c, 1 if cylinder else 0, flags, vx, vy, x_off, y_off, arr, len(weights),
+                             ptr(ws), ws.numel(), ptr(out), current_stream(dev)), "pv_dynamic_pfn")
+    return out
+
+
 def read_status(vb):
     rc = _lib.load().pv_read_status(ptr(vb.ws), current_stream(vb.ws.device))
     if rc != 0:

@@ -151,6 +151,51 @@ def _dynamic_from_grid_ind(features, grid_ind, grid_size, batch_size, want_inver
                               want_inverse=want_inverse)
 
 
+@READERS.register_module
+class DynamicPFNet(nn.Module):
+    """det3d/models/readers/pillar_encoder.py:262-411 (same constructor, forward(data) and state_dict keys;
+    the BatchNorm of each PFNLayer exists as in the reference but the dynamic forward never applies it)."""
+
+    def __init__(self, num_input_features=4, num_filters=(64,), voxel_shape="cuboid", xyz_cluster=False,
+                 raz_cluster=False, xy_center=False, ra_center=False, voxel_size=(0.2, 0.2, 4),
+                 pc_range=(0, -40, -3, 70.4, 40, 1), norm_cfg=None, grid_size=None, batch_size=None):
+        super().__init__()
+        self.name = "DynamicPFNet"
+        assert len(num_filters) > 0
+        self.num_input = num_input_features
+        self.voxel_shape = voxel_shape
+        self.xyz_cluster, self.raz_cluster = xyz_cluster, raz_cluster
+        self.xy_center, self.ra_center = xy_center, ra_center
+        if xyz_cluster:
+            num_input_features += 3
+        if xy_center:
+            num_input_features += 2
+        if raz_cluster:
+            num_input_features += 2 if xyz_cluster else 3
+        if ra_center:
+            num_input_features += 2
+        num_filters = [num_input_features] + list(num_filters)
+        self.pfn_layers = nn.ModuleList(
+            [PFNLayer(num_filters[i], num_filters[i + 1], norm_cfg=norm_cfg, last_layer=(i >= len(num_filters) - 2))
+             for i in range(len(num_filters) - 1)])
+        self.vx = voxel_size[0]
+        self.vy = voxel_size[1]
+        self.x_offset = self.vx / 2 + pc_range[0]
+        self.y_offset = self.vy / 2 + pc_range[1]
+        self.grid_size, self.batch_size = grid_size, batch_size
+
+    def forward(self, data):
+        points = data["points"].contiguous()
+        grid_ind = data["grid_ind"]
+        r = _dynamic_from_grid_ind(points, grid_ind, self.grid_size, self.batch_size, want_inverse=True)
+        m = r.total()
+        weights = [l.linear.weight.detach().contiguous() for l in self.pfn_layers]
+        feats = F.dynamic_pfn(points, r, m, weights, self.vx, self.vy, self.x_offset, self.y_offset,
+                              self.voxel_shape != "cuboid", self.xyz_cluster, self.raz_cluster, self.xy_center,
+                              self.ra_center)
+        return feats, r.unq[:m].to(torch.int64)
+
+
 @BACKBONES.register_module
 class DynamicPPScatter(nn.Module):
     """det3d/models/readers/pillar_encoder.py:413-432."""

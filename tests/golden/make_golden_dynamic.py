@@ -56,6 +56,13 @@ def main():
         return out / cnt.clamp(min=1).view(-1, *([1] * (src.dim() - 1)))
     torch_scatter.scatter_mean = scatter_mean
 
+    def scatter_max(src, index, dim=0):
+        m = int(index.max()) + 1
+        out = torch.full((m,) + tuple(src.shape[1:]), float("-inf"), dtype=src.dtype)
+        out = out.scatter_reduce(0, index.view(-1, *([1] * (src.dim() - 1))).expand_as(src), src, "amax", include_self=True)
+        return out, None
+    torch_scatter.scatter_max = scatter_max
+
     g = synth.GRIDS["NUSC-PILLAR"]
     vg = ref["VoxelGenerator"](g["voxel_size"], g["range"], g["max_points"], g["max_voxels"])
     nusc = synth.nusc_frame(21)
@@ -73,12 +80,29 @@ def main():
         feats, unq = enc(dict(points=torch.from_numpy(pts), grid_ind=torch.from_numpy(gi4.astype(np.int64))))
         _, inv, cnt = torch.unique(torch.from_numpy(gi4.astype(np.int64)), return_inverse=True, return_counts=True, dim=0)
         canvas = ref["pe"].DynamicPPScatter()(feats, unq, len(frames), [512, 512, 1]).numpy()
+    # ---- DynamicPFNet (pillar_encoder.py:262-411): the polarstream config (all four decorations,
+    # [64, 128] filters, reader left at voxel_shape='cuboid') and a cylinder-shaped single-layer one
+    pfn = {}
+    gl = torch.from_numpy(gi4.astype(np.int64))
+    with torch.no_grad():
+        for tag, shape, filters, flags in (("pfn_cuboid_64_128", "cuboid", (64, 128), dict(xyz_cluster=True, raz_cluster=True, xy_center=True, ra_center=True)),
+                                           ("pfn_cyl_64", "cylinder", (64,), dict(xyz_cluster=True, raz_cluster=True, xy_center=True, ra_center=True)),
+                                           ("pfn_cyl_raz_32_64", "cylinder", (32, 64), dict(raz_cluster=True, ra_center=True))):
+            torch.manual_seed(1)
+            net = ref["pe"].DynamicPFNet(num_input_features=7, num_filters=filters, voxel_shape=shape,
+                                         voxel_size=g["voxel_size"], pc_range=g["range"], **flags)
+            net.eval()
+            o, u = net(dict(points=torch.from_numpy(pts), grid_ind=gl))
+            pfn[f"{tag}_out"] = o.numpy()
+            for i, l in enumerate(net.pfn_layers):
+                pfn[f"{tag}_w{i}"] = l.linear.weight.numpy()
+            assert np.array_equal(u.numpy(), unq.numpy())
     nzi = np.flatnonzero(canvas.reshape(-1))
     out = dict(voxel_size=vg.voxel_size, range=vg.point_cloud_range, grid_size=vg.grid_size,
                sizes=np.array([f.shape[0] for f in frames], np.int64), cart=np.concatenate(frames), polar=pts,
                grid_ind=gi4.astype(np.int32), features=feats.numpy(), unq=unq.numpy().astype(np.int32),
                unq_inv=inv.numpy(), unq_cnt=cnt.numpy(), canvas_shape=np.array(canvas.shape, np.int64),
-               canvas_idx=nzi.astype(np.int64), canvas_val=canvas.reshape(-1)[nzi])
+               canvas_idx=nzi.astype(np.int64), canvas_val=canvas.reshape(-1)[nzi], **pfn)
     np.savez_compressed(os.path.join(HERE, "dynamic.npz"), **out)
     print("dynamic: N=%d M=%d frames=%d" % (pts.shape[0], feats.shape[0], len(frames)))
 

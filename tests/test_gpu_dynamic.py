@@ -119,3 +119,59 @@ def test_dynamic_rejects_bad_rows_and_large_grids():
     big, _ = _cfg("WAYMO-PARTNER")                         # 1152 x 2048 x 40 cells: no direct map
     with pytest.raises(ValueError):
         F.dynamic_voxelize(big, pts, torch.tensor([0, 3], dtype=torch.int32).cuda(), 1, 3, False)
+
+
+PFN_CASES = [("pfn_cuboid_64_128", "cuboid", (64, 128), dict(xyz_cluster=True, raz_cluster=True, xy_center=True, ra_center=True)),
+             ("pfn_cyl_64", "cylinder", (64,), dict(xyz_cluster=True, raz_cluster=True, xy_center=True, ra_center=True)),
+             ("pfn_cyl_raz_32_64", "cylinder", (32, 64), dict(raz_cluster=True, ra_center=True))]
+
+
+@pytest.mark.parametrize("tag,shape,filters,flags", PFN_CASES)
+def test_dynamic_pfnet_matches_reference_golden(tag, shape, filters, flags, golden_dir):
+    """Drop-in DynamicPFNet with the reference's weights (state_dict keys of the reference) on the
+    reference's points + grid_ind -> the reference module's own output."""
+    import torch
+    from partner_b200.readers import DynamicPFNet
+    g = np.load(os.path.join(golden_dir, "dynamic.npz"))
+    gcfg = synth.GRIDS["NUSC-PILLAR"]
+    net = DynamicPFNet(num_input_features=7, num_filters=filters, voxel_shape=shape, voxel_size=gcfg["voxel_size"],
+                       pc_range=gcfg["range"], **flags)
+    sd = net.state_dict()
+    for i in range(len(filters)):
+        key = "pfn_layers.%d.linear.weight" % i
+        assert key in sd and tuple(sd[key].shape) == g[f"{tag}_w{i}"].shape
+        sd[key] = torch.from_numpy(g[f"{tag}_w{i}"])
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    feats, unq = net(dict(points=torch.from_numpy(g["polar"]).cuda(),
+                          grid_ind=torch.from_numpy(g["grid_ind"].astype(np.int64)).cuda()))
+    assert np.array_equal(unq.cpu().numpy(), g["unq"])
+    assert_close_fp32(feats.cpu().numpy(), g[f"{tag}_out"], tag)
+
+
+def test_dynamic_pfnet_full_size_vs_oracle():
+    """Whole pipeline at frame size: fused Cartesian voxelization -> DynamicPFNet (polarstream reader config)."""
+    import torch
+    from partner_b200 import functional as F
+    cfg, g = _cfg()
+    frames = synth.make_batch("nusc", 3, 2)
+    sizes = [f.shape[0] for f in frames]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    polars = [oracle.transform_points(f) for f in frames]
+    polar = np.concatenate(polars)
+    gi = np.concatenate([np.pad(oracle.dynamic_grid_ind(p, g["voxel_size"], g["range"]), ((0, 0), (1, 0)),
+                                constant_values=b) for b, p in enumerate(polars)])
+    mean, unq, inv, cnt = oracle.dynamic_mean(gi, polar)
+    rng = np.random.default_rng(0)
+    ws = [rng.normal(0, 0.2, (32, 16)).astype(np.float32), rng.normal(0, 0.1, (128, 64)).astype(np.float32)]
+    flags = dict(xyz_cluster=True, raz_cluster=True, xy_center=True, ra_center=True)
+    ref = oracle.dynamic_pfn(polar, inv, unq, ws, g["voxel_size"], g["range"], "cuboid", **flags)
+    pts = torch.from_numpy(np.concatenate(frames)).cuda()
+    r = F.dynamic_voxelize(cfg, pts, torch.from_numpy(off).cuda(), len(frames), max(sizes), True)
+    m = r.total()
+    assert np.array_equal(r.unq[:m].cpu().numpy(), unq)
+    polar_dev = F.transform_points(pts)                    # the rows the reader sees (bit-exact vs the oracle)
+    vx, vy = g["voxel_size"][0], g["voxel_size"][1]
+    out = F.dynamic_pfn(polar_dev, r, m, [torch.from_numpy(w).cuda() for w in ws], vx, vy,
+                        vx / 2 + g["range"][0], vy / 2 + g["range"][1], False, True, True, True, True)
+    assert_close_fp32(out.cpu().numpy(), ref, "dynamic pfn")

@@ -125,3 +125,16 @@ def test_dynamic_grid_ind_and_mean_golden(golden_dir):
     assert_close_fp32(mean, g["features"], "scatter_mean")
     canvas, _ = oracle.scatter(mean, unq, len(sizes), [512, 512, 1])
     assert_close_fp32(canvas, densify(g["canvas_idx"], g["canvas_val"], g["canvas_shape"]), "canvas")
+
+
+@pytest.mark.parametrize("tag,shape,flags", [
+    ("pfn_cuboid_64_128", "cuboid", dict(xyz_cluster=True, raz_cluster=True, xy_center=True, ra_center=True)),
+    ("pfn_cyl_64", "cylinder", dict(xyz_cluster=True, raz_cluster=True, xy_center=True, ra_center=True)),
+    ("pfn_cyl_raz_32_64", "cylinder", dict(raz_cluster=True, ra_center=True))])
+def test_dynamic_pfn_golden(tag, shape, flags, golden_dir):
+    g = np.load(os.path.join(golden_dir, "dynamic.npz"))
+    ws = []
+    while f"{tag}_w{len(ws)}" in g.files:
+        ws.append(g[f"{tag}_w{len(ws)}"])
+    out = oracle.dynamic_pfn(g["polar"], g["unq_inv"], g["unq"], ws, g["voxel_size"], g["range"], shape, **flags)
+    assert_close_fp32(out, g[f"{tag}_out"], tag)
