@@ -4,6 +4,9 @@ Drop-in classes (same names / signatures as the reference):
     VoxelGenerator                         det3d/core/input/voxel_generator.py
     VoxelFeatureExtractorV3                det3d/models/readers/voxel_encoder.py
     PillarFeatureNet, PointPillarsScatter  det3d/models/readers/pillar_encoder.py
+    DynamicVoxelEncoderV1                  det3d/models/readers/voxel_encoder.py
+    DynamicPFNet, DynamicPPScatter         det3d/models/readers/pillar_encoder.py
+    Voxelization                           det3d/datasets/pipelines/voxelization.py (hard + double flip, dynamic)
     transform_points                       det3d/datasets/pipelines/utils.py
 and the fused batched path ``PolarFrontEnd``.  All compute runs in hand-written CUDA kernels
 reached through the C ABI of include/polar_voxel_b200.h; importing the package does not need a
@@ -20,7 +23,11 @@ def __getattr__(name):
     if name in ("VoxelGenerator",):
         from .voxel_generator import VoxelGenerator
         return VoxelGenerator
-    if name in ("VoxelFeatureExtractorV3", "PillarFeatureNet", "PointPillarsScatter", "PFNLayer"):
+    if name == "Voxelization":
+        from .voxelization import Voxelization
+        return Voxelization
+    if name in ("VoxelFeatureExtractorV3", "PillarFeatureNet", "PointPillarsScatter", "PFNLayer",
+                "DynamicVoxelEncoderV1", "DynamicPFNet", "DynamicPPScatter"):
         from . import readers
         return getattr(readers, name)
     if name in ("PolarFrontEnd", "shard_range"):

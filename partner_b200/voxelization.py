@@ -1,0 +1,120 @@
+"""Drop-in for det3d's ``Voxelization`` pipeline step (det3d/datasets/pipelines/voxelization.py:12-181,
+462-476) for the non-streaming paths: ``voxelize_hard`` (incl. double-flip test-time augmentation,
+:98-144) and ``voxelize_dynamic`` (:148-181).  Same constructor (``cfg=...``, ``super_tasks=...``),
+same ``__call__(res, info)`` and the same keys written into ``res["lidar"]``; numpy in, numpy out.
+
+The four voxelizations of a double-flip sample run as ONE batched launch sequence on the GPU.
+Azimuth-sector streaming (``nsectors > 1``, :305-460), ``transform_type == 'feature'`` and the
+training-time label assignment of ``get_grid_ind`` (:40-60) are "next" rows
+and raise ``NotImplementedError``; training-time ``filter_gt`` is the caller's job (it edits
+annotations, not points).
+"""
+import numpy as np
+
+from . import functional as F
+from .voxel_generator import VoxelGenerator
+
+
+def _get(cfg, key, default=None, required=False):
+    if isinstance(cfg, dict):
+        if required and key not in cfg:
+            raise KeyError(key)
+        return cfg.get(key, default)
+    if required:
+        return getattr(cfg, key)
+    return getattr(cfg, key, default) if not hasattr(cfg, "get") else cfg.get(key, default)
+
+
+class Voxelization(object):
+    def __init__(self, **kwargs):
+        cfg = kwargs.get("cfg", None)
+        self.dynamic = _get(cfg, "dynamic", False)
+        self.range = _get(cfg, "range", required=True)
+        self.voxel_size = _get(cfg, "voxel_size", required=True)
+        self.max_points_in_voxel = _get(cfg, "max_points_in_voxel", required=True)
+        mv = _get(cfg, "max_voxel_num", required=True)
+        self.max_voxel_num = [mv, mv] if isinstance(mv, int) else mv
+        self.voxel_generator = VoxelGenerator(voxel_size=self.voxel_size, point_cloud_range=self.range,
+                                              max_num_points=self.max_points_in_voxel,
+                                              max_voxels=self.max_voxel_num[0])
+        self.return_density = _get(cfg, "return_density", False)
+        self.double_flip = _get(cfg, "double_flip", False)
+        self.super_tasks = kwargs.get("super_tasks", ["det"])
+        self.nsectors = _get(cfg, "nsectors", 1)
+        self.return_pc_grid_ind = False
+        if "seg" in self.super_tasks:
+            self.return_pc_grid_ind = True
+            assert not self.double_flip, "currently not supporting double flip for segmentation"
+
+    # voxelization.py:40-60 (evaluation branch)
+    def get_grid_ind(self, res, pc_grid_ind, grid_size):
+        if res["mode"] in ["train", "debug_gt"]:
+            raise NotImplementedError("training-time voxel label assignment (AssignLabel.assign_voxel_labels) "
+                                      "is a 'next' row")
+        pc_grid_ind = pc_grid_ind[:res["lidar"]["n_key_points"]]
+        res["lidar"]["voxels"].update({"valid_grid_ind": pc_grid_ind.copy()})
+        return res
+
+    def _pack(self, out, f):
+        """Frame f of a generate_batch result -> the reference's per-sample dict (:79-87)."""
+        vg = self.voxel_generator
+        counts = out["num_voxels"].numpy()
+        lo = int(counts[:f].sum())
+        hi = lo + int(counts[f])
+        return dict(voxels=out["voxels"][lo:hi].cpu().numpy(), coordinates=out["coordinates"][lo:hi, 1:].cpu().numpy(),
+                    num_points=out["num_points"][lo:hi].cpu().numpy(), num_voxels=np.array([hi - lo], dtype=np.int64),
+                    shape=vg.grid_size, range=vg.point_cloud_range, size=vg.voxel_size)
+
+    def voxelize_hard(self, res, info):
+        vg = self.voxel_generator
+        max_voxels = self.max_voxel_num[0] if res["mode"] in ["train", "debug_gt"] else self.max_voxel_num[1]
+        double_flip = self.double_flip and (res["mode"] != "train")
+        if not double_flip:
+            voxels, coordinates, num_points, pc_grid_ind, density = vg.generate(
+                res["lidar"]["points"], max_voxels=max_voxels, return_pc_grid_ind=self.return_pc_grid_ind,
+                return_density=self.return_density)
+            res["lidar"]["voxels"] = dict(voxels=voxels, coordinates=coordinates, num_points=num_points,
+                                          num_voxels=np.array([voxels.shape[0]], dtype=np.int64),
+                                          shape=vg.grid_size, range=vg.point_cloud_range, size=vg.voxel_size)
+        else:
+            # :98-144 -- the flipped copies use the generator's default max_voxels, like the reference
+            main = vg.generate_batch([res["lidar"]["points"]], max_voxels=max_voxels,
+                                     return_pc_grid_ind=self.return_pc_grid_ind, return_density=self.return_density)
+            res["lidar"]["voxels"] = self._pack(main, 0)
+            pc_grid_ind = main["pc_grid_ind"].cpu().numpy() if self.return_pc_grid_ind else None
+            density = main["n_points"][0].cpu().numpy() if self.return_density else None
+            keys = ["yflip", "xflip", "double_flip"]
+            flips = vg.generate_batch([res["lidar"][k + "_points"] for k in keys])      # one launch sequence
+            for f, k in enumerate(keys):
+                res["lidar"][k + "_voxels"] = self._pack(flips, f)
+        if "seg" in self.super_tasks:
+            res = self.get_grid_ind(res, pc_grid_ind, vg.grid_size)
+            if "part" in self.super_tasks:
+                raise NotImplementedError("AssignLabel.assign_part_2d is outside the front end")
+        if self.return_density:
+            res["lidar"]["voxels"].update({"n_points": density})
+        return res, info
+
+    def voxelize_dynamic(self, res, info, **kwargs):
+        import torch
+        vg = self.voxel_generator
+        points = np.ascontiguousarray(res["lidar"]["points"], dtype=np.float32)
+        n = points.shape[0]
+        dev = torch.device("cuda", torch.cuda.current_device())
+        off = torch.tensor([0, n], dtype=torch.int32, device=dev)
+        r = F.dynamic_voxelize(vg._cfg, torch.from_numpy(points).to(dev), off, 1, n, False, want_inverse=False,
+                               want_counts=False, want_grid_ind=True)
+        F.read_status(r)
+        pc_grid_ind = r.grid_ind[:, 1:].cpu().numpy().astype(np.int64)       # (z, y, x), np.int of the reference
+        res["lidar"]["voxels"] = dict(grid_ind=pc_grid_ind.copy(), shape=vg.grid_size, range=vg.point_cloud_range,
+                                      size=vg.voxel_size)
+        if ("seg" in self.super_tasks) and kwargs.get("seg", True):
+            res = self.get_grid_ind(res, pc_grid_ind, vg.grid_size)
+        return res, info
+
+    def __call__(self, res, info):
+        if res["lidar"].get("transform_type") == "feature" or self.nsectors > 1:
+            raise NotImplementedError("sector / sweep streaming voxelization is a 'next' row (SURVEY.md 8f-2)")
+        if not self.dynamic:
+            return self.voxelize_hard(res, info)
+        return self.voxelize_dynamic(res, info)

@@ -175,3 +175,47 @@ def test_dynamic_pfnet_full_size_vs_oracle():
     out = F.dynamic_pfn(polar_dev, r, m, [torch.from_numpy(w).cuda() for w in ws], vx, vy,
                         vx / 2 + g["range"][0], vy / 2 + g["range"][1], False, True, True, True, True)
     assert_close_fp32(out.cpu().numpy(), ref, "dynamic pfn")
+
+
+def test_voxelization_pipeline_step_hard_double_flip_and_dynamic():
+    """partner_b200.Voxelization: the reference's res['lidar'] keys for hard voxelization with
+    double-flip TTA (voxelization.py:62-144) and for dynamic voxelization (:148-181)."""
+    from partner_b200 import Voxelization
+    g = synth.GRIDS["NUSC-PILLAR"]
+    cart = synth.nusc_frame(31)[:60000]
+    polar = oracle.transform_points(cart)
+
+    def flipped(fx, fy):
+        c = cart.copy()
+        if fy:
+            c[:, 1] = -c[:, 1]
+        if fx:
+            c[:, 0] = -c[:, 0]
+        return oracle.transform_points(c)
+    cfg = dict(range=g["range"], voxel_size=g["voxel_size"], max_points_in_voxel=20, max_voxel_num=[3000, 5000],
+               return_density=True, double_flip=True)
+    step = Voxelization(cfg=cfg)
+    res = dict(mode="val", lidar=dict(points=polar, yflip_points=flipped(False, True), xflip_points=flipped(True, False),
+                                      double_flip_points=flipped(True, True), transform_type="point"))
+    res, _ = step(res, {})
+    ref = oracle.VoxelGenerator(g["voxel_size"], g["range"], 20, 3000)
+    v, c, n, _, den = ref.generate(polar, max_voxels=5000, return_density=True)
+    got = res["lidar"]["voxels"]
+    assert np.array_equal(got["voxels"], v) and np.array_equal(got["coordinates"], c) and np.array_equal(got["num_points"], n)
+    assert np.array_equal(got["n_points"], den) and got["num_voxels"].tolist() == [v.shape[0]]
+    for key, pts in (("yflip", res["lidar"]["yflip_points"]), ("xflip", res["lidar"]["xflip_points"]),
+                     ("double_flip", res["lidar"]["double_flip_points"])):
+        v, c, n, _, _ = ref.generate(pts)                     # flipped copies: the generator's own cap (3000)
+        got = res["lidar"][key + "_voxels"]
+        assert np.array_equal(got["voxels"], v), key
+        assert np.array_equal(got["coordinates"], c) and np.array_equal(got["num_points"], n), key
+        assert got["num_voxels"].tolist() == [v.shape[0]]
+    dyn = Voxelization(cfg=dict(cfg, dynamic=True, double_flip=False), super_tasks=["det", "seg"])
+    res = dict(mode="val", lidar=dict(points=polar, n_key_points=1000, transform_type="point"))
+    res, _ = dyn(res, {})
+    gi = oracle.dynamic_grid_ind(polar, g["voxel_size"], g["range"])
+    assert res["lidar"]["voxels"]["grid_ind"].dtype == np.int64
+    assert np.array_equal(res["lidar"]["voxels"]["grid_ind"], gi)
+    assert np.array_equal(res["lidar"]["voxels"]["valid_grid_ind"], gi[:1000])
+    with pytest.raises(NotImplementedError):
+        Voxelization(cfg=dict(cfg, nsectors=4, double_flip=False))(dict(mode="val", lidar=dict(points=polar, transform_type="point")), {})

@@ -49,3 +49,26 @@ npts = np.mean([s[3] for s in sets])
 m = np.mean([int(o.voxel_counts.sum()) for _, o in graphs])
 print(json.dumps({"workload": "nusc_pillar_dynamic_mean_canvas_b8", "ms_per_step": ms, "Mpoints_per_s": npts / ms / 1e3,
                   "points": npts, "voxels": m, "launch": "cuda-graph replay, single stream"}))
+
+# ---- DynamicPFNet (polarstream reader config: 16-d decoration, Linear 16->32, 64->128) on the same batch ----
+rng = np.random.default_rng(0)
+ws = [torch.from_numpy(rng.normal(0, 0.2, (32, 16)).astype(np.float32)).to(dev),
+      torch.from_numpy(rng.normal(0, 0.1, (128, 64)).astype(np.float32)).to(dev)]
+vx, vy = g["voxel_size"][0], g["voxel_size"][1]
+pts, off, _, n = sets[0]
+polar = F.transform_points(pts)
+r = F.dynamic_voxelize(cfg, pts, off, B, cap, True, ws_tag=9)
+m = r.total()
+run = lambda: F.dynamic_pfn(polar, r, m, ws, vx, vy, vx / 2 + g["range"][0], vy / 2 + g["range"][1], False, True, True, True, True)
+for _ in range(3):
+    run()
+torch.cuda.synchronize()
+e0.record()
+for _ in range(20):
+    run()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 20
+flop = 2.0 * n * (16 * 32 * 2 + 64 * 128)          # layer 1 runs twice (pass A and B)
+print(json.dumps({"workload": "nusc_dynamic_pfnet_b8", "ms_per_step": ms, "Mpoints_per_s": n / ms / 1e3, "voxels": m,
+                  "fp32_TFLOPs": flop / ms / 1e9}))
