@@ -207,6 +207,24 @@ int pv_dynamic_pfn(const float *points, const int32_t *unq, const int32_t *unq_i
                    float vx, float vy, float x_off, float y_off, const pv_pfn_layer *layers, int32_t n_layers,
                    void *workspace, size_t workspace_bytes, float *out, pv_stream_t stream);
 
+/*
+ * Azimuth-sector streaming of ONE polar point cloud: the point path of
+ * Voxelization.voxelize_streaming_polar (det3d/datasets/pipelines/voxelization.py:305-371) for all
+ * `nsectors` wedges in one stable partition.  points [n, c >= 5] are cylinder rows
+ * (rho, phi, z, x, y, ...); wedge i keeps phi in [lo + i * iv, lo + (i+1) * iv) with
+ * iv = (max_azimuth - lo) / nsectors in float32 (first wedge open below, last open above, :350-358),
+ * shifts phi to the first wedge (:360), recomputes x, y = rho * cos / sin(phi) (:361-362) and takes
+ * floor(clip((p - lo) / vs, 0, cur_grid - 1)) with cur_grid[1] = ny / nsectors (:366-368).
+ * Outputs are sector-major, original order inside a sector (what np.where gives):
+ *   points_out f32 [n, c], grid_ind_out int32 [n, 3] (z, y, x), point_index int32 [n] (source row),
+ *   sector_counts int32 [nsectors]; rows [0, sum(sector_counts)) are valid (NaN azimuths are in no wedge).
+ * max_azimuth = pc_range[4] (cfg keeps only the lower bounds).
+ */
+size_t pv_stream_workspace_bytes(int64_t n, int32_t nsectors);
+int pv_stream_sectors(const pv_config *cfg, const float *points, int64_t n, int32_t c, int32_t nsectors,
+                      float max_azimuth, void *workspace, size_t workspace_bytes, float *points_out,
+                      int32_t *grid_ind_out, int32_t *point_index, int32_t *sector_counts, pv_stream_t stream);
+
 /* Copies the device status word of the last pv_voxelize on `workspace` to the host
  * (synchronises `stream`).  Returns PV_OK or PV_ERR_TABLE_FULL / PV_ERR_CUDA. */
 int pv_read_status(const void *workspace, pv_stream_t stream);

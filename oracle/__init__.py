@@ -243,3 +243,27 @@ def dynamic_pfn(points, unq_inv, unq, weights, voxel_size, pc_range, voxel_shape
     if rc:
         raise MemoryError("oracle: allocation failed")
     return out
+
+
+def stream_polar(points, voxel_size, point_cloud_range, nsectors):
+    """Voxelization.voxelize_streaming_polar (voxelization.py:305-371, evaluation path).
+
+    -> list of (points [n_s, C], grid_ind int32 [n_s, 3] (z, y, x), point_index int32 [n_s]) per sector."""
+    pts = _f32c(points)
+    n, c = pts.shape
+    vs = np.asarray(voxel_size, dtype=np.float32)
+    rg = np.asarray(point_cloud_range, dtype=np.float32)
+    op = np.empty((max(n, 1), c), np.float32)
+    gi = np.empty((max(n, 1), 3), np.int32)
+    ix = np.empty((max(n, 1),), np.int32)
+    cnt = np.zeros((nsectors,), np.int64)
+    L = lib()
+    L.po_stream_polar.restype = ctypes.c_int64
+    L.po_stream_polar(_p(pts), ctypes.c_int64(n), ctypes.c_int(c), _p(vs), _p(rg), ctypes.c_int(nsectors),
+                      _p(op), _p(gi), _p(ix), _p(cnt))
+    out, o = [], 0
+    for s in range(nsectors):
+        k = int(cnt[s])
+        out.append((op[o:o + k], gi[o:o + k], ix[o:o + k]))
+        o += k
+    return out

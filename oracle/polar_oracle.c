@@ -463,3 +463,61 @@ int po_dynamic_pfn(const float *points, const int64_t *unq_inv, const int32_t *u
     free(mean); free(cnt); free(cur); free(nxt); free(xmax);
     return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Voxelization.voxelize_streaming_polar -- the per-sector point selection,   */
+/* azimuth shift and grid index of det3d/datasets/pipelines/voxelization.py   */
+/* :305-371 (evaluation path; the training-time ground-truth rotation is      */
+/* annotation work, not part of the point path).                             */
+/*   interval = (max_az - min_az) / nsectors          (float32, numpy >= 2)   */
+/*   sector i keeps phi in [min_az + i*interval, min_az + (i+1)*interval),    */
+/*   the first sector is open below, the last one open above (:352-357);      */
+/*   phi -= (lo_i - min_az); x = rho*cos(phi); y = rho*sin(phi)   (:360-362)   */
+/*   grid_ind = floor(clip((p[:3] - lo) / vs, 0, cur_grid - 1))[::-1] with     */
+/*   cur_grid[1] = grid[1] // nsectors                             (:366-368)  */
+/* points [n, c] are cylinder rows (rho, phi, z, x, y, ...).  Outputs are      */
+/* sector-major, original order inside a sector: out_points [n, c],           */
+/* out_gi [n, 3] (z, y, x), out_index [n] original row, counts [nsectors].    */
+/* Returns the number of rows written (NaN azimuths belong to no sector).     */
+/* ------------------------------------------------------------------------- */
+int64_t po_stream_polar(const float *points, int64_t n, int c, const float *voxel_size,
+                        const float *range, int nsectors, float *out_points, int32_t *out_gi,
+                        int32_t *out_index, int64_t *counts)
+{
+    int32_t grid[3];
+    po_grid_size(voxel_size, range, grid);
+    const float min_az = range[1], max_az = range[4];
+    const float interval = (max_az - min_az) / (float)nsectors;
+    int32_t cur_grid[3] = {grid[0], grid[1] / nsectors, grid[2]};
+    int64_t w = 0;
+    for (int s = 0; s < nsectors; ++s) {
+        const float lo = min_az + (float)s * interval;
+        const float hi = min_az + (float)(s + 1) * interval;
+        const float shift = lo - min_az;
+        counts[s] = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            const float phi = points[i * c + 1];
+            int keep;
+            if (s == 0) keep = phi < hi;                       /* :352-353 (also when nsectors == 1) */
+            else if (s == nsectors - 1) keep = phi >= lo;      /* :354-355 */
+            else keep = phi >= lo && phi < hi;                 /* :356-357 */
+            if (!keep) continue;
+            float *o = out_points + w * c;
+            memcpy(o, points + i * c, (size_t)c * sizeof(float));
+            o[1] = phi - shift;                                /* :360 */
+            o[3] = o[0] * cosf(o[1]);                          /* :361 */
+            o[4] = o[0] * sinf(o[1]);                          /* :362 */
+            for (int j = 0; j < 3; ++j) {
+                float q = (o[j] - range[j]) / voxel_size[j];
+                const float top = (float)(cur_grid[j] - 1);
+                if (!(q >= 0.0f)) q = 0.0f;
+                if (q > top) q = top;
+                out_gi[w * 3 + (2 - j)] = (int32_t)floorf(q);
+            }
+            out_index[w] = (int32_t)i;
+            counts[s] += 1;
+            ++w;
+        }
+    }
+    return w;
+}

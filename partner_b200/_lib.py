@@ -87,6 +87,8 @@ EXPORTS = {
     "pv_dynamic_pfn_workspace_bytes": (SZ, [I64, I64]),
     "pv_dynamic_pfn": (ctypes.c_int, [P, P, P, P, P, I64, I64, I32, I32, I32, F32, F32, F32, F32,
                                       ctypes.POINTER(PvPfnLayer), I32, P, SZ, P, P]),
+    "pv_stream_workspace_bytes": (SZ, [I64, I32]),
+    "pv_stream_sectors": (ctypes.c_int, [ctypes.POINTER(PvConfig), P, I64, I32, I32, F32, P, SZ, P, P, P, P, P]),
     "pv_read_status": (ctypes.c_int, [P, P]),
     "pv_vfe_mean": (ctypes.c_int, [P, P, I64, I32, I32, P, P]),
     "pv_pfn_forward": (ctypes.c_int, [P, P, P, I64, I32, I32, I32, F32, F32, F32, F32,

@@ -233,6 +233,25 @@ def dynamic_pfn(points, batch, m, weights, vx, vy, x_off, y_off, cylinder, xyz_c
     return out
 
 
+def stream_sectors(cfg, points, nsectors, max_azimuth):
+    """pv_stream_sectors: (points_out [N, C], grid_ind [N, 3] (z, y, x), point_index [N], counts [nsectors])."""
+    _need(points, torch.float32, "points", 2)
+    n, c = points.shape
+    dev = points.device
+    lib = _lib.load()
+    nbytes = lib.pv_stream_workspace_bytes(n, nsectors)
+    if nbytes == 0:
+        raise ValueError("nsectors must be in [1, 64]")
+    ws = workspace(nbytes, dev, "stream")
+    out = torch.empty((max(n, 1), c), dtype=torch.float32, device=dev)
+    gi = torch.empty((max(n, 1), 3), dtype=torch.int32, device=dev)
+    idx = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+    counts = torch.empty((nsectors,), dtype=torch.int32, device=dev)
+    check(lib.pv_stream_sectors(cfg, ptr(points), n, c, nsectors, float(np.float32(max_azimuth)), ptr(ws), ws.numel(),
+                                ptr(out), ptr(gi), ptr(idx), ptr(counts), current_stream(dev)), "pv_stream_sectors")
+    return out, gi, idx, counts
+
+
 def read_status(vb):
     rc = _lib.load().pv_read_status(ptr(vb.ws), current_stream(vb.ws.device))
     if rc != 0:

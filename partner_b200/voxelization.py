@@ -4,9 +4,10 @@
 same ``__call__(res, info)`` and the same keys written into ``res["lidar"]``; numpy in, numpy out.
 
 The four voxelizations of a double-flip sample run as ONE batched launch sequence on the GPU.
-Azimuth-sector streaming (``nsectors > 1``, :305-460), ``transform_type == 'feature'`` and the
-training-time label assignment of ``get_grid_ind`` (:40-60) are "next" rows
-and raise ``NotImplementedError``; training-time ``filter_gt`` is the caller's job (it edits
+Polar azimuth-sector streaming (``nsectors > 1``, :305-371) runs as one stable GPU partition
+(evaluation path).  Cartesian sector streaming (:183-303), sweep streaming
+(``transform_type == 'feature'``, :373-460) and the training-time label assignment of
+``get_grid_ind`` (:40-60) are "next" rows and raise ``NotImplementedError``; training-time ``filter_gt`` is the caller's job (it edits
 annotations, not points).
 """
 import numpy as np
@@ -112,9 +113,54 @@ class Voxelization(object):
             res = self.get_grid_ind(res, pc_grid_ind, vg.grid_size)
         return res, info
 
+    def voxelize_streaming_polar(self, res, info, **kwargs):
+        """voxelization.py:305-371, evaluation path: all sectors in one stable GPU partition."""
+        import copy
+        import torch
+        if res["mode"] in ["train", "debug_gt"]:
+            raise NotImplementedError("training-time sector streaming (ground-truth filtering / rotation) is a 'next' row")
+        vg = self.voxel_generator
+        grid_size, pc_range, voxel_size = vg.grid_size, vg.point_cloud_range, vg.voxel_size
+        nsectors = self.nsectors
+        min_az, max_az = pc_range[1], pc_range[4]
+        interval = (max_az - min_az) / nsectors
+        cur_grid_size = grid_size.copy()
+        cur_grid_size[1] //= nsectors
+        ref_pc_range = pc_range.copy()
+        ref_pc_range[4] = min_az + interval
+        load_range = info["load_range"] if "load_range" in info else range(nsectors)
+        points = np.ascontiguousarray(res["lidar"]["points"], dtype=np.float32)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        out, gi, idx, counts = F.stream_sectors(vg._cfg, torch.from_numpy(points).to(dev), nsectors, max_az)
+        counts = counts.cpu().numpy()
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        out, gi, idx = out.cpu().numpy(), gi.cpu().numpy().astype(np.int64), idx.cpu().numpy().astype(np.int64)
+        lidar_rest = {k: v for k, v in res["lidar"].items() if k != "points"}
+        sectors = []
+        for i in load_range:
+            lo, hi = int(offs[i]), int(offs[i + 1])
+            cur_res = {k: copy.deepcopy(v) for k, v in res.items() if k != "lidar"}
+            cur_res["lidar"] = copy.deepcopy(lidar_rest)
+            cur_res["lidar"]["points"] = out[lo:hi].copy()
+            pc_grid_ind = gi[lo:hi]
+            cur_res["lidar"]["voxels"] = dict(grid_ind=pc_grid_ind.copy(), shape=cur_grid_size, range=ref_pc_range,
+                                              size=voxel_size)
+            if ("seg" in self.super_tasks) and kwargs.get("seg", True):
+                points_index = idx[lo:hi]
+                key_points_index = points_index[points_index < res["lidar"]["n_key_points"]]
+                cur_res["lidar"]["n_key_points"] = len(key_points_index)
+                cur_res["lidar"]["key_points_index"] = key_points_index
+                cur_res = self.get_grid_ind(cur_res, pc_grid_ind, cur_grid_size)
+            sectors.append(cur_res)
+        return {"sectors": sectors}, info
+
     def __call__(self, res, info):
-        if res["lidar"].get("transform_type") == "feature" or self.nsectors > 1:
-            raise NotImplementedError("sector / sweep streaming voxelization is a 'next' row (SURVEY.md 8f-2)")
+        if res["lidar"].get("transform_type") == "feature":
+            raise NotImplementedError("sweep streaming (transform_type == 'feature') is a 'next' row (SURVEY.md 8f-2)")
+        if self.nsectors > 1:
+            if res.get("voxel_shape", "cylinder") == "cuboid":
+                raise NotImplementedError("Cartesian sector streaming is outside the polar front end")
+            return self.voxelize_streaming_polar(res, info)
         if not self.dynamic:
             return self.voxelize_hard(res, info)
         return self.voxelize_dynamic(res, info)

@@ -218,4 +218,50 @@ def test_voxelization_pipeline_step_hard_double_flip_and_dynamic():
     assert np.array_equal(res["lidar"]["voxels"]["grid_ind"], gi)
     assert np.array_equal(res["lidar"]["voxels"]["valid_grid_ind"], gi[:1000])
     with pytest.raises(NotImplementedError):
-        Voxelization(cfg=dict(cfg, nsectors=4, double_flip=False))(dict(mode="val", lidar=dict(points=polar, transform_type="point")), {})
+        Voxelization(cfg=dict(cfg, nsectors=4, double_flip=False))(
+            dict(mode="val", voxel_shape="cuboid", lidar=dict(points=polar, transform_type="point")), {})
+
+
+@pytest.mark.parametrize("nsec", [1, 4, 8])
+def test_stream_sectors_matches_reference_golden(nsec, golden_dir):
+    """pv_stream_sectors vs the reference's own per-sector statements (tests/golden/stream.npz)."""
+    import torch
+    from partner_b200 import functional as F
+    g = np.load(os.path.join(golden_dir, "stream.npz"))
+    cfg, _ = _cfg()
+    out, gi, idx, counts = F.stream_sectors(cfg, torch.from_numpy(g["polar"]).cuda(), nsec, float(g["range"][4]))
+    counts = counts.cpu().numpy()
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    out, gi, idx = out.cpu().numpy(), gi.cpu().numpy(), idx.cpu().numpy()
+    for i in range(nsec):
+        lo, hi = offs[i], offs[i + 1]
+        ref_pts = g[f"n{nsec}_s{i}_points"]
+        assert np.array_equal(idx[lo:hi], g[f"n{nsec}_s{i}_index"])                 # selection + stable order
+        assert np.array_equal(gi[lo:hi], g[f"n{nsec}_s{i}_grid_ind"])
+        other = [k for k in range(ref_pts.shape[1]) if k not in (3, 4)]
+        assert np.array_equal(out[lo:hi][:, other], ref_pts[:, other])                 # shifted azimuth bit-exact
+        assert np.allclose(out[lo:hi][:, 3:5], ref_pts[:, 3:5], rtol=1e-6, atol=2e-5)  # cos / sin: a few ulp
+
+
+def test_voxelization_streaming_polar_vs_oracle():
+    """Full-size frame through Voxelization(nsectors=4) with the seg keys; oracle as the checker."""
+    from partner_b200 import Voxelization
+    g = synth.GRIDS["NUSC-PILLAR"]
+    polar = oracle.transform_points(synth.nusc_frame(33))
+    cfg = dict(range=g["range"], voxel_size=g["voxel_size"], max_points_in_voxel=20, max_voxel_num=[30000, 60000],
+               dynamic=True, nsectors=4)
+    step = Voxelization(cfg=cfg, super_tasks=["det", "seg"])
+    res, _ = step(dict(mode="val", voxel_shape="cylinder",
+                       lidar=dict(points=polar, n_key_points=30000, transform_type="point")), {})
+    secs = oracle.stream_polar(polar, g["voxel_size"], g["range"], 4)
+    assert len(res["sectors"]) == 4
+    for cur, (pts, gi, idx) in zip(res["sectors"], secs):
+        got = cur["lidar"]["points"]
+        other = [k for k in range(pts.shape[1]) if k not in (3, 4)]
+        assert np.array_equal(got[:, other], pts[:, other])
+        assert np.allclose(got[:, 3:5], pts[:, 3:5], rtol=1e-6, atol=2e-5)
+        assert np.array_equal(cur["lidar"]["voxels"]["grid_ind"], gi)
+        assert list(cur["lidar"]["voxels"]["shape"]) == [512, 128, 1]
+        key = idx[idx < 30000]
+        assert np.array_equal(cur["lidar"]["key_points_index"], key) and cur["lidar"]["n_key_points"] == len(key)
+        assert np.array_equal(cur["lidar"]["voxels"]["valid_grid_ind"], gi[:len(key)])

@@ -138,3 +138,19 @@ def test_dynamic_pfn_golden(tag, shape, flags, golden_dir):
         ws.append(g[f"{tag}_w{len(ws)}"])
     out = oracle.dynamic_pfn(g["polar"], g["unq_inv"], g["unq"], ws, g["voxel_size"], g["range"], shape, **flags)
     assert_close_fp32(out, g[f"{tag}_out"], tag)
+
+
+# ---- azimuth-sector streaming: golden from tests/golden/make_golden_stream.py ----
+@pytest.mark.parametrize("nsec", [1, 4, 8])
+def test_stream_polar_golden(nsec, golden_dir):
+    g = np.load(os.path.join(golden_dir, "stream.npz"))
+    secs = oracle.stream_polar(g["polar"], g["voxel_size"], g["range"], nsec)
+    assert len(secs) == nsec
+    for i, (pts, gi, idx) in enumerate(secs):
+        ref_pts = g[f"n{nsec}_s{i}_points"]
+        assert np.array_equal(idx, g[f"n{nsec}_s{i}_index"])                  # which points, in which order
+        assert np.array_equal(gi, g[f"n{nsec}_s{i}_grid_ind"])
+        other = [k for k in range(pts.shape[1]) if k not in (3, 4)]
+        assert np.array_equal(pts[:, other], ref_pts[:, other])                  # incl. the shifted azimuth: bit-exact
+        # x, y = rho * cos / sin(phi): numpy's float32 cos / sin are vendor SIMD routines (not reproducible)
+        assert np.allclose(pts[:, 3:5], ref_pts[:, 3:5], rtol=1e-6, atol=2e-5)
