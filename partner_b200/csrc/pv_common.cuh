@@ -90,42 +90,12 @@ struct PvParams {
     int32_t *unq_inv;         // [N] voxel row of every point, or NULL
 };
 
-// ---------------------------------------------------------------------------------------------
-// Scan payload (64 bit): [63:62] look-back flag | [61] segment flag | [60:31] rank | [30:0] ksum.
-// rank = first points seen since the last frame start (segmented by frame), ksum = running sum
-// of min(count, T) over first points (global: offsets into kept[]).
-// ---------------------------------------------------------------------------------------------
-#define PV_KBITS 31
-#define PV_KMASK ((1ull << PV_KBITS) - 1)
-#define PV_SEG (1ull << 61)
-#define PV_RANK_ONE (1ull << PV_KBITS)
-#define PV_VAL_MASK ((1ull << 62) - 1)
-__device__ __forceinline__ unsigned long long pv_comb(unsigned long long a, unsigned long long b)
-{
-    const unsigned long long ks = (a & PV_KMASK) + (b & PV_KMASK);
-    const unsigned long long ah = a & ~PV_KMASK, bh = b & ~PV_KMASK;
-    return ((b & PV_SEG) ? bh : ah + bh) | ks;
-}
-__device__ __forceinline__ uint32_t pv_rank(unsigned long long v) { return (uint32_t)((v >> PV_KBITS) & 0x3FFFFFFFull); }
-__device__ __forceinline__ uint32_t pv_ksum(unsigned long long v) { return (uint32_t)(v & PV_KMASK); }
-
 __device__ __forceinline__ uint32_t pv_ld_volatile(const uint32_t *p)
 {
     uint32_t v;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-__device__ __forceinline__ unsigned long long pv_ld_volatile64(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void pv_st_volatile64(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 // L2 residency control (B200: 126 MB L2).  Point rows are read twice per call -- streamed by
 // k_bin_insert, gathered again by k_emit -- so their first read asks L2 to keep them
 // (evict_last), while write-once outputs are stored evict_first.

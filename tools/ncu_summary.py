@@ -48,6 +48,20 @@ for r in rows[2:]:
             k[key] = v * SCALE.get(units[i], 1.0)
     if "dram_read_bytes" in k:
         k["dram_traffic_bytes"] = k["dram_read_bytes"] + k.get("dram_write_bytes", 0.0)
+    if "dram_pct" not in k:      # this ncu reports the DRAM share per direction
+        tot = 0.0
+        for name in ("dram__bytes_read.sum.pct_of_peak_sustained_elapsed", "dram__bytes_write.sum.pct_of_peak_sustained_elapsed"):
+            if name in hdr:
+                try:
+                    tot += float(r[hdr.index(name)].replace(",", ""))
+                except ValueError:
+                    pass
+        k["dram_pct"] = tot
+    if "lts__t_tag_requests.avg.pct_of_peak_sustained_elapsed" in hdr:
+        try:
+            k["l2_tag_pct"] = float(r[hdr.index("lts__t_tag_requests.avg.pct_of_peak_sustained_elapsed")].replace(",", ""))
+        except ValueError:
+            pass
     kernels.append(k)
 
 launch_src = os.path.join(ROOT, "gpurun_out", "launches_%s.csv" % tag)
