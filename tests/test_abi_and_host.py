@@ -94,3 +94,37 @@ def test_synthetic_generator_reproduces_survey_statistics():
     w = synth.waymo_frame(0, nsweeps=1)
     assert w.shape == (169_600, 6)
     assert synth.waymo_frame(0, nsweeps=1, time_column=False).shape == (169_600, 5)
+
+
+def test_new_entry_points_validate_arguments_on_the_host():
+    """Argument checks of the dynamic / streaming entry points return before any CUDA call."""
+    lib = _lib.load()
+    from partner_b200.functional import make_config
+    cfg, _, _, _ = make_config([0.098, 0.0123, 8], [0.3, -3.1488, -5, 50.476, 3.1488, 3], 20, 60000)
+    N = ctypes.c_void_p(0)
+    assert lib.pv_set_pipeline(7) == -2 and lib.pv_set_pipeline(0) == 0
+    assert lib.pv_profile_pipeline(cfg) == 2                                  # direct map -> list-free
+    big, _, _, _ = make_config([0.065, 0.00307, 0.15], [0.3, -3.14368, -2.0, 75.18, 3.14368, 4.0], 5, 150000)
+    assert lib.pv_profile_pipeline(big) == 1                                  # hash map -> list-based
+    assert lib.pv_dynamic_voxelize(cfg, N, N, N, 1, 10, 5, 1, 100, 100, N, 0, N, N, N, N, N, N, N, N) == -2
+    assert lib.pv_stream_workspace_bytes(1000, 0) == 0 and lib.pv_stream_workspace_bytes(1000, 65) == 0
+    assert lib.pv_stream_workspace_bytes(1000, 4) > 0
+    assert lib.pv_stream_sectors(cfg, N, 10, 4, 4, 3.1488, N, 0, N, N, N, N, N) == -2      # c < 5
+    assert lib.pv_dynamic_pfn_workspace_bytes(1000, 100) > 0 and lib.pv_dynamic_pfn_workspace_bytes(-1, 1) == 0
+    layers = (_lib.PvPfnLayer * 3)()
+    assert lib.pv_dynamic_pfn(N, N, N, N, N, 10, 5, 7, 0, 15, 0.1, 0.1, 0.0, 0.0, layers, 3, N, 0, N, N) == -6   # 3 layers
+    assert lib.pv_dynamic_pfn(N, N, N, N, N, 10, 0, 7, 0, 15, 0.1, 0.1, 0.0, 0.0, layers, 2, N, 0, N, N) == 0    # no voxels
+
+
+def test_dynamic_reader_state_dict_keys_match_reference():
+    """pillar_encoder.py:262-335: DynamicPFNet keeps the PFNLayer parameter names (norm included, unused)."""
+    from partner_b200 import DynamicPFNet
+    net = DynamicPFNet(num_input_features=7, num_filters=[64, 128], xyz_cluster=True, raz_cluster=True, xy_center=True,
+                       ra_center=True, voxel_size=[0.098, 0.0123, 8], pc_range=[0.3, -3.1488, -5.0, 50.476, 3.1488, 3.0])
+    assert tuple(net.pfn_layers[0].linear.weight.shape) == (32, 16)
+    assert tuple(net.pfn_layers[1].linear.weight.shape) == (128, 64)
+    keys = set(net.state_dict())
+    for i in range(2):
+        for name in ("linear.weight", "norm.weight", "norm.bias", "norm.running_mean", "norm.running_var"):
+            assert f"pfn_layers.{i}.{name}" in keys
+    assert net.voxel_shape == "cuboid"                 # the reference's default, which its configs rely on
