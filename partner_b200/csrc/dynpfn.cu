@@ -359,7 +359,7 @@ int pv_dynamic_pfn(const float *points, const int32_t *unq, const int32_t *unq_i
     const size_t smem = sizeof(float) * ((size_t)c0p * q.u1 + (q.u2 ? (size_t)in2 * q.u2 : 0) + DP_VB * 12 +
                                          (size_t)DP_VB * q.u1 + (size_t)DP_VB * q.u2 + (size_t)DP_PC * c0p + (size_t)DP_PC * in2);
     if (smem > 200 * 1024) return PV_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024 &&
+    if (smem + 1024 > 48 * 1024 &&
         cudaFuncSetAttribute(k_dyn_pfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return PV_ERR_CUDA;
     k_dyn_pfn<<<(unsigned)((m + DP_VB - 1) / DP_VB), DP_THREADS, smem, st>>>(q);

@@ -826,7 +826,8 @@ static int pf_launch_insert(const PvParams &p, const PvF &f, cudaStream_t st)
     const unsigned grid = (p.n + PF_TILE - 1) / PF_TILE;
     const size_t smem = (size_t)PF_TILE * p.c_in * sizeof(float);
     auto kern = kf_insert<DENSE, CIN, CART, NV, DYN>;
-    if (smem > 48 * 1024 &&
+    // the 48 KB default covers dynamic + static shared memory (the kernel has a few static words)
+    if (smem + 1024 > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return PV_ERR_CUDA;
     kern<<<grid, PF_THREADS, smem, st>>>(p, f);
