@@ -166,3 +166,47 @@ def test_random_dynamic_pfnet_vs_oracle(seed):
     out = F.dynamic_pfn(d, r, m, [torch.from_numpy(w).cuda() for w in ws], vs[0], vs[1], vs[0] / 2 + rg[0], vs[1] / 2 + rg[1],
                         shape != "cuboid", flags["xyz_cluster"], flags["raz_cluster"], flags["xy_center"], flags["ra_center"])
     assert_close_fp32(out.cpu().numpy(), ref, "dynamic pfn %s %s" % (shape, flags))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_static_readers_vs_oracle(seed):
+    """Random padded voxel tensors (M, T, C, fill levels incl. full and single-point voxels) and random
+    PFN stacks (1-3 layers, widths, with_distance) through pv_vfe_mean / pv_pfn_forward / pv_scatter."""
+    import torch
+    from partner_b200 import functional as F
+    rng = np.random.default_rng(2000 + seed)
+    m = int(rng.choice([1, 2, 257, 5000, 40000]))
+    t = int(rng.choice([1, 5, 20, 32]))
+    c = int(rng.choice([4, 5, 7, 9]))
+    nx, ny, B = int(rng.integers(8, 200)), int(rng.integers(8, 200)), int(rng.integers(1, 4))
+    num = rng.integers(1, t + 1, m).astype(np.int32)
+    if rng.random() < 0.3:
+        num[:] = t                                          # every voxel full: no padded slot anywhere
+    vox = rng.normal(0, 3, (m, t, c)).astype(np.float32)
+    vox *= (np.arange(t)[None, :, None] < num[:, None, None])                 # zero padding, as points_to_voxel leaves it
+    cells = rng.choice(B * ny * nx, size=min(m, B * ny * nx), replace=False)
+    m = len(cells)
+    vox, num = vox[:m], num[:m]
+    coors = np.stack([cells // (ny * nx), np.zeros(m, np.int64), (cells // nx) % ny, cells % nx], 1).astype(np.int32)
+    dv, dn, dc = torch.from_numpy(vox).cuda(), torch.from_numpy(num).cuda(), torch.from_numpy(coors).cuda()
+    assert_close_fp32(F.vfe_mean(dv, dn).cpu().numpy(), oracle.vfe_mean(vox, num), "vfe_mean")
+    dist = bool(rng.integers(2))
+    nl = int(rng.integers(1, 4))
+    filters = [int(rng.choice([16, 32, 64, 128])) for _ in range(nl)]
+    vs, rg = [0.1, 0.02, 8.0], [0.3, -3.1, -5.0, 0.3 + 0.1 * nx, -3.1 + 0.02 * ny, 3.0]
+    width, layers, dev_layers = c + 5 + (1 if dist else 0), [], []
+    for i, fo in enumerate(filters):
+        u = fo if i == nl - 1 else fo // 2
+        L = dict(weight=rng.normal(0, 0.3, (u, width)).astype(np.float32), mean=rng.normal(0, 1, u).astype(np.float32),
+                 var=rng.uniform(0.5, 2, u).astype(np.float32), gamma=rng.normal(0, 1, u).astype(np.float32),
+                 beta=rng.normal(0, 1, u).astype(np.float32))
+        layers.append(L)
+        dev_layers.append(tuple(torch.from_numpy(L[k]).cuda() for k in ("weight", "mean", "var", "gamma", "beta")))
+        width = u if i == nl - 1 else 2 * u
+    ref = oracle.pfn_forward(vox, num, coors, layers, vs, rg, with_distance=dist, eps=1e-3)
+    out = F.pfn_forward(dv, dn, dc, dev_layers, vs[0], vs[1], vs[0] / 2 + rg[0], vs[1] / 2 + rg[1], dist, 1e-3)
+    assert_close_fp32(out.cpu().numpy(), ref, "pfn %s dist=%s m=%d t=%d c=%d" % (filters, dist, m, t, c))
+    canvas, bev = F.scatter(out, dc, B, ny, nx, want_bev_index=True)
+    rc, rb = oracle.scatter(ref, coors, B, [nx, ny, 1])
+    assert np.array_equal(bev.cpu().numpy(), rb)
+    assert_close_fp32(canvas.cpu().numpy(), rc, "canvas")
