@@ -75,12 +75,9 @@ __device__ __forceinline__ uint32_t pf_claim(uint32_t *keys, uint32_t mask, uint
 {
     uint32_t h = pv_hash(cell) & mask;
     for (uint32_t probe = 0; probe <= mask; ++probe) {
-        const uint32_t k = pv_ld_volatile(keys + h);
-        if (k == cell) return h;
-        if (k == PV_INF) {
-            const uint32_t old = atomicCAS(keys + h, PV_INF, cell);
-            if (old == PV_INF || old == cell) return h;
-        }
+        // CAS first: one L2 round trip whether the slot is free, already ours, or taken
+        const uint32_t old = atomicCAS(keys + h, PV_INF, cell);
+        if (old == PV_INF || old == cell) return h;
         h = (h + 1) & mask;
     }
     atomicOr(status, 1u);
