@@ -225,6 +225,13 @@ int pv_stream_sectors(const pv_config *cfg, const float *points, int64_t n, int3
                       float max_azimuth, void *workspace, size_t workspace_bytes, float *points_out,
                       int32_t *grid_ind_out, int32_t *point_index, int32_t *sector_counts, pv_stream_t stream);
 
+/* Rigid warp between sweeps of Voxelization.voxelize_streaming_by_sweep
+ * (det3d/datasets/pipelines/voxelization.py:439-447): out[:, :3] = float32(M[:3, :3] . xyz + M[:3, 3])
+ * evaluated in float64, out[:, c-1] = in[:, c-1] - t_shift (the time-lag fix), other columns copied.
+ * matrix3x4: HOST pointer to the first three rows of the 4 x 4 transform, row-major. */
+int pv_affine_points(const float *in, int64_t n, int32_t c, const double *matrix3x4, float t_shift,
+                     float *out, pv_stream_t stream);
+
 /* Copies the device status word of the last pv_voxelize on `workspace` to the host
  * (synchronises `stream`).  Returns PV_OK or PV_ERR_TABLE_FULL / PV_ERR_CUDA. */
 int pv_read_status(const void *workspace, pv_stream_t stream);

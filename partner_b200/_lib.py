@@ -89,6 +89,7 @@ EXPORTS = {
                                       ctypes.POINTER(PvPfnLayer), I32, P, SZ, P, P]),
     "pv_stream_workspace_bytes": (SZ, [I64, I32]),
     "pv_stream_sectors": (ctypes.c_int, [ctypes.POINTER(PvConfig), P, I64, I32, I32, F32, P, SZ, P, P, P, P, P]),
+    "pv_affine_points": (ctypes.c_int, [P, I64, I32, ctypes.POINTER(ctypes.c_double), F32, P, P]),
     "pv_read_status": (ctypes.c_int, [P, P]),
     "pv_vfe_mean": (ctypes.c_int, [P, P, I64, I32, I32, P, P]),
     "pv_pfn_forward": (ctypes.c_int, [P, P, P, I64, I32, I32, I32, F32, F32, F32, F32,

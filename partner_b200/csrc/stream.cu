@@ -187,3 +187,37 @@ int pv_stream_sectors(const pv_config *cfg, const float *points, int64_t n, int3
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Rigid warp of the xyz columns between sweeps (voxelize_streaming_by_sweep, voxelization.py:442-447:
+// points[:, :3] = (hstack(points[:, :3], 1) @ tm.T)[:, :3] in float64, stored back as float32) and
+// the time-lag fix of the last column (:439).  m = rows 0..2 of the 4 x 4 matrix, row-major.
+// ---------------------------------------------------------------------------------------------
+struct AffParams { double m[12]; float t_shift; };
+
+__global__ void __launch_bounds__(256) k_affine_points(const float *__restrict__ in, long long n, int c,
+                                                       const __grid_constant__ AffParams a, float *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *row = in + i * c;
+    float *o = out + i * c;
+    const double x = (double)row[0], y = (double)row[1], z = (double)row[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)      // dot product in the order numpy's matmul accumulates a length-4 row
+        o[r] = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, a.m[4 * r]), __dmul_rn(y, a.m[4 * r + 1])),
+                                          __dmul_rn(z, a.m[4 * r + 2])), a.m[4 * r + 3]);
+    for (int k = 3; k < c; ++k) o[k] = k == c - 1 ? __fsub_rn(row[k], a.t_shift) : row[k];
+}
+
+extern "C" int pv_affine_points(const float *in, int64_t n, int32_t c, const double *matrix3x4, float t_shift,
+                                float *out, pv_stream_t stream)
+{
+    if (n < 0 || c < 3 || !matrix3x4 || (n > 0 && (!in || !out))) return PV_ERR_BAD_ARGUMENT;
+    if (n == 0) return PV_OK;
+    AffParams a;
+    for (int k = 0; k < 12; ++k) a.m[k] = matrix3x4[k];
+    a.t_shift = t_shift;
+    k_affine_points<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, n, c, a, out);
+    return pv_last_cuda_error();
+}

@@ -252,6 +252,21 @@ def stream_sectors(cfg, points, nsectors, max_azimuth):
     return out, gi, idx, counts
 
 
+def affine_points(points, matrix, t_shift=0.0):
+    """pv_affine_points: xyz <- M[:3, :3] . xyz + M[:3, 3] (float64 arithmetic), last column -= t_shift."""
+    import ctypes
+    _need(points, torch.float32, "points", 2)
+    n, c = points.shape
+    m = np.ascontiguousarray(np.asarray(matrix, dtype=np.float64)[:3, :4])
+    if m.shape != (3, 4):
+        raise ValueError("matrix must be 4 x 4 (or 3 x 4)")
+    out = torch.empty_like(points)
+    check(_lib.load().pv_affine_points(ptr(points), n, c, m.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                       float(np.float32(t_shift)), ptr(out), current_stream(points.device)),
+          "pv_affine_points")
+    return out
+
+
 def read_status(vb):
     rc = _lib.load().pv_read_status(ptr(vb.ws), current_stream(vb.ws.device))
     if rc != 0:

@@ -5,8 +5,9 @@ same ``__call__(res, info)`` and the same keys written into ``res["lidar"]``; nu
 
 The four voxelizations of a double-flip sample run as ONE batched launch sequence on the GPU.
 Polar azimuth-sector streaming (``nsectors > 1``, :305-371) runs as one stable GPU partition
-(evaluation path).  Cartesian sector streaming (:183-303), sweep streaming
-(``transform_type == 'feature'``, :373-460) and the training-time label assignment of
+(evaluation path); sweep streaming with bidirectional padding (``transform_type == 'feature'``,
+cylinder branch of :393-460) composes the GPU warp, cylinder transform and sector partition.
+Cartesian sector / sweep streaming (:183-303, :404-422) and the training-time label assignment of
 ``get_grid_ind`` (:40-60) are "next" rows and raise ``NotImplementedError``; training-time ``filter_gt`` is the caller's job (it edits
 annotations, not points).
 """
@@ -154,9 +155,49 @@ class Voxelization(object):
             sectors.append(cur_res)
         return {"sectors": sectors}, info
 
+    def voxelize_streaming_by_sweep(self, res, info):
+        """voxelization.py:393-460, cylinder branch (bidirectional padding): the later sweeps as they are
+        and the earlier sweeps warped back by one pose, each through transform_points +
+        voxelize_streaming_polar; the warp, the cylinder transform and the sector partition run on the GPU."""
+        import copy
+        import torch
+        if res.get("voxel_shape", "cylinder") == "cuboid":
+            raise NotImplementedError("Cartesian sweep streaming is outside the polar front end")
+        if res["mode"] in ["train", "debug_gt"]:
+            raise NotImplementedError("training-time sweep streaming is a 'next' row")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        npoints_sweep = np.cumsum(res["lidar"]["npoints_sweep"])
+        nsweeps = len(npoints_sweep)
+        npoints_sweep = np.insert(npoints_sweep, 0, 0)
+        pivot = nsweeps - 1
+        points = np.ascontiguousarray(res["lidar"]["points"], dtype=np.float32)
+        rest = {k: v for k, v in res.items() if k != "lidar"}
+        lidar_rest = {k: v for k, v in res["lidar"].items() if k != "points"}
+
+        def run(cart_dev, seg, extra=None):
+            cur = copy.deepcopy(rest)
+            if extra:
+                cur.update(extra)
+            cur["lidar"] = copy.deepcopy(lidar_rest)
+            polar = F.transform_points(cart_dev[:, :5].contiguous(), "cylinder")          # utils.py:34-44
+            cur["lidar"]["points"] = polar.cpu().numpy()
+            out, _ = self.voxelize_streaming_polar(cur, info, seg=seg)
+            return out["sectors"]
+
+        # later sweeps (:424-429)
+        later = run(torch.from_numpy(points[:npoints_sweep[pivot]]).to(dev), True)
+        # earlier sweeps, warped back to the previous pose (:431-449)
+        prev = points[npoints_sweep[1]:]
+        tm = np.linalg.inv(res["lidar"]["transform_matrices"][1])
+        t0 = prev[0, -1] if prev.shape[0] else np.float32(0)
+        warped = F.affine_points(torch.from_numpy(np.ascontiguousarray(prev)).to(dev), tm, t0)
+        earlier = run(warped, False, extra={"transform_matrix": tm[:2, :2]})
+        sweeps = earlier + later
+        return {"sweeps": sweeps, "nsweeps": 2, "nsectors": len(earlier)}, info
+
     def __call__(self, res, info):
         if res["lidar"].get("transform_type") == "feature":
-            raise NotImplementedError("sweep streaming (transform_type == 'feature') is a 'next' row (SURVEY.md 8f-2)")
+            return self.voxelize_streaming_by_sweep(res, info)
         if self.nsectors > 1:
             if res.get("voxel_shape", "cylinder") == "cuboid":
                 raise NotImplementedError("Cartesian sector streaming is outside the polar front end")

@@ -265,3 +265,35 @@ def test_voxelization_streaming_polar_vs_oracle():
         key = idx[idx < 30000]
         assert np.array_equal(cur["lidar"]["key_points_index"], key) and cur["lidar"]["n_key_points"] == len(key)
         assert np.array_equal(cur["lidar"]["voxels"]["valid_grid_ind"], gi[:len(key)])
+
+
+def test_voxelization_sweep_streaming_bidirectional_vs_oracle():
+    """transform_type == 'feature', cylinder branch of voxelize_streaming_by_sweep (voxelization.py:393-460):
+    later sweeps + earlier sweeps warped back by one pose, each cut into azimuth sectors."""
+    from partner_b200 import Voxelization
+    g = synth.GRIDS["NUSC-PILLAR"]
+    pts = synth.nusc_frame(35, nsweeps=4)
+    counts = [int((pts[:, 4] == np.float32(0.05 * s)).sum()) for s in range(4)]
+    assert sum(counts) == pts.shape[0]
+    th = 0.03
+    tm1 = np.array([[np.cos(th), -np.sin(th), 0, 0.4], [np.sin(th), np.cos(th), 0, -0.1], [0, 0, 1, 0.02], [0, 0, 0, 1]])
+    mats = [np.eye(4), tm1, tm1 @ tm1, tm1 @ tm1 @ tm1]
+    cfg = dict(range=g["range"], voxel_size=g["voxel_size"], max_points_in_voxel=20, max_voxel_num=[30000, 60000],
+               dynamic=True, nsectors=4)
+    step = Voxelization(cfg=cfg)
+    res, _ = step(dict(mode="val", voxel_shape="cylinder",
+                       lidar=dict(points=pts, npoints_sweep=counts, transform_matrices=mats, transform_type="feature")), {})
+    assert res["nsweeps"] == 2 and res["nsectors"] == 4 and len(res["sweeps"]) == 8
+    cs = np.insert(np.cumsum(counts), 0, 0)
+    later = oracle.stream_polar(oracle.transform_points(np.ascontiguousarray(pts[:cs[3], :5])), g["voxel_size"], g["range"], 4)
+    p = pts[cs[1]:].copy()
+    p[:, -1] -= p[0, -1]
+    tm = np.linalg.inv(mats[1])
+    p[:, :3] = (np.hstack((p[:, :3], np.ones((p.shape[0], 1)))) @ tm.T)[:, :3]
+    earlier = oracle.stream_polar(oracle.transform_points(np.ascontiguousarray(p[:, :5])), g["voxel_size"], g["range"], 4)
+    assert np.allclose(res["sweeps"][0]["transform_matrix"], tm[:2, :2])
+    for cur, (rp, gi, idx) in zip(res["sweeps"], earlier + later):
+        got = cur["lidar"]["points"]
+        assert got.shape == rp.shape
+        assert np.allclose(got, rp, rtol=1e-6, atol=2e-5)          # float64 warp / cos / sin: last-bit differences
+        assert (cur["lidar"]["voxels"]["grid_ind"] != gi).sum() <= 2   # a warped coordinate within an ulp of a bin edge
