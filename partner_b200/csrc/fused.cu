@@ -91,7 +91,13 @@ __device__ __forceinline__ uint32_t pf_claim(uint32_t *keys, uint32_t mask, uint
 // DYN: dynamic voxelization (voxelization.py:169-172): bins are CLAMPED into the grid instead of
 // range-tested, every point lands in a cell; the cell's bit in the cell-order occupancy bitmap
 // replaces the first-point minimum (voxels are ordered by cell, not by first occurrence).
-template <bool DENSE, int CIN, bool CART, int NV, bool DYN = false>
+// MODE 2 (lists): the same binning front end for the list-based pipeline of voxelize.cu: per run
+// RED.MIN(first) + RED.ADD(count) on its {first, cnt} map, per point the map slot, the cleared scan
+// word and (hash maps) the cell index; no accumulator rows.
+#define PF_MODE_FREE 0
+#define PF_MODE_DYN 1
+#define PF_MODE_LISTS 2
+template <bool DENSE, int CIN, bool CART, int NV, int MODE = PF_MODE_FREE>
 __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ PvParams p,
                                                         const __grid_constant__ PvF f)
 {
@@ -100,6 +106,7 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
     __shared__ int s_b0;
     __shared__ uint32_t s_next;
     constexpr int CT = NV * 4;
+    constexpr bool DYN = MODE == PF_MODE_DYN, LISTS = MODE == PF_MODE_LISTS;
     const uint32_t tid = threadIdx.x;
     const int c_in = CIN ? CIN : p.c_in;
     const bool cart = CIN ? CART : (p.cart != 0);
@@ -157,6 +164,11 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
     uint32_t sa_out[PF_PPT];
     auto flush = [&]() {
         if (cur_s != PV_INF) {
+            if constexpr (LISTS) {           // list-based map entry {first, count - 1}
+                atomicMin(&p.ws.table[cur_s].first, cur_i);
+                atomicAdd(&p.ws.table[cur_s].cnt, (uint32_t)cur_n);
+                return;
+            }
             if constexpr (DYN) atomicOr(f.bits + (cur_i >> 5), 1u << (cur_i & 31u));   // cur_i = the cell's bit address
             else atomicMin(f.first + cur_s, cur_i);
             float o[CT];                     // the count rides in channel C of the row
@@ -227,7 +239,16 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
         const uint32_t cx = (uint32_t)(int)c0, cy = (uint32_t)(int)c1, cz = (uint32_t)(int)c2;
         const uint32_t cell = (cz * ny + cy) * nx + cx;
         uint32_t s, sa;
-        if (DYN) {
+        if (LISTS) {
+            if (DENSE) s = (uint32_t)b * p.ws.capf + (cz * nx + cx) * ny + cy;     // voxelize.cu's direct map: phi fastest
+            else {
+                const uint32_t h = pf_claim(p.ws.keys + (size_t)b * p.ws.capf, p.ws.capf - 1, cell, p.ws.ctrl + 1);
+                if (h == PV_INF) continue;
+                s = (uint32_t)b * p.ws.capf + h;
+                p.ws.pcell[i] = cell;
+            }
+            sa = s;
+        } else if (DYN) {
             s = (uint32_t)b * f.capf + cell;
             sa = (uint32_t)b * (f.wcap * 32u) + cell;            // bit address in the occupancy bitmap
         } else if (DENSE) {
@@ -242,9 +263,11 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
         }
         sa_out[j] = sa;
         if (s == cur_s) {
+            if constexpr (!LISTS) {
 #pragma unroll
-            for (int k = 0; k < CT; ++k)
-                if (k < C) cur[k] = __fadd_rn(cur[k], v[k]);
+                for (int k = 0; k < CT; ++k)
+                    if (k < C) cur[k] = __fadd_rn(cur[k], v[k]);
+            }
             cur_n += 1.0f;
         } else {
             flush();
@@ -255,12 +278,17 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
     }
     flush();
     if (DYN && !p.unq_inv) return;           // the per-point map is only needed for the inverse index
+    uint32_t *sa_dst = LISTS ? p.ws.slot : f.sa;
     if (t0 + PF_PPT <= n_tile) {
-        *reinterpret_cast<uint4 *>(f.sa + tile_base + t0) = make_uint4(sa_out[0], sa_out[1], sa_out[2], sa_out[3]);
+        *reinterpret_cast<uint4 *>(sa_dst + tile_base + t0) = make_uint4(sa_out[0], sa_out[1], sa_out[2], sa_out[3]);
+        if (LISTS) *reinterpret_cast<uint4 *>(p.ws.pv + tile_base + t0) = make_uint4(0u, 0u, 0u, 0u);
     } else {
 #pragma unroll
         for (int j = 0; j < PF_PPT; ++j)
-            if (t0 + j < n_tile) f.sa[tile_base + t0 + j] = sa_out[j];
+            if (t0 + j < n_tile) {
+                sa_dst[tile_base + t0 + j] = sa_out[j];
+                if (LISTS) p.ws.pv[tile_base + t0 + j] = 0u;
+            }
     }
 }
 
@@ -681,7 +709,7 @@ __global__ void __launch_bounds__(256) kf_heavy_cells(const __grid_constant__ Pv
 // DynamicVoxelEncoderV1 (models/readers/voxel_encoder.py:38-44) + DynamicPPScatter
 // (models/readers/pillar_encoder.py:413-432).  No max_points / max_voxels caps, voxels ordered by
 // (b, z, y, x) = cell order, so the rank of a cell is the popcount prefix of the CELL-order
-// occupancy bitmap that kf_insert<DYN> sets: insert -> scan -> finalize, three launches, and the
+// occupancy bitmap that kf_insert<PF_MODE_DYN> sets: insert -> scan -> finalize, three launches, and the
 // finalize pass writes every per-voxel output in increasing row order.
 // ---------------------------------------------------------------------------------------------
 template <int NV, int CC, bool CANVAS>
@@ -817,12 +845,12 @@ int pvf_init(const PvF &f, int32_t batch, int64_t n_cap, cudaStream_t st)
     return PV_OK;
 }
 
-template <bool DENSE, int CIN, bool CART, int NV, bool DYN = false>
+template <bool DENSE, int CIN, bool CART, int NV, int MODE = PF_MODE_FREE>
 static int pf_launch_insert(const PvParams &p, const PvF &f, cudaStream_t st)
 {
     const unsigned grid = (p.n + PF_TILE - 1) / PF_TILE;
     const size_t smem = (size_t)PF_TILE * p.c_in * sizeof(float);
-    auto kern = kf_insert<DENSE, CIN, CART, NV, DYN>;
+    auto kern = kf_insert<DENSE, CIN, CART, NV, MODE>;
     // the 48 KB default covers dynamic + static shared memory (the kernel has a few static words)
     if (smem + 1024 > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -849,16 +877,34 @@ static int pf_dispatch_insert(const PvParams &p, const PvF &f, cudaStream_t st)
     }
 }
 
+// Binning front end of the list-based pipeline (voxelize.cu): only the three coordinates matter.
+template <bool DENSE>
+static int pf_dispatch_insert_lists(const PvParams &p, const PvF &f, cudaStream_t st)
+{
+    if (p.n == 0) return PV_OK;
+    if (p.cart && p.c_in == 5) return pf_launch_insert<DENSE, 5, true, 2, PF_MODE_LISTS>(p, f, st);
+    if (p.cart && p.c_in == 6) return pf_launch_insert<DENSE, 6, true, 2, PF_MODE_LISTS>(p, f, st);
+    if (!p.cart && p.c_in == 7) return pf_launch_insert<DENSE, 7, false, 1, PF_MODE_LISTS>(p, f, st);
+    if (!p.cart && p.c_in == 8) return pf_launch_insert<DENSE, 8, false, 1, PF_MODE_LISTS>(p, f, st);
+    return p.cart ? pf_launch_insert<DENSE, 0, false, 2, PF_MODE_LISTS>(p, f, st)
+                  : pf_launch_insert<DENSE, 0, false, 1, PF_MODE_LISTS>(p, f, st);
+}
+
+int pvf_insert_lists(PvParams &p, PvF &f, cudaStream_t st)
+{
+    return p.ws.dense ? pf_dispatch_insert_lists<true>(p, f, st) : pf_dispatch_insert_lists<false>(p, f, st);
+}
+
 static int pf_dispatch_insert_dyn(const PvParams &p, const PvF &f, cudaStream_t st)
 {
-    if (p.cart && p.c_in == 5) return pf_launch_insert<true, 5, true, 2, true>(p, f, st);
-    if (!p.cart && p.c_in == 7) return pf_launch_insert<true, 7, false, 2, true>(p, f, st);
+    if (p.cart && p.c_in == 5) return pf_launch_insert<true, 5, true, 2, PF_MODE_DYN>(p, f, st);
+    if (!p.cart && p.c_in == 7) return pf_launch_insert<true, 7, false, 2, PF_MODE_DYN>(p, f, st);
     switch ((int)f.rowf / 4) {
-    case 1: return pf_launch_insert<true, 0, false, 1, true>(p, f, st);
-    case 2: return pf_launch_insert<true, 0, false, 2, true>(p, f, st);
-    case 3: return pf_launch_insert<true, 0, false, 3, true>(p, f, st);
-    case 4: return pf_launch_insert<true, 0, false, 4, true>(p, f, st);
-    default: return pf_launch_insert<true, 0, false, 5, true>(p, f, st);
+    case 1: return pf_launch_insert<true, 0, false, 1, PF_MODE_DYN>(p, f, st);
+    case 2: return pf_launch_insert<true, 0, false, 2, PF_MODE_DYN>(p, f, st);
+    case 3: return pf_launch_insert<true, 0, false, 3, PF_MODE_DYN>(p, f, st);
+    case 4: return pf_launch_insert<true, 0, false, 4, PF_MODE_DYN>(p, f, st);
+    default: return pf_launch_insert<true, 0, false, 5, PF_MODE_DYN>(p, f, st);
     }
 }
 

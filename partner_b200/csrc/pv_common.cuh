@@ -240,3 +240,4 @@ int pvf_init(const PvF &f, int32_t batch, int64_t n_cap, cudaStream_t st);
 // list-free front end; ev (optional) = PV_PROFILE_STAGES + 1 events recorded at the stage boundaries
 int pvf_run(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev);
 int pvf_run_dynamic(PvParams &p, PvF &f, cudaStream_t st);
+int pvf_insert_lists(PvParams &p, PvF &f, cudaStream_t st);     // binning front end of the list-based pipeline

@@ -5,9 +5,8 @@
 // order-free formulation that reproduces it exactly:
 //
 //   K1 bin_insert  point -> (rho, phi, z) bin -> cell; per cell atomicMin(first point index) and
-//                  atomicAdd(count) in a per-frame map (direct map for small grids, hash else),
-//                  warp-aggregated so one lane per distinct cell issues the atomics.  Pillar
-//                  grids: the BEV canvas zero fill rides in the shadow of the arithmetic.
+//                  atomicAdd(count) in a per-frame map (direct map for small grids, hash else);
+//                  the binning kernel is shared with the list-free pipeline (fused.cu).
 //   K2 cell_flags  streams over the MAP (coalesced): every occupied cell marks its first point
 //                  pv[first] = FIRST | count, and the entry is restored to its clean state.
 //   K3 scan        frame-segmented scan over pv[], in point order, of (is_first, min(count, T)):
@@ -47,7 +46,26 @@ __device__ __forceinline__ uint32_t pv_dense_cell(const PvParams &p, uint32_t lo
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1 -- bin + insert (+ canvas zero fill)
+// K1 -- bin + insert: kf_insert<..., PF_MODE_LISTS> of fused.cu (TMA-staged tiles, 4 points per
+// thread, reciprocal binning, runs of equal cells merged): per run atomicMin(first) +
+// atomicAdd(count) on the {first, cnt} map, per point slot[] / pv[] (/ pcell[]).  This kernel only
+// lays out the scan tiles (tiles never straddle frames).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_scan_layout(const __grid_constant__ PvParams p)
+{
+    if (threadIdx.x != 0) return;
+    uint32_t acc = 0;
+    for (int b = 0; b < p.B; ++b) {
+        p.ws.cum_tiles[b] = acc;
+        acc += ((uint32_t)(p.offsets[b + 1] - p.offsets[b]) + SCAN_TILE - 1) / SCAN_TILE;
+    }
+    p.ws.cum_tiles[p.B] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 (hash maps) -- bin + insert, one point per thread: the slot claim is a dependent L2 round
+// trip per probe, so hash maps want as many independent threads in flight as possible (the
+// 4-points-per-thread kernel of fused.cu measured 182 us vs 121 us here on the Waymo batch)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pv_claim(uint32_t *keys, uint32_t mask, uint32_t cell,
                                              uint32_t *status)
@@ -73,14 +91,6 @@ __global__ void __launch_bounds__(K1_THREADS) k_bin_insert(const __grid_constant
     const uint32_t n_tile = tile_base < p.n ? min((uint32_t)K1_THREADS, p.n - tile_base) : 0u;
     const int c_in = p.c_in;
     if (tid == 0) s_b0 = pv_frame_of(p.offsets, p.B, tile_base);
-    if (blockIdx.x == 0 && tid == 32) {        // scan tiles per frame (tiles never straddle frames)
-        uint32_t acc = 0;
-        for (int b = 0; b < p.B; ++b) {
-            p.ws.cum_tiles[b] = acc;
-            acc += ((uint32_t)(p.offsets[b + 1] - p.offsets[b]) + SCAN_TILE - 1) / SCAN_TILE;
-        }
-        p.ws.cum_tiles[p.B] = acc;
-    }
 
     // ---- stage the tile's rows: coalesced 128-bit loads of the contiguous float range ----
     {
@@ -97,15 +107,6 @@ __global__ void __launch_bounds__(K1_THREADS) k_bin_insert(const __grid_constant
         } else {
             for (uint32_t k = tid; k < nf; k += K1_THREADS) s_pts[k] = pv_ld_keep(src + k, keep);
         }
-    }
-    // ---- this block's slice of the canvas zero fill (pillar grids; k_emit scatters into it) ----
-    if (p.canvas) {
-        const size_t total4 = ((size_t)p.B * p.C * p.cells) >> 2;
-        const size_t chunk = (total4 + gridDim.x - 1) / gridDim.x;
-        const size_t lo4 = (size_t)blockIdx.x * chunk;
-        const size_t hi4 = min(total4, lo4 + chunk);
-        float4 *c4 = reinterpret_cast<float4 *>(p.canvas);
-        for (size_t k = lo4 + tid; k < hi4; k += K1_THREADS) __stcs(c4 + k, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     __syncthreads();
 
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_bin_insert(const __grid_constant
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             // point_cloud_ops.py:45 -- float32 subtract, IEEE divide, floor
-            const float cf = floorf(__fdiv_rn(__fsub_rn(q[j], p.lo[j]), p.vs[j]));
+            const float cf = pv_bin(q[j], p.lo[j], p.vs[j], p.inv_vs[j]);
             int c;
             if (cf != cf) { ok = false; c = 0; }
             else if (cf < 0.0f) { ok = false; c = 0; }
@@ -694,18 +695,21 @@ static void launch_emit(const PvParams &p, cudaStream_t st)
 #define PV_STAGES 5
 #define PV_MARK(k) do { if (ev && cudaEventRecord(ev[k], st) != cudaSuccess) return PV_ERR_CUDA; } while (0)
 
-static int run_voxelize(PvParams &p, cudaStream_t st, cudaEvent_t *ev = nullptr)
+static int run_voxelize(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev = nullptr)
 {
     const PvWs &w = p.ws;
     if (p.density &&
         cudaMemsetAsync(p.density, 0, (size_t)p.B * p.cells * sizeof(int32_t), st) != cudaSuccess)
         return PV_ERR_CUDA;
+    if (p.canvas &&        // k_emit scatters into a zero-filled canvas
+        cudaMemsetAsync(p.canvas, 0, (size_t)p.B * p.C * p.cells * sizeof(float), st) != cudaSuccess)
+        return PV_ERR_CUDA;
     PV_MARK(0);
-    unsigned g1 = (p.n + K1_THREADS - 1) / K1_THREADS;
-    if (g1 < 1) g1 = 1;                                   // block 0 also lays out the scan tiles
-    if (p.canvas && g1 < 592) g1 = 592;                   // enough blocks to zero the canvas quickly
-    if (w.dense) k_bin_insert<true><<<g1, K1_THREADS, 0, st>>>(p);
-    else k_bin_insert<false><<<g1, K1_THREADS, 0, st>>>(p);
+    k_scan_layout<<<1, 32, 0, st>>>(p);
+    if (w.dense) {
+        const int rc = pvf_insert_lists(p, f, st);
+        if (rc) return rc;
+    } else if (p.n > 0) k_bin_insert<false><<<(p.n + K1_THREADS - 1) / K1_THREADS, K1_THREADS, 0, st>>>(p);
     PV_MARK(1);
     {
         const size_t pairs = ((size_t)p.B * w.capf + 1) / 2;
@@ -820,7 +824,7 @@ int pv_voxelize(const pv_config *cfg, const float *points, const int32_t *frame_
     p.coors = coors; p.num_points = num_points; p.voxel_counts = voxel_counts;
     p.voxels = voxels; p.feats = mean_feats; p.grid_ind = pc_grid_ind; p.density = density;
     // the padded [M, T, C] tensor needs per-voxel point lists; everything else runs list-free
-    if (use_lists(f, voxels != nullptr)) return run_voxelize(p, (cudaStream_t)stream);
+    if (use_lists(f, voxels != nullptr)) return run_voxelize(p, f, (cudaStream_t)stream);
     return pvf_run(p, f, (cudaStream_t)stream, nullptr);
 }
 
@@ -853,7 +857,7 @@ int pv_forward_mean_canvas(const pv_config *cfg, const float *points, const int3
     if (!canvas) return PV_ERR_BAD_ARGUMENT;
     rc = setup_canvas_call(p, cfg, coors, num_points, voxel_counts, mean_feats, canvas);
     if (rc) return rc;
-    if (use_lists(f, false)) return run_voxelize(p, (cudaStream_t)stream);
+    if (use_lists(f, false)) return run_voxelize(p, f, (cudaStream_t)stream);
     return pvf_run(p, f, (cudaStream_t)stream, nullptr);
 }
 
@@ -878,7 +882,7 @@ int pv_profile_mean_canvas(const pv_config *cfg, const float *points, const int3
         if (cudaEventCreate(&ev[k]) != cudaSuccess) return PV_ERR_CUDA;
     for (int k = 0; k < PV_STAGES; ++k) stage_ms[k] = 0.0f;
     for (int it = 0; it < iters && rc == PV_OK; ++it) {
-        rc = use_lists(f, false) ? run_voxelize(p, st, ev) : pvf_run(p, f, st, ev);
+        rc = use_lists(f, false) ? run_voxelize(p, f, st, ev) : pvf_run(p, f, st, ev);
         if (rc == PV_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = PV_ERR_CUDA;
         for (int k = 0; k < PV_STAGES && rc == PV_OK; ++k) {
             float ms = 0.0f;
