@@ -51,7 +51,7 @@ STAGE_KERNELS = {"insert": ("kf_insert",), "cells": ("kf_cells",), "scan": ("kf_
                  "heavy": ("kf_heavy_points", "kf_heavy_cells"), "finalize": ("kf_finalize",),
                  "bin_insert": ("k_bin_insert",), "cell_flags": ("k_cell_flags",), "place": ("k_place",),
                  "emit": ("k_emit",)}
-LAUNCHES_PER_STEP = 6      # both pipelines launch six kernels per step
+LAUNCHES_PER_STEP = {1: 7, 2: 6}      # kernels per step: list-based (incl. the scan-tile layout), list-free
 
 
 def ncu_traffic(stage):
@@ -386,7 +386,7 @@ def main():
                     "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                     "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": e2e_wall / e2e_steps, "steps": e2e_steps,
                     "streams": n_streams, "synchronous_ms_per_step": e2e_sync_ms},
-            "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+            "gpu_launches": LAUNCHES_PER_STEP[pipeline] * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": (ach / peak) if ach else None, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
