@@ -922,6 +922,7 @@ int pvf_run_dynamic(PvParams &p, PvF &f, cudaStream_t st)
     f.rowf = (uint32_t)((p.C + 1 + 3) / 4 * 4);
     if (f.rowf > f.rowf_cap) return PV_ERR_WORKSPACE;
     if (!f.dense || (unsigned)p.grid[1] * (unsigned)p.grid[2] > 65535u || p.B > 65535) return PV_ERR_UNSUPPORTED;
+    if ((unsigned long long)p.B * f.wcap * 32ull >= 0xFFFFFF00ull) return PV_ERR_BAD_ARGUMENT;   // bit addresses are 32-bit
     if (p.n > 0) {
         const int rc = pf_dispatch_insert_dyn(p, f, st);
         if (rc) return rc;

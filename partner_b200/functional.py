@@ -171,7 +171,7 @@ class DynamicBatch:
 
 
 def dynamic_voxelize(cfg, points, frame_offsets, batch, frame_capacity, is_cartesian=False, grid_ind=None,
-                     want_inverse=True, want_counts=True, want_grid_ind=False, canvas=False, ws_tag=0):
+                     want_inverse=True, want_counts=True, want_grid_ind=False, canvas=False, ws_tag=0, want_mean=True):
     """pv_dynamic_voxelize on CUDA tensors: dynamic voxelization + unique + scatter_mean (+ scatter).
 
     points [N, c_in] f32; either frame_offsets [batch+1] int32 (the points are binned here) or
@@ -199,7 +199,7 @@ def dynamic_voxelize(cfg, points, frame_offsets, batch, frame_capacity, is_carte
     r.unq_inv = torch.empty((n,), dtype=torch.int32, device=dev) if want_inverse else None
     r.unq_cnt = torch.empty((rows,), dtype=torch.int32, device=dev) if want_counts else None
     r.voxel_counts = torch.empty((batch,), dtype=torch.int32, device=dev)
-    r.mean_feats = torch.empty((rows, C), dtype=torch.float32, device=dev)
+    r.mean_feats = torch.empty((rows, C), dtype=torch.float32, device=dev) if (want_mean or canvas) else None
     r.grid_ind = torch.empty((n, 4), dtype=torch.int32, device=dev) if want_grid_ind else None
     r.canvas = (torch.empty((batch, C, cfg.grid[1], cfg.grid[0]), dtype=torch.float32, device=dev)
                 if canvas else None)

@@ -105,7 +105,7 @@ class Voxelization(object):
         dev = torch.device("cuda", torch.cuda.current_device())
         off = torch.tensor([0, n], dtype=torch.int32, device=dev)
         r = F.dynamic_voxelize(vg._cfg, torch.from_numpy(points).to(dev), off, 1, n, False, want_inverse=False,
-                               want_counts=False, want_grid_ind=True)
+                               want_counts=False, want_grid_ind=True, want_mean=False)
         F.read_status(r)
         pc_grid_ind = r.grid_ind[:, 1:].cpu().numpy().astype(np.int64)       # (z, y, x), np.int of the reference
         res["lidar"]["voxels"] = dict(grid_ind=pc_grid_ind.copy(), shape=vg.grid_size, range=vg.point_cloud_range,
