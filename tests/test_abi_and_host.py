@@ -29,6 +29,13 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "missing export " + n
     assert set(names) == set(_lib.EXPORTS), "ctypes binding table and header disagree"
+    # ... and nothing else: every unmangled pv_* export of the library is declared in the header
+    import shutil
+    import subprocess
+    if shutil.which("nm"):
+        out = subprocess.run(["nm", "-D", "--defined-only", _lib.SO_PATH], capture_output=True, text=True).stdout
+        exported = {l.split()[-1] for l in out.splitlines() if " T pv_" in l}
+        assert exported == set(names), exported ^ set(names)
 
 
 def test_host_only_entry_points():
