@@ -51,7 +51,7 @@ STAGE_KERNELS = {"insert": ("kf_insert",), "cells": ("kf_cells",), "scan": ("kf_
                  "heavy": ("kf_heavy_points", "kf_heavy_cells"), "finalize": ("kf_finalize",),
                  "bin_insert": ("k_bin_insert",), "cell_flags": ("k_cell_flags",), "place": ("k_place",),
                  "emit": ("k_emit",)}
-LAUNCHES_PER_STEP = {1: 7, 2: 6}      # kernels per step: list-based (incl. the scan-tile layout), list-free
+LAUNCHES_PER_STEP = {1: 7, 2: 5}      # kernels per step: list-based (incl. the scan-tile layout), list-free
 
 
 def ncu_traffic(stage):

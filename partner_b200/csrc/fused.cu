@@ -29,6 +29,8 @@
 //                  scatter; the map is restored to its clean state on the way.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "pv_common.cuh"
 
 #define PF_THREADS 256
@@ -162,6 +164,26 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
     uint32_t cur_s = PV_INF, cur_i = 0;      // current run of consecutive points in one cell
     float cur[CT], cur_n = 0.0f;             // its feature sums and point count
     uint32_t sa_out[PF_PPT];
+    // First-point bitmap (bit i <=> point i is its cell's first point), built on the fly: the
+    // minimum is taken with a RETURNING atomic; a run that became its cell's minimum (old > i)
+    // marks its own bit and, if it displaced an earlier minimum, toggles that one's bit.  Every bit
+    // is toggled at most twice -- once by its owner, once by the run that displaced it -- and XOR
+    // commutes, so when the grid has drained exactly the final first points are set, whatever the
+    // arrival order.  The returned value is consumed one flush later (the L2 round trip stays off
+    // the critical path); own bits are collected per thread and leave as ONE reduction per 32
+    // points (8 lanes x 4 points = one bitmap word).
+    uint32_t pend_old = 0, pend_i = 0;       // old <= i: nothing to do
+    uint32_t mine = 0;                       // bit j: point t0 + j became its cell's minimum
+    auto resolve = [&]() {
+#ifdef PF_DBG_NOXOR
+        if (pend_old == 12345u) atomicOr(p.ws.ctrl + 1, 4u);
+        return;
+#endif
+        if (pend_old > pend_i) {
+            mine |= 1u << (pend_i - (tile_base + t0));
+            if (pend_old != PV_INF) atomicXor(f.bits + (pend_old >> 5), 1u << (pend_old & 31u));
+        }
+    };
     auto flush = [&]() {
         if (cur_s != PV_INF) {
             if constexpr (LISTS) {           // list-based map entry {first, count - 1}
@@ -170,7 +192,11 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
                 return;
             }
             if constexpr (DYN) atomicOr(f.bits + (cur_i >> 5), 1u << (cur_i & 31u));   // cur_i = the cell's bit address
-            else atomicMin(f.first + cur_s, cur_i);
+            else {
+                const uint32_t old = atomicMin(f.first + cur_s, cur_i);
+                resolve();                   // the previous run's answer has long arrived
+                pend_old = old; pend_i = cur_i;
+            }
             float o[CT];                     // the count rides in channel C of the row
 #pragma unroll
             for (int k = 0; k < CT; ++k) o[k] = k < C ? cur[k] : (k == C ? cur_n : 0.0f);
@@ -290,32 +316,13 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
                 if (LISTS) p.ws.pv[tile_base + t0 + j] = 0u;
             }
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// F2 -- stream over the map: every occupied cell sets the bit of its first point.
-// grid = (slots / 4 / 256, B)
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) kf_cells(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
-{
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
-        *reinterpret_cast<unsigned long long *>(f.ctrl + 4) = 0ull;        // heavy-cell allocator of this call
-    const uint32_t l0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-    const int b = blockIdx.y;
-    if (l0 >= f.capf) return;
-    const uint32_t s0 = (uint32_t)b * f.capf + l0;
-    const uint4 fv = __ldcg(reinterpret_cast<const uint4 *>(f.first + s0));
-    if ((fv.x & fv.y & fv.z & fv.w) == PV_INF) return;
-    const uint32_t fi4[4] = {fv.x, fv.y, fv.z, fv.w};
-    const uint32_t off_b = (uint32_t)__ldg(p.offsets + b);
-    uint32_t *bits = f.bits + (size_t)b * f.wcap;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t fi = fi4[j];
-        if (fi == PV_INF) continue;
-        const uint32_t ib = fi - off_b;
-        if (ib >= f.wcap * 32u) { atomicOr(p.ws.ctrl + 1, 1u); continue; }     // frame larger than frame_capacity
-        atomicOr(bits + (ib >> 5), 1u << (ib & 31u));
+    if constexpr (MODE == PF_MODE_FREE) {
+        resolve();                           // the last run's answer
+        uint32_t word = mine << (4u * (tid & 7u));
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);
+        word |= __shfl_xor_sync(0xffffffffu, word, 4);
+        if ((tid & 7u) == 0 && word) atomicXor(f.bits + ((tile_base + t0) >> 5), word);
     }
 }
 
@@ -334,7 +341,10 @@ __global__ void __launch_bounds__(PF_SCAN_THREADS) kf_scan(const __grid_constant
     const uint32_t nw = min((n_b + 31u) >> 5, f.wcap);
     uint32_t *bits = f.bits + (size_t)b * f.wcap;
     uint2 *wb = f.wb + (size_t)b * f.wcap;
-    if (tid == 0) s_carry = 0;
+    if (tid == 0) {
+        s_carry = 0;
+        if (b == 0) *reinterpret_cast<unsigned long long *>(f.ctrl + 4) = 0ull;   // heavy-cell allocator of this call
+    }
     __syncthreads();
     // each thread owns PF_SCAN_VEC consecutive 4-word vectors per iteration: one block scan covers
     // 16k words (512k points), so a LiDAR frame is a single iteration
@@ -386,6 +396,110 @@ __global__ void __launch_bounds__(PF_SCAN_THREADS) kf_scan(const __grid_constant
         const uint32_t raw = s_carry;
         f.counts_raw[b] = raw;
         p.voxel_counts[b] = (int32_t)(p.dyn ? raw : min(raw, (uint32_t)p.V));    // no max_voxels cap on the dynamic path
+        __threadfence();
+        const uint32_t done = atomicAdd(f.ctrl + 3, 1u);
+        s_last = done == gridDim.x - 1 ? 1u : 0u;
+        if (s_last) f.ctrl[3] = 0u;
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {                           // row bases: exclusive sum of the capped counts
+        __threadfence();
+        uint32_t carry = 0;
+        for (int b0 = 0; b0 < p.B; b0 += 32) {
+            const int bb = b0 + (int)lane;
+            const uint32_t m = bb < p.B ? (uint32_t)__ldcg(p.voxel_counts + bb) : 0u;
+            uint32_t incl = m;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (unsigned)d) incl += o;
+            }
+            if (bb < p.B) f.base[bb] = (int32_t)(carry + incl - m);
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) f.base[p.B] = (int32_t)carry;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// F3 (static path) -- popcount scan over the first-point bitmap, one block per frame.  The bitmap
+// is addressed by the GLOBAL point index, so a frame is the bit range [offsets[b], offsets[b+1]),
+// not word aligned: the partial words at both ends are masked for counting, and wb[w] = {first
+// points of the frame containing point 32 w that precede the word, the whole word} is written by
+// that frame's block ("owner").  A cell whose first point sits in a word that starts in an earlier
+// frame has prefix 0 and masks the word from its own frame's first bit (kf_finalize).  The bitmap
+// is cleared later by kf_heavy_points (straddling words are read by two blocks here).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PF_SCAN_THREADS) kf_scan_pts(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
+{
+    __shared__ uint32_t s_warp[PF_SCAN_THREADS / 32];
+    __shared__ uint32_t s_carry, s_last;
+    const int b = blockIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t off0 = (uint32_t)p.offsets[b], off1 = (uint32_t)p.offsets[b + 1];
+    const uint32_t wlo = off0 >> 5, whi = off1 > off0 ? (off1 + 31u) >> 5 : wlo;     // words [wlo, whi)
+    const uint32_t mlo = 0xFFFFFFFFu << (off0 & 31u);
+    const uint32_t mhi = (off1 & 31u) ? (1u << (off1 & 31u)) - 1u : 0xFFFFFFFFu;
+    if (tid == 0) {
+        s_carry = 0;
+        if (b == 0) *reinterpret_cast<unsigned long long *>(f.ctrl + 4) = 0ull;   // heavy-cell allocator of this call
+    }
+    __syncthreads();
+    constexpr uint32_t WPT = 4u * PF_SCAN_VEC;               // words per thread per iteration
+    for (uint32_t w0 = wlo & ~3u; w0 < whi; w0 += PF_SCAN_THREADS * WPT) {
+        const uint32_t wt = w0 + tid * WPT;
+        uint32_t v[WPT], c[WPT];
+        uint32_t tsum = 0;
+#pragma unroll
+        for (int q = 0; q < PF_SCAN_VEC; ++q) {               // the bitmap is padded to a multiple of 4 words
+            const uint32_t w = wt + 4u * q;
+            const uint4 x = (w < whi && w + 4u > wlo) ? __ldcg(reinterpret_cast<const uint4 *>(f.bits + w)) : make_uint4(0, 0, 0, 0);
+            v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+        }
+#pragma unroll
+        for (int k = 0; k < (int)WPT; ++k) {
+            const uint32_t w = wt + k;
+            uint32_t m = (w >= wlo && w < whi) ? 0xFFFFFFFFu : 0u;
+            if (w == wlo) m &= mlo;
+            if (w + 1u == whi) m &= mhi;
+            c[k] = __popc(v[k] & m);
+            tsum += c[k];
+        }
+        uint32_t incl = tsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (unsigned)d) incl += o;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t wsum = lane < PF_SCAN_THREADS / 32 ? s_warp[lane] : 0u;     // every warp scans the warp totals
+        uint32_t wincl = wsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, wincl, d);
+            if (lane >= (unsigned)d) wincl += o;
+        }
+        const uint32_t warp_excl = __shfl_sync(0xffffffffu, wincl - wsum, warp);
+        const uint32_t total = __shfl_sync(0xffffffffu, wincl, 31);
+        uint32_t run = s_carry + warp_excl + incl - tsum;
+#pragma unroll
+        for (int k = 0; k < (int)WPT; k += 2) {              // owner: the word starts inside this frame
+            const uint32_t w = wt + k;
+            const bool own0 = w < whi && (w << 5) >= off0, own1 = w + 1u < whi && ((w + 1u) << 5) >= off0;
+            if (own0 && own1) *reinterpret_cast<uint4 *>(f.wb + w) = make_uint4(run, v[k], run + c[k], v[k + 1]);
+            else if (own0) f.wb[w] = make_uint2(run, v[k]);
+            else if (own1) f.wb[w + 1] = make_uint2(run + c[k], v[k + 1]);
+            run += c[k] + c[k + 1];
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const uint32_t raw = s_carry;
+        f.counts_raw[b] = raw;
+        p.voxel_counts[b] = (int32_t)min(raw, (uint32_t)p.V);
         __threadfence();
         const uint32_t done = atomicAdd(f.ctrl + 3, 1u);
         s_last = done == gridDim.x - 1 ? 1u : 0u;
@@ -514,14 +628,16 @@ __global__ void __launch_bounds__(256) kf_finalize(const __grid_constant__ PvPar
         float *rowp = f.acc + (size_t)s * f.rowf;
         float r[CT];
         pf_ld_row<NV>(rowp, r);
-        const uint32_t ib = fi - (uint32_t)__ldg(p.offsets + b);
-        const bool fits = ib < f.wcap * 32u;                              // else flagged by kf_cells
-        const uint2 wv = fits ? __ldg(f.wb + (size_t)b * f.wcap + (ib >> 5)) : make_uint2(0xFFFFFFFFu, 0u);
+        const uint2 wv = __ldg(f.wb + (fi >> 5));
+        const uint32_t off_b = (uint32_t)__ldg(p.offsets + b);
         uint32_t cell = l;
         if (!ROWMAP && !f.dense) cell = __ldcg(f.keys + s);
-        const uint32_t rank = wv.x + __popc(wv.y & ((1u << (ib & 31u)) - 1u));
+        // first points of this frame before point fi: the word's prefix belongs to the frame the
+        // word starts in; if that is an earlier frame, this frame starts inside the word
+        const uint32_t below = wv.y & ((1u << (fi & 31u)) - 1u);
+        const uint32_t rank = (fi & ~31u) >= off_b ? wv.x + __popc(below) : __popc(below & (0xFFFFFFFFu << (off_b & 31u)));
         float keep0 = 0.0f;
-        if (fits && rank < (uint32_t)p.V) {                               // :60-61 max_voxels
+        if (rank < (uint32_t)p.V) {                                       // :60-61 max_voxels
             float cntf = 0.0f;
 #pragma unroll
             for (int k = 0; k < CT; ++k) cntf = k == C ? r[k] : cntf;
@@ -593,9 +709,10 @@ __global__ void __launch_bounds__(256) kf_finalize(const __grid_constant__ PvPar
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PF_THREADS) kf_heavy_points(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
 {
-    if (__ldg(reinterpret_cast<const unsigned long long *>(f.ctrl + 4)) == 0ull) return;   // no heavy cell in this batch
     const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * PF_PPT;
     if (i0 >= p.n) return;
+    if ((i0 & 31u) == 0) f.bits[i0 >> 5] = 0u;      // the first-point bitmap is consumed: back to its clean state
+    if (__ldg(reinterpret_cast<const unsigned long long *>(f.ctrl + 4)) == 0ull) return;   // no heavy cell in this batch
     uint32_t sa[PF_PPT];
     if (i0 + PF_PPT <= p.n) {
         const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(f.sa + i0));
@@ -818,7 +935,9 @@ int pvf_make_layout(const pv_config *cfg, int64_t n_cap, int32_t batch, int64_t 
     size_t o = 0;
     // ---- clean = 0 ----
     w->ctrl = (uint32_t *)(p0 + o);        o = pf_align(o + 16 * 4, 256);
-    w->bits = (uint32_t *)(p0 + o);        o = pf_align(o + (size_t)w->wcap * batch * 4, 256);
+    // static path: one bit per point of the batch (global index); dynamic path: per-frame cell bitmaps
+    const size_t bit_words = std::max((size_t)w->wcap * batch, (n + 31) / 32 + 8);
+    w->bits = (uint32_t *)(p0 + o);        o = pf_align(o + bit_words * 4, 256);
     w->hbits = (uint32_t *)(p0 + o);       o = pf_align(o + (slots / 32 + 2) * 4, 256);
     w->acc = (float *)(p0 + o);            o = pf_align(o + slots * w->rowf_cap * 4, 256);
     // ---- clean = all ones ----
@@ -830,7 +949,7 @@ int pvf_make_layout(const pv_config *cfg, int64_t n_cap, int32_t batch, int64_t 
     w->base = (int32_t *)(p0 + o);         o = pf_align(o + (size_t)(batch + 1) * 4, 256);
     w->counts_raw = (uint32_t *)(p0 + o);  o = pf_align(o + (size_t)batch * 4, 256);
     w->sa = (uint32_t *)(p0 + o);          o = pf_align(o + n * 4 + 32, 256);
-    w->wb = (uint2 *)(p0 + o);             o = pf_align(o + (size_t)w->wcap * batch * 8, 256);
+    w->wb = (uint2 *)(p0 + o);             o = pf_align(o + bit_words * 8, 256);
     w->total_bytes = o;
     return PV_OK;
 }
@@ -985,9 +1104,8 @@ int pvf_run(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev)
         if (rc) return rc;
     }
     PF_MARK(1);
-    kf_cells<<<dim3((f.capf / 4 + 255) / 256, (unsigned)p.B), 256, 0, st>>>(p, f);
-    PF_MARK(2);
-    kf_scan<<<(unsigned)p.B, PF_SCAN_THREADS, 0, st>>>(p, f);
+    PF_MARK(2);                              // (the first-point bitmap is built by the insert kernel)
+    kf_scan_pts<<<(unsigned)p.B, PF_SCAN_THREADS, 0, st>>>(p, f);
     PF_MARK(3);
     pf_launch_finalize(p, f, st);
     PF_MARK(4);

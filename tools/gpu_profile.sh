@@ -5,7 +5,7 @@ set -u
 TAG=${1:-r01}
 WL=${2:-nusc_pillar_mean_canvas_b8}
 OUT=gpurun_out
-KPS=6    # kernels per step
+KPS=5    # kernels per step
 mkdir -p $OUT
 python bench.py --workload $WL > $OUT/bench_${TAG}.json 2> $OUT/bench_${TAG}.err
 tail -c 3000 $OUT/bench_${TAG}.json
