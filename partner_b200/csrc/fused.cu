@@ -278,9 +278,10 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
             s = (uint32_t)b * f.capf + cell;
             sa = (uint32_t)b * (f.wcap * 32u) + cell;            // bit address in the occupancy bitmap
         } else if (DENSE) {
-            s = (uint32_t)b * f.capf + cell;
-            // heavy-bitmap order: phi fastest, so azimuth neighbours share a bitmap word
-            sa = (uint32_t)b * f.capf + (cz * nx + cx) * ny + cy;
+            // direct map, PHI FASTEST: consecutive points of a LiDAR ring are azimuth neighbours, so
+            // the rows they reduce into (and the heavy-bitmap words) share 128-byte lines
+            s = (uint32_t)b * f.capf + (cz * nx + cx) * ny + cy;
+            sa = s;
         } else {
             const uint32_t h = pf_claim(f.keys + (size_t)b * f.capf, f.capf - 1, cell, p.ws.ctrl + 1);
             if (h == PV_INF) continue;       // map full: status bit set
@@ -596,109 +597,158 @@ __device__ __forceinline__ void pf_store_feats(float *feats, int32_t vid, int C,
     }
 }
 
-// ROWMAP (direct map only): grid = (ceil(nx / 256), ny * nz, B), one thread per cell of one grid
-// row -- (z, y, x) come from the block index, no integer division anywhere.  Otherwise
-// grid = (slots / 256, B) over the linear slot index.  CC = compile-time channel count (0 = runtime).
-template <int NV, int CC, bool CANVAS, bool ROWMAP>
-__global__ void __launch_bounds__(256) kf_finalize(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
+// One occupied map slot s of frame b = cell (cz, cy, cx): rank lookup, per-voxel outputs, heavy
+// registration, map restore.  m[] / dens receive what the dense canvas / density hold for the cell.
+template <int NV, int CC, bool CANVAS>
+__device__ __forceinline__ void pf_finalize_cell(const PvParams &p, const PvF &f, const uint32_t s, const int b,
+                                                 const uint32_t fi, const uint32_t cx, const uint32_t cy,
+                                                 const uint32_t cz, float (&m)[CANVAS ? NV * 4 : 1], int32_t &dens)
 {
     constexpr int CT = NV * 4;
     const int C = CC ? CC : p.C;
-    const int b = ROWMAP ? blockIdx.z : blockIdx.y;
-    const uint32_t nx = p.grid[0], ny = p.grid[1];
-    uint32_t l, x = 0, yz = 0;
-    if (ROWMAP) {
-        x = blockIdx.x * blockDim.x + threadIdx.x;
-        yz = blockIdx.y;
-        if (x >= nx) return;
-        l = yz * nx + x;
-    } else {
-        l = blockIdx.x * blockDim.x + threadIdx.x;
-        if (l >= f.capf) return;
-    }
-    const uint32_t s = (uint32_t)b * f.capf + l;
-    const uint32_t fi = __ldcs(f.first + s);
-    float m[CANVAS ? CT : 1];
-    int32_t dens = 0;
-    if (CANVAS) {
+    float *rowp = f.acc + (size_t)s * f.rowf;
+    float r[CT];
+    pf_ld_row<NV>(rowp, r);
+    const uint2 wv = __ldg(f.wb + (fi >> 5));
+    const uint32_t off_b = (uint32_t)__ldg(p.offsets + b);
+    // first points of this frame before point fi: the word's prefix belongs to the frame the word
+    // starts in; if that is an earlier frame, this frame starts inside the word
+    const uint32_t below = wv.y & ((1u << (fi & 31u)) - 1u);
+    const uint32_t rank = (fi & ~31u) >= off_b ? wv.x + __popc(below) : __popc(below & (0xFFFFFFFFu << (off_b & 31u)));
+    float keep0 = 0.0f;
+    if (rank < (uint32_t)p.V) {                                           // :60-61 max_voxels
+        float cntf = 0.0f;
 #pragma unroll
-        for (int k = 0; k < CT; ++k) m[k] = 0.0f;
-    }
-    if (fi != PV_INF) {
-        float *rowp = f.acc + (size_t)s * f.rowf;
-        float r[CT];
-        pf_ld_row<NV>(rowp, r);
-        const uint2 wv = __ldg(f.wb + (fi >> 5));
-        const uint32_t off_b = (uint32_t)__ldg(p.offsets + b);
-        uint32_t cell = l;
-        if (!ROWMAP && !f.dense) cell = __ldcg(f.keys + s);
-        // first points of this frame before point fi: the word's prefix belongs to the frame the
-        // word starts in; if that is an earlier frame, this frame starts inside the word
-        const uint32_t below = wv.y & ((1u << (fi & 31u)) - 1u);
-        const uint32_t rank = (fi & ~31u) >= off_b ? wv.x + __popc(below) : __popc(below & (0xFFFFFFFFu << (off_b & 31u)));
-        float keep0 = 0.0f;
-        if (rank < (uint32_t)p.V) {                                       // :60-61 max_voxels
-            float cntf = 0.0f;
-#pragma unroll
-            for (int k = 0; k < CT; ++k) cntf = k == C ? r[k] : cntf;
-            const uint32_t cnt = (uint32_t)cntf;
-            const uint32_t T = (uint32_t)p.T;
-            const uint32_t L = min(cnt, T);
-            const int32_t vid = __ldg(f.base + b) + (int32_t)rank;
-            if (!ROWMAP) { x = cell % nx; yz = cell / nx; }
-            uint32_t cy, cz;
-            if (ROWMAP) { cz = blockIdx.y / ny; cy = blockIdx.y - cz * ny; }   // uniform
-            else { cz = yz / ny; cy = yz - cz * ny; }
-            reinterpret_cast<int4 *>(p.coors)[vid] = make_int4(b, (int)cz, (int)cy, (int)x);
-            p.num_points[vid] = (int32_t)L;
-            dens = (int32_t)cnt;                                          // :70-71 un-capped count
-            if (cnt > T) {
-                // heavy: the row holds the sum over ALL points; F5 re-sums the T smallest indices
-                const unsigned long long a = atomicAdd(reinterpret_cast<unsigned long long *>(f.ctrl + 4),
-                                                       (1ull << 32) | (unsigned long long)cnt);
-                const uint32_t hid = (uint32_t)(a >> 32), off = (uint32_t)a;
-                if (hid < f.hmax) {
-                    uint4 *hi = f.hinfo + 2 * (size_t)hid;
-                    hi[0] = make_uint4(s, (uint32_t)vid, off, cnt);
-                    hi[1] = make_uint4(cell, (uint32_t)b, 0u, 0u);           // .z = arrival cursor
-                    keep0 = __uint_as_float(hid);
-                    const uint32_t hb = f.dense ? (uint32_t)b * f.capf + (cz * nx + x) * ny + cy : s;
-                    atomicOr(f.hbits + (hb >> 5), 1u << (hb & 31u));
-                } else atomicOr(p.ws.ctrl + 1, 1u);
-            } else {
-                const float nf = (float)L, inv = __frcp_rn(nf);
-                float mean[CT];
-#pragma unroll
-                for (int k = 0; k < CT; ++k) {
-                    mean[k] = k < C ? pv_div_count(r[k], nf, inv) : 0.0f; // voxel_encoder.py:18-22
-                    if (CANVAS) m[k] = mean[k];
-                }
-                if (!CANVAS && !f.dense && p.canvas) {
-                    float *cv = p.canvas + (size_t)b * C * p.cells + cell;
-#pragma unroll
-                    for (int k = 0; k < CT; ++k)
-                        if (k < C) cv[(size_t)k * p.cells] = mean[k];
-                }
-                if (p.feats) pf_store_feats<CT>(p.feats, vid, C, mean);
-            }
-            if (!f.dense && p.density) p.density[(size_t)b * p.cells + cell] = (int32_t)cnt;
-        }
-        // restore the map -- after the loaded row was consumed (see kf_scan)
-        pf_st_row_clean<NV>(rowp, keep0);
-        f.first[s] = PV_INF;
-        if (!f.dense) f.keys[s] = PV_INF;
-    }
-    if (f.dense && l < p.cells) {
-        // direct map: slot order == cell order, so canvas and density are written here in full,
-        // zeros included: no zero fill, no scatter                        pillar_encoder.py:211-217
-        if (CANVAS) {
-            float *cv = p.canvas + (size_t)b * C * p.cells + l;
+        for (int k = 0; k < CT; ++k) cntf = k == C ? r[k] : cntf;
+        const uint32_t cnt = (uint32_t)cntf;
+        const uint32_t T = (uint32_t)p.T;
+        const uint32_t L = min(cnt, T);
+        const int32_t vid = __ldg(f.base + b) + (int32_t)rank;
+        const uint32_t cell = (cz * (uint32_t)p.grid[1] + cy) * (uint32_t)p.grid[0] + cx;
+        reinterpret_cast<int4 *>(p.coors)[vid] = make_int4(b, (int)cz, (int)cy, (int)cx);
+        p.num_points[vid] = (int32_t)L;
+        dens = (int32_t)cnt;                                              // :70-71 un-capped count
+        if (cnt > T) {
+            // heavy: the row holds the sum over ALL points; F5 re-sums the T smallest indices
+            const unsigned long long a = atomicAdd(reinterpret_cast<unsigned long long *>(f.ctrl + 4),
+                                                   (1ull << 32) | (unsigned long long)cnt);
+            const uint32_t hid = (uint32_t)(a >> 32), off = (uint32_t)a;
+            if (hid < f.hmax) {
+                uint4 *hi = f.hinfo + 2 * (size_t)hid;
+                hi[0] = make_uint4(s, (uint32_t)vid, off, cnt);
+                hi[1] = make_uint4(cell, (uint32_t)b, 0u, 0u);               // .z = arrival cursor
+                keep0 = __uint_as_float(hid);
+                atomicOr(f.hbits + (s >> 5), 1u << (s & 31u));
+            } else atomicOr(p.ws.ctrl + 1, 1u);
+        } else {
+            const float nf = (float)L, inv = __frcp_rn(nf);
+            float mean[CT];
 #pragma unroll
             for (int k = 0; k < CT; ++k) {
-                if (k < C) { __stcs(cv, m[k]); cv += p.cells; }
+                mean[k] = k < C ? pv_div_count(r[k], nf, inv) : 0.0f;     // voxel_encoder.py:18-22
+                if (CANVAS) m[k] = mean[k];
             }
+            if (!CANVAS && !f.dense && p.canvas) {
+                float *cv = p.canvas + (size_t)b * C * p.cells + cell;
+#pragma unroll
+                for (int k = 0; k < CT; ++k)
+                    if (k < C) cv[(size_t)k * p.cells] = mean[k];
+            }
+            if (p.feats) pf_store_feats<CT>(p.feats, vid, C, mean);
         }
-        if (p.density) p.density[(size_t)b * p.cells + l] = dens;
+        if (!f.dense && p.density) p.density[(size_t)b * p.cells + cell] = (int32_t)cnt;
+    }
+    // restore the map -- after the loaded row was consumed (see kf_scan)
+    pf_st_row_clean<NV>(rowp, keep0);
+    f.first[s] = PV_INF;
+    if (!f.dense) f.keys[s] = PV_INF;
+}
+
+// Hash maps: grid = (slots / 256, B) over the slot index; dense outputs were zero-filled by the host.
+template <int NV, int CC>
+__global__ void __launch_bounds__(256) kf_finalize(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
+{
+    const int b = blockIdx.y;
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= f.capf) return;
+    const uint32_t s = (uint32_t)b * f.capf + l;
+    const uint32_t fi = __ldcs(f.first + s);
+    if (fi == PV_INF) return;
+    const uint32_t cell = __ldcg(f.keys + s), nx = p.grid[0], ny = p.grid[1];
+    const uint32_t x = cell % nx, yz = cell / nx, cz = yz / ny, cy = yz - cz * ny;
+    float m[1];
+    int32_t dens;
+    pf_finalize_cell<NV, CC, false>(p, f, s, b, fi, x, cy, cz, m, dens);
+}
+
+// Direct maps: one block per patch of PF_PATCH azimuth x PF_PATCH range cells of one z layer.  The
+// map is PHI FASTEST (the order LiDAR points arrive in), the canvas RHO FASTEST
+// (pillar_encoder.py:211-217), so the block works in two phases around a shared-memory transpose:
+//   1. a warp reads 32 azimuth-consecutive slots (coalesced; their rows, first-point words and --
+//      because azimuth neighbours are mostly first hit by consecutive points -- their output rows
+//      are neighbours too, so the per-voxel loads and stores of a warp share 128-byte lines),
+//   2. a warp writes 32 range-consecutive canvas cells per channel (one full line per store),
+//      every element exactly once, zeros included: no zero fill, no scatter.
+// grid = (patches_x * patches_y * nz, B); each thread owns PF_PATCH / 8 cells of the patch.
+#define PF_PATCH 32
+template <int NV, int CC, bool CANVAS>
+__global__ void __launch_bounds__(256) kf_finalize_patch(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
+{
+    constexpr int CT = NV * 4;
+    constexpr int KP = PF_PATCH / 8;                         // cells per thread
+    extern __shared__ float s_t[];                           // [C (+1 density)][PF_PATCH rho][PF_PATCH + 1 phi]
+    const int C = CC ? CC : p.C;
+    const int b = blockIdx.y;
+    const uint32_t nx = p.grid[0], ny = p.grid[1];
+    const uint32_t px = (nx + PF_PATCH - 1) / PF_PATCH, py = (ny + PF_PATCH - 1) / PF_PATCH;
+    uint32_t pid = blockIdx.x;
+    const uint32_t pxi = pid % px; pid /= px;
+    const uint32_t pyi = pid % py, z = pid / py;
+    const uint32_t lane = threadIdx.x & 31u, wq = threadIdx.x >> 5;
+    int32_t *s_d = reinterpret_cast<int32_t *>(s_t) + (CANVAS ? (size_t)C : 0) * PF_PATCH * (PF_PATCH + 1);
+
+    // ---- phase 1: lane = azimuth ----
+    const uint32_t y = pyi * PF_PATCH + lane;
+    uint32_t fi[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const uint32_t x = pxi * PF_PATCH + wq + 8u * k;
+        fi[k] = (x < nx && y < ny) ? __ldcs(f.first + (size_t)b * f.capf + (z * nx + x) * ny + y) : PV_INF;
+    }
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const uint32_t xl = wq + 8u * k, x = pxi * PF_PATCH + xl;
+        float m[CANVAS ? CT : 1];
+        int32_t dens = 0;
+        if (CANVAS) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) m[c] = 0.0f;
+        }
+        if (fi[k] != PV_INF)
+            pf_finalize_cell<NV, CC, CANVAS>(p, f, (uint32_t)b * f.capf + (z * nx + x) * ny + y, b, fi[k], x, y, z, m, dens);
+        if (CANVAS) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+                if (c < C) s_t[((size_t)c * PF_PATCH + xl) * (PF_PATCH + 1) + lane] = m[c];
+        }
+        if (p.density) s_d[xl * (PF_PATCH + 1) + lane] = dens;
+    }
+    if (!CANVAS && !p.density) return;
+    __syncthreads();
+    // ---- phase 2: lane = range ----
+    const uint32_t x2 = pxi * PF_PATCH + lane;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        const uint32_t yl = wq + 8u * k, y2 = pyi * PF_PATCH + yl;
+        if (x2 >= nx || y2 >= ny) continue;
+        const size_t cell = ((size_t)z * ny + y2) * nx + x2;
+        if (CANVAS) {
+            float *cv = p.canvas + (size_t)b * C * p.cells + cell;
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+                if (c < C) { __stcs(cv, s_t[((size_t)c * PF_PATCH + lane) * (PF_PATCH + 1) + yl]); cv += p.cells; }
+        }
+        if (p.density) p.density[(size_t)b * p.cells + cell] = s_d[lane * (PF_PATCH + 1) + yl];
     }
 }
 
@@ -727,12 +777,7 @@ __global__ void __launch_bounds__(PF_THREADS) kf_heavy_points(const __grid_const
 #pragma unroll
     for (int j = 0; j < PF_PPT; ++j) {
         if (!((w[j] >> (sa[j] & 31u)) & 1u)) continue;
-        uint32_t s = sa[j];
-        if (f.dense) {
-            const uint32_t bb = s / f.capf, l = s - bb * f.capf, nx = p.grid[0], ny = p.grid[1];
-            const uint32_t y = l % ny, t = l / ny, x = t % nx, z = t / nx;
-            s = bb * f.capf + (z * ny + y) * nx + x;
-        }
+        const uint32_t s = sa[j];
         const uint32_t hid = __float_as_uint(__ldcg(f.acc + (size_t)s * f.rowf));
         uint32_t *hi = reinterpret_cast<uint32_t *>(f.hinfo + 2 * (size_t)hid);
         const uint32_t off = __ldcg(hi + 2);
@@ -809,12 +854,7 @@ __global__ void __launch_bounds__(256) kf_heavy_cells(const __grid_constant__ Pv
         }
         if (lane == 0) {
             f.acc[(size_t)s * f.rowf] = 0.0f;    // the row's last dirty word (held the heavy-cell id)
-            uint32_t hb = s;
-            if (f.dense) {
-                const uint32_t l = s - b * f.capf, nx = p.grid[0], ny = p.grid[1];
-                const uint32_t x = l % nx, t = l / nx, y = t % ny, z = t / ny;
-                hb = b * f.capf + (z * nx + x) * ny + y;
-            }
+            const uint32_t hb = s;
             atomicAnd(f.hbits + (hb >> 5), ~(1u << (hb & 31u)));
         }
     }
@@ -1059,29 +1099,31 @@ int pvf_run_dynamic(PvParams &p, PvF &f, cudaStream_t st)
 }
 
 template <int NV, int CC>
-static void pf_launch_finalize_nv(const PvParams &p, const PvF &f, cudaStream_t st)
+static int pf_launch_finalize_nv(const PvParams &p, const PvF &f, cudaStream_t st)
 {
-    const bool canvas = p.canvas && f.dense;
-    const unsigned rows = (unsigned)p.grid[1] * (unsigned)p.grid[2];
-    if (f.dense && rows <= 65535u && p.B <= 65535) {     // one thread per cell of a grid row
-        const dim3 grid(((unsigned)p.grid[0] + 255) / 256, rows, (unsigned)p.B);
-        if (canvas) kf_finalize<NV, CC, true, true><<<grid, 256, 0, st>>>(p, f);
-        else kf_finalize<NV, CC, false, true><<<grid, 256, 0, st>>>(p, f);
-    } else {
-        const dim3 grid((f.capf + 255) / 256, (unsigned)p.B);
-        if (canvas) kf_finalize<NV, CC, true, false><<<grid, 256, 0, st>>>(p, f);
-        else kf_finalize<NV, CC, false, false><<<grid, 256, 0, st>>>(p, f);
+    if (!f.dense) {
+        kf_finalize<NV, CC><<<dim3((f.capf + 255) / 256, (unsigned)p.B), 256, 0, st>>>(p, f);
+        return PV_OK;
     }
+    const unsigned px = ((unsigned)p.grid[0] + PF_PATCH - 1) / PF_PATCH, py = ((unsigned)p.grid[1] + PF_PATCH - 1) / PF_PATCH;
+    const dim3 grid(px * py * (unsigned)p.grid[2], (unsigned)p.B);
+    if (p.B > 65535) return PV_ERR_UNSUPPORTED;
+    const size_t smem = ((p.canvas ? (size_t)p.C : 0) + (p.density ? 1 : 0)) * PF_PATCH * (PF_PATCH + 1) * sizeof(float);
+    auto kern = p.canvas ? kf_finalize_patch<NV, CC, true> : kf_finalize_patch<NV, CC, false>;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return PV_ERR_CUDA;
+    kern<<<grid, 256, smem, st>>>(p, f);
+    return PV_OK;
 }
 
-static void pf_launch_finalize(const PvParams &p, const PvF &f, cudaStream_t st)
+static int pf_launch_finalize(const PvParams &p, const PvF &f, cudaStream_t st)
 {
     switch ((int)f.rowf / 4) {
-    case 1: pf_launch_finalize_nv<1, 0>(p, f, st); break;
-    case 2: if (p.C == 7) pf_launch_finalize_nv<2, 7>(p, f, st); else pf_launch_finalize_nv<2, 0>(p, f, st); break;
-    case 3: if (p.C == 8) pf_launch_finalize_nv<3, 8>(p, f, st); else pf_launch_finalize_nv<3, 0>(p, f, st); break;
-    case 4: pf_launch_finalize_nv<4, 0>(p, f, st); break;
-    default: pf_launch_finalize_nv<5, 0>(p, f, st); break;
+    case 1: return pf_launch_finalize_nv<1, 0>(p, f, st);
+    case 2: return p.C == 7 ? pf_launch_finalize_nv<2, 7>(p, f, st) : pf_launch_finalize_nv<2, 0>(p, f, st);
+    case 3: return p.C == 8 ? pf_launch_finalize_nv<3, 8>(p, f, st) : pf_launch_finalize_nv<3, 0>(p, f, st);
+    case 4: return pf_launch_finalize_nv<4, 0>(p, f, st);
+    default: return pf_launch_finalize_nv<5, 0>(p, f, st);
     }
 }
 
@@ -1098,20 +1140,24 @@ int pvf_run(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev)
         if (p.density && cudaMemsetAsync(p.density, 0, (size_t)p.B * p.cells * sizeof(int32_t), st) != cudaSuccess)
             return PV_ERR_CUDA;
     }
+    static const int dbg_skip = [] { const char *e = getenv("PF_SKIP"); return e ? atoi(e) : 0; }();   // DBG
     PF_MARK(0);
-    if (p.n > 0) {
+    if (p.n > 0 && !(dbg_skip & 16)) {
         const int rc = f.dense ? pf_dispatch_insert<true>(p, f, st) : pf_dispatch_insert<false>(p, f, st);
         if (rc) return rc;
     }
     PF_MARK(1);
     PF_MARK(2);                              // (the first-point bitmap is built by the insert kernel)
-    kf_scan_pts<<<(unsigned)p.B, PF_SCAN_THREADS, 0, st>>>(p, f);
+    if (!(dbg_skip & 1)) kf_scan_pts<<<(unsigned)p.B, PF_SCAN_THREADS, 0, st>>>(p, f);
     PF_MARK(3);
-    pf_launch_finalize(p, f, st);
+    if (!(dbg_skip & 2)) {
+        const int rc = pf_launch_finalize(p, f, st);
+        if (rc) return rc;
+    }
     PF_MARK(4);
     if (p.n > 0) {
-        kf_heavy_points<<<(p.n + PF_TILE - 1) / PF_TILE, PF_THREADS, 0, st>>>(p, f);
-        kf_heavy_cells<<<296, 256, 0, st>>>(p, f);
+        if (!(dbg_skip & 4)) kf_heavy_points<<<(p.n + PF_TILE - 1) / PF_TILE, PF_THREADS, 0, st>>>(p, f);
+        if (!(dbg_skip & 8)) kf_heavy_cells<<<296, 256, 0, st>>>(p, f);
     }
     PF_MARK(5);
     return pv_last_cuda_error();
