@@ -12,21 +12,26 @@
 // 16-byte vector reduction costs the same as a 4-byte one.  The design therefore minimises
 // SCATTERED OPERATIONS PER POINT:
 //
-//   F1 insert      per point: bin -> cell slot; RED.MIN(first[slot], i) and one 16-byte
-//                  RED.ADD.F32x4 per 4 floats of the row {C feature sums, count}.  Fire-and-forget:
-//                  nothing returns, no thread waits on L2.  Rows staged with one TMA bulk copy per
-//                  tile; consecutive points of one thread that share a cell are merged first.
-//   F2 cells       stream over the map: every occupied cell sets the bit of its first point; cells
-//                  with more than T points are registered as heavy.
-//   F3 scan        popcount scan over the first-point bitmap (N/32 words) -> rank of every first
+//   F1 insert      per point: bin -> cell slot (direct maps are PHI FASTEST: consecutive points of a
+//                  LiDAR ring are azimuth neighbours, so the lanes of a warp reduce into rows that
+//                  share 128-byte lines); a RETURNING atomicMin(first[slot], i) and one 16-byte
+//                  RED.ADD.F32x4 per 4 floats of the row {C feature sums, count}.  The returned
+//                  minimum feeds the first-point bitmap (bit i <=> point i is its cell's first
+//                  point): own bits leave as one aggregated reduction per 32 points, a displaced
+//                  earlier minimum is toggled back; XOR commutes, so the bitmap is exact when the
+//                  grid has drained.  Rows staged with one TMA bulk copy per tile; consecutive
+//                  points of one thread that share a cell are merged first.
+//   F2 scan        popcount scan over the first-point bitmap (N/32 words) -> rank of every first
 //                  point in its frame = first-occurrence rank of its cell; voxel counts, row bases.
-//   F4 heavy       (rare cells, 2-5 % of the points) points of heavy cells insert their index into
-//                  the cell's T-entry list (atomicMin chain -> the T smallest, ascending); one
-//                  warp per heavy cell then re-sums exactly those rows.
-//   F5 finalize    stream over the map again: occupied cell -> rank lookup, mean = sum / min(n, T),
-//                  coors / num_points / features rows; the BEV canvas (and density) is written
-//                  IN CELL ORDER, every element exactly once, zeros included -- no zero fill, no
-//                  scatter; the map is restored to its clean state on the way.
+//   F3 finalize    one block per 32 x 32 patch of cells: occupied cell -> rank lookup, mean = sum /
+//                  min(n, T), coors / num_points / features rows (azimuth neighbours have
+//                  consecutive ranks, so a warp's rows are neighbours); the BEV canvas (and
+//                  density) goes through a shared-memory transpose and is written IN CELL ORDER,
+//                  every element exactly once, zeros included -- no zero fill, no scatter; the map
+//                  is restored to its clean state on the way.
+//   F4 heavy       (rare cells, 2-5 % of the points) points of heavy cells append their index to
+//                  the cell's candidate range; one warp per heavy cell selects the T smallest
+//                  (REDUX.MIN rounds) and re-sums exactly those rows.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -99,7 +104,7 @@ __device__ __forceinline__ uint32_t pf_claim(uint32_t *keys, uint32_t mask, uint
 #define PF_MODE_FREE 0
 #define PF_MODE_DYN 1
 #define PF_MODE_LISTS 2
-template <bool DENSE, int CIN, bool CART, int NV, int MODE = PF_MODE_FREE>
+template <bool DENSE, int CIN, bool CART, int NV, int MODE = PF_MODE_FREE, bool GI = true>
 __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ PvParams p,
                                                         const __grid_constant__ PvF f)
 {
@@ -175,10 +180,6 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
     uint32_t pend_old = 0, pend_i = 0;       // old <= i: nothing to do
     uint32_t mine = 0;                       // bit j: point t0 + j became its cell's minimum
     auto resolve = [&]() {
-#ifdef PF_DBG_NOXOR
-        if (pend_old == 12345u) atomicOr(p.ws.ctrl + 1, 4u);
-        return;
-#endif
         if (pend_old > pend_i) {
             mine |= 1u << (pend_i - (tile_base + t0));
             if (pend_old != PV_INF) atomicXor(f.bits + (pend_old >> 5), 1u << (pend_old & 31u));
@@ -193,9 +194,10 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
             }
             if constexpr (DYN) atomicOr(f.bits + (cur_i >> 5), 1u << (cur_i & 31u));   // cur_i = the cell's bit address
             else {
-                const uint32_t old = atomicMin(f.first + cur_s, cur_i);
                 resolve();                   // the previous run's answer has long arrived
-                pend_old = old; pend_i = cur_i;
+                // straight into the pending register: a copy of the result would wait for the round trip
+                pend_old = atomicMin(f.first + cur_s, cur_i);
+                pend_i = cur_i;
             }
             float o[CT];                     // the count rides in channel C of the row
 #pragma unroll
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
                 if (!ok) atomicOr(p.ws.ctrl + 1, 2u);
             }
             if (p.grid_ind) reinterpret_cast<int4 *>(p.grid_ind)[i] = make_int4(b, (int)c2, (int)c1, (int)c0);
-        } else if (p.grid_ind) {             // :46-54 clamped (z, y, x) for every point (NaN -> 0)
+        } else if (GI && p.grid_ind) {       // :46-54 clamped (z, y, x) for every point (NaN -> 0)
             int32_t *gi = p.grid_ind + (size_t)i * 3;
             gi[0] = (int)fminf(fmaxf(c2, 0.0f), g2 - 1.0f);
             gi[1] = (int)fminf(fmaxf(c1, 0.0f), g1 - 1.0f);
@@ -599,17 +601,15 @@ __device__ __forceinline__ void pf_store_feats(float *feats, int32_t vid, int C,
 
 // One occupied map slot s of frame b = cell (cz, cy, cx): rank lookup, per-voxel outputs, heavy
 // registration, map restore.  m[] / dens receive what the dense canvas / density hold for the cell.
-template <int NV, int CC, bool CANVAS>
+template <int NV, int CC, bool CANVAS, bool DENSE>
 __device__ __forceinline__ void pf_finalize_cell(const PvParams &p, const PvF &f, const uint32_t s, const int b,
                                                  const uint32_t fi, const uint32_t cx, const uint32_t cy,
-                                                 const uint32_t cz, float (&m)[CANVAS ? NV * 4 : 1], int32_t &dens)
+                                                 const uint32_t cz, const float (&r)[NV * 4], const uint2 wv,
+                                                 float (&m)[CANVAS ? NV * 4 : 1], int32_t &dens)
 {
     constexpr int CT = NV * 4;
     const int C = CC ? CC : p.C;
     float *rowp = f.acc + (size_t)s * f.rowf;
-    float r[CT];
-    pf_ld_row<NV>(rowp, r);
-    const uint2 wv = __ldg(f.wb + (fi >> 5));
     const uint32_t off_b = (uint32_t)__ldg(p.offsets + b);
     // first points of this frame before point fi: the word's prefix belongs to the frame the word
     // starts in; if that is an earlier frame, this frame starts inside the word
@@ -648,7 +648,7 @@ __device__ __forceinline__ void pf_finalize_cell(const PvParams &p, const PvF &f
                 mean[k] = k < C ? pv_div_count(r[k], nf, inv) : 0.0f;     // voxel_encoder.py:18-22
                 if (CANVAS) m[k] = mean[k];
             }
-            if (!CANVAS && !f.dense && p.canvas) {
+            if (!CANVAS && !DENSE && p.canvas) {
                 float *cv = p.canvas + (size_t)b * C * p.cells + cell;
 #pragma unroll
                 for (int k = 0; k < CT; ++k)
@@ -656,12 +656,12 @@ __device__ __forceinline__ void pf_finalize_cell(const PvParams &p, const PvF &f
             }
             if (p.feats) pf_store_feats<CT>(p.feats, vid, C, mean);
         }
-        if (!f.dense && p.density) p.density[(size_t)b * p.cells + cell] = (int32_t)cnt;
+        if (!DENSE && p.density) p.density[(size_t)b * p.cells + cell] = (int32_t)cnt;
     }
     // restore the map -- after the loaded row was consumed (see kf_scan)
     pf_st_row_clean<NV>(rowp, keep0);
     f.first[s] = PV_INF;
-    if (!f.dense) f.keys[s] = PV_INF;
+    if (!DENSE) f.keys[s] = PV_INF;
 }
 
 // Hash maps: grid = (slots / 256, B) over the slot index; dense outputs were zero-filled by the host.
@@ -676,9 +676,11 @@ __global__ void __launch_bounds__(256) kf_finalize(const __grid_constant__ PvPar
     if (fi == PV_INF) return;
     const uint32_t cell = __ldcg(f.keys + s), nx = p.grid[0], ny = p.grid[1];
     const uint32_t x = cell % nx, yz = cell / nx, cz = yz / ny, cy = yz - cz * ny;
-    float m[1];
+    float m[1], r[NV * 4];
     int32_t dens;
-    pf_finalize_cell<NV, CC, false>(p, f, s, b, fi, x, cy, cz, m, dens);
+    pf_ld_row<NV>(f.acc + (size_t)s * f.rowf, r);
+    const uint2 wv = __ldg(f.wb + (fi >> 5));
+    pf_finalize_cell<NV, CC, false, false>(p, f, s, b, fi, x, cy, cz, r, wv, m, dens);
 }
 
 // Direct maps: one block per patch of PF_PATCH azimuth x PF_PATCH range cells of one z layer.  The
@@ -689,7 +691,10 @@ __global__ void __launch_bounds__(256) kf_finalize(const __grid_constant__ PvPar
 //      are neighbours too, so the per-voxel loads and stores of a warp share 128-byte lines),
 //   2. a warp writes 32 range-consecutive canvas cells per channel (one full line per store),
 //      every element exactly once, zeros included: no zero fill, no scatter.
-// grid = (patches_x * patches_y * nz, B); each thread owns PF_PATCH / 8 cells of the patch.
+// grid = (patches_x, patches_y * nz, B); each thread owns PF_PATCH / 8 cells of the patch.
+// Tried and slower: fetching all rows of a thread up front with cp.async into shared memory
+// (512 threads, 2 cells each: 37 vs 33 us), 16-byte canvas stores, unaligned per-channel feature
+// stores -- the kernel is insensitive to its instruction count.
 #define PF_PATCH 32
 template <int NV, int CC, bool CANVAS>
 __global__ void __launch_bounds__(256) kf_finalize_patch(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
@@ -698,12 +703,12 @@ __global__ void __launch_bounds__(256) kf_finalize_patch(const __grid_constant__
     constexpr int KP = PF_PATCH / 8;                         // cells per thread
     extern __shared__ float s_t[];                           // [C (+1 density)][PF_PATCH rho][PF_PATCH + 1 phi]
     const int C = CC ? CC : p.C;
-    const int b = blockIdx.y;
+    const int b = blockIdx.z;
     const uint32_t nx = p.grid[0], ny = p.grid[1];
-    const uint32_t px = (nx + PF_PATCH - 1) / PF_PATCH, py = (ny + PF_PATCH - 1) / PF_PATCH;
-    uint32_t pid = blockIdx.x;
-    const uint32_t pxi = pid % px; pid /= px;
-    const uint32_t pyi = pid % py, z = pid / py;
+    const uint32_t py = (ny + PF_PATCH - 1) / PF_PATCH;
+    const uint32_t pxi = blockIdx.x;
+    uint32_t pyi = blockIdx.y, z = 0;
+    if (p.grid[2] > 1) { z = pyi / py; pyi -= z * py; }
     const uint32_t lane = threadIdx.x & 31u, wq = threadIdx.x >> 5;
     int32_t *s_d = reinterpret_cast<int32_t *>(s_t) + (CANVAS ? (size_t)C : 0) * PF_PATCH * (PF_PATCH + 1);
 
@@ -724,8 +729,13 @@ __global__ void __launch_bounds__(256) kf_finalize_patch(const __grid_constant__
 #pragma unroll
             for (int c = 0; c < CT; ++c) m[c] = 0.0f;
         }
-        if (fi[k] != PV_INF)
-            pf_finalize_cell<NV, CC, CANVAS>(p, f, (uint32_t)b * f.capf + (z * nx + x) * ny + y, b, fi[k], x, y, z, m, dens);
+        if (fi[k] != PV_INF) {
+            const uint32_t s = (uint32_t)b * f.capf + (z * nx + x) * ny + y;
+            float r[CT];
+            pf_ld_row<NV>(f.acc + (size_t)s * f.rowf, r);
+            const uint2 wv = __ldg(f.wb + (fi[k] >> 5));
+            pf_finalize_cell<NV, CC, CANVAS, true>(p, f, s, b, fi[k], x, y, z, r, wv, m, dens);
+        }
         if (CANVAS) {
 #pragma unroll
             for (int c = 0; c < CT; ++c)
@@ -1009,7 +1019,9 @@ static int pf_launch_insert(const PvParams &p, const PvF &f, cudaStream_t st)
 {
     const unsigned grid = (p.n + PF_TILE - 1) / PF_TILE;
     const size_t smem = (size_t)PF_TILE * p.c_in * sizeof(float);
-    auto kern = kf_insert<DENSE, CIN, CART, NV, MODE>;
+    // the fused front end never asks for pc_grid_ind: compile that branch out of its kernels
+    constexpr bool SPLIT = MODE == PF_MODE_FREE && CIN > 0;
+    auto kern = (SPLIT && !p.grid_ind) ? kf_insert<DENSE, CIN, CART, NV, MODE, !SPLIT> : kf_insert<DENSE, CIN, CART, NV, MODE, true>;
     // the 48 KB default covers dynamic + static shared memory (the kernel has a few static words)
     if (smem + 1024 > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -1106,8 +1118,8 @@ static int pf_launch_finalize_nv(const PvParams &p, const PvF &f, cudaStream_t s
         return PV_OK;
     }
     const unsigned px = ((unsigned)p.grid[0] + PF_PATCH - 1) / PF_PATCH, py = ((unsigned)p.grid[1] + PF_PATCH - 1) / PF_PATCH;
-    const dim3 grid(px * py * (unsigned)p.grid[2], (unsigned)p.B);
-    if (p.B > 65535) return PV_ERR_UNSUPPORTED;
+    const dim3 grid(px, py * (unsigned)p.grid[2], (unsigned)p.B);
+    if (p.B > 65535 || grid.y > 65535u) return PV_ERR_UNSUPPORTED;
     const size_t smem = ((p.canvas ? (size_t)p.C : 0) + (p.density ? 1 : 0)) * PF_PATCH * (PF_PATCH + 1) * sizeof(float);
     auto kern = p.canvas ? kf_finalize_patch<NV, CC, true> : kf_finalize_patch<NV, CC, false>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -1140,24 +1152,23 @@ int pvf_run(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev)
         if (p.density && cudaMemsetAsync(p.density, 0, (size_t)p.B * p.cells * sizeof(int32_t), st) != cudaSuccess)
             return PV_ERR_CUDA;
     }
-    static const int dbg_skip = [] { const char *e = getenv("PF_SKIP"); return e ? atoi(e) : 0; }();   // DBG
     PF_MARK(0);
-    if (p.n > 0 && !(dbg_skip & 16)) {
+    if (p.n > 0) {
         const int rc = f.dense ? pf_dispatch_insert<true>(p, f, st) : pf_dispatch_insert<false>(p, f, st);
         if (rc) return rc;
     }
     PF_MARK(1);
     PF_MARK(2);                              // (the first-point bitmap is built by the insert kernel)
-    if (!(dbg_skip & 1)) kf_scan_pts<<<(unsigned)p.B, PF_SCAN_THREADS, 0, st>>>(p, f);
+    kf_scan_pts<<<(unsigned)p.B, PF_SCAN_THREADS, 0, st>>>(p, f);
     PF_MARK(3);
-    if (!(dbg_skip & 2)) {
+    {
         const int rc = pf_launch_finalize(p, f, st);
         if (rc) return rc;
     }
     PF_MARK(4);
     if (p.n > 0) {
-        if (!(dbg_skip & 4)) kf_heavy_points<<<(p.n + PF_TILE - 1) / PF_TILE, PF_THREADS, 0, st>>>(p, f);
-        if (!(dbg_skip & 8)) kf_heavy_cells<<<296, 256, 0, st>>>(p, f);
+        kf_heavy_points<<<(p.n + PF_TILE - 1) / PF_TILE, PF_THREADS, 0, st>>>(p, f);
+        kf_heavy_cells<<<296, 256, 0, st>>>(p, f);
     }
     PF_MARK(5);
     return pv_last_cuda_error();
