@@ -232,6 +232,35 @@ int pv_stream_sectors(const pv_config *cfg, const float *points, int64_t n, int3
 int pv_affine_points(const float *in, int64_t n, int32_t c, const double *matrix3x4, float t_shift,
                      float *out, pv_stream_t stream);
 
+/* Segmentation voxel labels: the train branch of
+ * Voxelization.get_grid_ind (det3d/datasets/pipelines/voxelization.py:40-60) followed by
+ * AssignLabel.assign_voxel_labels (det3d/datasets/pipelines/preprocess.py:170-191), batched.
+ *   pc_grid_ind int32 [n, 3] (z, y, x): the clamped per-point grid index pv_voxelize returns
+ *   pc_label    int32 [n]: semantic label of every point; < 0 = unlabelled (dropped, :44); must be < 256
+ * Outputs:
+ *   voxel_labels   int64 [batch, nz, ny, nx]: per cell the label held by most of its valid points
+ *                  (ties -> smallest label, np.argmax; the reference's uint16 counter wraps at 65536
+ *                  and so does this), 0 for cells without valid points; every element is written
+ *   valid_grid_ind int32 [n, 3]: the rows of the valid points in their original order (:45, :58);
+ *                  frame b owns rows [valid_offsets[b], valid_offsets[b + 1])
+ *   valid_offsets  int32 [batch + 1]
+ *   status         int32 [1] (device): 0, bit 0 = table full, bit 1 = a label > 255 or a grid index
+ *                  outside the grid was skipped (undefined behaviour in the reference)
+ * The reference sorts the rows by cell only to group them; the vote is order free (bit-exact). */
+size_t pv_seg_workspace_bytes(const pv_config *cfg, int64_t n_total, int32_t batch);
+int pv_seg_voxel_labels(const pv_config *cfg, const int32_t *pc_grid_ind, const int32_t *pc_label,
+                        const int32_t *frame_offsets, int32_t batch, int64_t n_total, void *workspace,
+                        size_t workspace_bytes, int64_t *voxel_labels, int32_t *valid_grid_ind,
+                        int32_t *valid_offsets, int32_t *status, pv_stream_t stream);
+
+/* SegHead.predict (det3d/models/seg_heads/seg_head.py:171-193): out[i] = pred_labels[b][z, y, x]
+ * for every valid point i of frame b; pred_labels int64 [batch, nz_pred, ny, nx].  nz_pred == 0
+ * selects the 2-D form pred_labels [batch, ny, nx] indexed [y, x] (:188).  status as above (bit 1 =
+ * an index outside the map; that row reads 0). */
+int pv_seg_gather_points(const int64_t *pred_labels, int32_t nz_pred, int32_t ny, int32_t nx,
+                         const int32_t *valid_grid_ind, const int32_t *valid_offsets, int32_t batch,
+                         int64_t n_valid, int64_t *out, int32_t *status, pv_stream_t stream);
+
 /* Copies the device status word of the last pv_voxelize on `workspace` to the host
  * (synchronises `stream`).  Returns PV_OK or PV_ERR_TABLE_FULL / PV_ERR_CUDA. */
 int pv_read_status(const void *workspace, pv_stream_t stream);

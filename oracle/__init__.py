@@ -267,3 +267,31 @@ def stream_polar(points, voxel_size, point_cloud_range, nsectors):
         out.append((op[o:o + k], gi[o:o + k], ix[o:o + k]))
         o += k
     return out
+
+
+def seg_voxel_labels(pc_grid_ind, pc_label, grid_size):
+    """Voxelization.get_grid_ind, train branch (voxelization.py:40-60) + AssignLabel.assign_voxel_labels
+    (preprocess.py:170-191).  grid_size is (nx, ny, nz) as VoxelGenerator.grid_size.
+
+    -> (voxel_labels int64 [1, nz, ny, nx], valid_grid_ind int32 [n_valid, 3])."""
+    gi = np.ascontiguousarray(pc_grid_ind, dtype=np.int32)
+    lab = np.ascontiguousarray(np.asarray(pc_label).reshape(-1), dtype=np.int32)
+    n = gi.shape[0]
+    nx, ny, nz = (int(v) for v in grid_size)
+    labels = np.empty((1, nz, ny, nx), np.int64)
+    valid = np.empty((max(n, 1), 3), np.int32)
+    L = lib()
+    L.po_seg_voxel_labels.restype = ctypes.c_int64
+    m = L.po_seg_voxel_labels(_p(gi), _p(lab), ctypes.c_int64(n), ctypes.c_int(nz), ctypes.c_int(ny), ctypes.c_int(nx),
+                              _p(labels), _p(valid))
+    if m < 0:
+        raise MemoryError("oracle: allocation failed")
+    return labels, valid[:m]
+
+
+def seg_gather_points(pred_labels, valid_grid_ind):
+    """SegHead.predict (seg_heads/seg_head.py:184-191) for one sample: pred_labels [nz, ny, nx] or [ny, nx]."""
+    g = np.asarray(valid_grid_ind)
+    if pred_labels.ndim == 2:
+        return pred_labels[g[:, 1], g[:, 2]]
+    return pred_labels[g[:, 0], g[:, 1], g[:, 2]]

@@ -521,3 +521,71 @@ int64_t po_stream_polar(const float *points, int64_t n, int c, const float *voxe
     }
     return w;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Voxelization.get_grid_ind, train branch (det3d/datasets/pipelines/        */
+/* voxelization.py:40-60) + AssignLabel.assign_voxel_labels (det3d/datasets/  */
+/* pipelines/preprocess.py:170-191).                                          */
+/*   valid = pc_label >= 0                                           (:44)     */
+/*   rows (z, y, x, label) of the valid points, lexsorted with x as the       */
+/*   primary key, then y, then z (np.lexsort((g0, g1, g2)), :47)               */
+/*   sequential scan with a 256-entry uint16 counter per run of equal cells;   */
+/*   voxel_labels[z, y, x] = argmax(counter), first maximum   (preprocess.py   */
+/*   :178-191); cells without a valid point stay 0            (:50)            */
+/* pc_grid_ind [n, 3] (z, y, x), pc_label [n]; voxel_labels int64 [nz, ny, nx] */
+/* (zeroed here), valid_grid_ind [n, 3] receives the valid rows in their       */
+/* original order (:45, :58).  Returns the number of valid rows, -1 on         */
+/* allocation failure.                                                        */
+/* ------------------------------------------------------------------------- */
+typedef struct { int32_t z, y, x, l; } po_pair;
+
+static int po_pair_cmp(const void *a, const void *b)
+{
+    const po_pair *p = (const po_pair *)a, *q = (const po_pair *)b;
+    if (p->x != q->x) return p->x < q->x ? -1 : 1;
+    if (p->y != q->y) return p->y < q->y ? -1 : 1;
+    if (p->z != q->z) return p->z < q->z ? -1 : 1;
+    return 0;       /* rows of one cell: their order does not change the counter */
+}
+
+static int64_t po_argmax_u16(const uint16_t *c)
+{
+    int best = 0;
+    for (int k = 1; k < 256; ++k)
+        if (c[k] > c[best]) best = k;
+    return best;
+}
+
+int64_t po_seg_voxel_labels(const int32_t *pc_grid_ind, const int32_t *pc_label, int64_t n, int nz,
+                            int ny, int nx, int64_t *voxel_labels, int32_t *valid_grid_ind)
+{
+    memset(voxel_labels, 0, (size_t)nz * ny * nx * sizeof(int64_t));
+    po_pair *pairs = (po_pair *)malloc((size_t)(n > 0 ? n : 1) * sizeof(po_pair));
+    if (!pairs) return -1;
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (pc_label[i] < 0) continue;
+        pairs[m].z = pc_grid_ind[i * 3]; pairs[m].y = pc_grid_ind[i * 3 + 1]; pairs[m].x = pc_grid_ind[i * 3 + 2];
+        pairs[m].l = pc_label[i];
+        memcpy(valid_grid_ind + m * 3, pc_grid_ind + i * 3, 3 * sizeof(int32_t));
+        ++m;
+    }
+    if (m > 0) {
+        qsort(pairs, (size_t)m, sizeof(po_pair), po_pair_cmp);
+        uint16_t counter[256];
+        memset(counter, 0, sizeof counter);
+        counter[pairs[0].l] = 1;                                         /* :179 */
+        po_pair cur = pairs[0];
+        for (int64_t i = 1; i < m; ++i) {
+            if (pairs[i].z != cur.z || pairs[i].y != cur.y || pairs[i].x != cur.x) {       /* :185 */
+                voxel_labels[((int64_t)cur.z * ny + cur.y) * nx + cur.x] = po_argmax_u16(counter);
+                memset(counter, 0, sizeof counter);
+                cur = pairs[i];
+            }
+            counter[pairs[i].l] = (uint16_t)(counter[pairs[i].l] + 1);    /* uint16: wraps at 65536 */
+        }
+        voxel_labels[((int64_t)cur.z * ny + cur.y) * nx + cur.x] = po_argmax_u16(counter);
+    }
+    free(pairs);
+    return m;
+}

@@ -90,6 +90,9 @@ EXPORTS = {
     "pv_stream_workspace_bytes": (SZ, [I64, I32]),
     "pv_stream_sectors": (ctypes.c_int, [ctypes.POINTER(PvConfig), P, I64, I32, I32, F32, P, SZ, P, P, P, P, P]),
     "pv_affine_points": (ctypes.c_int, [P, I64, I32, ctypes.POINTER(ctypes.c_double), F32, P, P]),
+    "pv_seg_workspace_bytes": (SZ, [ctypes.POINTER(PvConfig), I64, I32]),
+    "pv_seg_voxel_labels": (ctypes.c_int, [ctypes.POINTER(PvConfig), P, P, P, I32, I64, P, SZ, P, P, P, P, P]),
+    "pv_seg_gather_points": (ctypes.c_int, [P, I32, I32, I32, P, P, I32, I64, P, P, P]),
     "pv_read_status": (ctypes.c_int, [P, P]),
     "pv_vfe_mean": (ctypes.c_int, [P, P, I64, I32, I32, P, P]),
     "pv_pfn_forward": (ctypes.c_int, [P, P, P, I64, I32, I32, I32, F32, F32, F32, F32,

@@ -252,6 +252,61 @@ def stream_sectors(cfg, points, nsectors, max_azimuth):
     return out, gi, idx, counts
 
 
+def seg_voxel_labels(cfg, pc_grid_ind, pc_label, frame_offsets, batch):
+    """pv_seg_voxel_labels: (voxel_labels int64 [batch, nz, ny, nx], valid_grid_ind int32 [n_valid, 3],
+    valid_offsets int32 [batch + 1]).  Synchronises once to read the status word and the valid count."""
+    _need(pc_grid_ind, torch.int32, "pc_grid_ind", 2)
+    _need(pc_label, torch.int32, "pc_label", 1)
+    _need(frame_offsets, torch.int32, "frame_offsets", 1)
+    n = pc_grid_ind.shape[0]
+    if pc_grid_ind.shape[1] != 3 or pc_label.shape[0] != n or frame_offsets.shape[0] != batch + 1:
+        raise ValueError("pc_grid_ind must be [n, 3], pc_label [n], frame_offsets [batch + 1]")
+    dev = pc_grid_ind.device
+    lib = _lib.load()
+    nbytes = lib.pv_seg_workspace_bytes(cfg, n, batch)
+    if nbytes == 0:
+        raise ValueError("bad configuration for pv_seg_voxel_labels")
+    ws = workspace(nbytes, dev, "seg")
+    nx, ny, nz = (int(v) for v in cfg.grid)
+    labels = torch.empty((batch, nz, ny, nx), dtype=torch.int64, device=dev)
+    valid = torch.empty((max(n, 1), 3), dtype=torch.int32, device=dev)
+    voff = torch.empty((batch + 1,), dtype=torch.int32, device=dev)
+    status = torch.empty((1,), dtype=torch.int32, device=dev)
+    check(lib.pv_seg_voxel_labels(cfg, ptr(pc_grid_ind), ptr(pc_label), ptr(frame_offsets), batch, n, ptr(ws), ws.numel(),
+                                  ptr(labels), ptr(valid), ptr(voff), ptr(status), current_stream(dev)),
+          "pv_seg_voxel_labels")
+    st, n_valid = int(status.item()), int(voff[-1].item())
+    if st & 1:
+        raise RuntimeError("pv_seg_voxel_labels: label table full")
+    if st & 2:
+        raise ValueError("pv_seg_voxel_labels: a label > 255 or a grid index outside the grid")
+    return labels, valid[:n_valid], voff
+
+
+def seg_gather_points(pred_labels, valid_grid_ind, valid_offsets):
+    """pv_seg_gather_points: per-point predictions pred_labels[b][z, y, x] (pred_labels [B, nz, ny, nx]) or
+    pred_labels[b][y, x] (pred_labels [B, ny, nx]) -- SegHead.predict, seg_head.py:171-193."""
+    _need(pred_labels, torch.int64, "pred_labels")
+    _need(valid_grid_ind, torch.int32, "valid_grid_ind", 2)
+    _need(valid_offsets, torch.int32, "valid_offsets", 1)
+    if pred_labels.dim() not in (3, 4):
+        raise ValueError("pred_labels must be [B, ny, nx] or [B, nz, ny, nx]")
+    batch = pred_labels.shape[0]
+    nz = pred_labels.shape[1] if pred_labels.dim() == 4 else 0
+    ny, nx = int(pred_labels.shape[-2]), int(pred_labels.shape[-1])
+    if valid_offsets.shape[0] != batch + 1 or valid_grid_ind.shape[1] != 3:
+        raise ValueError("valid_offsets must be [B + 1], valid_grid_ind [n, 3]")
+    n = valid_grid_ind.shape[0]
+    dev = pred_labels.device
+    out = torch.empty((n,), dtype=torch.int64, device=dev)
+    status = torch.empty((1,), dtype=torch.int32, device=dev)
+    check(_lib.load().pv_seg_gather_points(ptr(pred_labels), nz, ny, nx, ptr(valid_grid_ind), ptr(valid_offsets), batch,
+                                           n, ptr(out), ptr(status), current_stream(dev)), "pv_seg_gather_points")
+    if int(status.item()) & 2:
+        raise ValueError("pv_seg_gather_points: a grid index outside the prediction map")
+    return out
+
+
 def affine_points(points, matrix, t_shift=0.0):
     """pv_affine_points: xyz <- M[:3, :3] . xyz + M[:3, 3] (float64 arithmetic), last column -= t_shift."""
     import ctypes

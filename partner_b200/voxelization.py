@@ -48,12 +48,28 @@ class Voxelization(object):
             self.return_pc_grid_ind = True
             assert not self.double_flip, "currently not supporting double flip for segmentation"
 
-    # voxelization.py:40-60 (evaluation branch)
+    # voxelization.py:40-60
     def get_grid_ind(self, res, pc_grid_ind, grid_size):
         if res["mode"] in ["train", "debug_gt"]:
-            raise NotImplementedError("training-time voxel label assignment (AssignLabel.assign_voxel_labels) "
-                                      "is a 'next' row")
-        pc_grid_ind = pc_grid_ind[:res["lidar"]["n_key_points"]]
+            # :42-54 -- drop unlabelled points, majority label per cell (AssignLabel.assign_voxel_labels,
+            # preprocess.py:170-191) on the GPU: pv_seg_voxel_labels
+            import torch
+            import ctypes
+            from ._lib import PvConfig
+            dev = torch.device("cuda", torch.cuda.current_device())
+            cfg = PvConfig()
+            ctypes.memmove(ctypes.byref(cfg), ctypes.byref(self.voxel_generator._cfg), ctypes.sizeof(PvConfig))
+            for j in range(3):      # a sector's reduced grid (:316-317): only the grid extent matters here
+                cfg.grid[j] = int(grid_size[j])
+            out_dtype = pc_grid_ind.dtype
+            gi = torch.from_numpy(np.ascontiguousarray(pc_grid_ind, dtype=np.int32)).to(dev)
+            lab = torch.from_numpy(np.ascontiguousarray(res["lidar"]["pc_label"]).reshape(-1).astype(np.int32)).to(dev)
+            off = torch.tensor([0, gi.shape[0]], dtype=torch.int32, device=dev)
+            labels, valid, _ = F.seg_voxel_labels(cfg, gi, lab, off, 1)
+            res["lidar"]["voxels"].update({"labels": labels.cpu().numpy()})          # [1, nz, ny, nx] int64 (:52)
+            pc_grid_ind = valid.cpu().numpy().astype(out_dtype)
+        else:
+            pc_grid_ind = pc_grid_ind[:res["lidar"]["n_key_points"]]
         res["lidar"]["voxels"].update({"valid_grid_ind": pc_grid_ind.copy()})
         return res
 

@@ -154,3 +154,32 @@ def test_stream_polar_golden(nsec, golden_dir):
         assert np.array_equal(pts[:, other], ref_pts[:, other])                  # incl. the shifted azimuth: bit-exact
         # x, y = rho * cos / sin(phi): numpy's float32 cos / sin are vendor SIMD routines (not reproducible)
         assert np.allclose(pts[:, 3:5], ref_pts[:, 3:5], rtol=1e-6, atol=2e-5)
+
+
+# ---- segmentation voxel labels, tests/golden/make_golden_seg.py ----
+def seg_pred_map(nz, ny, nx):
+    """The formula-defined prediction map of make_golden_seg.pred_map."""
+    z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    return ((z * 7 + y * 3 + x * 5 + (x * y) // 11) % 16 + 1).astype(np.int64)
+
+
+@pytest.mark.parametrize("case", ["pillar", "cyl"])
+def test_seg_voxel_labels_match_reference(case, golden_dir):
+    g = np.load(os.path.join(golden_dir, "seg.npz"))
+    gs = g[f"{case}_grid_size"]
+    labels, valid = oracle.seg_voxel_labels(g[f"{case}_grid_ind"], g[f"{case}_label"], gs)
+    want = densify(g[f"{case}_labels_nz_index"], g[f"{case}_labels_nz_value"], (1,) + tuple(gs[::-1]))
+    assert labels.dtype == np.int64 and np.array_equal(labels, want)
+    assert np.array_equal(valid, g[f"{case}_valid_grid_ind"])
+    nx, ny, nz = (int(v) for v in gs)
+    pred = seg_pred_map(nz, ny, nx)
+    got = oracle.seg_gather_points(pred[0] if nz == 1 else pred, valid)
+    assert np.array_equal(got, g[f"{case}_point_preds"])
+
+
+@pytest.mark.parametrize("case", ["wrap_a", "wrap_b"])
+def test_seg_voxel_labels_uint16_counter_wraps(case, golden_dir):
+    g = np.load(os.path.join(golden_dir, "seg.npz"))
+    labels, _ = oracle.seg_voxel_labels(g[f"{case}_grid_ind"], g[f"{case}_label"], [8, 8, 1])
+    assert np.array_equal(labels, g[f"{case}_labels"])
+    assert int(labels[0, 0, 3, 4]) == (9 if case == "wrap_a" else 2)
