@@ -41,6 +41,9 @@
 #define PF_THREADS 256
 #define PF_PPT 4                          // consecutive points per thread in the point passes
 #define PF_TILE (PF_THREADS * PF_PPT)
+#ifndef PF_INSERT_MIN_BLOCKS
+#define PF_INSERT_MIN_BLOCKS 4
+#endif
 #define PF_SCAN_THREADS 1024
 #define PF_SCAN_VEC 4                    // 4-word vectors per thread per scan iteration
 
@@ -105,7 +108,7 @@ __device__ __forceinline__ uint32_t pf_claim(uint32_t *keys, uint32_t mask, uint
 #define PF_MODE_DYN 1
 #define PF_MODE_LISTS 2
 template <bool DENSE, int CIN, bool CART, int NV, int MODE = PF_MODE_FREE, bool GI = true>
-__global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ PvParams p,
+__global__ void __launch_bounds__(PF_THREADS, PF_INSERT_MIN_BLOCKS) kf_insert(const __grid_constant__ PvParams p,
                                                         const __grid_constant__ PvF f)
 {
     extern __shared__ __align__(128) float s_pts[];
@@ -174,18 +177,15 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
     // marks its own bit and, if it displaced an earlier minimum, toggles that one's bit.  Every bit
     // is toggled at most twice -- once by its owner, once by the run that displaced it -- and XOR
     // commutes, so when the grid has drained exactly the final first points are set, whatever the
-    // arrival order.  The returned value is consumed one flush later (the L2 round trip stays off
-    // the critical path); own bits are collected per thread and leave as ONE reduction per 32
-    // points (8 lanes x 4 points = one bitmap word).
-    uint32_t pend_old = 0, pend_i = 0;       // old <= i: nothing to do
-    uint32_t mine = 0;                       // bit j: point t0 + j became its cell's minimum
-    auto resolve = [&]() {
-        if (pend_old > pend_i) {
-            mine |= 1u << (pend_i - (tile_base + t0));
-            if (pend_old != PV_INF) atomicXor(f.bits + (pend_old >> 5), 1u << (pend_old & 31u));
-        }
-    };
-    auto flush = [&]() {
+    // arrival order.  The returned values are only looked at when the thread has issued all its
+    // runs (one wait for up to four round trips in flight, not one per run); own bits are
+    // collected per thread and leave as ONE reduction per 32 points (8 lanes x 4 points = one
+    // bitmap word).
+    uint32_t olds[PF_PPT];                   // per flush site: what the minimum was before (0: site unused)
+    uint32_t starts = 0;                     // 2 bits per site: the run's first point, relative to t0
+#pragma unroll
+    for (int j = 0; j < PF_PPT; ++j) olds[j] = 0u;
+    auto flush = [&](const int site) {
         if (cur_s != PV_INF) {
             if constexpr (LISTS) {           // list-based map entry {first, count - 1}
                 atomicMin(&p.ws.table[cur_s].first, cur_i);
@@ -194,10 +194,9 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
             }
             if constexpr (DYN) atomicOr(f.bits + (cur_i >> 5), 1u << (cur_i & 31u));   // cur_i = the cell's bit address
             else {
-                resolve();                   // the previous run's answer has long arrived
-                // straight into the pending register: a copy of the result would wait for the round trip
-                pend_old = atomicMin(f.first + cur_s, cur_i);
-                pend_i = cur_i;
+                // straight into the site's register: a copy of the result would wait for the round trip
+                olds[site] = atomicMin(f.first + cur_s, cur_i);
+                starts |= (cur_i - (tile_base + t0)) << (2 * site);
             }
             float o[CT];                     // the count rides in channel C of the row
 #pragma unroll
@@ -299,13 +298,13 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
             }
             cur_n += 1.0f;
         } else {
-            flush();
+            flush(j);                        // (never a run at j == 0: site 0 is the final flush's)
             cur_s = s; cur_i = DYN ? sa : i; cur_n = 1.0f;
 #pragma unroll
             for (int k = 0; k < CT; ++k) cur[k] = v[k];
         }
     }
-    flush();
+    flush(0);
     if (DYN && !p.unq_inv) return;           // the per-point map is only needed for the inverse index
     uint32_t *sa_dst = LISTS ? p.ws.slot : f.sa;
     if (t0 + PF_PPT <= n_tile) {
@@ -320,7 +319,15 @@ __global__ void __launch_bounds__(PF_THREADS) kf_insert(const __grid_constant__ 
             }
     }
     if constexpr (MODE == PF_MODE_FREE) {
-        resolve();                           // the last run's answer
+        uint32_t mine = 0;                   // bit j: point t0 + j became its cell's minimum
+#pragma unroll
+        for (int site = 0; site < PF_PPT; ++site) {
+            const uint32_t j0 = (starts >> (2 * site)) & 3u, i0 = tile_base + t0 + j0, old = olds[site];
+            if (old > i0) {
+                mine |= 1u << j0;
+                if (old != PV_INF) atomicXor(f.bits + (old >> 5), 1u << (old & 31u));
+            }
+        }
         uint32_t word = mine << (4u * (tid & 7u));
         word |= __shfl_xor_sync(0xffffffffu, word, 1);
         word |= __shfl_xor_sync(0xffffffffu, word, 2);
