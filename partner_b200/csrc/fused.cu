@@ -81,14 +81,13 @@ __device__ __forceinline__ void pf_bulk_g2s(uint32_t dst, const void *src, uint3
 }
 
 // Hash-mode slot claim (same protocol as voxelize.cu): keys[] = cell, clean = INF.
-__device__ __forceinline__ uint32_t pf_claim(uint32_t *keys, uint32_t mask, uint32_t cell, uint32_t *status)
+__device__ __forceinline__ uint32_t pf_claim(uint32_t *keys, uint32_t mask, uint32_t cell, uint32_t h, uint32_t *status)
 {
-    uint32_t h = pv_hash(cell) & mask;
     for (uint32_t probe = 0; probe <= mask; ++probe) {
         // CAS first: one L2 round trip whether the slot is free, already ours, or taken
         const uint32_t old = atomicCAS(keys + h, PV_INF, cell);
         if (old == PV_INF || old == cell) return h;
-        h = (h + 1) & mask;
+        h = pv_probe_next(h, probe, mask);
     }
     atomicOr(status, 1u);
     return PV_INF;
@@ -269,7 +268,8 @@ __global__ void __launch_bounds__(PF_THREADS, PF_INSERT_MIN_BLOCKS) kf_insert(co
         if (LISTS) {
             if (DENSE) s = (uint32_t)b * p.ws.capf + (cz * nx + cx) * ny + cy;     // voxelize.cu's direct map: phi fastest
             else {
-                const uint32_t h = pf_claim(p.ws.keys + (size_t)b * p.ws.capf, p.ws.capf - 1, cell, p.ws.ctrl + 1);
+                const uint32_t h = pf_claim(p.ws.keys + (size_t)b * p.ws.capf, p.ws.capf - 1, cell,
+                                          pv_slot_home(cx, cy, cz, nx, ny, p.ws.capf - 1), p.ws.ctrl + 1);
                 if (h == PV_INF) continue;
                 s = (uint32_t)b * p.ws.capf + h;
                 p.ws.pcell[i] = cell;
@@ -284,7 +284,8 @@ __global__ void __launch_bounds__(PF_THREADS, PF_INSERT_MIN_BLOCKS) kf_insert(co
             s = (uint32_t)b * f.capf + (cz * nx + cx) * ny + cy;
             sa = s;
         } else {
-            const uint32_t h = pf_claim(f.keys + (size_t)b * f.capf, f.capf - 1, cell, p.ws.ctrl + 1);
+            const uint32_t h = pf_claim(f.keys + (size_t)b * f.capf, f.capf - 1, cell,
+                                      pv_slot_home(cx, cy, cz, nx, ny, f.capf - 1), p.ws.ctrl + 1);
             if (h == PV_INF) continue;       // map full: status bit set
             s = (uint32_t)b * f.capf + h;
             sa = s;

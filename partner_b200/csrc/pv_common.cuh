@@ -125,6 +125,36 @@ __device__ __forceinline__ uint32_t pv_hash(uint32_t k)
     return k;
 }
 
+// Home slot of cell (cz, cy, cx) in a hash map of mask + 1 slots (power of two >= 1024).  LOCALITY
+// PRESERVING: the 16 azimuth-consecutive cells of one (z, range) share a row of 16 consecutive
+// slots -- the group is hashed, the low 4 azimuth bits are kept -- so the keys, first-point words,
+// map entries and accumulator rows that consecutive points of a LiDAR ring touch share 128-byte
+// lines, exactly as in the direct (phi-fastest) map.  Probing moves a whole row at a time
+// (PV_PROBE_STEP), which keeps the in-row position; pv_probe_next walks all rows of that position
+// before it moves to the next position, so every slot of the map is reachable.
+#ifdef PV_HASH_FLAT
+#define PV_PROBE_STEP 1u
+__device__ __forceinline__ uint32_t pv_slot_home(uint32_t cx, uint32_t cy, uint32_t cz, uint32_t nx, uint32_t ny, uint32_t mask)
+{
+    return pv_hash((cz * ny + cy) * nx + cx) & mask;
+}
+#else
+#define PV_PROBE_STEP 16u
+__device__ __forceinline__ uint32_t pv_slot_home(uint32_t cx, uint32_t cy, uint32_t cz, uint32_t nx, uint32_t ny, uint32_t mask)
+{
+    if (ny < 16u) return pv_hash((cz * ny + cy) * nx + cx) & mask;      // no azimuth rows to keep together
+    const uint32_t group = (cz * nx + cx) * ((ny + 15u) >> 4) + (cy >> 4);
+    return ((pv_hash(group) << 4) | (cy & 15u)) & mask;
+}
+#endif
+
+__device__ __forceinline__ uint32_t pv_probe_next(uint32_t h, uint32_t probe, uint32_t mask)
+{
+    h = (h + PV_PROBE_STEP) & mask;
+    if (PV_PROBE_STEP > 1u && ((probe + 1u) & (mask / PV_PROBE_STEP)) == 0u) h = (h + 1u) & mask;
+    return h;
+}
+
 // Largest b in [0, B) with offsets[b] <= i  (frames may be empty).
 __device__ __forceinline__ int pv_frame_of(const int32_t *__restrict__ off, int B, uint32_t i)
 {

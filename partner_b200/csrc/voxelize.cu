@@ -67,15 +67,14 @@ __global__ void __launch_bounds__(32) k_scan_layout(const __grid_constant__ PvPa
 // trip per probe, so hash maps want as many independent threads in flight as possible (the
 // 4-points-per-thread kernel of fused.cu measured 182 us vs 121 us here on the Waymo batch)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pv_claim(uint32_t *keys, uint32_t mask, uint32_t cell,
+__device__ __forceinline__ uint32_t pv_claim(uint32_t *keys, uint32_t mask, uint32_t cell, uint32_t h,
                                              uint32_t *status)
 {
-    uint32_t h = pv_hash(cell) & mask;
     for (uint32_t probe = 0; probe <= mask; ++probe) {
         // CAS first: one L2 round trip whether the slot is free, already ours, or taken
         const uint32_t old = atomicCAS(keys + h, PV_INF, cell);
         if (old == PV_INF || old == cell) return h;
-        h = (h + 1) & mask;
+        h = pv_probe_next(h, probe, mask);
     }
     atomicOr(status, 1u);
     return PV_INF;
@@ -113,7 +112,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_bin_insert(const __grid_constant
     const uint32_t i = tile_base + tid;
     const bool live = tid < n_tile;
     bool ok = live;
-    uint32_t cell = 0, local = 0;
+    uint32_t cell = 0, local = 0, home = 0;
     int b = s_b0;
     if (live) {
         const float *row = s_pts + tid * c_in;
@@ -143,6 +142,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_bin_insert(const __grid_constant
         }
         cell = ((uint32_t)ci[2] * (uint32_t)p.grid[1] + (uint32_t)ci[1]) * (uint32_t)p.grid[0] + (uint32_t)ci[0];
         if (DENSE) local = pv_dense_slot(p, ci[2], ci[1], ci[0]);
+        else home = pv_slot_home((uint32_t)ci[0], (uint32_t)ci[1], (uint32_t)ci[2], (uint32_t)p.grid[0], (uint32_t)p.grid[1], p.ws.capf - 1);
         while (b + 1 < p.B && i >= (uint32_t)__ldg(p.offsets + b + 1)) ++b;   // tile may straddle frames
     }
 
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(K1_THREADS) k_bin_insert(const __grid_constant
     const int leader = __ffs(peers) - 1;
     uint32_t s = PV_INF;
     if (ok && (int)lane == leader) {
-        if (!DENSE) local = pv_claim(p.ws.keys + (size_t)b * p.ws.capf, p.ws.capf - 1, cell, p.ws.ctrl + 1);
+        if (!DENSE) local = pv_claim(p.ws.keys + (size_t)b * p.ws.capf, p.ws.capf - 1, cell, home, p.ws.ctrl + 1);
         if (local != PV_INF) {
             s = (uint32_t)b * p.ws.capf + local;
             atomicMin(&p.ws.table[s].first, i);          // lanes are in index order: leader is the min
