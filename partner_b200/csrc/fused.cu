@@ -569,44 +569,6 @@ __device__ __forceinline__ void pf_st_row_clean(float *row, float keep0)
     }
 }
 
-// One feature row [C] at row vid of a packed [M, C] array.  A scattered store costs one load/store
-// unit slot per lane whatever its width, so 28-byte rows (C = 7) go out as one 16-, one 8- and one
-// 4-byte store chosen by the row's alignment, 32-byte rows (C = 8) as two 16-byte stores.
-template <int CT>
-__device__ __forceinline__ void pf_store_feats(float *feats, int32_t vid, int C, const float (&mean)[CT])
-{
-    float *o = feats + (size_t)vid * C;
-    const bool al16 = (reinterpret_cast<uintptr_t>(feats) & 15u) == 0;
-    if (CT == 8 && C == 7 && al16) {
-        float2 *o2; float4 *o4;
-        switch (vid & 3) {
-        case 0:
-            o4 = reinterpret_cast<float4 *>(o); o2 = reinterpret_cast<float2 *>(o + 4);
-            *o4 = make_float4(mean[0], mean[1], mean[2], mean[3]); *o2 = make_float2(mean[4 % CT], mean[5 % CT]); o[6] = mean[6 % CT];
-            break;
-        case 1:     // row starts 12 bytes past a 16-byte boundary
-            o2 = reinterpret_cast<float2 *>(o + 5); o4 = reinterpret_cast<float4 *>(o + 1);
-            o[0] = mean[0]; *o4 = make_float4(mean[1], mean[2], mean[3], mean[4 % CT]); *o2 = make_float2(mean[5 % CT], mean[6 % CT]);
-            break;
-        case 2:     // 8 bytes past
-            o2 = reinterpret_cast<float2 *>(o); o4 = reinterpret_cast<float4 *>(o + 2);
-            *o2 = make_float2(mean[0], mean[1]); *o4 = make_float4(mean[2], mean[3], mean[4 % CT], mean[5 % CT]); o[6] = mean[6 % CT];
-            break;
-        default:    // 4 bytes past
-            o2 = reinterpret_cast<float2 *>(o + 1); o4 = reinterpret_cast<float4 *>(o + 3);
-            o[0] = mean[0]; *o2 = make_float2(mean[1], mean[2]); *o4 = make_float4(mean[3], mean[4 % CT], mean[5 % CT], mean[6 % CT]);
-            break;
-        }
-    } else if (CT == 12 && C == 8 && al16) {
-        reinterpret_cast<float4 *>(o)[0] = make_float4(mean[0], mean[1], mean[2], mean[3]);
-        reinterpret_cast<float4 *>(o)[1] = make_float4(mean[4 % CT], mean[5 % CT], mean[6 % CT], mean[7 % CT]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < CT; ++k)
-            if (k < C) o[k] = mean[k];
-    }
-}
-
 // One occupied map slot s of frame b = cell (cz, cy, cx): rank lookup, per-voxel outputs, heavy
 // registration, map restore.  m[] / dens receive what the dense canvas / density hold for the cell.
 template <int NV, int CC, bool CANVAS, bool DENSE>
@@ -662,7 +624,7 @@ __device__ __forceinline__ void pf_finalize_cell(const PvParams &p, const PvF &f
                 for (int k = 0; k < CT; ++k)
                     if (k < C) cv[(size_t)k * p.cells] = mean[k];
             }
-            if (p.feats) pf_store_feats<CT>(p.feats, vid, C, mean);
+            if (p.feats) pv_store_feats<CT>(p.feats, vid, C, mean);
         }
         if (!DENSE && p.density) p.density[(size_t)b * p.cells + cell] = (int32_t)cnt;
     }
@@ -923,7 +885,7 @@ __global__ void __launch_bounds__(256) kf_dyn_finalize(const __grid_constant__ P
             mean[k] = k < C ? pv_div_count(r[k], cntf, inv) : 0.0f;       // scatter_mean: sum / count
             if (CANVAS) m[k] = mean[k];
         }
-        if (p.feats) pf_store_feats<CT>(p.feats, vid, C, mean);
+        if (p.feats) pv_store_feats<CT>(p.feats, vid, C, mean);
         pf_st_row_clean<NV>(rowp, 0.0f);                                  // restore the row (after use)
     }
     if (CANVAS) {                                                         // DynamicPPScatter, zeros included

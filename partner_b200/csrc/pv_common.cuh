@@ -238,15 +238,32 @@ __device__ __forceinline__ float pv_rho(float x, float y)
     return __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));
 }
 
+// Point i's raw row, zero padded.  A gathered load costs one load/store slot per lane whatever its
+// width, so rows with an even number of floats (8-byte aligned) are fetched as float2.
+template <int N>
+__device__ __forceinline__ void pv_load_row(const float *__restrict__ pts, uint32_t i, int c_in, float (&in)[N])
+{
+    const float *row = pts + (size_t)i * c_in;
+    if ((c_in & 1) == 0 && (reinterpret_cast<uintptr_t>(pts) & 7u) == 0) {
+#pragma unroll
+        for (int k = 0; k < N; k += 2) {
+            const float2 v = (k < c_in) ? __ldg(reinterpret_cast<const float2 *>(row + k)) : make_float2(0.0f, 0.0f);
+            in[k] = v.x;
+            if (k + 1 < N) in[k + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) in[k] = (k < c_in) ? __ldg(row + k) : 0.0f;
+    }
+}
+
 // Loads point i's row and expands it to the C-channel feature row the reference voxelizes:
 // Cartesian input -> (rho, phi, z, x, y, feat3..) (utils.py:42-44); polar input -> as is.
 __device__ __forceinline__ void pv_feature_row(const float *__restrict__ pts, uint32_t i, int c_in,
                                                int cart, float (&out)[PV_MAX_CHANNELS])
 {
-    const float *row = pts + (size_t)i * c_in;
     float in[PV_MAX_CHANNELS];
-#pragma unroll
-    for (int k = 0; k < PV_MAX_CHANNELS; ++k) in[k] = (k < c_in) ? __ldg(row + k) : 0.0f;
+    pv_load_row(pts, i, c_in, in);
     if (cart) {
         out[0] = pv_rho(in[0], in[1]);
         out[1] = pv_atan2f(in[1], in[0]);
@@ -258,6 +275,45 @@ __device__ __forceinline__ void pv_feature_row(const float *__restrict__ pts, ui
         for (int k = 0; k < PV_MAX_CHANNELS; ++k) out[k] = in[k];
     }
 }
+
+// One feature row [C] at row vid of a packed [M, C] array.  A scattered store costs one load/store
+// unit slot per lane whatever its width, so 28-byte rows (C = 7) go out as one 16-, one 8- and one
+// 4-byte store chosen by the row's alignment, 32-byte rows (C = 8) as two 16-byte stores.
+template <int CT>
+__device__ __forceinline__ void pv_store_feats(float *feats, int32_t vid, int C, const float (&mean)[CT])
+{
+    float *o = feats + (size_t)vid * C;
+    const bool al16 = (reinterpret_cast<uintptr_t>(feats) & 15u) == 0;
+    if (CT >= 7 && C == 7 && al16) {
+        float2 *o2; float4 *o4;
+        switch (vid & 3) {
+        case 0:
+            o4 = reinterpret_cast<float4 *>(o); o2 = reinterpret_cast<float2 *>(o + 4);
+            *o4 = make_float4(mean[0], mean[1], mean[2], mean[3]); *o2 = make_float2(mean[4 % CT], mean[5 % CT]); o[6] = mean[6 % CT];
+            break;
+        case 1:     // row starts 12 bytes past a 16-byte boundary
+            o2 = reinterpret_cast<float2 *>(o + 5); o4 = reinterpret_cast<float4 *>(o + 1);
+            o[0] = mean[0]; *o4 = make_float4(mean[1], mean[2], mean[3], mean[4 % CT]); *o2 = make_float2(mean[5 % CT], mean[6 % CT]);
+            break;
+        case 2:     // 8 bytes past
+            o2 = reinterpret_cast<float2 *>(o); o4 = reinterpret_cast<float4 *>(o + 2);
+            *o2 = make_float2(mean[0], mean[1]); *o4 = make_float4(mean[2], mean[3], mean[4 % CT], mean[5 % CT]); o[6] = mean[6 % CT];
+            break;
+        default:    // 4 bytes past
+            o2 = reinterpret_cast<float2 *>(o + 1); o4 = reinterpret_cast<float4 *>(o + 3);
+            o[0] = mean[0]; *o2 = make_float2(mean[1], mean[2]); *o4 = make_float4(mean[3], mean[4 % CT], mean[5 % CT], mean[6 % CT]);
+            break;
+        }
+    } else if (CT >= 8 && C == 8 && al16) {
+        reinterpret_cast<float4 *>(o)[0] = make_float4(mean[0], mean[1], mean[2], mean[3]);
+        reinterpret_cast<float4 *>(o)[1] = make_float4(mean[4 % CT], mean[5 % CT], mean[6 % CT], mean[7 % CT]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < CT; ++k)
+            if (k < C) o[k] = mean[k];
+    }
+}
+
 
 // Host-side helpers shared by the translation units.
 int pv_check_config(const pv_config *cfg);

@@ -361,6 +361,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_reduce(const __grid_const
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const __grid_constant__ PvParams p)
 {
     __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
+    // per-voxel records of the tile, indexed by rank inside the tile: a thread owns SCAN_ITEMS
+    // consecutive points, so writing them straight out would put the lanes of a store 32 bytes
+    // apart; staged here they leave as coalesced rows
+    __shared__ uint32_t s_cell[SCAN_TILE], s_kg[SCAN_TILE], s_c[SCAN_TILE];
     const TileRange t = pv_tile_range(p, blockIdx.x);
     if (t.b < 0) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -375,13 +379,32 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const __grid_consta
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    unsigned long long excl = p.ws.tile_pre[blockIdx.x] - ((unsigned long long)p.ws.frame_rank0[t.b] << 32);
-    for (uint32_t k = 0; k < warp; ++k) excl += s_warp[k];
+    const unsigned long long tile0 = p.ws.tile_pre[blockIdx.x] - ((unsigned long long)p.ws.frame_rank0[t.b] << 32);
+    unsigned long long excl = tile0, tile_total = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < SCAN_THREADS / 32; ++k) {
+        if (k < warp) excl += s_warp[k];
+        tile_total += s_warp[k];
+    }
     excl += incl - tsum;
+    const uint32_t r_tile = (uint32_t)(tile0 >> 32);                     // rank of the tile's first voxel
     const uint32_t i0 = t.lo + tid * SCAN_ITEMS;
     uint32_t sl[SCAN_ITEMS];                               // all slot loads in flight before any use
+    uint32_t pc[SCAN_ITEMS];                               // hash maps: the cell index travels per point
+    if (i0 + SCAN_ITEMS <= t.hi && (i0 & 3u) == 0 && tsum) {   // 16-byte loads: 4 lines per warp, not 32 sectors
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) sl[j] = val[j] ? __ldcs(p.ws.slot + i0 + j) : 0u;
+        for (int h = 0; h < SCAN_ITEMS / 4; ++h) {
+            const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(p.ws.slot + i0) + h);
+            sl[4 * h] = a.x; sl[4 * h + 1] = a.y; sl[4 * h + 2] = a.z; sl[4 * h + 3] = a.w;
+            const uint4 c4 = p.ws.dense ? make_uint4(0, 0, 0, 0) : __ldcs(reinterpret_cast<const uint4 *>(p.ws.pcell + i0) + h);
+            pc[4 * h] = c4.x; pc[4 * h + 1] = c4.y; pc[4 * h + 2] = c4.z; pc[4 * h + 3] = c4.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) sl[j] = val[j] ? __ldcs(p.ws.slot + i0 + j) : 0u;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) pc[j] = (val[j] && !p.ws.dense) ? __ldcs(p.ws.pcell + i0 + j) : 0u;
+    }
 #pragma unroll
     for (int j = 0; j < SCAN_ITEMS; ++j) {
         if (val[j]) {
@@ -392,17 +415,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const __grid_consta
             const uint32_t s = sl[j];
             const bool keep = r < (uint32_t)p.V;                          // :60-61 max_voxels
             p.ws.meta[s] = ((unsigned long long)min(c, 65535u) << 32) | (keep ? kg : PV_INF);
-            if (keep) {
-                p.ws.kept[kg] = i;                                        // list element 0 = first point
-                if (r < p.ws.fcap) {
-                    const size_t v = (size_t)t.b * p.ws.fcap + r;
-                    p.ws.vox_cell[v] = p.ws.dense ? pv_dense_cell(p, s - (uint32_t)t.b * p.ws.capf) : p.ws.pcell[i];
-                    p.ws.vox_kg[v] = kg;
-                    p.ws.vox_c[v] = c;
-                } else atomicOr(p.ws.ctrl + 1, 1u);                       // frame larger than frame_capacity
-            }
+            if (keep) p.ws.kept[kg] = i;                                  // list element 0 = first point
+            const uint32_t k = r - r_tile;                                // < SCAN_TILE: one voxel per first point
+            s_cell[k] = p.ws.dense ? pv_dense_cell(p, s - (uint32_t)t.b * p.ws.capf) : pc[j];
+            s_kg[k] = kg;
+            s_c[k] = c;
         }
         excl += val[j];
+    }
+    __syncthreads();
+    const uint32_t n_vox = (uint32_t)(tile_total >> 32);
+    const uint32_t r_kept = min(r_tile + n_vox, (uint32_t)p.V);          // :60-61 max_voxels
+    const uint32_t r_end = min(r_kept, p.ws.fcap);                        // kept voxels that fit
+    if (tid == 0 && r_kept > p.ws.fcap && r_kept > r_tile) atomicOr(p.ws.ctrl + 1, 1u);   // frame larger than frame_capacity
+    for (uint32_t r = r_tile + tid; r < r_end; r += SCAN_THREADS) {
+        const size_t v = (size_t)t.b * p.ws.fcap + r;
+        p.ws.vox_cell[v] = s_cell[r - r_tile];
+        p.ws.vox_kg[v] = s_kg[r - r_tile];
+        p.ws.vox_c[v] = s_c[r - r_tile];
     }
 }
 
@@ -489,9 +519,11 @@ __global__ void __launch_bounds__(256, 4) k_emit(const __grid_constant__ PvParam
         float raw[4][CT];                                 // up to 4 * c_in independent loads in flight
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float *row = p.pts + (size_t)id[q] * c_in;
+            if (id[q] != PV_INF) pv_load_row(p.pts, id[q], c_in, raw[q]);
+            else {
 #pragma unroll
-            for (int k = 0; k < CT; ++k) raw[q][k] = (id[q] != PV_INF && k < c_in) ? __ldg(row + k) : 0.0f;
+                for (int k = 0; k < CT; ++k) raw[q][k] = 0.0f;
+            }
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -526,16 +558,14 @@ __global__ void __launch_bounds__(256, 4) k_emit(const __grid_constant__ PvParam
     __stcs(p.num_points + vid, (int32_t)L);
     if (p.density) p.density[(size_t)b * p.cells + cell] = (int32_t)c;   // :70-71 un-capped count
     const float nf = (float)L;
-    float *o = p.feats ? p.feats + (size_t)vid * C : nullptr;
     float *cv = p.canvas ? p.canvas + (size_t)b * C * p.cells + cell : nullptr;
+    float mean[CT];
 #pragma unroll
     for (int k = 0; k < CT; ++k) {
-        if (k < C) {
-            const float m = __fdiv_rn(acc[k], nf);                      // voxel_encoder.py:18-22
-            if (o) __stcs(o + k, m);
-            if (cv) __stcs(cv + (size_t)k * p.cells, m);                // pillar_encoder.py:211-217
-        }
+        mean[k] = k < C ? __fdiv_rn(acc[k], nf) : 0.0f;                 // voxel_encoder.py:18-22
+        if (k < C && cv) __stcs(cv + (size_t)k * p.cells, mean[k]);     // pillar_encoder.py:211-217
     }
+    if (p.feats) pv_store_feats<CT>(p.feats, vid, C, mean);
 }
 
 __global__ void __launch_bounds__(256) k_transform(const float *__restrict__ in, long long n,
