@@ -368,6 +368,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const __grid_consta
     const TileRange t = pv_tile_range(p, blockIdx.x);
     if (t.b < 0) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    // everything this thread will need is requested up front: one memory round trip, not three
+    const uint32_t i0 = t.lo + tid * SCAN_ITEMS;
+    const unsigned long long tile_pre = __ldcg(p.ws.tile_pre + blockIdx.x);
+    const uint32_t frame_rank0 = __ldcg(p.ws.frame_rank0 + t.b);
+    uint32_t sl[SCAN_ITEMS];                               // all slot loads in flight before any use
+    uint32_t pc[SCAN_ITEMS];                               // hash maps: the cell index travels per point
+    if (i0 + SCAN_ITEMS <= t.hi && (i0 & 3u) == 0) {   // 16-byte loads: 4 lines per warp, not 32 sectors
+#pragma unroll
+        for (int h = 0; h < SCAN_ITEMS / 4; ++h) {
+            const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(p.ws.slot + i0) + h);
+            sl[4 * h] = a.x; sl[4 * h + 1] = a.y; sl[4 * h + 2] = a.z; sl[4 * h + 3] = a.w;
+            const uint4 c4 = p.ws.dense ? make_uint4(0, 0, 0, 0) : __ldcs(reinterpret_cast<const uint4 *>(p.ws.pcell + i0) + h);
+            pc[4 * h] = c4.x; pc[4 * h + 1] = c4.y; pc[4 * h + 2] = c4.z; pc[4 * h + 3] = c4.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) sl[j] = i0 + j < t.hi ? __ldcs(p.ws.slot + i0 + j) : 0u;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) pc[j] = (i0 + j < t.hi && !p.ws.dense) ? __ldcs(p.ws.pcell + i0 + j) : 0u;
+    }
     uint32_t w[SCAN_ITEMS];
     unsigned long long val[SCAN_ITEMS];
     const unsigned long long tsum = pv_load_items(p, t, w, val);
@@ -379,7 +399,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const __grid_consta
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    const unsigned long long tile0 = p.ws.tile_pre[blockIdx.x] - ((unsigned long long)p.ws.frame_rank0[t.b] << 32);
+    const unsigned long long tile0 = tile_pre - ((unsigned long long)frame_rank0 << 32);
     unsigned long long excl = tile0, tile_total = 0;
 #pragma unroll
     for (uint32_t k = 0; k < SCAN_THREADS / 32; ++k) {
@@ -388,23 +408,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const __grid_consta
     }
     excl += incl - tsum;
     const uint32_t r_tile = (uint32_t)(tile0 >> 32);                     // rank of the tile's first voxel
-    const uint32_t i0 = t.lo + tid * SCAN_ITEMS;
-    uint32_t sl[SCAN_ITEMS];                               // all slot loads in flight before any use
-    uint32_t pc[SCAN_ITEMS];                               // hash maps: the cell index travels per point
-    if (i0 + SCAN_ITEMS <= t.hi && (i0 & 3u) == 0 && tsum) {   // 16-byte loads: 4 lines per warp, not 32 sectors
-#pragma unroll
-        for (int h = 0; h < SCAN_ITEMS / 4; ++h) {
-            const uint4 a = __ldcs(reinterpret_cast<const uint4 *>(p.ws.slot + i0) + h);
-            sl[4 * h] = a.x; sl[4 * h + 1] = a.y; sl[4 * h + 2] = a.z; sl[4 * h + 3] = a.w;
-            const uint4 c4 = p.ws.dense ? make_uint4(0, 0, 0, 0) : __ldcs(reinterpret_cast<const uint4 *>(p.ws.pcell + i0) + h);
-            pc[4 * h] = c4.x; pc[4 * h + 1] = c4.y; pc[4 * h + 2] = c4.z; pc[4 * h + 3] = c4.w;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j) sl[j] = val[j] ? __ldcs(p.ws.slot + i0 + j) : 0u;
-#pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j) pc[j] = (val[j] && !p.ws.dense) ? __ldcs(p.ws.pcell + i0 + j) : 0u;
-    }
 #pragma unroll
     for (int j = 0; j < SCAN_ITEMS; ++j) {
         if (val[j]) {
