@@ -148,7 +148,8 @@ int pv_forward_mean_canvas(const pv_config *cfg, const float *points, const int3
 /* Measurement aid for bench.py: runs pv_forward_mean_canvas (canvas may be NULL for 3-D grids)
  * `iters` times with CUDA events recorded on `stream` between the stages and returns the average
  * milliseconds per stage in stage_ms (HOST, PV_PROFILE_STAGES floats).  List-free pipeline:
- * 0 insert, 1 cells, 2 scan, 3 finalize (+ canvas), 4 heavy cells; list-based pipeline:
+ * 0 insert (builds the first-point bitmap), 1 (empty; was the cells pass), 2 scan, 3 finalize (+ canvas),
+ * 4 heavy cells; list-based pipeline:
  * 0 bin_insert, 1 cell_flags, 2 scan, 3 place, 4 emit (see pv_profile_pipeline).  Synchronises. */
 #define PV_PROFILE_STAGES 5
 int pv_profile_mean_canvas(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
