@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(256, 4) k_emit(const __grid_constant__ PvParam
     const uint32_t L = min(c, (uint32_t)p.T);
     uint32_t *list = p.ws.kept + kg;
     const int C = p.C, c_in = p.c_in;
+    const bool fill = p.voxels != nullptr;                // the padded tensor: k_fill_voxels, which also restores the list
 
     // first eight indices into registers; small cells hold them in arrival order -> sort
     uint32_t e[8];
@@ -506,11 +507,15 @@ __global__ void __launch_bounds__(256, 4) k_emit(const __grid_constant__ PvParam
         PV_CSWAP(e[0], e[4]); PV_CSWAP(e[1], e[5]); PV_CSWAP(e[2], e[6]); PV_CSWAP(e[3], e[7]);
         PV_CSWAP(e[2], e[4]); PV_CSWAP(e[3], e[5]);
         PV_CSWAP(e[1], e[2]); PV_CSWAP(e[3], e[4]); PV_CSWAP(e[5], e[6]);
+        if (fill) {                                       // k_fill_voxels reads the list in index order
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if ((uint32_t)k < L) list[k] = e[k];
+        }
     }
     float acc[CT];
 #pragma unroll
     for (int k = 0; k < CT; ++k) acc[k] = 0.0f;
-    float *vox = p.voxels ? p.voxels + (size_t)vid * p.T * C : nullptr;
     for (uint32_t j0 = 0; j0 < L; j0 += 4) {
         uint32_t id[4];
         if (j0 == 0) { id[0] = e[0]; id[1] = e[1]; id[2] = e[2]; id[3] = e[3]; }
@@ -531,7 +536,7 @@ __global__ void __launch_bounds__(256, 4) k_emit(const __grid_constant__ PvParam
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (id[q] == PV_INF) break;
-            list[j0 + q] = PV_INF;                        // restore the list for the next call
+            if (!fill) list[j0 + q] = PV_INF;             // restore the list for the next call
             float f[CT];
             if (p.cart) {   // utils.py:42-44: (rho, phi, z, x, y, feat3..)
                 f[0] = pv_rho(raw[q][0], raw[q][1]);
@@ -545,15 +550,7 @@ __global__ void __launch_bounds__(256, 4) k_emit(const __grid_constant__ PvParam
             }
 #pragma unroll
             for (int k = 0; k < CT; ++k) acc[k] = __fadd_rn(acc[k], f[k]);   // index order, like sum(dim=1)
-            if (vox) {
-#pragma unroll
-                for (int k = 0; k < CT; ++k)
-                    if (k < C) vox[(size_t)(j0 + q) * C + k] = f[k];
-            }
         }
-    }
-    if (vox) {                                                           // zero padding (:187)
-        for (uint32_t e2 = L * C; e2 < (uint32_t)(p.T * C); ++e2) vox[e2] = 0.0f;
     }
     const uint32_t nx = p.grid[0], ny = p.grid[1];
     const uint32_t x = cell % nx, yz = cell / nx;
@@ -714,12 +711,56 @@ static int fill_params(PvParams *p, PvF *f, const pv_config *cfg, const float *p
     return PV_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// K6 (drop-in calls that return the padded tensor) -- voxels [M, T, C], point_cloud_ops.py:65-68,187:
+// one WARP per voxel.  Lane q gathers the row of the voxel's q-th kept point (index order, as
+// k_emit left the list), the warp parks the rows in shared memory and writes the voxel's T * C
+// floats as whole 128-byte lines, zero padding included -- a thread-per-voxel writer puts every
+// lane of a store into a different voxel (560 bytes apart for T = 20, C = 7).  Restores the list.
+// ---------------------------------------------------------------------------------------------
+#define FILL_WARPS 8
+__global__ void __launch_bounds__(FILL_WARPS * 32) k_fill_voxels(const __grid_constant__ PvParams p)
+{
+    __shared__ float s_rows[FILL_WARPS][32 * PV_MAX_CHANNELS];
+    const uint32_t lane = threadIdx.x & 31u, wq = threadIdx.x >> 5;
+    const uint32_t r = blockIdx.x * FILL_WARPS + wq;
+    const int b = blockIdx.y;
+    if (r >= (uint32_t)p.voxel_counts[b]) return;
+    const size_t v = (size_t)b * p.ws.fcap + r;
+    const uint32_t kg = __ldcs(p.ws.vox_kg + v);
+    const uint32_t L = min(__ldcs(p.ws.vox_c + v), (uint32_t)p.T);
+    const int32_t vid = p.ws.base[b] + (int32_t)r;
+    const int C = p.C, c_in = p.c_in;
+    uint32_t *list = p.ws.kept + kg;
+    float *vox = p.voxels + (size_t)vid * p.T * C;
+    float *rows = s_rows[wq];
+    const uint32_t total = (uint32_t)p.T * (uint32_t)C;
+    for (uint32_t q0 = 0; q0 < (uint32_t)p.T; q0 += 32) {             // 32 slots per round
+        const uint32_t q = q0 + lane;
+        if (q < L) {
+            const uint32_t i = __ldcg(list + q);
+            float f[PV_MAX_CHANNELS];
+            pv_feature_row(p.pts, i, c_in, p.cart, f);
+#pragma unroll
+            for (int k = 0; k < PV_MAX_CHANNELS; ++k)
+                if (k < C) rows[lane * C + k] = f[k];
+            list[q] = PV_INF;                                            // restore the list for the next call
+        }
+        __syncwarp();
+        const uint32_t e0 = q0 * C, e1 = min(total, (q0 + 32u) * C), filled = L > q0 ? (L - q0) * C : 0u;
+        for (uint32_t e = e0 + lane; e < e1; e += 32)
+            __stcs(vox + e, e - e0 < filled ? rows[e - e0] : 0.0f);   // zero padding (:187)
+        __syncwarp();
+    }
+}
+
 template <int CT>
 static void launch_emit(const PvParams &p, cudaStream_t st)
 {
     const uint32_t vmax = min((uint32_t)p.V, p.ws.fcap);
     dim3 grid((vmax + 255) / 256, (unsigned)p.B);
     k_emit<CT><<<grid, 256, 0, st>>>(p);
+    if (p.voxels) k_fill_voxels<<<dim3((vmax + FILL_WARPS - 1) / FILL_WARPS, (unsigned)p.B), FILL_WARPS * 32, 0, st>>>(p);
 }
 
 // Stage boundaries (for pv_profile_*): ev[k] is recorded BEFORE stage k, ev[PV_STAGES] after the
