@@ -80,6 +80,14 @@ __device__ __forceinline__ void pf_bulk_g2s(uint32_t dst, const void *src, uint3
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// Programmatic dependent launch (PDL): the kernels of one call form a chain; each is launched with
+// programmatic stream serialization, lets its successor's blocks be scheduled while its own last
+// wave is still running (pf_pdl_trigger) and waits for its predecessor to have completed and
+// flushed (pf_pdl_wait) before it touches anything the predecessor wrote.  Hides the launch
+// latency and the block ramp at every kernel boundary of a single-stream step.
+__device__ __forceinline__ void pf_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pf_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Hash-mode slot claim (same protocol as voxelize.cu): keys[] = cell, clean = INF.
 __device__ __forceinline__ uint32_t pf_claim(uint32_t *keys, uint32_t mask, uint32_t cell, uint32_t h, uint32_t *status)
 {
@@ -110,6 +118,7 @@ template <bool DENSE, int CIN, bool CART, int NV, int MODE = PF_MODE_FREE, bool 
 __global__ void __launch_bounds__(PF_THREADS, PF_INSERT_MIN_BLOCKS) kf_insert(const __grid_constant__ PvParams p,
                                                         const __grid_constant__ PvF f)
 {
+    pf_pdl_trigger();
     extern __shared__ __align__(128) float s_pts[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ int s_b0;
@@ -447,7 +456,9 @@ __global__ void __launch_bounds__(PF_SCAN_THREADS) kf_scan_pts(const __grid_cons
     __shared__ uint32_t s_carry, s_last;
     const int b = blockIdx.x;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t off0 = (uint32_t)p.offsets[b], off1 = (uint32_t)p.offsets[b + 1];
+    const uint32_t off0 = (uint32_t)p.offsets[b], off1 = (uint32_t)p.offsets[b + 1];   // caller's input: no dependency
+    pf_pdl_trigger();
+    pf_pdl_wait();                           // the bitmap of kf_insert
     const uint32_t wlo = off0 >> 5, whi = off1 > off0 ? (off1 + 31u) >> 5 : wlo;     // words [wlo, whi)
     const uint32_t mlo = 0xFFFFFFFFu << (off0 & 31u);
     const uint32_t mhi = (off1 & 31u) ? (1u << (off1 & 31u)) - 1u : 0xFFFFFFFFu;
@@ -638,6 +649,8 @@ __device__ __forceinline__ void pf_finalize_cell(const PvParams &p, const PvF &f
 template <int NV, int CC>
 __global__ void __launch_bounds__(256) kf_finalize(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
 {
+    pf_pdl_trigger();
+    pf_pdl_wait();
     const int b = blockIdx.y;
     const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= f.capf) return;
@@ -682,6 +695,8 @@ __global__ void __launch_bounds__(256) kf_finalize_patch(const __grid_constant__
     const uint32_t lane = threadIdx.x & 31u, wq = threadIdx.x >> 5;
     int32_t *s_d = reinterpret_cast<int32_t *>(s_t) + (CANVAS ? (size_t)C : 0) * PF_PATCH * (PF_PATCH + 1);
 
+    pf_pdl_trigger();
+    pf_pdl_wait();                           // map, bitmap prefix and row bases of the earlier kernels
     // ---- phase 1: lane = azimuth ----
     const uint32_t y = pyi * PF_PATCH + lane;
     uint32_t fi[KP];
@@ -739,6 +754,8 @@ __global__ void __launch_bounds__(256) kf_finalize_patch(const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PF_THREADS) kf_heavy_points(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
 {
+    pf_pdl_trigger();
+    pf_pdl_wait();
     const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * PF_PPT;
     if (i0 >= p.n) return;
     if ((i0 & 31u) == 0) f.bits[i0 >> 5] = 0u;      // the first-point bitmap is consumed: back to its clean state
@@ -775,7 +792,8 @@ __global__ void __launch_bounds__(PF_THREADS) kf_heavy_points(const __grid_const
 #define PF_CAND_REGS 8
 __global__ void __launch_bounds__(256) kf_heavy_cells(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
 {
-    const unsigned long long alloc = __ldg(reinterpret_cast<const unsigned long long *>(f.ctrl + 4));
+    pf_pdl_wait();
+    const unsigned long long alloc = __ldcg(reinterpret_cast<const unsigned long long *>(f.ctrl + 4));
     const uint32_t nh = min((uint32_t)(alloc >> 32), f.hmax);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -984,6 +1002,20 @@ int pvf_init(const PvF &f, int32_t batch, int64_t n_cap, cudaStream_t st)
     return PV_OK;
 }
 
+// Launch with programmatic stream serialization (see pf_pdl_wait): the kernel may start while the
+// previous kernel of the stream is still draining; it synchronises itself with pf_pdl_wait.
+template <typename K>
+static int pf_launch_pdl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PvParams &p, const PvF &f)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p, f) == cudaSuccess ? PV_OK : PV_ERR_CUDA;
+}
+
 template <bool DENSE, int CIN, bool CART, int NV, int MODE = PF_MODE_FREE>
 static int pf_launch_insert(const PvParams &p, const PvF &f, cudaStream_t st)
 {
@@ -1084,8 +1116,7 @@ template <int NV, int CC>
 static int pf_launch_finalize_nv(const PvParams &p, const PvF &f, cudaStream_t st)
 {
     if (!f.dense) {
-        kf_finalize<NV, CC><<<dim3((f.capf + 255) / 256, (unsigned)p.B), 256, 0, st>>>(p, f);
-        return PV_OK;
+        return pf_launch_pdl(kf_finalize<NV, CC>, dim3((f.capf + 255) / 256, (unsigned)p.B), dim3(256), 0, st, p, f);
     }
     const unsigned px = ((unsigned)p.grid[0] + PF_PATCH - 1) / PF_PATCH, py = ((unsigned)p.grid[1] + PF_PATCH - 1) / PF_PATCH;
     const dim3 grid(px, py * (unsigned)p.grid[2], (unsigned)p.B);
@@ -1094,8 +1125,7 @@ static int pf_launch_finalize_nv(const PvParams &p, const PvF &f, cudaStream_t s
     auto kern = p.canvas ? kf_finalize_patch<NV, CC, true> : kf_finalize_patch<NV, CC, false>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return PV_ERR_CUDA;
-    kern<<<grid, 256, smem, st>>>(p, f);
-    return PV_OK;
+    return pf_launch_pdl(kern, grid, dim3(256), smem, st, p, f);
 }
 
 static int pf_launch_finalize(const PvParams &p, const PvF &f, cudaStream_t st)
@@ -1129,7 +1159,7 @@ int pvf_run(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev)
     }
     PF_MARK(1);
     PF_MARK(2);                              // (the first-point bitmap is built by the insert kernel)
-    kf_scan_pts<<<(unsigned)p.B, PF_SCAN_THREADS, 0, st>>>(p, f);
+    if (pf_launch_pdl(kf_scan_pts, dim3((unsigned)p.B), dim3(PF_SCAN_THREADS), 0, st, p, f)) return PV_ERR_CUDA;
     PF_MARK(3);
     {
         const int rc = pf_launch_finalize(p, f, st);
@@ -1137,8 +1167,8 @@ int pvf_run(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev)
     }
     PF_MARK(4);
     if (p.n > 0) {
-        kf_heavy_points<<<(p.n + PF_TILE - 1) / PF_TILE, PF_THREADS, 0, st>>>(p, f);
-        kf_heavy_cells<<<296, 256, 0, st>>>(p, f);
+        if (pf_launch_pdl(kf_heavy_points, dim3((p.n + PF_TILE - 1) / PF_TILE), dim3(PF_THREADS), 0, st, p, f)) return PV_ERR_CUDA;
+        if (pf_launch_pdl(kf_heavy_cells, dim3(296), dim3(256), 0, st, p, f)) return PV_ERR_CUDA;
     }
     PF_MARK(5);
     return pv_last_cuda_error();
