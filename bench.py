@@ -160,7 +160,7 @@ def run_reference(args, rank, world):
     dt = sum(times)
     val = npts * args.steps / dt / 1e6
     sample = "%d steps x %d frames (%d points), one frame per thread" % (args.steps, len(frames), npts)
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -170,11 +170,31 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    banner when NCCL_DEBUG is set on the box), so the real stdout is kept for the result line and
+    file descriptor 1 is pointed at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(result):
+    _JSON_OUT.write(json.dumps(result) + "\n")
+    _JSON_OUT.flush()
 
 
 def main():
     global N_SETS
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -412,7 +432,7 @@ def main():
                 "sample": "%d passes over %d frames (%d points), one frame per thread, oracle C port of the "
                           "reference's numba/numpy/torch CPU path" % (reps_cpu, len(frames), sets[0]["n"]),
                 "frames_per_s": len(frames) * reps_cpu / dt}
-        print(json.dumps(result))
+        _emit(result)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
