@@ -623,8 +623,8 @@ __device__ __forceinline__ void pf_finalize_cell(const PvParams &p, const PvF &f
         const uint32_t L = min(cnt, T);
         const int32_t vid = __ldg(f.base + b) + (int32_t)rank;
         const uint32_t cell = (cz * (uint32_t)p.grid[1] + cy) * (uint32_t)p.grid[0] + cx;
-        reinterpret_cast<int4 *>(p.coors)[vid] = make_int4(b, (int)cz, (int)cy, (int)cx);
-        p.num_points[vid] = (int32_t)L;
+        __stcs(reinterpret_cast<int4 *>(p.coors) + vid, make_int4(b, (int)cz, (int)cy, (int)cx));   // write-once outputs: streaming
+        __stcs(p.num_points + vid, (int32_t)L);
         dens = (int32_t)cnt;                                              // :70-71 un-capped count
         if (cnt > T) {
             // heavy: the row holds the sum over ALL points; F5 re-sums the T smallest indices

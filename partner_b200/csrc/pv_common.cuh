@@ -289,28 +289,28 @@ __device__ __forceinline__ void pv_store_feats(float *feats, int32_t vid, int C,
         switch (vid & 3) {
         case 0:
             o4 = reinterpret_cast<float4 *>(o); o2 = reinterpret_cast<float2 *>(o + 4);
-            *o4 = make_float4(mean[0], mean[1], mean[2], mean[3]); *o2 = make_float2(mean[4 % CT], mean[5 % CT]); o[6] = mean[6 % CT];
+            __stcs(o4, make_float4(mean[0], mean[1], mean[2], mean[3])); __stcs(o2, make_float2(mean[4 % CT], mean[5 % CT])); __stcs(o + 6, mean[6 % CT]);
             break;
         case 1:     // row starts 12 bytes past a 16-byte boundary
             o2 = reinterpret_cast<float2 *>(o + 5); o4 = reinterpret_cast<float4 *>(o + 1);
-            o[0] = mean[0]; *o4 = make_float4(mean[1], mean[2], mean[3], mean[4 % CT]); *o2 = make_float2(mean[5 % CT], mean[6 % CT]);
+            __stcs(o + 0, mean[0]); __stcs(o4, make_float4(mean[1], mean[2], mean[3], mean[4 % CT])); __stcs(o2, make_float2(mean[5 % CT], mean[6 % CT]));
             break;
         case 2:     // 8 bytes past
             o2 = reinterpret_cast<float2 *>(o); o4 = reinterpret_cast<float4 *>(o + 2);
-            *o2 = make_float2(mean[0], mean[1]); *o4 = make_float4(mean[2], mean[3], mean[4 % CT], mean[5 % CT]); o[6] = mean[6 % CT];
+            __stcs(o2, make_float2(mean[0], mean[1])); __stcs(o4, make_float4(mean[2], mean[3], mean[4 % CT], mean[5 % CT])); __stcs(o + 6, mean[6 % CT]);
             break;
         default:    // 4 bytes past
             o2 = reinterpret_cast<float2 *>(o + 1); o4 = reinterpret_cast<float4 *>(o + 3);
-            o[0] = mean[0]; *o2 = make_float2(mean[1], mean[2]); *o4 = make_float4(mean[3], mean[4 % CT], mean[5 % CT], mean[6 % CT]);
+            __stcs(o + 0, mean[0]); __stcs(o2, make_float2(mean[1], mean[2])); __stcs(o4, make_float4(mean[3], mean[4 % CT], mean[5 % CT], mean[6 % CT]));
             break;
         }
     } else if (CT >= 8 && C == 8 && al16) {
-        reinterpret_cast<float4 *>(o)[0] = make_float4(mean[0], mean[1], mean[2], mean[3]);
-        reinterpret_cast<float4 *>(o)[1] = make_float4(mean[4 % CT], mean[5 % CT], mean[6 % CT], mean[7 % CT]);
+        __stcs(reinterpret_cast<float4 *>(o), make_float4(mean[0], mean[1], mean[2], mean[3]));
+        __stcs(reinterpret_cast<float4 *>(o) + 1, make_float4(mean[4 % CT], mean[5 % CT], mean[6 % CT], mean[7 % CT]));
     } else {
 #pragma unroll
         for (int k = 0; k < CT; ++k)
-            if (k < C) o[k] = mean[k];
+            if (k < C) __stcs(o + k, mean[k]);
     }
 }
 
