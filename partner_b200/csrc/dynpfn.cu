@@ -198,12 +198,12 @@ __global__ void __launch_bounds__(DP_THREADS) k_dyn_pfn(const __grid_constant__ 
     float *Y = D + DP_PC * c0p;                           // [PC][in2]
     __shared__ int s_vl[DP_PC];
 
-    const long long v0 = (long long)blockIdx.x * DP_VB;
-    const int nv = (int)min((long long)DP_VB, q.m - v0);
-    const uint32_t pbeg = q.offs[v0], pend = q.offs[v0 + nv];
     const int tid = threadIdx.x;
 
-    // ---- weights, transposed to [k][o]; padded input rows are zero ----
+    // ---- weights, transposed to [k][o]; padded input rows are zero.  PERSISTENT blocks: the
+    // transposition (34 strided loads per thread for the 64 -> 128 layer) is paid once per block,
+    // not once per 32 voxels (a group of 32 voxels holds ~100 points: the weights used to cost as
+    // much as the arithmetic) ----
     for (int e = tid; e < c0p * u1; e += DP_THREADS) {
         const int k = e / u1, o = e - k * u1;
         w1t[e] = k < c0 ? __ldg(q.w1 + (size_t)o * c0 + k) : 0.0f;
@@ -212,6 +212,15 @@ __global__ void __launch_bounds__(DP_THREADS) k_dyn_pfn(const __grid_constant__ 
         const int k = e / u2, o = e - k * u2;
         w2t[e] = __ldg(q.w2 + (size_t)o * in2 + k);
     }
+    const bool xyz_cluster = q.flags & 1, raz_cluster = q.flags & 2, xy_center = q.flags & 4, ra_center = q.flags & 8;
+    const int xi[3] = {q.cylinder ? 3 : 0, q.cylinder ? 4 : 1, 2};
+    const int ri[2] = {q.cylinder ? 0 : c - 2, q.cylinder ? 1 : c - 1};
+    const long long n_groups = (q.m + DP_VB - 1) / DP_VB;
+    for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const long long v0 = grp * DP_VB;
+    const int nv = (int)min((long long)DP_VB, q.m - v0);
+    const uint32_t pbeg = q.offs[v0], pend = q.offs[v0 + nv];
+    __syncthreads();                                     // the previous group's maxima have been written out
     for (int e = tid; e < DP_VB * u1; e += DP_THREADS) max1[e] = 0;
     for (int e = tid; e < DP_VB * u2; e += DP_THREADS) max2[e] = 0;
     // ---- per-voxel constants: the means get_cluster subtracts, the cell centre in both frames ----
@@ -231,10 +240,6 @@ __global__ void __launch_bounds__(DP_THREADS) k_dyn_pfn(const __grid_constant__ 
         mt[5] = xc; mt[6] = yc; mt[7] = rc; mt[8] = ac;
     }
     __syncthreads();
-
-    const bool xyz_cluster = q.flags & 1, raz_cluster = q.flags & 2, xy_center = q.flags & 4, ra_center = q.flags & 8;
-    const int xi[3] = {q.cylinder ? 3 : 0, q.cylinder ? 4 : 1, 2};
-    const int ri[2] = {q.cylinder ? 0 : c - 2, q.cylinder ? 1 : c - 1};
 
     // decorated rows of one chunk -> D, voxel-local ids -> s_vl
     auto build = [&](uint32_t p0, int npts) {
@@ -280,7 +285,7 @@ __global__ void __launch_bounds__(DP_THREADS) k_dyn_pfn(const __grid_constant__ 
             __syncthreads();
         }
         for (int e = tid; e < nv * u1; e += DP_THREADS) q.out[(size_t)v0 * u1 + e] = __int_as_float(max1[e]);
-        return;
+        continue;
     }
     // pass A: first-layer maxima of every voxel of the block
     for (uint32_t p0 = pbeg; p0 < pend; p0 += DP_PC) {
@@ -305,6 +310,7 @@ __global__ void __launch_bounds__(DP_THREADS) k_dyn_pfn(const __grid_constant__ 
         __syncthreads();
     }
     for (int e = tid; e < nv * u2; e += DP_THREADS) q.out[(size_t)v0 * u2 + e] = __int_as_float(max2[e]);
+    }
 }
 
 static size_t dp_align(size_t v) { return (v + 255) / 256 * 256; }
@@ -362,7 +368,9 @@ int pv_dynamic_pfn(const float *points, const int32_t *unq, const int32_t *unq_i
     if (smem + 1024 > 48 * 1024 &&
         cudaFuncSetAttribute(k_dyn_pfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return PV_ERR_CUDA;
-    k_dyn_pfn<<<(unsigned)((m + DP_VB - 1) / DP_VB), DP_THREADS, smem, st>>>(q);
+    const long long groups = (m + DP_VB - 1) / DP_VB;
+    const long long resident = 148ll * (smem > 110 * 1024 ? 1 : 2);   // persistent blocks (117 registers: two per SM)
+    k_dyn_pfn<<<(unsigned)(groups < resident ? groups : resident), DP_THREADS, smem, st>>>(q);
     return pv_last_cuda_error();
 }
 
