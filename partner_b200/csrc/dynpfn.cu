@@ -18,7 +18,7 @@
 #include "pv_common.cuh"
 
 #define DP_VB 32          // voxels per block
-#define DP_PC 64          // points per chunk
+#define DP_PC 128         // points per chunk (a group of 32 voxels holds ~100 points: usually one chunk)
 #define DP_THREADS 256
 #define DP_MAX_C0 32      // decorated row width
 #define DP_MAX_U1 64      // units of the non-last layer (input of the last one: 2 * U1)
@@ -137,9 +137,12 @@ __global__ void __launch_bounds__(256) k_dp_sort(const int32_t *__restrict__ unq
 // ---------------------------------------------------------------------------------------------
 // y[p][o] = relu(sum_k x[p][k] * wt[k][o]) for the chunk's points, register tile 4 points x 4 units;
 // STORE: write y to ys[p][o]; every output is max-reduced into smax[vl[p]][o] (integer compare).
-template <bool STORE>
+// init (optional): per-voxel start value of the accumulators, init[vl[p]][o] (the x_max half of the
+// last layer's input is the same for every point of a voxel: its product is taken once per voxel).
+template <bool STORE, bool MAX = true>
 __device__ __forceinline__ void dp_layer(const float *__restrict__ xs, int xs_ld, int K, const float *__restrict__ wt, int U,
-                                         int npts, const int *__restrict__ vl, float *__restrict__ ys, int ys_ld, int *__restrict__ smax)
+                                         int npts, const int *__restrict__ vl, float *__restrict__ ys, int ys_ld, int *__restrict__ smax,
+                                         const float *__restrict__ init = nullptr)
 {
     const int ugroups = U >> 2, tiles = (DP_PC / 4) * ugroups;
     for (int t = threadIdx.x; t < tiles; t += DP_THREADS) {
@@ -148,9 +151,15 @@ __device__ __forceinline__ void dp_layer(const float *__restrict__ xs, int xs_ld
         if (p0 >= npts) continue;
         float acc[4][4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 4; ++a) {
+            if (init) {
+                const float4 i4 = *reinterpret_cast<const float4 *>(init + vl[min(p0 + a, npts - 1)] * U + ug * 4);
+                acc[a][0] = i4.x; acc[a][1] = i4.y; acc[a][2] = i4.z; acc[a][3] = i4.w;
+            } else {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+            }
+        }
         const float *x0 = xs + (size_t)p0 * xs_ld;
         for (int k = 0; k < K; k += 4) {
             float4 xv[4];
@@ -172,6 +181,11 @@ __device__ __forceinline__ void dp_layer(const float *__restrict__ xs, int xs_ld
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             if (p0 + a >= npts) break;
+            if (!MAX) {                                                   // plain product rows (no activation)
+                if (STORE) *reinterpret_cast<float4 *>(ys + (size_t)(p0 + a) * ys_ld + ug * 4) =
+                    make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+                continue;
+            }
             int *mx = smax + vl[p0 + a] * U + ug * 4;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
@@ -195,7 +209,8 @@ __global__ void __launch_bounds__(DP_THREADS) k_dyn_pfn(const __grid_constant__ 
     int *max1 = reinterpret_cast<int *>(meta + DP_VB * 12);   // [VB][u1]
     int *max2 = max1 + DP_VB * u1;                        // [VB][u2]
     float *D = reinterpret_cast<float *>(max2 + DP_VB * (u2 ? u2 : 0));   // [PC][c0p]
-    float *Y = D + DP_PC * c0p;                           // [PC][in2]
+    float *Y = D + DP_PC * c0p;                           // [PC][u1] first-layer outputs of the chunk
+    float *P = Y + DP_PC * u1;                            // [VB][u2] per-voxel half of the last layer: W2[:, u1:] . x_max
     __shared__ int s_vl[DP_PC];
 
     const int tid = threadIdx.x;
@@ -295,18 +310,21 @@ __global__ void __launch_bounds__(DP_THREADS) k_dyn_pfn(const __grid_constant__ 
         dp_layer<false>(D, c0p, c0p, w1t, u1, npts, s_vl, nullptr, 0, max1);
         __syncthreads();
     }
-    // pass B: recompute layer 1 (cheap), concatenate with the voxel maxima, run the last layer
+    // the last layer's input is cat([x, x_max[unq_inv]]) (:70): its x_max half is the same for all
+    // points of a voxel, so W2[:, u1:] . x_max is taken once per voxel and seeds the accumulators
+    // (fp32 sum in the order x_max terms first, then the point's own terms)
+    for (int e = tid; e < DP_PC; e += DP_THREADS) s_vl[e] = e < DP_VB ? e : 0;
+    __syncthreads();
+    dp_layer<true, false>(reinterpret_cast<const float *>(max1), u1, u1, w2t + (size_t)u1 * u2, u2, nv, s_vl, P, u2, nullptr);
+    __syncthreads();
+    // pass B: recompute layer 1 (cheap), run the last layer on the point's own half
     for (uint32_t p0 = pbeg; p0 < pend; p0 += DP_PC) {
         const int npts = (int)min((uint32_t)DP_PC, pend - p0);
         build(p0, npts);
         __syncthreads();
-        dp_layer<true>(D, c0p, c0p, w1t, u1, npts, s_vl, Y, in2, max1);    // maxima are final already: the atomics are no-ops
-        for (int e = tid; e < DP_PC * u1; e += DP_THREADS) {              // x_max[unq_inv] half of the row (:70)
-            const int p = e / u1, o = e - p * u1;
-            Y[(size_t)p * in2 + u1 + o] = p < npts ? __int_as_float(max1[s_vl[p] * u1 + o]) : 0.0f;
-        }
+        dp_layer<true>(D, c0p, c0p, w1t, u1, npts, s_vl, Y, u1, max1);     // maxima are final already: the atomics are no-ops
         __syncthreads();
-        dp_layer<false>(Y, in2, in2, w2t, u2, npts, s_vl, nullptr, 0, max2);
+        dp_layer<false>(Y, u1, u1, w2t, u2, npts, s_vl, nullptr, 0, max2, P);
         __syncthreads();
     }
     for (int e = tid; e < nv * u2; e += DP_THREADS) q.out[(size_t)v0 * u2 + e] = __int_as_float(max2[e]);
@@ -363,7 +381,8 @@ int pv_dynamic_pfn(const float *points, const int32_t *unq, const int32_t *unq_i
     if (n > 0) k_dp_sort<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(unq_inv, n, m, offs, cursor, perm);
     const int c0p = (c0 + 3) & ~3, in2 = 2 * q.u1;
     const size_t smem = sizeof(float) * ((size_t)c0p * q.u1 + (q.u2 ? (size_t)in2 * q.u2 : 0) + DP_VB * 12 +
-                                         (size_t)DP_VB * q.u1 + (size_t)DP_VB * q.u2 + (size_t)DP_PC * c0p + (size_t)DP_PC * in2);
+                                         (size_t)DP_VB * q.u1 + (size_t)DP_VB * q.u2 + (size_t)DP_PC * c0p + (size_t)DP_PC * q.u1 +
+                                         (size_t)DP_VB * q.u2);
     if (smem > 200 * 1024) return PV_ERR_UNSUPPORTED;
     if (smem + 1024 > 48 * 1024 &&
         cudaFuncSetAttribute(k_dyn_pfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
