@@ -256,16 +256,17 @@ __global__ void __launch_bounds__(DP_THREADS) k_dyn_pfn(const __grid_constant__ 
     }
     __syncthreads();
 
-    // decorated rows of one chunk -> D, voxel-local ids -> s_vl
+    // decorated rows of one chunk -> D, voxel-local ids -> s_vl.  Two threads per point (all 256
+    // threads busy: the others would only wait at the barrier): one copies the raw columns, the
+    // other computes the decorations.
     auto build = [&](uint32_t p0, int npts) {
-        if (tid < DP_PC) {
-            float *row = D + (size_t)tid * c0p;
-            if (tid < npts) {
-                const uint32_t i = q.perm[p0 + tid];
+        const int pt = tid >> 1, half = tid & 1;
+        if (pt < DP_PC) {
+            float *row = D + (size_t)pt * c0p;
+            if (pt < npts) {
+                const uint32_t i = q.perm[p0 + pt];
                 const float *pr = q.points + (size_t)i * c;
                 const int vl = (int)(q.unq_inv[i] - v0);
-                s_vl[tid] = vl;
-                const float *mt = meta + vl * 12;
                 float pv[PV_MAX_CHANNELS];
 #pragma unroll
                 for (int k = 0; k < PV_MAX_CHANNELS; ++k) pv[k] = k < c ? __ldg(pr + k) : 0.0f;
@@ -273,18 +274,23 @@ __global__ void __launch_bounds__(DP_THREADS) k_dyn_pfn(const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < PV_MAX_CHANNELS; ++j) r = j == k ? pv[j] : r;
                     return r; };
-                int o = 0;
-                for (int k = 0; k < c; ++k) row[o++] = col(k);
-                if (xyz_cluster) for (int k = 0; k < 3; ++k) row[o++] = __fsub_rn(col(xi[k]), mt[k]);       // :363-364
-                if (xy_center) { row[o++] = __fsub_rn(col(xi[0]), mt[5]); row[o++] = __fsub_rn(col(xi[1]), mt[6]); }   // :366-372
-                if (raz_cluster) {                                                                           // :373-384
-                    row[o++] = __fsub_rn(col(ri[0]), mt[3]); row[o++] = __fsub_rn(col(ri[1]), mt[4]);
-                    if (!xyz_cluster) row[o++] = __fsub_rn(col(2), mt[2]);
+                if (half == 0) {
+                    s_vl[pt] = vl;
+                    for (int k = 0; k < c; ++k) row[k] = col(k);
+                } else {
+                    const float *mt = meta + vl * 12;
+                    int o = c;
+                    if (xyz_cluster) for (int k = 0; k < 3; ++k) row[o++] = __fsub_rn(col(xi[k]), mt[k]);       // :363-364
+                    if (xy_center) { row[o++] = __fsub_rn(col(xi[0]), mt[5]); row[o++] = __fsub_rn(col(xi[1]), mt[6]); }   // :366-372
+                    if (raz_cluster) {                                                                           // :373-384
+                        row[o++] = __fsub_rn(col(ri[0]), mt[3]); row[o++] = __fsub_rn(col(ri[1]), mt[4]);
+                        if (!xyz_cluster) row[o++] = __fsub_rn(col(2), mt[2]);
+                    }
+                    if (ra_center) { row[o++] = __fsub_rn(col(ri[0]), mt[7]); row[o++] = __fsub_rn(col(ri[1]), mt[8]); }   // :385-391
+                    for (; o < c0p; ++o) row[o] = 0.0f;
                 }
-                if (ra_center) { row[o++] = __fsub_rn(col(ri[0]), mt[7]); row[o++] = __fsub_rn(col(ri[1]), mt[8]); }   // :385-391
-                for (; o < c0p; ++o) row[o] = 0.0f;
-            } else {
-                s_vl[tid] = 0;
+            } else if (half == 0) {
+                s_vl[pt] = 0;
                 for (int o = 0; o < c0p; ++o) row[o] = 0.0f;
             }
         }
