@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(256) kf_finalize(const __grid_constant__ PvPar
 //      are neighbours too, so the per-voxel loads and stores of a warp share 128-byte lines),
 //   2. a warp writes 32 range-consecutive canvas cells per channel (one full line per store),
 //      every element exactly once, zeros included: no zero fill, no scatter.
-// grid = (patches_x, patches_y * nz, B); each thread owns PF_PATCH / 8 cells of the patch.
+// grid = (patches_y * nz, patches_x, B); each thread owns PF_PATCH / 8 cells of the patch.
 // Tried and slower: fetching all rows of a thread up front with cp.async into shared memory
 // (512 threads, 2 cells each: 37 vs 33 us), 16-byte canvas stores, unaligned per-channel feature
 // stores -- the kernel is insensitive to its instruction count.
@@ -706,8 +706,8 @@ __global__ void __launch_bounds__(256) kf_finalize_patch(const __grid_constant__
     const int b = blockIdx.z;
     const uint32_t nx = p.grid[0], ny = p.grid[1];
     const uint32_t py = (ny + PF_PATCH - 1) / PF_PATCH;
-    const uint32_t pxi = blockIdx.x;
-    uint32_t pyi = blockIdx.y, z = 0;
+    const uint32_t pxi = blockIdx.y;
+    uint32_t pyi = blockIdx.x, z = 0;
     if (p.grid[2] > 1) { z = pyi / py; pyi -= z * py; }
     const uint32_t lane = threadIdx.x & 31u, wq = threadIdx.x >> 5;
     int32_t *s_d = reinterpret_cast<int32_t *>(s_t) + (CANVAS ? (size_t)C : 0) * PF_PATCH * (PF_PATCH + 1);
@@ -1136,7 +1136,7 @@ static int pf_launch_finalize_nv(const PvParams &p, const PvF &f, cudaStream_t s
         return pf_launch_pdl(kf_finalize<NV, CC>, dim3((f.capf + 255) / 256, (unsigned)p.B), dim3(256), 0, st, p, f);
     }
     const unsigned px = ((unsigned)p.grid[0] + PF_PATCH - 1) / PF_PATCH, py = ((unsigned)p.grid[1] + PF_PATCH - 1) / PF_PATCH;
-    const dim3 grid(px, py * (unsigned)p.grid[2], (unsigned)p.B);
+    const dim3 grid(py * (unsigned)p.grid[2], px, (unsigned)p.B);        // px <= 2^15 for a direct map
     if (p.B > 65535 || grid.y > 65535u) return PV_ERR_UNSUPPORTED;
     const size_t smem = ((p.canvas ? (size_t)p.C : 0) + (p.density ? 1 : 0)) * PF_PATCH * (PF_PATCH + 1) * sizeof(float);
     auto kern = p.canvas ? kf_finalize_patch<NV, CC, true> : kf_finalize_patch<NV, CC, false>;
