@@ -584,16 +584,17 @@ __device__ __forceinline__ void pf_ld_row(const float *row, float (&r)[NV * 4])
         }
     }
 }
-// Restores a row: zeros, except channel 0 which keeps `keep0` (the heavy-cell id until F5 is done).
+// Restores a row: zeros, except words 0 and 1 which keep `keep0`, `keep1` -- for a heavy cell its
+// candidate-range offset and (word 2, starting at zero) its arrival cursor, until F4 is done.
 template <int NV>
-__device__ __forceinline__ void pf_st_row_clean(float *row, float keep0)
+__device__ __forceinline__ void pf_st_row_clean(float *row, float keep0, float keep1 = 0.0f)
 {
     if constexpr (NV == 2) {
-        asm volatile("st.global.v8.f32 [%0], {%1,%2,%2,%2,%2,%2,%2,%2};" ::"l"(row), "f"(keep0), "f"(0.0f) : "memory");
+        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%3,%3,%3,%3,%3};" ::"l"(row), "f"(keep0), "f"(keep1), "f"(0.0f) : "memory");
     } else {
 #pragma unroll
         for (int q = 0; q < NV; ++q)
-            __stcg(reinterpret_cast<float4 *>(row) + q, make_float4(q == 0 ? keep0 : 0.f, 0.f, 0.f, 0.f));
+            __stcg(reinterpret_cast<float4 *>(row) + q, make_float4(q == 0 ? keep0 : 0.f, q == 0 ? keep1 : 0.f, 0.f, 0.f));
     }
 }
 
@@ -613,7 +614,7 @@ __device__ __forceinline__ void pf_finalize_cell(const PvParams &p, const PvF &f
     // starts in; if that is an earlier frame, this frame starts inside the word
     const uint32_t below = wv.y & ((1u << (fi & 31u)) - 1u);
     const uint32_t rank = (fi & ~31u) >= off_b ? wv.x + __popc(below) : __popc(below & (0xFFFFFFFFu << (off_b & 31u)));
-    float keep0 = 0.0f;
+    float keep0 = 0.0f, keep1 = 0.0f;
     if (rank < (uint32_t)p.V) {                                           // :60-61 max_voxels
         float cntf = 0.0f;
 #pragma unroll
@@ -635,7 +636,8 @@ __device__ __forceinline__ void pf_finalize_cell(const PvParams &p, const PvF &f
                 uint4 *hi = f.hinfo + 2 * (size_t)hid;
                 hi[0] = make_uint4(s, (uint32_t)vid, off, cnt);
                 hi[1] = make_uint4(cell, (uint32_t)b, 0u, 0u);               // .z = arrival cursor
-                keep0 = __uint_as_float(hid);
+                keep0 = __uint_as_float(hid);                         // (informational)
+                keep1 = __uint_as_float(off);                         // kf_heavy_points: hlist[off + cursor++]
                 atomicOr(f.hbits + (s >> 5), 1u << (s & 31u));
             } else atomicOr(p.ws.ctrl + 1, 1u);
         } else {
@@ -657,7 +659,7 @@ __device__ __forceinline__ void pf_finalize_cell(const PvParams &p, const PvF &f
         if (!DENSE && p.density) p.density[(size_t)b * p.cells + cell] = (int32_t)cnt;
     }
     // restore the map -- after the loaded row was consumed (see kf_scan)
-    pf_st_row_clean<NV>(rowp, keep0);
+    pf_st_row_clean<NV>(rowp, keep0, keep1);
     f.first[s] = PV_INF;
     if (!DENSE) f.keys[s] = PV_INF;
 }
@@ -769,33 +771,37 @@ __global__ void __launch_bounds__(256) kf_finalize_patch(const __grid_constant__
 // cursor per cell; the range was sized from the exact count).  The bitmap lookup has warp
 // locality (phi-fastest bit order).
 // ---------------------------------------------------------------------------------------------
+#define PF_HPT 8                         // points per thread in the heavy-point pass
 __global__ void __launch_bounds__(PF_THREADS) kf_heavy_points(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
 {
     pf_pdl_trigger();
     pf_pdl_wait();
-    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * PF_PPT;
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * PF_HPT;
     if (i0 >= p.n) return;
     if ((i0 & 31u) == 0) f.bits[i0 >> 5] = 0u;      // the first-point bitmap is consumed: back to its clean state
-    if (__ldg(reinterpret_cast<const unsigned long long *>(f.ctrl + 4)) == 0ull) return;   // no heavy cell in this batch
-    uint32_t sa[PF_PPT];
-    if (i0 + PF_PPT <= p.n) {
-        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(f.sa + i0));
-        sa[0] = v.x; sa[1] = v.y; sa[2] = v.z; sa[3] = v.w;
+    // the slot words are requested before the "any heavy cell at all?" word is looked at: one round trip
+    uint32_t sa[PF_HPT];
+    if (i0 + PF_HPT <= p.n) {
+#pragma unroll
+        for (int h = 0; h < PF_HPT / 4; ++h) {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(f.sa + i0) + h);
+            sa[4 * h] = v.x; sa[4 * h + 1] = v.y; sa[4 * h + 2] = v.z; sa[4 * h + 3] = v.w;
+        }
     } else {
 #pragma unroll
-        for (int j = 0; j < PF_PPT; ++j) sa[j] = i0 + j < p.n ? f.sa[i0 + j] : PV_INF;
+        for (int j = 0; j < PF_HPT; ++j) sa[j] = i0 + j < p.n ? f.sa[i0 + j] : PV_INF;
     }
-    uint32_t w[PF_PPT];
+    if (__ldg(reinterpret_cast<const unsigned long long *>(f.ctrl + 4)) == 0ull) return;   // no heavy cell in this batch
+    uint32_t w[PF_HPT];
 #pragma unroll
-    for (int j = 0; j < PF_PPT; ++j) w[j] = sa[j] != PV_INF ? __ldg(f.hbits + (sa[j] >> 5)) : 0u;
+    for (int j = 0; j < PF_HPT; ++j) w[j] = sa[j] != PV_INF ? __ldg(f.hbits + (sa[j] >> 5)) : 0u;
 #pragma unroll
-    for (int j = 0; j < PF_PPT; ++j) {
+    for (int j = 0; j < PF_HPT; ++j) {
         if (!((w[j] >> (sa[j] & 31u)) & 1u)) continue;
-        const uint32_t s = sa[j];
-        const uint32_t hid = __float_as_uint(__ldcg(f.acc + (size_t)s * f.rowf));
-        uint32_t *hi = reinterpret_cast<uint32_t *>(f.hinfo + 2 * (size_t)hid);
-        const uint32_t off = __ldcg(hi + 2);
-        const uint32_t pos = atomicAdd(hi + 6, 1u);
+        // the heavy cell's row holds {id, candidate-range offset, arrival cursor}: one line, no indirection
+        uint32_t *row = reinterpret_cast<uint32_t *>(f.acc + (size_t)sa[j] * f.rowf);
+        const uint32_t off = __ldcg(row + 1);
+        const uint32_t pos = atomicAdd(row + 2, 1u);
         f.hlist[off + pos] = i0 + j;
     }
 }
@@ -868,7 +874,7 @@ __global__ void __launch_bounds__(256) kf_heavy_cells(const __grid_constant__ Pv
             }
         }
         if (lane == 0) {
-            f.acc[(size_t)s * f.rowf] = 0.0f;    // the row's last dirty word (held the heavy-cell id)
+            *reinterpret_cast<float4 *>(f.acc + (size_t)s * f.rowf) = make_float4(0.f, 0.f, 0.f, 0.f);   // the row's last dirty words
             const uint32_t hb = s;
             atomicAnd(f.hbits + (hb >> 5), ~(1u << (hb & 31u)));
         }
@@ -1184,7 +1190,7 @@ int pvf_run(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev)
     }
     PF_MARK(4);
     if (p.n > 0) {
-        if (pf_launch_pdl(kf_heavy_points, dim3((p.n + PF_TILE - 1) / PF_TILE), dim3(PF_THREADS), 0, st, p, f)) return PV_ERR_CUDA;
+        if (pf_launch_pdl(kf_heavy_points, dim3((p.n + PF_THREADS * PF_HPT - 1) / (PF_THREADS * PF_HPT)), dim3(PF_THREADS), 0, st, p, f)) return PV_ERR_CUDA;
         if (pf_launch_pdl(kf_heavy_cells, dim3(296), dim3(256), 0, st, p, f)) return PV_ERR_CUDA;
     }
     PF_MARK(5);
