@@ -57,6 +57,22 @@ __global__ void __launch_bounds__(256) k_canvas_from_index(const float *__restri
 #pragma unroll
     for (int k = 0; k < VEC; ++k) row[k] = map[(size_t)b * cells + cell0 + k];
     float *dst = canvas + (size_t)b * c * cells + cell0;
+    if (VEC == 4 && (c & 3) == 0 && (reinterpret_cast<uintptr_t>(feats) & 15u) == 0) {
+        // four channels at a time: one 16-byte gather per cell (a gathered load costs one slot per
+        // lane whatever its width), a 4 x 4 transpose in registers, one 16-byte store per channel
+        for (int ch = 0; ch < c; ch += 4) {
+            float4 r[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                r[k] = row[k] >= 0 ? __ldg(reinterpret_cast<const float4 *>(feats + (size_t)row[k] * c + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float *d = dst + (size_t)ch * cells;
+            __stcs(reinterpret_cast<float4 *>(d), make_float4(r[0].x, r[1 % VEC].x, r[2 % VEC].x, r[3 % VEC].x));
+            __stcs(reinterpret_cast<float4 *>(d + cells), make_float4(r[0].y, r[1 % VEC].y, r[2 % VEC].y, r[3 % VEC].y));
+            __stcs(reinterpret_cast<float4 *>(d + 2 * (size_t)cells), make_float4(r[0].z, r[1 % VEC].z, r[2 % VEC].z, r[3 % VEC].z));
+            __stcs(reinterpret_cast<float4 *>(d + 3 * (size_t)cells), make_float4(r[0].w, r[1 % VEC].w, r[2 % VEC].w, r[3 % VEC].w));
+        }
+        return;
+    }
     for (int ch = 0; ch < c; ++ch) {
         float v[VEC];
 #pragma unroll
