@@ -371,6 +371,8 @@ __global__ void __launch_bounds__(PF_SCAN_THREADS) kf_scan(const __grid_constant
 {
     __shared__ uint32_t s_warp[PF_SCAN_THREADS / 32];
     __shared__ uint32_t s_carry, s_last;
+    pf_pdl_trigger();
+    pf_pdl_wait();
     const int b = blockIdx.x;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     // static: one bit per point of the frame; dynamic: one bit per cell of the grid
@@ -897,6 +899,8 @@ template <int NV, int CC, bool CANVAS>
 __global__ void __launch_bounds__(256) kf_dyn_finalize(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
 {
     constexpr int CT = NV * 4;
+    pf_pdl_trigger();
+    pf_pdl_wait();
     const int C = CC ? CC : p.C;
     const int b = blockIdx.z;
     const uint32_t nx = p.grid[0], ny = p.grid[1];
@@ -943,6 +947,7 @@ __global__ void __launch_bounds__(256) kf_dyn_finalize(const __grid_constant__ P
 // unq_inv[i] = row of point i's voxel (torch.unique's return_inverse)
 __global__ void __launch_bounds__(PF_THREADS) kf_dyn_inverse(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
 {
+    pf_pdl_wait();
     const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * PF_PPT;
     if (i0 >= p.n) return;
     const uint32_t frame_bits = f.wcap * 32u;
@@ -1111,8 +1116,8 @@ template <int NV, int CC>
 static void pf_launch_dyn_finalize(const PvParams &p, const PvF &f, cudaStream_t st)
 {
     const dim3 grid(((unsigned)p.grid[0] + 255) / 256, (unsigned)p.grid[1] * (unsigned)p.grid[2], (unsigned)p.B);
-    if (p.canvas) kf_dyn_finalize<NV, CC, true><<<grid, 256, 0, st>>>(p, f);
-    else kf_dyn_finalize<NV, CC, false><<<grid, 256, 0, st>>>(p, f);
+    if (p.canvas) pf_launch_pdl(kf_dyn_finalize<NV, CC, true>, grid, dim3(256), 0, st, p, f);
+    else pf_launch_pdl(kf_dyn_finalize<NV, CC, false>, grid, dim3(256), 0, st, p, f);
 }
 
 // Dynamic voxelization launch sequence (direct maps only).
@@ -1126,7 +1131,7 @@ int pvf_run_dynamic(PvParams &p, PvF &f, cudaStream_t st)
         const int rc = pf_dispatch_insert_dyn(p, f, st);
         if (rc) return rc;
     }
-    kf_scan<<<(unsigned)p.B, PF_SCAN_THREADS, 0, st>>>(p, f);
+    if (pf_launch_pdl(kf_scan, dim3((unsigned)p.B), dim3(PF_SCAN_THREADS), 0, st, p, f)) return PV_ERR_CUDA;
     switch ((int)f.rowf / 4) {
     case 1: pf_launch_dyn_finalize<1, 0>(p, f, st); break;
     case 2: if (p.C == 7) pf_launch_dyn_finalize<2, 7>(p, f, st); else pf_launch_dyn_finalize<2, 0>(p, f, st); break;
@@ -1134,7 +1139,8 @@ int pvf_run_dynamic(PvParams &p, PvF &f, cudaStream_t st)
     case 4: pf_launch_dyn_finalize<4, 0>(p, f, st); break;
     default: pf_launch_dyn_finalize<5, 0>(p, f, st); break;
     }
-    if (p.unq_inv && p.n > 0) kf_dyn_inverse<<<(p.n + PF_TILE - 1) / PF_TILE, PF_THREADS, 0, st>>>(p, f);
+    if (p.unq_inv && p.n > 0 &&
+        pf_launch_pdl(kf_dyn_inverse, dim3((p.n + PF_TILE - 1) / PF_TILE), dim3(PF_THREADS), 0, st, p, f)) return PV_ERR_CUDA;
     return pv_last_cuda_error();
 }
 
