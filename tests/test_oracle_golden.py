@@ -183,3 +183,22 @@ def test_seg_voxel_labels_uint16_counter_wraps(case, golden_dir):
     labels, _ = oracle.seg_voxel_labels(g[f"{case}_grid_ind"], g[f"{case}_label"], [8, 8, 1])
     assert np.array_equal(labels, g[f"{case}_labels"])
     assert int(labels[0, 0, 3, 4]) == (9 if case == "wrap_a" else 2)
+
+
+def test_seg_voxel_labels_oracle_vs_numpy_vote():
+    """Independent check of the C restatement: per-cell majority vote written with numpy (ties -> the
+    smallest label, as np.argmax over the reference's 256-entry counter)."""
+    rng = np.random.default_rng(11)
+    gs = np.array([9, 7, 3])                                  # nx, ny, nz
+    n = 5000
+    gi = np.stack([rng.integers(0, gs[2], n), rng.integers(0, gs[1], n), rng.integers(0, gs[0], n)], 1).astype(np.int32)
+    lab = rng.integers(-1, 6, n).astype(np.int32)             # few labels -> many ties
+    labels, valid = oracle.seg_voxel_labels(gi, lab, gs)
+    keep = lab >= 0
+    assert np.array_equal(valid, gi[keep])
+    want = np.zeros((1, gs[2], gs[1], gs[0]), np.int64)
+    cells = (gi[keep, 0] * gs[1] + gi[keep, 1]) * gs[0] + gi[keep, 2]
+    counts = np.zeros((gs.prod(), 256), np.int64)
+    np.add.at(counts, (cells, lab[keep]), 1)
+    want.reshape(-1)[:] = np.where(counts.sum(1) > 0, counts.argmax(1), 0)
+    assert np.array_equal(labels, want)
