@@ -34,8 +34,7 @@ class VoxelGenerator:
         ind = vb.pc_grid_ind
         den = vb.density[0] if vb.density is not None else None
         if as_numpy:
-            cv = lambda t: None if t is None else t.cpu().numpy()   # noqa: E731
-            return cv(voxels), cv(coors), cv(num), cv(ind), cv(den)
+            return F.to_numpy(voxels, coors, num, ind, den)     # page-locked staging, one synchronisation
         return voxels, coors, num, ind, den
 
     @property
@@ -91,7 +90,12 @@ class VoxelGenerator:
             if points.ndim != 2:
                 raise ValueError("points must be [N, C]")
             dev = self._device or torch.device("cuda", torch.cuda.current_device())
-            return torch.from_numpy(np.ascontiguousarray(points)).to(dev)
+            src = torch.from_numpy(np.ascontiguousarray(points))
+            if src.numel() == 0:
+                return src.to(dev)
+            stage = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)     # cached page-locked staging
+            stage.copy_(src)
+            return stage.to(dev, non_blocking=True)
         if isinstance(points, torch.Tensor):
             if not points.is_cuda:
                 raise ValueError("tensor input must live on the GPU (pass numpy for host data)")

@@ -79,8 +79,10 @@ class Voxelization(object):
         counts = out["num_voxels"].numpy()
         lo = int(counts[:f].sum())
         hi = lo + int(counts[f])
-        return dict(voxels=out["voxels"][lo:hi].cpu().numpy(), coordinates=out["coordinates"][lo:hi, 1:].cpu().numpy(),
-                    num_points=out["num_points"][lo:hi].cpu().numpy(), num_voxels=np.array([hi - lo], dtype=np.int64),
+        voxels, coordinates, num_points = F.to_numpy(out["voxels"][lo:hi], out["coordinates"][lo:hi, 1:].contiguous(),
+                                                     out["num_points"][lo:hi])
+        return dict(voxels=voxels, coordinates=coordinates, num_points=num_points,
+                    num_voxels=np.array([hi - lo], dtype=np.int64),
                     shape=vg.grid_size, range=vg.point_cloud_range, size=vg.voxel_size)
 
     def voxelize_hard(self, res, info):
