@@ -66,8 +66,9 @@ class Voxelization(object):
             lab = torch.from_numpy(np.ascontiguousarray(res["lidar"]["pc_label"]).reshape(-1).astype(np.int32)).to(dev)
             off = torch.tensor([0, gi.shape[0]], dtype=torch.int32, device=dev)
             labels, valid, _ = F.seg_voxel_labels(cfg, gi, lab, off, 1)
-            res["lidar"]["voxels"].update({"labels": labels.cpu().numpy()})          # [1, nz, ny, nx] int64 (:52)
-            pc_grid_ind = valid.cpu().numpy().astype(out_dtype)
+            labels, valid = F.to_numpy(labels, valid)
+            res["lidar"]["voxels"].update({"labels": labels})                       # [1, nz, ny, nx] int64 (:52)
+            pc_grid_ind = valid.astype(out_dtype)
         else:
             pc_grid_ind = pc_grid_ind[:res["lidar"]["n_key_points"]]
         res["lidar"]["voxels"].update({"valid_grid_ind": pc_grid_ind.copy()})
@@ -125,7 +126,7 @@ class Voxelization(object):
         r = F.dynamic_voxelize(vg._cfg, torch.from_numpy(points).to(dev), off, 1, n, False, want_inverse=False,
                                want_counts=False, want_grid_ind=True, want_mean=False)
         F.read_status(r)
-        pc_grid_ind = r.grid_ind[:, 1:].cpu().numpy().astype(np.int64)       # (z, y, x), np.int of the reference
+        pc_grid_ind = F.to_numpy(r.grid_ind[:, 1:].contiguous())[0].astype(np.int64)   # (z, y, x), np.int of the reference
         res["lidar"]["voxels"] = dict(grid_ind=pc_grid_ind.copy(), shape=vg.grid_size, range=vg.point_cloud_range,
                                       size=vg.voxel_size)
         if ("seg" in self.super_tasks) and kwargs.get("seg", True):
@@ -151,9 +152,9 @@ class Voxelization(object):
         points = np.ascontiguousarray(res["lidar"]["points"], dtype=np.float32)
         dev = torch.device("cuda", torch.cuda.current_device())
         out, gi, idx, counts = F.stream_sectors(vg._cfg, torch.from_numpy(points).to(dev), nsectors, max_az)
-        counts = counts.cpu().numpy()
+        counts, out, gi, idx = F.to_numpy(counts, out, gi, idx)
         offs = np.concatenate([[0], np.cumsum(counts)])
-        out, gi, idx = out.cpu().numpy(), gi.cpu().numpy().astype(np.int64), idx.cpu().numpy().astype(np.int64)
+        gi, idx = gi.astype(np.int64), idx.astype(np.int64)
         lidar_rest = {k: v for k, v in res["lidar"].items() if k != "points"}
         sectors = []
         for i in load_range:
