@@ -125,8 +125,9 @@ class PolarFrontEnd:
         counts = vb.voxel_counts.cpu().numpy()
         F.read_status(vb)
         m = int(counts.sum())
-        out = dict(coordinates=vb.coors[:m].cpu().numpy(), num_points=vb.num_points[:m].cpu().numpy(),
-                   num_voxels=counts.astype(np.int64), features=vb.mean_feats[:m].cpu().numpy())
+        coors, num, feats, canvas = F.to_numpy(vb.coors[:m], vb.num_points[:m], vb.mean_feats[:m],
+                                               vb.canvas if self.canvas else None)      # page-locked staging
+        out = dict(coordinates=coors, num_points=num, num_voxels=counts.astype(np.int64), features=feats)
         if self.canvas:
-            out["canvas"] = vb.canvas.cpu().numpy()
+            out["canvas"] = canvas
         return out

@@ -102,8 +102,8 @@ class Voxelization(object):
             main = vg.generate_batch([res["lidar"]["points"]], max_voxels=max_voxels,
                                      return_pc_grid_ind=self.return_pc_grid_ind, return_density=self.return_density)
             res["lidar"]["voxels"] = self._pack(main, 0)
-            pc_grid_ind = main["pc_grid_ind"].cpu().numpy() if self.return_pc_grid_ind else None
-            density = main["n_points"][0].cpu().numpy() if self.return_density else None
+            pc_grid_ind, density = F.to_numpy(main["pc_grid_ind"] if self.return_pc_grid_ind else None,
+                                              main["n_points"][0] if self.return_density else None)
             keys = ["yflip", "xflip", "double_flip"]
             flips = vg.generate_batch([res["lidar"][k + "_points"] for k in keys])      # one launch sequence
             for f, k in enumerate(keys):
