@@ -35,6 +35,8 @@ from partner_b200 import synth  # noqa: E402
 WORKLOADS = {
     # name: (grid tag, frame kind, generator kwargs, frames per GPU, config id, has canvas)
     "nusc_pillar_mean_canvas_b8": ("NUSC-PILLAR", "nusc", {}, 8, 2, True),
+    "nusc_pillar_mean_canvas_b2": ("NUSC-PILLAR", "nusc", {}, 2, 2, True),      # experiments: L2-sized batches
+    "nusc_pillar_mean_canvas_b4": ("NUSC-PILLAR", "nusc", {}, 4, 2, True),
     "waymo_partner_mean_b16": ("WAYMO-PARTNER", "waymo", dict(nsweeps=1, time_column=True), 16, 4, False),
     "waymo3_partner_mean_b8": ("WAYMO-PARTNER", "waymo", dict(nsweeps=3, time_column=True), 8, 5, False),
 }
@@ -206,6 +208,11 @@ def main():
                     help="independent batches in flight on separate CUDA streams (1 = strictly serial steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sets", type=int, default=4, help="rotating input sets (each with its own workspace/graph)")
+    ap.add_argument("--launch", default="graph", choices=["graph", "python"],
+                    help="graph: multi-step CUDA graphs (no host call between steps); python: one replay per step from Python")
+    ap.add_argument("--graph-steps", type=int, default=20, help="steps captured per CUDA graph")
+    ap.add_argument("--ws-per-stream", type=int, default=0, help="1: one workspace per stream instead of per input set")
+    ap.add_argument("--lib", default=None, help="development aid: time another build of the C-ABI library (A/B runs)")
     args = ap.parse_args()
     N_SETS = max(1, args.sets)
     rank = int(os.environ.get("RANK", "0"))
@@ -220,6 +227,8 @@ def main():
 
     import torch
     from partner_b200 import PolarFrontEnd, _lib
+    if args.lib:
+        _lib.SO_PATH = os.path.abspath(args.lib)
     from partner_b200 import functional as F
     from partner_b200._lib import ptr, current_stream
     import ctypes
@@ -253,12 +262,15 @@ def main():
     cap_all = max(s["cap"] for s in sets)
     in_bytes = sum(s["n"] for s in sets) * c_in * 4
 
-    # ---- device-resident path: one CUDA graph per input set, each with its own workspace ------
+    # ---- device-resident path: one CUDA graph per input set ------------------------------------
+    n_streams = max(1, min(args.streams, N_SETS))
     runners = []
     fes = []
     for k, s in enumerate(sets):
+        # one workspace per STREAM, not per input set: a batch in flight owns its workspace, and a workspace
+        # that comes round again every n_streams steps stays in the 126 MB L2 (inputs and outputs still rotate)
         fe_s = PolarFrontEnd(g["voxel_size"], g["range"], g["max_points"], g["max_voxels"], cartesian=True,
-                             device=dev, workspace_tag=k)
+                             device=dev, workspace_tag=k % n_streams if args.ws_per_stream else k)
         fes.append(fe_s)
         if args.no_graph:
             out = fe_s.forward_device(s["d_points"], s["d_off"], per_gpu, cap_all)
@@ -297,14 +309,67 @@ def main():
         barrier()
         return e0.elapsed_time(e1)
 
-    n_streams = max(1, min(args.streams, N_SETS))
     step = lambda k: runners[k % N_SETS][0]()        # noqa: E731
-    timed(step, args.warmup, n_streams)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ms_total = timed(step, args.steps, n_streams)
-    ms_single = timed(step, args.steps, 1) if n_streams > 1 else ms_total
+
+    def capture_rounds(rounds, branches_n):
+        """ONE CUDA graph holding rounds * N_SETS steps: set k runs on branch k % branches_n (fork / join
+        inside the capture), so a replay puts that many independent batches in flight without a
+        single host call in between -- a Python `with stream: graph.replay()` per step costs more
+        host time (~70 us) than the step takes on the device."""
+        gr = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(dev)
+        side = [torch.cuda.Stream(dev) for _ in range(branches_n - 1)]
+        branches = [cap] + side
+        cap.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.graph(gr, stream=cap):
+            fork = torch.cuda.Event()
+            fork.record(cap)
+            for st in side:
+                st.wait_event(fork)
+            for _ in range(rounds):
+                for k, s_ in enumerate(sets):
+                    with torch.cuda.stream(branches[k % branches_n]):
+                        fes[k].forward_device(s_["d_points"], s_["d_off"], per_gpu, cap_all, out=runners[k][1])
+            for st in side:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                cap.wait_event(ev)
+        return gr
+
+    def timed_graphs(gr, per_replay, steps):
+        """steps = q * per_replay + r: q replays of the multi-step graph, then r single-step graphs."""
+        cur = torch.cuda.current_stream(dev)
+        q, r = divmod(steps, per_replay)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        for _ in range(q):
+            gr.replay()
+        for k in range(r):
+            step(k)
+        e1.record(cur)
+        barrier()
+        return e0.elapsed_time(e1)
+
+    if args.no_graph or args.launch == "python":
+        timed(step, args.warmup, n_streams)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ms_total = timed(step, args.steps, n_streams)
+        ms_single = timed(step, args.steps, 1) if n_streams > 1 else ms_total
+        steps_per_graph = 1
+    else:
+        rounds = max(1, args.graph_steps // N_SETS)
+        steps_per_graph = rounds * N_SETS
+        g_multi = capture_rounds(rounds, n_streams)
+        g_serial = capture_rounds(rounds, 1) if n_streams > 1 else g_multi
+        timed_graphs(g_multi, steps_per_graph, max(args.warmup, steps_per_graph))
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ms_total = timed_graphs(g_multi, steps_per_graph, args.steps)
+        ms_single = timed_graphs(g_serial, steps_per_graph, args.steps) if n_streams > 1 else ms_total
     pts_done = sum(sets[k % N_SETS]["n"] for k in range(args.steps))
 
     # ---- end-to-end path: pinned host buffers, H2D + D2H inside the timed region ----------
@@ -395,7 +460,10 @@ def main():
                        "max_points": g["max_points"], "max_voxels": g["max_voxels"],
                        "parallelism": "frame-sharded x%d, no collective" % world,
                        "l2": "%d rotating input sets (%.0f MB) + outputs exceed the 126 MB L2" % (N_SETS, in_bytes / 1e6),
-                       "launch": "eager" if args.no_graph else "cuda-graph replay",
+                       "launch": ("eager" if args.no_graph else "cuda-graph replay, one per step issued from Python"
+                                  if args.launch == "python" else
+                                  "cuda-graph replay, %d steps per graph on %d branches (no host call between steps)"
+                                  % (steps_per_graph, n_streams)),
                        "pipeline": {1: "list-based (voxelize.cu)", 2: "list-free (fused.cu)"}[pipeline],
                        "streams": n_streams,
                        "note": "steps are independent batches; with streams > 1 consecutive steps overlap on "

@@ -59,6 +59,10 @@ typedef struct pv_config {
     int32_t grid[3];    /* nx, ny, nz                                         */
     int32_t max_points; /* T = max_points_in_voxel                            */
     int32_t max_voxels; /* V = max_voxels per frame                           */
+    int32_t pipeline;   /* which of the two pipelines serves calls that do not ask for the padded
+                           voxels tensor: 0 auto (list-free on direct-map grids of <= 2^20 cells per
+                           frame, list-based on hash-map grids), 1 list-based, 2 list-free.  Part of
+                           the configuration, not process state: 1 / 2 exist for measurements and tests */
 } pv_config;
 
 /* One PFNLayer (det3d/models/readers/pillar_encoder.py:19-61) in eval mode. */
@@ -75,16 +79,8 @@ typedef struct pv_pfn_layer {
 int pv_version(void);
 const char *pv_error_string(int code);
 
-/* Process-wide pipeline choice for calls that do not request the padded voxels tensor
- * (measurement / test aid; the default, 0, is what production uses):
- *   0 auto       list-free (fused.cu) on direct-map grids (<= 2^20 cells per frame), list-based
- *                (voxelize.cu) on hash-map grids
- *   1 lists      list-based everywhere      2 list-free  list-free everywhere
- * The PV_PIPELINE environment variable sets the initial value.  Not thread-safe. */
-int pv_set_pipeline(int mode);
-
 /* Which pipeline (1 lists, 2 list-free) pv_forward_mean_canvas / pv_profile_mean_canvas run for
- * this grid under the current setting; names the stages pv_profile_mean_canvas reports. */
+ * this configuration (cfg->pipeline resolved); names the stages pv_profile_mean_canvas reports. */
 int pv_profile_pipeline(const pv_config *cfg);
 
 /* Bytes of workspace for a batch of `batch` frames holding at most

@@ -32,7 +32,7 @@ _VALUE_ERRORS = (-1, -2, -6)   # bad config / bad argument / unsupported -> Valu
 class PvConfig(ctypes.Structure):
     _fields_ = [("lo", ctypes.c_float * 3), ("vs", ctypes.c_float * 3),
                 ("grid", ctypes.c_int32 * 3), ("max_points", ctypes.c_int32),
-                ("max_voxels", ctypes.c_int32)]
+                ("max_voxels", ctypes.c_int32), ("pipeline", ctypes.c_int32)]
 
 
 class PvPfnLayer(ctypes.Structure):
@@ -50,14 +50,30 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """nvcc-compile every kernel for sm_100a into the in-tree shared object."""
+    """nvcc-compile every kernel for sm_100a into the in-tree shared object (one object per
+    translation unit, compiled in parallel, objects kept under build/ and reused when unchanged)."""
     if not force and not needs_build():
         return SO_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-o", SO_PATH] + _SOURCES
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.check_call(cmd)
+    objdir = os.path.join(_ROOT, "build", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(h) for h in _HEADERS)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj
+        cmd = [nvcc] + flags + ["-I", os.path.join(_ROOT, "include"), "-c", "-o", obj, src]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.check_call(cmd)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(_SOURCES))) as ex:
+        objs = list(ex.map(compile_one, _SOURCES))
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO_PATH] + objs)
     return SO_PATH
 
 
@@ -71,7 +87,6 @@ SZ = ctypes.c_size_t
 EXPORTS = {
     "pv_version": (ctypes.c_int, []),
     "pv_error_string": (ctypes.c_char_p, [ctypes.c_int]),
-    "pv_set_pipeline": (ctypes.c_int, [ctypes.c_int]),
     "pv_profile_pipeline": (ctypes.c_int, [ctypes.POINTER(PvConfig)]),
     "pv_workspace_bytes": (SZ, [ctypes.POINTER(PvConfig), I64, I32, I64, I32]),
     "pv_transform_points": (ctypes.c_int, [P, I64, I32, I32, P, P]),

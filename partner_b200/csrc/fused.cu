@@ -32,6 +32,7 @@
 //   F4 heavy       (rare cells, 2-5 % of the points) points of heavy cells append their index to
 //                  the cell's candidate range; one warp per heavy cell selects the T smallest
 //                  (REDUX.MIN rounds) and re-sums exactly those rows.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -364,6 +365,305 @@ __global__ void __launch_bounds__(PF_THREADS, PF_INSERT_MIN_BLOCKS) kf_insert(co
 }
 
 // ---------------------------------------------------------------------------------------------
+// F1, streaming form (direct maps, list-free, no pc_grid_ind -- the fused front end's hot path).
+// Same contract as kf_insert<true, CIN, CART, NV, PF_MODE_FREE, false>, restructured around what the
+// ncu captures of that kernel showed (issue slots 52 % busy, 220 instructions per point, 41 % of
+// the stall samples on the returned minima, warps idle while their tile is in flight):
+//   * every WARP is its own software pipeline over tiles of 128 consecutive points (32 lanes x 4):
+//     a two-stage ring of 128 * CIN * 4-byte shared-memory buffers per warp, each filled by one TMA
+//     bulk copy that the warp's lane 0 issues as soon as the previous occupant has been read into
+//     registers -- no block-level barrier anywhere, so warps drift apart instead of bunching
+//     their reductions; the load of tile k+1 is in flight while tile k is binned;
+//   * the minima returned for tile k are consumed just before tile k+1 issues its own atomics
+//     (same registers, no copy), i.e. a full tile of arithmetic after they were requested;
+//   * the per-point path is branch free: bins through the reciprocal with a CONSTANT guard band
+//     (3e-7 * (grid + 2) >= the 1.8e-7 |q| worst-case distance between t * fl(1 / vs) and the
+//     correctly rounded quotient; inside the band, and for NaN / huge values, the IEEE division
+//     decides -- one rare divergent branch per thread), range test on the converted integers,
+//     runs of equal cells merged with selects, atomics predicated inside the PTX.
+// Persistent grid: 4 warps per block, 4 blocks per SM; warp g takes tiles g, g + G, g + 2G, ...
+// ---------------------------------------------------------------------------------------------
+#ifndef KI_WARPS
+#define KI_WARPS 4
+#endif
+#ifndef KI_STAGES
+#define KI_STAGES 2
+#endif
+#ifndef KI_BLOCKS_PER_SM
+#define KI_BLOCKS_PER_SM 4
+#endif
+#ifndef KI_XLANE
+#define KI_XLANE 0     // merge runs across the lane boundary: -12 % reductions, +18 % instructions, no gain measured
+#endif
+#ifndef KI_EXP
+#define KI_EXP 0      // timing experiments (never defined in product builds)
+#endif
+#ifndef KF_EXP
+#define KF_EXP 0
+#endif
+
+// predicated returning minimum: old stays what it was (0) when pred == 0
+__device__ __forceinline__ void ki_atom_min(uint32_t &old, uint32_t *addr, uint32_t val, uint32_t pred)
+{
+    const unsigned long long pol = pv_policy_evict_last();    // first[] is part of the map: keep it in L2
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q atom.global.min.L2::cache_hint.u32 %0, [%1], %2, %4;\n\t}"
+                 : "+r"(old) : "l"(addr), "r"(val), "r"(pred), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void ki_red_add_v4(float *p, float a, float b, float c, float d, unsigned long long pol, uint32_t pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %6, 0;\n\t"
+                 "@q red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;\n\t}"
+                 ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol), "r"(pred) : "memory");
+}
+
+template <int CIN, bool CART, int NV>
+__global__ void __launch_bounds__(KI_WARPS * 32, KI_BLOCKS_PER_SM) kf_insert_stream(const __grid_constant__ PvParams p,
+                                                                                  const __grid_constant__ PvF f,
+                                                                                  const uint32_t n_tiles, const uint32_t n_warps)
+{
+    constexpr int C = CIN + (CART ? 2 : 0);
+    constexpr int CT = NV * 4;
+    constexpr uint32_t TILE_FLOATS = 128u * CIN, TILE_BYTES = TILE_FLOATS * 4u;
+    extern __shared__ __align__(128) float s_ring[];                 // [KI_WARPS][KI_STAGES][TILE_FLOATS]
+    __shared__ __align__(8) unsigned long long s_bar[KI_WARPS][KI_STAGES];
+    pf_pdl_trigger();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * KI_WARPS + warp;
+    float *ring = s_ring + (size_t)warp * KI_STAGES * TILE_FLOATS;
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < KI_STAGES; ++st) pf_mbar_init(pf_smem_addr(&s_bar[warp][st]), 1);
+    }
+    __syncwarp();
+    auto issue = [&](uint32_t tile, int st) {             // lane 0: one bulk copy of a FULL tile into stage st
+        const uint32_t bar = pf_smem_addr(&s_bar[warp][st]);
+        pf_mbar_expect_tx(bar, TILE_BYTES);
+        pf_bulk_g2s(pf_smem_addr(ring + (size_t)st * TILE_FLOATS), p.pts + (size_t)tile * TILE_FLOATS, TILE_BYTES, bar);
+    };
+    const uint32_t n_full = p.n >> 7;                      // tiles [0, n_full) are full; tile n_full (if any) is the tail
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < KI_STAGES; ++st) {
+            const uint32_t t = gw + (uint32_t)st * n_warps;
+            if (t < n_full) issue(t, st);
+        }
+    }
+    const float lo0 = p.lo[0], lo1 = p.lo[1], lo2 = p.lo[2];
+    const float iv0 = p.inv_vs[0], iv1 = p.inv_vs[1], iv2 = p.inv_vs[2];
+    const uint32_t nx = (uint32_t)p.grid[0], ny = (uint32_t)p.grid[1], nz = (uint32_t)p.grid[2];
+    const float th0 = 3e-7f * (p.gridf[0] + 2.0f), th1 = 3e-7f * (p.gridf[1] + 2.0f), th2 = 3e-7f * (p.gridf[2] + 2.0f);
+    const unsigned long long keep = pv_policy_evict_last();
+    uint32_t olds[PF_PPT] = {0u, 0u, 0u, 0u};              // minima returned for the previous tile (0: site unused)
+    uint32_t prev_first = 0, prev_starts = 0;              // its first point (this lane) and the run starts, 2 bits per site
+    int prev_acc = -1;                                     // its site whose run started in the previous lane ...
+    uint32_t prev_head = 0;                                // ... at this point index
+    bool prev_valid = false;
+    // the first-point bits of a finished tile: see kf_insert
+    auto settle = [&]() {
+        uint32_t mine = 0, handed = 0;                    // handed: the run taken over from the previous lane became a minimum
+#pragma unroll
+        for (int site = 0; site < PF_PPT; ++site) {
+            const bool taken = KI_XLANE && site == prev_acc;
+            const uint32_t j0 = (prev_starts >> (2 * site)) & 3u, i0 = taken ? prev_head : prev_first + j0, old = olds[site];
+            if (old > i0) {
+                if (taken) handed = 1u; else mine |= 1u << j0;
+                if (old != PV_INF) atomicXor(f.bits + (old >> 5), 1u << (old & 31u));
+            }
+            olds[site] = 0u;
+        }
+        if (KI_XLANE) {                                    // the bit of a handed-over run lives in the giver's nibble
+            const uint32_t back = __shfl_down_sync(0xffffffffu, handed, 1);
+            if (back && lane < 31) mine |= 1u << ((prev_starts >> 6) & 3u);
+        }
+        uint32_t word = mine << (4u * (lane & 7u));
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);
+        word |= __shfl_xor_sync(0xffffffffu, word, 4);
+        if ((lane & 7u) == 0 && word) atomicXor(f.bits + (prev_first >> 5), word);
+    };
+
+    const uint32_t my_off = (int)lane + 1 < p.B ? (uint32_t)__ldg(p.offsets + lane + 1) : PV_INF;   // interior frame boundaries
+    uint32_t it = 0;
+    for (uint32_t tile = gw; tile < n_tiles; tile += n_warps, ++it) {
+        const int st = (int)(it % KI_STAGES);
+        const uint32_t tile_base = tile << 7;
+        const uint32_t i0 = tile_base + lane * PF_PPT;    // this lane's first point
+        float rows[PF_PPT * CIN];
+        uint32_t n_here = PF_PPT;                          // valid points of this lane
+        float *stage = ring + (size_t)st * TILE_FLOATS;
+        if (tile < n_full) pf_mbar_wait(pf_smem_addr(&s_bar[warp][st]), (it / KI_STAGES) & 1u);
+        else {                                             // the batch's last, partial tile: guarded loads into the stage
+            n_here = i0 < p.n ? min((uint32_t)PF_PPT, p.n - i0) : 0u;
+            const uint32_t nf = (p.n - tile_base) * CIN;
+            for (uint32_t e = lane; e < TILE_FLOATS; e += 32u) stage[e] = e < nf ? __ldg(p.pts + (size_t)tile_base * CIN + e) : 0.0f;
+            __syncwarp();
+        }
+        {
+            const float4 *q4 = reinterpret_cast<const float4 *>(stage) + lane * CIN;
+#pragma unroll
+            for (int k = 0; k < CIN; ++k) {
+                const float4 v4 = q4[k];
+                rows[4 * k] = v4.x; rows[4 * k + 1] = v4.y; rows[4 * k + 2] = v4.z; rows[4 * k + 3] = v4.w;
+            }
+            __syncwarp();                                  // every lane has its rows: the stage may be refilled
+            const uint32_t nt = tile + KI_STAGES * n_warps;
+            if (lane == 0 && nt < n_full) issue(nt, st);
+        }
+        // ---- frame of the tile's first point (lane l holds offsets[l + 1]); boundaries inside the tile are rare ----
+        int b0 = 0;
+        uint32_t next_off = PV_INF;
+        if (p.B <= 33) {
+            b0 = __popc(__ballot_sync(0xffffffffu, my_off <= tile_base));
+            next_off = __reduce_min_sync(0xffffffffu, my_off > tile_base ? my_off : PV_INF);
+        } else {
+            for (int bb0 = 1; bb0 < p.B; bb0 += 32) {
+                const int bb = bb0 + (int)lane;
+                const uint32_t o = bb < p.B ? (uint32_t)__ldg(p.offsets + bb) : PV_INF;
+                b0 += __popc(__ballot_sync(0xffffffffu, o <= tile_base));
+                next_off = min(next_off, __reduce_min_sync(0xffffffffu, o > tile_base ? o : PV_INF));
+            }
+        }
+        const bool straddle = next_off < tile_base + 128u;
+        // ---- per point: transform, bins, slot ----
+        float v[PF_PPT][CT];
+        uint32_t slot[PF_PPT];
+        uint32_t okm = 0;                                  // bit j: point j is inside the grid
+        float t[PF_PPT][3], c[PF_PPT][3];
+        uint32_t unsure = 0;
+#pragma unroll
+        for (int j = 0; j < PF_PPT; ++j) {
+            const float *in = rows + j * CIN;
+            if (CART) {                                    // utils.py:42-44: (rho, phi, z, x, y, feat3..)
+                v[j][0] = pv_rho(in[0], in[1]);
+                v[j][1] = pv_atan2f(in[1], in[0]);
+                v[j][2] = in[2]; v[j][3] = in[0]; v[j][4] = in[1];
+#pragma unroll
+                for (int k = 5; k < CT; ++k) v[j][k] = k < C ? in[k - 2 < CIN ? k - 2 : 0] : 0.0f;
+            } else {
+#pragma unroll
+                for (int k = 0; k < CT; ++k) v[j][k] = k < C ? in[k < CIN ? k : 0] : 0.0f;
+            }
+            v[j][C] = 1.0f;                                // the count rides in channel C of the row
+            // point_cloud_ops.py:45 through the reciprocal; outside the guard band floor(t * inv) is
+            // the floor of the correctly rounded quotient (unordered compare: NaN takes the division)
+            t[j][0] = __fsub_rn(v[j][0], lo0); t[j][1] = __fsub_rn(v[j][1], lo1); t[j][2] = __fsub_rn(v[j][2], lo2);
+            const float r0 = __fmul_rn(t[j][0], iv0), r1 = __fmul_rn(t[j][1], iv1), r2 = __fmul_rn(t[j][2], iv2);
+            c[j][0] = floorf(r0); c[j][1] = floorf(r1); c[j][2] = floorf(r2);
+            const float d0 = __fsub_rn(__fsub_rn(r0, c[j][0]), 0.5f), d1 = __fsub_rn(__fsub_rn(r1, c[j][1]), 0.5f),
+                        d2 = __fsub_rn(__fsub_rn(r2, c[j][2]), 0.5f);
+            if (!(fabsf(d0) < 0.5f - th0)) unsure |= 1u << (3 * j);
+            if (!(fabsf(d1) < 0.5f - th1)) unsure |= 2u << (3 * j);
+            if (!(fabsf(d2) < 0.5f - th2)) unsure |= 4u << (3 * j);
+        }
+        if (unsure) {                                      // rare: the IEEE division decides (NaN -> outside)
+#pragma unroll
+            for (int j = 0; j < PF_PPT; ++j)
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                    if ((unsure >> (3 * j + d)) & 1u) {
+                        const float q = floorf(__fdiv_rn(t[j][d], p.vs[d]));
+                        c[j][d] = q == q ? q : -1.0f;
+                    }
+        }
+        const uint32_t sb0 = (uint32_t)b0 * f.capf;
+#pragma unroll
+        for (int j = 0; j < PF_PPT; ++j) {
+            const uint32_t cx = (uint32_t)__float2int_rz(c[j][0]), cy = (uint32_t)__float2int_rz(c[j][1]), cz = (uint32_t)__float2int_rz(c[j][2]);
+            const bool ok = cx < nx && cy < ny && cz < nz && (uint32_t)j < n_here;
+            slot[j] = ok ? sb0 + (cz * nx + cx) * ny + cy : PV_INF;   // direct map, PHI FASTEST
+            okm |= ok ? 1u << j : 0u;
+        }
+        if (straddle) {                                    // a frame boundary inside the tile: per-point frame
+            int b = b0;
+            uint32_t nxt = next_off;
+#pragma unroll
+            for (int j = 0; j < PF_PPT; ++j) {
+                while (i0 + j >= nxt) {                    // frames may be empty
+                    ++b;
+                    nxt = b + 1 < p.B ? (uint32_t)__ldg(p.offsets + b + 1) : PV_INF;
+                }
+                if ((okm >> j) & 1u) slot[j] += (uint32_t)(b - b0) * f.capf;
+            }
+        }
+        // ---- runs of consecutive points in one cell: sums carried forward, emitted at the run's last point ----
+        uint32_t starts = 0, emit = 0;
+        {
+            uint32_t start = 0;
+#pragma unroll
+            for (int j = 0; j < PF_PPT; ++j) {
+                const bool merge = j > 0 && ((okm >> j) & (okm >> (j - 1)) & 1u) && slot[j] == slot[j > 0 ? j - 1 : 0];
+                if (j > 0) {
+#pragma unroll
+                    for (int k = 0; k <= C; ++k) v[j][k] = __fadd_rn(v[j][k], merge ? v[j - 1][k] : 0.0f);
+                }
+                start = merge ? start : (uint32_t)j;
+                starts |= start << (2 * j);
+                const bool last = j + 1 == PF_PPT || !(((okm >> (j + 1)) & 1u) && slot[j + 1 < PF_PPT ? j + 1 : j] == slot[j]);
+                emit |= (((okm >> j) & 1u) && last) ? 1u << j : 0u;
+            }
+        }
+        // ---- a run that is cut by the thread boundary continues in the next lane: hand the tail run
+        // (the one ending at point 3) to the neighbour when it continues there as that lane's head run
+        // and ends inside that lane (no chains), so the pair costs one set of atomics instead of two ----
+        int acc_site = -1;                                 // site whose run starts in the previous lane
+        uint32_t head_abs = 0;                             // ... and the point index it starts at
+        if (KI_XLANE) {
+            const uint32_t t_slot = ((emit >> 3) & 1u) ? slot[3] : PV_INF;
+            const uint32_t r_slot = __shfl_up_sync(0xffffffffu, t_slot, 1);
+            const uint32_t r_start = __shfl_up_sync(0xffffffffu, i0 + ((starts >> 6) & 3u), 1);
+            float r_v[CT];
+#pragma unroll
+            for (int k = 0; k <= C; ++k) r_v[k] = __shfl_up_sync(0xffffffffu, v[3][k], 1);
+            const int jh = __ffs(emit) - 1;                // end of the run that starts at point 0, if it does
+            const bool accept = lane > 0 && jh >= 0 && jh < 3 && (okm & 1u) && ((starts >> (2 * jh)) & 3u) == 0u && r_slot == slot[0];
+            const bool given = __shfl_down_sync(0xffffffffu, accept ? 1u : 0u, 1) != 0u && lane < 31;
+            if (accept) {
+                acc_site = jh; head_abs = r_start;
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+#pragma unroll
+                    for (int k = 0; k <= C; ++k) v[j][k] = __fadd_rn(v[j][k], j == jh ? r_v[k] : 0.0f);
+            }
+            if (given) emit &= ~8u;
+        }
+        // A run can only become its cell's minimum if the cell's current minimum is larger: look first
+        // (a plain load with lane locality costs a fraction of a returning atomic, and first[] only
+        // ever decreases, so a stale value errs on the side of issuing the atomic).  Tiles are taken
+        // in roughly ascending order, so every sweep after the first mostly finds the cell claimed.
+        uint32_t seen[PF_PPT];
+#pragma unroll
+        for (int j = 0; j < PF_PPT; ++j) {
+            seen[j] = 0u;
+            if ((emit >> j) & 1u)
+                asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(seen[j]) : "l"(f.first + slot[j]), "l"(keep));
+        }
+        // ---- the previous tile's minima have had a whole tile of arithmetic to come back ----
+        if (prev_valid) settle();
+        prev_first = i0; prev_starts = starts; prev_valid = true; prev_acc = acc_site; prev_head = head_abs;
+#pragma unroll
+        for (int j = 0; j < PF_PPT; ++j) {
+            const uint32_t pred = (emit >> j) & 1u;
+            uint32_t sj = pred ? slot[j] : 0u;             // keep the address computation in range when predicated off
+            if (KI_EXP == 2) sj &= 0x3FFFFu;               // experiment: an L2-resident 8 MB window
+            const uint32_t i_run = j == acc_site ? head_abs : i0 + ((starts >> (2 * j)) & 3u);
+            if (KI_EXP != 1 && KI_EXP != 3) ki_atom_min(olds[j], f.first + sj, i_run, (KI_EXP == 5 || seen[j] > i_run) ? pred : 0u);
+            float *row = f.acc + (size_t)sj * f.rowf;
+            if (KI_EXP != 1 && KI_EXP != 4) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q) ki_red_add_v4(row + 4 * q, v[j][4 * q], v[j][4 * q + 1], v[j][4 * q + 2], v[j][4 * q + 3], keep, pred);
+            }
+        }
+        if (n_here == PF_PPT) __stcs(reinterpret_cast<uint4 *>(f.sa + i0), make_uint4(slot[0], slot[1], slot[2], slot[3]));
+        else {
+#pragma unroll
+            for (int j = 0; j < PF_PPT; ++j)
+                if ((uint32_t)j < n_here) f.sa[i0 + j] = slot[j];
+        }
+    }
+    if (prev_valid) settle();
+}
+
+// ---------------------------------------------------------------------------------------------
 // F3 -- popcount scan over the first-point bitmap, one block per frame; consumes (zeroes) bits[]
 // and publishes wb[] = {prefix, word}.  The last block to finish computes the output row bases.
 // ---------------------------------------------------------------------------------------------
@@ -461,109 +761,131 @@ __global__ void __launch_bounds__(PF_SCAN_THREADS) kf_scan(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
-// F3 (static path) -- popcount scan over the first-point bitmap, one block per frame.  The bitmap
-// is addressed by the GLOBAL point index, so a frame is the bit range [offsets[b], offsets[b+1]),
-// not word aligned: the partial words at both ends are masked for counting, and wb[w] = {first
-// points of the frame containing point 32 w that precede the word, the whole word} is written by
-// that frame's block ("owner").  A cell whose first point sits in a word that starts in an earlier
-// frame has prefix 0 and masks the word from its own frame's first bit (kf_finalize).  The bitmap
-// is cleared later by kf_heavy_points (straddling words are read by two blocks here).
+// F2 (static path) -- popcount scan over the first-point bitmap.  The bitmap is addressed by the
+// GLOBAL point index, so the scan ignores frames: one block per chunk of PF_CHUNK_WORDS words
+// (16k points) publishes wb[w] = {first points of the chunk before word w, the word} and the
+// chunk's total; the LAST block to finish turns the totals into chunk bases and evaluates the
+// batch-wide prefix G(i) = first points with index < i at the frame boundaries:
+//     frank0[b] = G(offsets[b]),  raw count of frame b = G(offsets[b+1]) - G(offsets[b]),
+// so a first point fi of frame b has first-occurrence rank G(fi) - frank0[b] (pf_rank).  One wave
+// of independent blocks + one short tail instead of one block per frame (10 -> 3 us for 8 frames).
+// The bitmap is cleared later by kf_heavy_points.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PF_SCAN_THREADS) kf_scan_pts(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
+#define PF_CHUNK_WORDS 512
+#define PF_CHUNK_SHIFT 9
+#define PF_SCAN2_THREADS 128             // 4 words per thread
+
+// G(i): first points of the batch with index < i (valid once kf_scan2's last block has published cbase)
+__device__ __forceinline__ uint32_t pf_prefix_at(const PvF &f, uint32_t i)
 {
-    __shared__ uint32_t s_warp[PF_SCAN_THREADS / 32];
-    __shared__ uint32_t s_carry, s_last;
-    const int b = blockIdx.x;
+    const uint32_t w = i >> 5;
+    const uint2 wv = __ldcg(f.wb + w);
+    return __ldcg(f.cbase + (w >> PF_CHUNK_SHIFT)) + wv.x + __popc(wv.y & ((1u << (i & 31u)) - 1u));
+}
+
+__global__ void __launch_bounds__(PF_SCAN2_THREADS) kf_scan2(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
+{
+    __shared__ uint32_t s_warp[PF_SCAN2_THREADS / 32];
+    __shared__ uint32_t s_last, s_carry;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t off0 = (uint32_t)p.offsets[b], off1 = (uint32_t)p.offsets[b + 1];   // caller's input: no dependency
+    const uint32_t nw = (p.n >> 5) + 1u;                    // words [0, nw) cover bit n (always clear)
+    const uint32_t w = blockIdx.x * PF_CHUNK_WORDS + tid * 4u;
     pf_pdl_trigger();
+    if (blockIdx.x == 0 && tid == 0) *reinterpret_cast<unsigned long long *>(f.ctrl + 4) = 0ull;   // heavy-cell allocator of this call
     pf_pdl_wait();                           // the bitmap of kf_insert
-    const uint32_t wlo = off0 >> 5, whi = off1 > off0 ? (off1 + 31u) >> 5 : wlo;     // words [wlo, whi)
-    const uint32_t mlo = 0xFFFFFFFFu << (off0 & 31u);
-    const uint32_t mhi = (off1 & 31u) ? (1u << (off1 & 31u)) - 1u : 0xFFFFFFFFu;
-    if (tid == 0) {
-        s_carry = 0;
-        if (b == 0) *reinterpret_cast<unsigned long long *>(f.ctrl + 4) = 0ull;   // heavy-cell allocator of this call
+    // the bitmap is padded with clear words past nw (pvf_make_layout), so a vector never reads outside
+    const uint4 x = w < nw ? __ldcg(reinterpret_cast<const uint4 *>(f.bits + w)) : make_uint4(0, 0, 0, 0);
+    const uint32_t c0 = __popc(x.x), c1 = __popc(x.y), c2 = __popc(x.z), c3 = __popc(x.w);
+    const uint32_t tsum = c0 + c1 + c2 + c3;
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (unsigned)d) incl += o;
     }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    constexpr uint32_t WPT = 4u * PF_SCAN_VEC;               // words per thread per iteration
-    for (uint32_t w0 = wlo & ~3u; w0 < whi; w0 += PF_SCAN_THREADS * WPT) {
-        const uint32_t wt = w0 + tid * WPT;
-        uint32_t v[WPT], c[WPT];
-        uint32_t tsum = 0;
+    uint32_t run = incl - tsum, total = 0;
 #pragma unroll
-        for (int q = 0; q < PF_SCAN_VEC; ++q) {               // the bitmap is padded to a multiple of 4 words
-            const uint32_t w = wt + 4u * q;
-            const uint4 x = (w < whi && w + 4u > wlo) ? __ldcg(reinterpret_cast<const uint4 *>(f.bits + w)) : make_uint4(0, 0, 0, 0);
-            v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-        }
-#pragma unroll
-        for (int k = 0; k < (int)WPT; ++k) {
-            const uint32_t w = wt + k;
-            uint32_t m = (w >= wlo && w < whi) ? 0xFFFFFFFFu : 0u;
-            if (w == wlo) m &= mlo;
-            if (w + 1u == whi) m &= mhi;
-            c[k] = __popc(v[k] & m);
-            tsum += c[k];
-        }
-        uint32_t incl = tsum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (unsigned)d) incl += o;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        uint32_t wsum = lane < PF_SCAN_THREADS / 32 ? s_warp[lane] : 0u;     // every warp scans the warp totals
-        uint32_t wincl = wsum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, wincl, d);
-            if (lane >= (unsigned)d) wincl += o;
-        }
-        const uint32_t warp_excl = __shfl_sync(0xffffffffu, wincl - wsum, warp);
-        const uint32_t total = __shfl_sync(0xffffffffu, wincl, 31);
-        uint32_t run = s_carry + warp_excl + incl - tsum;
-#pragma unroll
-        for (int k = 0; k < (int)WPT; k += 2) {              // owner: the word starts inside this frame
-            const uint32_t w = wt + k;
-            const bool own0 = w < whi && (w << 5) >= off0, own1 = w + 1u < whi && ((w + 1u) << 5) >= off0;
-            if (own0 && own1) *reinterpret_cast<uint4 *>(f.wb + w) = make_uint4(run, v[k], run + c[k], v[k + 1]);
-            else if (own0) f.wb[w] = make_uint2(run, v[k]);
-            else if (own1) f.wb[w + 1] = make_uint2(run + c[k], v[k + 1]);
-            run += c[k] + c[k + 1];
-        }
-        __syncthreads();
-        if (tid == 0) s_carry += total;
-        __syncthreads();
+    for (int k = 0; k < PF_SCAN2_THREADS / 32; ++k) {
+        const uint32_t v = s_warp[k];
+        if ((uint32_t)k < warp) run += v;
+        total += v;
+    }
+    if (w < nw) {                            // wb is sized like the bitmap: the padding words may be written too
+        uint4 *dst = reinterpret_cast<uint4 *>(f.wb + w);
+        dst[0] = make_uint4(run, x.x, run + c0, x.y);
+        dst[1] = make_uint4(run + c0 + c1, x.z, run + c0 + c1 + c2, x.w);
     }
     if (tid == 0) {
-        const uint32_t raw = s_carry;
-        f.counts_raw[b] = raw;
-        p.voxel_counts[b] = (int32_t)min(raw, (uint32_t)p.V);
+        f.cagg[blockIdx.x] = total;
         __threadfence();
         const uint32_t done = atomicAdd(f.ctrl + 3, 1u);
         s_last = done == gridDim.x - 1 ? 1u : 0u;
         if (s_last) f.ctrl[3] = 0u;
+        s_carry = 0u;
     }
     __syncthreads();
-    if (s_last && warp == 0) {                           // row bases: exclusive sum of the capped counts
-        __threadfence();
+    if (!s_last) return;
+    __threadfence();
+    // ---- tail (one block): chunk bases, then the per-frame quantities ----
+    const uint32_t nchunks = gridDim.x;
+    for (uint32_t c0b = 0; c0b < nchunks; c0b += PF_SCAN2_THREADS) {
+        const uint32_t c = c0b + tid;
+        const uint32_t v = c < nchunks ? __ldcg(f.cagg + c) : 0u;
+        uint32_t in2 = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, in2, d);
+            if (lane >= (unsigned)d) in2 += o;
+        }
+        if (lane == 31) s_warp[warp] = in2;
+        __syncthreads();
+        uint32_t off = s_carry, tot = 0;
+#pragma unroll
+        for (int k = 0; k < PF_SCAN2_THREADS / 32; ++k) {
+            const uint32_t t = s_warp[k];
+            if ((uint32_t)k < warp) off += t;
+            tot += t;
+        }
+        if (c < nchunks) f.cbase[c] = off + in2 - v;
+        __syncthreads();
+        if (tid == 0) s_carry += tot;
+        __syncthreads();
+    }
+    __threadfence_block();
+    __syncthreads();
+    // frames: G at every boundary (cbase written by this block: read back through L2)
+    if (warp == 0) {
         uint32_t carry = 0;
         for (int b0 = 0; b0 < p.B; b0 += 32) {
             const int bb = b0 + (int)lane;
-            const uint32_t m = bb < p.B ? (uint32_t)__ldcg(p.voxel_counts + bb) : 0u;
-            uint32_t incl = m;
+            uint32_t m = 0;
+            if (bb < p.B) {
+                const uint32_t g0 = pf_prefix_at(f, (uint32_t)p.offsets[bb]), g1 = pf_prefix_at(f, (uint32_t)p.offsets[bb + 1]);
+                const uint32_t raw = g1 - g0;
+                f.frank0[bb] = g0;
+                f.counts_raw[bb] = raw;
+                m = min(raw, (uint32_t)p.V);
+                p.voxel_counts[bb] = (int32_t)m;
+            }
+            uint32_t in3 = m;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= (unsigned)d) incl += o;
+                const uint32_t o = __shfl_up_sync(0xffffffffu, in3, d);
+                if (lane >= (unsigned)d) in3 += o;
             }
-            if (bb < p.B) f.base[bb] = (int32_t)(carry + incl - m);
-            carry += __shfl_sync(0xffffffffu, incl, 31);
+            if (bb < p.B) f.base[bb] = (int32_t)(carry + in3 - m);
+            carry += __shfl_sync(0xffffffffu, in3, 31);
         }
         if (lane == 0) f.base[p.B] = (int32_t)carry;
     }
+}
+
+// First-occurrence rank of the cell whose first point is fi (frame b); wv = wb[fi >> 5].
+__device__ __forceinline__ uint32_t pf_rank(const PvF &f, const int b, const uint32_t fi, const uint2 wv)
+{
+    return __ldg(f.cbase + (fi >> (5 + PF_CHUNK_SHIFT))) + wv.x + __popc(wv.y & ((1u << (fi & 31u)) - 1u)) - __ldg(f.frank0 + b);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -571,17 +893,32 @@ __global__ void __launch_bounds__(PF_SCAN_THREADS) kf_scan_pts(const __grid_cons
 // Cells holding more than T points ("heavy", 2-5 % of the points) get coors / num_points here and
 // are registered for F5, which selects their T smallest point indices and writes their features.
 // ---------------------------------------------------------------------------------------------
+// The map (first[], accumulator rows) is the part of the workspace that is touched at random; with
+// PF_WS_KEEP its accesses carry an L2 evict_last policy (and the streams around it evict_first), so
+// a workspace that comes round again soon is still in the 126 MB L2 and its rows neither have to be
+// filled from nor written back to DRAM one 32-byte sector at a time.
+#ifndef PF_WS_KEEP
+#define PF_WS_KEEP 1
+#endif
 template <int NV>
 __device__ __forceinline__ void pf_ld_row(const float *row, float (&r)[NV * 4])
 {
     if constexpr (NV == 2) {        // one 256-bit load per 32-byte row
+        if (PF_WS_KEEP) {
+            const unsigned long long pol = pv_policy_evict_last();
+            asm volatile("ld.global.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                         : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                         : "l"(row), "l"(pol));
+        } else
         asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
                      : "l"(row));
     } else {
+        const unsigned long long pol = pv_policy_evict_last();
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
-            const float4 v = __ldcg(reinterpret_cast<const float4 *>(row) + q);
+            const float4 v = PF_WS_KEEP ? pv_ld_keep(reinterpret_cast<const float4 *>(row) + q, pol)
+                                        : __ldcg(reinterpret_cast<const float4 *>(row) + q);
             r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
         }
     }
@@ -592,12 +929,31 @@ template <int NV>
 __device__ __forceinline__ void pf_st_row_clean(float *row, float keep0, float keep1 = 0.0f)
 {
     if constexpr (NV == 2) {
+        if (PF_WS_KEEP) {
+            const unsigned long long pol = pv_policy_evict_last();
+            asm volatile("st.global.L2::cache_hint.v8.f32 [%0], {%1,%2,%3,%3,%3,%3,%3,%3}, %4;"
+                         ::"l"(row), "f"(keep0), "f"(keep1), "f"(0.0f), "l"(pol) : "memory");
+        } else
         asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%3,%3,%3,%3,%3};" ::"l"(row), "f"(keep0), "f"(keep1), "f"(0.0f) : "memory");
     } else {
 #pragma unroll
         for (int q = 0; q < NV; ++q)
             __stcg(reinterpret_cast<float4 *>(row) + q, make_float4(q == 0 ? keep0 : 0.f, q == 0 ? keep1 : 0.f, 0.f, 0.f));
     }
+}
+__device__ __forceinline__ uint32_t pf_ld_first(const uint32_t *p)
+{
+    if (!PF_WS_KEEP) return __ldcs(p);
+    uint32_t v;
+    const unsigned long long pol = pv_policy_evict_last();
+    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void pf_st_first(uint32_t *p, uint32_t v)
+{
+    if (!PF_WS_KEEP) { *p = v; return; }
+    const unsigned long long pol = pv_policy_evict_last();
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 
 // One occupied map slot s of frame b = cell (cz, cy, cx): rank lookup, per-voxel outputs, heavy
@@ -611,11 +967,7 @@ __device__ __forceinline__ void pf_finalize_cell(const PvParams &p, const PvF &f
     constexpr int CT = NV * 4;
     const int C = CC ? CC : p.C;
     float *rowp = f.acc + (size_t)s * f.rowf;
-    const uint32_t off_b = (uint32_t)__ldg(p.offsets + b);
-    // first points of this frame before point fi: the word's prefix belongs to the frame the word
-    // starts in; if that is an earlier frame, this frame starts inside the word
-    const uint32_t below = wv.y & ((1u << (fi & 31u)) - 1u);
-    const uint32_t rank = (fi & ~31u) >= off_b ? wv.x + __popc(below) : __popc(below & (0xFFFFFFFFu << (off_b & 31u)));
+    const uint32_t rank = pf_rank(f, b, fi, wv);
     float keep0 = 0.0f, keep1 = 0.0f;
     if (rank < (uint32_t)p.V) {                                           // :60-61 max_voxels
         float cntf = 0.0f;
@@ -626,8 +978,8 @@ __device__ __forceinline__ void pf_finalize_cell(const PvParams &p, const PvF &f
         const uint32_t L = min(cnt, T);
         const int32_t vid = __ldg(f.base + b) + (int32_t)rank;
         const uint32_t cell = (cz * (uint32_t)p.grid[1] + cy) * (uint32_t)p.grid[0] + cx;
-        __stcs(reinterpret_cast<int4 *>(p.coors) + vid, make_int4(b, (int)cz, (int)cy, (int)cx));   // write-once outputs: streaming
-        __stcs(p.num_points + vid, (int32_t)L);
+        if (KF_EXP != 4) __stcs(reinterpret_cast<int4 *>(p.coors) + vid, make_int4(b, (int)cz, (int)cy, (int)cx));   // write-once outputs: streaming
+        if (KF_EXP != 4) __stcs(p.num_points + vid, (int32_t)L);
         dens = (int32_t)cnt;                                              // :70-71 un-capped count
         if (cnt > T) {
             // heavy: the row holds the sum over ALL points; F5 re-sums the T smallest indices
@@ -656,13 +1008,13 @@ __device__ __forceinline__ void pf_finalize_cell(const PvParams &p, const PvF &f
                 for (int k = 0; k < CT; ++k)
                     if (k < C) cv[(size_t)k * p.cells] = mean[k];
             }
-            if (p.feats) pv_store_feats<CT>(p.feats, vid, C, mean);
+            if (p.feats && KF_EXP != 4) pv_store_feats<CT>(p.feats, vid, C, mean);
         }
         if (!DENSE && p.density) p.density[(size_t)b * p.cells + cell] = (int32_t)cnt;
     }
     // restore the map -- after the loaded row was consumed (see kf_scan)
-    pf_st_row_clean<NV>(rowp, keep0, keep1);
-    f.first[s] = PV_INF;
+    if (KF_EXP != 2) pf_st_row_clean<NV>(rowp, keep0, keep1);
+    if (KF_EXP != 2) pf_st_first(f.first + s, PV_INF);
     if (!DENSE) f.keys[s] = PV_INF;
 }
 
@@ -727,7 +1079,7 @@ __global__ void __launch_bounds__(PF_FIN_WARPS * 32) kf_finalize_patch(const __g
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
         const uint32_t x = pxi * PF_PATCH + wq + (uint32_t)PF_FIN_WARPS * k;
-        fi[k] = (x < nx && y < ny) ? __ldcs(f.first + (size_t)b * f.capf + (z * nx + x) * ny + y) : PV_INF;
+        fi[k] = (x < nx && y < ny) ? pf_ld_first(f.first + (size_t)b * f.capf + (z * nx + x) * ny + y) : PV_INF;
     }
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
@@ -768,6 +1120,92 @@ __global__ void __launch_bounds__(PF_FIN_WARPS * 32) kf_finalize_patch(const __g
                 if (c < C) { __stcs(cv, s_t[((size_t)c * PF_PATCH + lane) * (PF_PATCH + 1) + yl]); cv += p.cells; }
         }
         if (p.density) p.density[(size_t)b * p.cells + cell] = s_d[lane * (PF_PATCH + 1) + yl];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// F3, pillar grids with a canvas (the headline path): one block per 32 x 32 patch like
+// kf_finalize_patch, but
+//   * the occupied cells of a warp's 128 cells (23-30 % on a LiDAR frame) are COMPACTED first
+//     (ballot + popcount into a per-warp list), so the long per-voxel path runs on full warps:
+//     1-2 dense iterations instead of 4 sparse ones;
+//   * the patch's canvas tile [C][32 phi][32 rho] is assembled in shared memory (zero filled while
+//     the predecessor kernel drains, means scattered in by the packed lanes) and leaves as ONE TMA
+//     tensor store (cp.async.bulk.tensor.3d, 128-byte swizzle so the scatter is at most 4-way
+//     conflicted): no per-element LDS / STG phase, every canvas element still written exactly once.
+// ---------------------------------------------------------------------------------------------
+#define PF_TMA_SWZ(row, col) ((uint32_t)(row) * 32u + (((((uint32_t)(col)) >> 2) ^ ((uint32_t)(row) & 7u)) << 2) + ((uint32_t)(col) & 3u))
+template <int NV, int CC>
+__global__ void __launch_bounds__(256) kf_finalize_tma(const __grid_constant__ PvParams p, const __grid_constant__ PvF f,
+                                                       const __grid_constant__ CUtensorMap tmap)
+{
+    constexpr int CT = NV * 4;
+    extern __shared__ __align__(1024) unsigned char s_dyn[];
+    __shared__ uint32_t s_fi[8][128];
+    __shared__ uint8_t s_id[8][128];
+    const int C = CC ? CC : p.C;
+    const int b = blockIdx.z;
+    const uint32_t nx = p.grid[0], ny = p.grid[1];
+    const uint32_t pxi = blockIdx.y, pyi = blockIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wq = tid >> 5;
+    // the swizzle pattern repeats every 1024 bytes: align the tile in the shared window
+    const uint32_t dyn0 = pf_smem_addr(s_dyn), tile0 = (dyn0 + 1023u) & ~1023u;
+    float *s_t = reinterpret_cast<float *>(s_dyn + (tile0 - dyn0));
+
+    pf_pdl_trigger();
+    {   // zero fill: independent of the earlier kernels, overlaps their tail
+        float4 *t4 = reinterpret_cast<float4 *>(s_t);
+        for (int q = (int)tid; q < C * 256; q += 256) t4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    pf_pdl_wait();                           // map, bitmap prefix and row bases of the earlier kernels
+    const uint32_t y = pyi * 32u + lane;
+    uint32_t fi[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t x = pxi * 32u + wq + 8u * k;
+        fi[k] = (x < nx && y < ny) ? pf_ld_first(f.first + (size_t)b * f.capf + x * ny + y) : PV_INF;
+    }
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const bool occ = fi[k] != PV_INF;
+        const uint32_t mask = __ballot_sync(0xffffffffu, occ);
+        if (occ) {
+            const uint32_t pos = cnt + __popc(mask & ((1u << lane) - 1u));
+            s_fi[wq][pos] = fi[k];
+            s_id[wq][pos] = (uint8_t)(k * 32 + (int)lane);
+        }
+        cnt += __popc(mask);
+    }
+    __syncthreads();                         // tile zeroed (all warps), lists visible
+    for (uint32_t e = lane; e < cnt; e += 32u) {
+        const uint32_t fiv = s_fi[wq][e], id = s_id[wq][e];
+        const uint32_t yl = id & 31u, xl = wq + 8u * (id >> 5);
+        const uint32_t x = pxi * 32u + xl, yy = pyi * 32u + yl;
+        const uint32_t s = (uint32_t)b * f.capf + x * ny + yy;
+        float r[CT], m[CT];
+        if (KF_EXP == 1) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) r[c] = 1.0f;
+        } else pf_ld_row<NV>(f.acc + (size_t)s * f.rowf, r);
+        const uint2 wv = __ldg(f.wb + (fiv >> 5));
+#pragma unroll
+        for (int c = 0; c < CT; ++c) m[c] = 0.0f;
+        int32_t dens = 0;
+        pf_finalize_cell<NV, CC, true, true>(p, f, s, b, fiv, x, yy, 0u, r, wv, m, dens);
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+            if (c < C) s_t[PF_TMA_SWZ(c * 32 + (int)yl, xl)] = m[c];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> the TMA's async proxy
+    __syncthreads();
+    if (tid == 0 && KF_EXP != 3) {
+        const unsigned long long pol = pf_policy_evict_first();      // the canvas is write-once
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;"
+                     ::"l"(reinterpret_cast<unsigned long long>(&tmap)), "r"((int)(pxi * 32u)), "r"((int)(pyi * 32u)),
+                       "r"(b * C), "r"(tile0), "l"(pol) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the tile must outlive the read
     }
 }
 
@@ -1019,6 +1457,10 @@ int pvf_make_layout(const pv_config *cfg, int64_t n_cap, int32_t batch, int64_t 
     w->counts_raw = (uint32_t *)(p0 + o);  o = pf_align(o + (size_t)batch * 4, 256);
     w->sa = (uint32_t *)(p0 + o);          o = pf_align(o + n * 4 + 32, 256);
     w->wb = (uint2 *)(p0 + o);             o = pf_align(o + bit_words * 8, 256);
+    w->max_chunks = (uint32_t)((n >> 5) / PF_CHUNK_WORDS + 2);
+    w->cagg = (uint32_t *)(p0 + o);        o = pf_align(o + (size_t)w->max_chunks * 4, 256);
+    w->cbase = (uint32_t *)(p0 + o);       o = pf_align(o + ((size_t)w->max_chunks + 1) * 4, 256);
+    w->frank0 = (uint32_t *)(p0 + o);      o = pf_align(o + (size_t)batch * 4, 256);
     w->total_bytes = o;
     return PV_OK;
 }
@@ -1035,8 +1477,8 @@ int pvf_init(const PvF &f, int32_t batch, int64_t n_cap, cudaStream_t st)
 
 // Launch with programmatic stream serialization (see pf_pdl_wait): the kernel may start while the
 // previous kernel of the stream is still draining; it synchronises itself with pf_pdl_wait.
-template <typename K>
-static int pf_launch_pdl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const PvParams &p, const PvF &f)
+template <typename K, typename... Args>
+static int pf_launch_pdl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Args &...args)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -1044,7 +1486,38 @@ static int pf_launch_pdl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, p, f) == cudaSuccess ? PV_OK : PV_ERR_CUDA;
+    return cudaLaunchKernelEx(&cfg, kern, args...) == cudaSuccess ? PV_OK : PV_ERR_CUDA;
+}
+
+// Tensor map of the canvas [B * C][ny][nx] f32 for kf_finalize_tma's stores: box = C x 32 x 32,
+// 128-byte swizzle.  Encoded on the host per call (no device work, no allocation); the driver entry
+// point is looked up once (immutable after that).
+typedef CUresult (*pf_encode_tiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static pf_encode_tiled_t pf_encode_tiled()
+{
+    static const pf_encode_tiled_t fn = [] {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            sym = nullptr;
+        return reinterpret_cast<pf_encode_tiled_t>(sym);
+    }();
+    return fn;
+}
+
+static bool pf_canvas_tmap(const PvParams &p, CUtensorMap *tm)
+{
+    const pf_encode_tiled_t enc = pf_encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)p.grid[0], (cuuint64_t)p.grid[1], (cuuint64_t)p.B * (cuuint64_t)p.C};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.grid[0] * 4ull, (cuuint64_t)p.grid[0] * (cuuint64_t)p.grid[1] * 4ull};
+    const cuuint32_t box[3] = {32u, 32u, (cuuint32_t)p.C};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.canvas, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <bool DENSE, int CIN, bool CART, int NV, int MODE = PF_MODE_FREE>
@@ -1063,10 +1536,43 @@ static int pf_launch_insert(const PvParams &p, const PvF &f, cudaStream_t st)
     return PV_OK;
 }
 
+// SM count of the current device (queried, not assumed; cached per device ordinal).
+int pv_sm_count()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+template <int CIN, bool CART, int NV>
+static int pf_launch_insert_stream(const PvParams &p, const PvF &f, cudaStream_t st)
+{
+    const uint32_t n_tiles = (p.n + 127u) >> 7;
+    const uint32_t want = (n_tiles + KI_WARPS - 1) / KI_WARPS, cap = (uint32_t)pv_sm_count() * KI_BLOCKS_PER_SM;
+    const uint32_t grid = want < cap ? want : cap;
+    const size_t smem = (size_t)KI_WARPS * KI_STAGES * 128 * CIN * sizeof(float);
+    kf_insert_stream<CIN, CART, NV><<<grid, KI_WARPS * 32, smem, st>>>(p, f, n_tiles, grid * KI_WARPS);
+    return PV_OK;
+}
+
 template <bool DENSE>
 static int pf_dispatch_insert(const PvParams &p, const PvF &f, cudaStream_t st)
 {
     const int nv = (int)f.rowf / 4;
+    // the fused front end's hot path: direct map, no pc_grid_ind, 16-byte aligned rows
+    if (DENSE && !p.grid_ind && (reinterpret_cast<uintptr_t>(p.pts) & 15u) == 0) {
+        if (p.cart && p.c_in == 5) return pf_launch_insert_stream<5, true, 2>(p, f, st);    // nuScenes (x,y,z,i,dt)
+        if (p.cart && p.c_in == 6) return pf_launch_insert_stream<6, true, 3>(p, f, st);    // Waymo (x,y,z,i,e,dt)
+        if (p.cart && p.c_in == 4) return pf_launch_insert_stream<4, true, 2>(p, f, st);
+        if (!p.cart && p.c_in == 7) return pf_launch_insert_stream<7, false, 2>(p, f, st);
+        if (!p.cart && p.c_in == 8) return pf_launch_insert_stream<8, false, 3>(p, f, st);
+    }
     if (p.cart && p.c_in == 5) return pf_launch_insert<DENSE, 5, true, 2>(p, f, st);     // nuScenes (x,y,z,i,dt)
     if (p.cart && p.c_in == 6) return pf_launch_insert<DENSE, 6, true, 3>(p, f, st);     // Waymo (x,y,z,i,e,dt)
     if (p.cart && p.c_in == 4) return pf_launch_insert<DENSE, 4, true, 2>(p, f, st);
@@ -1153,6 +1659,18 @@ static int pf_launch_finalize_nv(const PvParams &p, const PvF &f, cudaStream_t s
     const unsigned px = ((unsigned)p.grid[0] + PF_PATCH - 1) / PF_PATCH, py = ((unsigned)p.grid[1] + PF_PATCH - 1) / PF_PATCH;
     const dim3 grid(py * (unsigned)p.grid[2], px, (unsigned)p.B);        // px <= 2^15 for a direct map
     if (p.B > 65535 || grid.y > 65535u) return PV_ERR_UNSUPPORTED;
+    // canvas without density on a pillar grid: compacted cells + one TMA tensor store per patch
+    if (p.canvas && !p.density && p.grid[2] == 1 && (p.grid[0] & 3) == 0 && (reinterpret_cast<uintptr_t>(p.canvas) & 15u) == 0) {
+        CUtensorMap tm;
+        if (pf_canvas_tmap(p, &tm)) {
+            const size_t smem_t = (size_t)p.C * 32 * 32 * sizeof(float) + 1024;
+            auto kt = kf_finalize_tma<NV, CC>;
+            if (smem_t + 5 * 1024 > 48 * 1024 &&
+                cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t) != cudaSuccess)
+                return PV_ERR_CUDA;
+            return pf_launch_pdl(kt, grid, dim3(256), smem_t, st, p, f, tm);
+        }
+    }
     const size_t smem = ((p.canvas ? (size_t)p.C : 0) + (p.density ? 1 : 0)) * PF_PATCH * (PF_PATCH + 1) * sizeof(float);
     auto kern = p.canvas ? kf_finalize_patch<NV, CC, true> : kf_finalize_patch<NV, CC, false>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -1191,14 +1709,14 @@ int pvf_run(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev)
     }
     PF_MARK(1);
     PF_MARK(2);                              // (the first-point bitmap is built by the insert kernel)
-    if (pf_launch_pdl(kf_scan_pts, dim3((unsigned)p.B), dim3(PF_SCAN_THREADS), 0, st, p, f)) return PV_ERR_CUDA;
+    if (pf_launch_pdl(kf_scan2, dim3(((p.n >> 5) + PF_CHUNK_WORDS) / PF_CHUNK_WORDS), dim3(PF_SCAN2_THREADS), 0, st, p, f)) return PV_ERR_CUDA;
     PF_MARK(3);
     {
         const int rc = pf_launch_finalize(p, f, st);
         if (rc) return rc;
     }
     PF_MARK(4);
-    if (p.n > 0) {
+    if (p.n > 0 && KF_EXP != 9) {
         if (pf_launch_pdl(kf_heavy_points, dim3((p.n + PF_THREADS * PF_HPT - 1) / (PF_THREADS * PF_HPT)), dim3(PF_THREADS), 0, st, p, f)) return PV_ERR_CUDA;
         if (pf_launch_pdl(kf_heavy_cells, dim3(296), dim3(256), 0, st, p, f)) return PV_ERR_CUDA;
     }

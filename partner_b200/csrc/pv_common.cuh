@@ -56,7 +56,11 @@ struct PvF {
     float *acc;            // [B * capf * rowf] per-cell row: C feature sums, then the count   (clean 0)
     uint32_t *sa;          // [n_cap] per point: heavy-bitmap index of its cell (INF = out of range)
     uint32_t *bits;        // [B * wcap] bit (i - frame start) set <=> point i is its cell's first point (clean 0)
-    uint2 *wb;             // [B * wcap] {first points before this word in the frame, the word}
+    uint2 *wb;             // [B * wcap] static path: {first points before this word in its scan chunk, the word};
+                           //            dynamic path: {occupied cells before this word in the frame, the word}
+    uint32_t *cagg;        // [max_chunks] static path: first points per scan chunk (PF_CHUNK_WORDS bitmap words)
+    uint32_t *cbase;       // [max_chunks + 1] first points of the batch before the chunk
+    uint32_t *frank0;      // [B] first points of the batch before the frame's first point
     uint32_t *hbits;       // [B * capf / 32 + 1] bitmap of cells holding more than T points   (clean 0)
     uint4 *hinfo;          // [2 * hmax] heavy cell h: {slot, output row, candidate offset, count}, {cell, frame, cursor, -}
     uint32_t *hlist;       // [n_cap + 32] candidate point indices of the heavy cells, one range per cell
@@ -66,6 +70,7 @@ struct PvF {
     uint32_t rowf;         // floats per row in THIS call: C + 1 rounded up to 4
     uint32_t dense;
     uint32_t hmax;
+    uint32_t max_chunks;
     size_t total_bytes;
 };
 
@@ -320,6 +325,7 @@ int pv_check_config(const pv_config *cfg);
 int pv_make_layout(const pv_config *cfg, int64_t n_cap, int32_t batch, int64_t frame_capacity,
                    void *base, PvWs *out);
 int pv_last_cuda_error();
+int pv_sm_count();      // SMs of the current device
 int pvf_make_layout(const pv_config *cfg, int64_t n_cap, int32_t batch, int64_t frame_capacity,
                     int32_t max_channels, void *base, PvF *out);
 int pvf_init(const PvF &f, int32_t batch, int64_t n_cap, cudaStream_t st);

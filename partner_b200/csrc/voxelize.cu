@@ -601,6 +601,7 @@ int pv_check_config(const pv_config *cfg)
         if (cells >= (1ll << 31)) return PV_ERR_BAD_CONFIG;
     }
     if (cfg->max_points <= 0 || cfg->max_points > 32767 || cfg->max_voxels <= 0) return PV_ERR_BAD_CONFIG;
+    if (cfg->pipeline < 0 || cfg->pipeline > 2) return PV_ERR_BAD_CONFIG;
     return PV_OK;
 }
 
@@ -667,17 +668,15 @@ static int make_layouts(const pv_config *cfg, int64_t n_cap, int32_t batch, int6
     return PV_OK;
 }
 
-// Pipeline choice (pv_set_pipeline; the PV_PIPELINE environment variable sets the initial value):
+// Pipeline choice = pv_config::pipeline (part of the caller's configuration, no process state):
 // 0 auto      list-free on direct-map grids, list-based on hash-map grids (per-cell rows in a hash
 //             map cost more random DRAM sectors than point lists when most voxels hold 1-2 points)
 // 1 lists     list-based everywhere
 // 2 list-free list-free wherever the padded voxels tensor is not requested
-static int g_pipeline = [] { const char *e = getenv("PV_PIPELINE"); return e ? atoi(e) : 0; }();
-
-static bool use_lists(const PvF &f, bool want_voxels)
+static bool use_lists(const pv_config *cfg, const PvF &f, bool want_voxels)
 {
-    if (want_voxels || g_pipeline == 1) return true;
-    if (g_pipeline == 2) return false;
+    if (want_voxels || cfg->pipeline == 1) return true;
+    if (cfg->pipeline == 2) return false;
     return !f.dense;
 }
 
@@ -811,20 +810,13 @@ extern "C" {
 
 int pv_version(void) { return 300; }
 
-int pv_set_pipeline(int mode)
-{
-    if (mode < 0 || mode > 2) return PV_ERR_BAD_ARGUMENT;
-    g_pipeline = mode;
-    return PV_OK;
-}
-
 int pv_profile_pipeline(const pv_config *cfg)
 {
     if (pv_check_config(cfg)) return PV_ERR_BAD_CONFIG;
     const uint64_t cells = (uint64_t)cfg->grid[0] * cfg->grid[1] * cfg->grid[2];
     PvF f;
     f.dense = cells <= PV_DENSE_MAX_CELLS ? 1u : 0u;
-    return use_lists(f, false) ? 1 : 2;
+    return use_lists(cfg, f, false) ? 1 : 2;
 }
 
 const char *pv_error_string(int code)
@@ -898,7 +890,7 @@ int pv_voxelize(const pv_config *cfg, const float *points, const int32_t *frame_
     p.coors = coors; p.num_points = num_points; p.voxel_counts = voxel_counts;
     p.voxels = voxels; p.feats = mean_feats; p.grid_ind = pc_grid_ind; p.density = density;
     // the padded [M, T, C] tensor needs per-voxel point lists; everything else runs list-free
-    if (use_lists(f, voxels != nullptr)) return run_voxelize(p, f, (cudaStream_t)stream);
+    if (use_lists(cfg, f, voxels != nullptr)) return run_voxelize(p, f, (cudaStream_t)stream);
     return pvf_run(p, f, (cudaStream_t)stream, nullptr);
 }
 
@@ -931,7 +923,7 @@ int pv_forward_mean_canvas(const pv_config *cfg, const float *points, const int3
     if (!canvas) return PV_ERR_BAD_ARGUMENT;
     rc = setup_canvas_call(p, cfg, coors, num_points, voxel_counts, mean_feats, canvas);
     if (rc) return rc;
-    if (use_lists(f, false)) return run_voxelize(p, f, (cudaStream_t)stream);
+    if (use_lists(cfg, f, false)) return run_voxelize(p, f, (cudaStream_t)stream);
     return pvf_run(p, f, (cudaStream_t)stream, nullptr);
 }
 
@@ -956,7 +948,7 @@ int pv_profile_mean_canvas(const pv_config *cfg, const float *points, const int3
         if (cudaEventCreate(&ev[k]) != cudaSuccess) return PV_ERR_CUDA;
     for (int k = 0; k < PV_STAGES; ++k) stage_ms[k] = 0.0f;
     for (int it = 0; it < iters && rc == PV_OK; ++it) {
-        rc = use_lists(f, false) ? run_voxelize(p, f, st, ev) : pvf_run(p, f, st, ev);
+        rc = use_lists(cfg, f, false) ? run_voxelize(p, f, st, ev) : pvf_run(p, f, st, ev);
         if (rc == PV_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = PV_ERR_CUDA;
         for (int k = 0; k < PV_STAGES && rc == PV_OK; ++k) {
             float ms = 0.0f;

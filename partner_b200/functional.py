@@ -13,7 +13,19 @@ from ._lib import PvConfig, PvPfnLayer, check, current_stream, ptr
 _workspaces = {}
 
 
-def make_config(voxel_size, point_cloud_range, max_points, max_voxels):
+_default_pipeline = 0
+
+
+def set_default_pipeline(mode):
+    """Test / measurement aid: pv_config.pipeline of every configuration made from now on
+    (0 auto, 1 list-based, 2 list-free).  Host-side only; the library itself keeps no state."""
+    global _default_pipeline
+    if mode not in (0, 1, 2):
+        raise ValueError("pipeline must be 0 (auto), 1 (list-based) or 2 (list-free)")
+    _default_pipeline = mode
+
+
+def make_config(voxel_size, point_cloud_range, max_points, max_voxels, pipeline=None):
     """VoxelGenerator.__init__ arithmetic (det3d/core/input/voxel_generator.py:6-11)."""
     rng = np.array(point_cloud_range, dtype=np.float32)
     vs = np.array(voxel_size, dtype=np.float32)
@@ -25,6 +37,7 @@ def make_config(voxel_size, point_cloud_range, max_points, max_voxels):
         cfg.grid[j] = int(grid[j])
     cfg.max_points = int(max_points)
     cfg.max_voxels = int(max_voxels)
+    cfg.pipeline = _default_pipeline if pipeline is None else int(pipeline)
     return cfg, vs, rng, grid
 
 
@@ -65,7 +78,7 @@ def voxel_workspace(cfg, n_cap, batch, frame_cap, channels, device, tag=0):
 
     ``tag`` separates workspaces of callers that run concurrently on different streams."""
     dev_index = device.index if device.index is not None else torch.cuda.current_device()
-    key = (dev_index, tag, tuple(cfg.lo), tuple(cfg.vs), tuple(cfg.grid), cfg.max_points, n_cap, batch, frame_cap, channels)
+    key = (dev_index, tag, tuple(cfg.lo), tuple(cfg.vs), tuple(cfg.grid), cfg.max_points, n_cap, batch, frame_cap, channels)   # both pipelines share one layout
     ws = _voxel_ws.pop(key, None)
     if ws is None:
         lib = _lib.load()

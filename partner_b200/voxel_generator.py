@@ -111,6 +111,7 @@ class VoxelGenerator:
         cfg.lo, cfg.vs, cfg.grid = self._cfg.lo, self._cfg.vs, self._cfg.grid
         cfg.max_points = self._cfg.max_points
         cfg.max_voxels = int(max_voxels)
+        cfg.pipeline = self._cfg.pipeline
         sizes = [int(p.shape[0]) for p in pts]
         if len({p.shape[1] for p in pts}) != 1:
             raise ValueError("all frames need the same number of columns")

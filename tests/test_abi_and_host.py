@@ -109,8 +109,11 @@ def test_new_entry_points_validate_arguments_on_the_host():
     from partner_b200.functional import make_config
     cfg, _, _, _ = make_config([0.098, 0.0123, 8], [0.3, -3.1488, -5, 50.476, 3.1488, 3], 20, 60000)
     N = ctypes.c_void_p(0)
-    assert lib.pv_set_pipeline(7) == -2 and lib.pv_set_pipeline(0) == 0
     assert lib.pv_profile_pipeline(cfg) == 2                                  # direct map -> list-free
+    forced, _, _, _ = make_config([0.098, 0.0123, 8], [0.3, -3.1488, -5, 50.476, 3.1488, 3], 20, 60000, pipeline=1)
+    assert lib.pv_profile_pipeline(forced) == 1                               # pv_config.pipeline, no process state
+    forced.pipeline = 7
+    assert lib.pv_profile_pipeline(forced) == -1                              # bad configuration
     big, _, _, _ = make_config([0.065, 0.00307, 0.15], [0.3, -3.14368, -2.0, 75.18, 3.14368, 4.0], 5, 150000)
     assert lib.pv_profile_pipeline(big) == 1                                  # hash map -> list-based
     assert lib.pv_dynamic_voxelize(cfg, N, N, N, 1, 10, 5, 1, 100, 100, N, 0, N, N, N, N, N, N, N, N) == -2

@@ -83,15 +83,11 @@ def test_random_configs_all_pipelines_vs_oracle(seed):
     pts = buf[pad:pad + n * c_dev].view(n, c_dev)
     pts.copy_(torch.from_numpy(devp))
     d_off = torch.from_numpy(off).cuda()
-    lib = _lib.load()
     for pipeline, want_voxels in ((2, False), (0, False), (0, True)):
-        assert lib.pv_set_pipeline(pipeline) == 0
-        try:
-            vb = F.voxelize(cfg, pts, d_off, len(frames), max(sizes + [1]), cart, want_voxels=want_voxels,
-                            want_mean=True, want_grid_ind=True, want_density=want_den)
-            F.read_status(vb)
-        finally:
-            lib.pv_set_pipeline(0)
+        cfg.pipeline = pipeline                 # per-call configuration, no process state
+        vb = F.voxelize(cfg, pts, d_off, len(frames), max(sizes + [1]), cart, want_voxels=want_voxels,
+                        want_mean=True, want_grid_ind=True, want_density=want_den)
+        F.read_status(vb)
         m = vb.total()
         tag = "pipeline %d voxels %s" % (pipeline, want_voxels)
         assert np.array_equal(vb.voxel_counts.cpu().numpy(), nv), tag

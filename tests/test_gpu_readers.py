@@ -110,3 +110,54 @@ def test_registry_builds_reference_config_dicts():
     assert [tuple(l.linear.weight.shape) for l in reader.pfn_layers] == [(32, 10), (64, 64)]
     bb = build_from_cfg(dict(type="PointPillarsScatter", ds_factor=1, num_input_features=64), BACKBONES)
     assert bb.nchannels == 64
+
+
+def _random_pfn_state(net, seed=0):
+    """SURVEY.md section 8d weights: Linear default init, BN running stats / affine drawn at random
+    (eval mode), so the padded-slot quirk (relu(shift) != 0 takes part in the max) is exercised."""
+    import torch
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for layer in net.pfn_layers:
+            u = layer.norm.num_features
+            layer.norm.running_mean.copy_(torch.randn(u, generator=gen))
+            layer.norm.running_var.copy_(torch.rand(u, generator=gen) * 1.5 + 0.5)
+            layer.norm.weight.copy_(torch.randn(u, generator=gen))
+            layer.norm.bias.copy_(torch.randn(u, generator=gen))
+    return net
+
+
+def test_static_pfn_full_size_vs_oracle():
+    """BASELINE config 3 at full size: two nuScenes 10-sweep frames on the NUSC-PILLAR grid (max_voxels
+    binding, T = 20, heavy and non-full voxels mixed) through VoxelGenerator.generate ->
+    PillarFeatureNet(7, [64, 128]) -> PointPillarsScatter(128) vs oracle.pfn_forward / oracle.scatter."""
+    import torch
+    from partner_b200 import PillarFeatureNet, PointPillarsScatter, VoxelGenerator, synth
+    g = synth.GRIDS["NUSC-PILLAR"]
+    gen = VoxelGenerator(g["voxel_size"], g["range"], g["max_points"], g["max_voxels"])
+    ref_gen = oracle.VoxelGenerator(g["voxel_size"], g["range"], g["max_points"], g["max_voxels"])
+    frames = [oracle.transform_points(synth.nusc_frame(3100 + k)) for k in range(2)]
+    vox, coor, num = [], [], []
+    for b, f in enumerate(frames):
+        v, c, n = gen.generate(f)[:3]
+        rv, rc, rn = ref_gen.generate(f)[:3]
+        assert np.array_equal(c, rc) and np.array_equal(n, rn) and np.array_equal(v, rv)
+        vox.append(v)
+        num.append(n)
+        coor.append(np.pad(c, ((0, 0), (1, 0)), constant_values=b))      # collate_kitti batch column
+    vox, coor, num = np.concatenate(vox), np.concatenate(coor).astype(np.int32), np.concatenate(num)
+    assert vox.shape[0] == 2 * g["max_voxels"] and (num == g["max_points"]).any() and (num < g["max_points"]).any()
+    torch.manual_seed(0)
+    net = _random_pfn_state(PillarFeatureNet(7, (64, 128), False, tuple(g["voxel_size"]), tuple(g["range"]))).cuda().eval()
+    layers = [dict(weight=L.linear.weight.detach().cpu().numpy(), mean=L.norm.running_mean.cpu().numpy(),
+                   var=L.norm.running_var.cpu().numpy(), gamma=L.norm.weight.detach().cpu().numpy(),
+                   beta=L.norm.bias.detach().cpu().numpy()) for L in net.pfn_layers]
+    ref = oracle.pfn_forward(vox, num, coor, layers, g["voxel_size"], g["range"], with_distance=False, eps=1e-3)
+    dc = _cuda(coor)
+    out = net(_cuda(vox), _cuda(num), dc)
+    assert_close_fp32(out.cpu().numpy(), ref, "static PFN [64, 128], full size")
+    canvas = PointPillarsScatter(128)(out, dc, 2, [512, 512, 1])
+    rc, _ = oracle.scatter(ref, coor, 2, [512, 512, 1])
+    got = canvas.cpu().numpy()
+    assert got.shape == rc.shape == (2, 128, 512, 512)
+    assert_close_fp32(got, rc, "PFN canvas, full size")

@@ -294,12 +294,12 @@ def _list_free(grid, frames_polar, max_points=None, max_voxels=None, want_densit
 @pytest.fixture(autouse=True, params=["auto", "list-free"])
 def pipeline(request):
     """Every test runs under the production pipeline choice and with the list-free pipeline forced
-    (hash-map grids default to the list-based one); pv_set_pipeline is a process-wide test aid."""
-    from partner_b200 import _lib
-    lib = _lib.load()
-    assert lib.pv_set_pipeline(2 if request.param == "list-free" else 0) == 0
+    (hash-map grids default to the list-based one): pv_config.pipeline of every configuration the
+    test builds, through the host-side default of functional.make_config."""
+    from partner_b200 import functional as F
+    F.set_default_pipeline(2 if request.param == "list-free" else 0)
     yield request.param
-    lib.pv_set_pipeline(0)
+    F.set_default_pipeline(0)
 
 
 def _check_list_free(grid, polars, max_points=None, max_voxels=None, want_density=False, **kw):
