@@ -1,0 +1,515 @@
+// pfn_fused.cu -- PillarFeatureNet (two PFN layers, eval) as ONE warp-specialised kernel with the
+// second layer's GEMM on the 5th-generation tensor cores (sm_100a: tcgen05.mma, accumulators in TMEM).
+//
+// Reference: PillarFeatureNet.forward / PFNLayer.forward_static, det3d/models/readers/pillar_encoder.py
+// :131-169 / :49-61 -- decoration (cluster offset :137-140, pillar-centre offset :145-150, optional
+// distance :154-156), padding mask :161-164, then per layer Linear (no bias) -> BatchNorm1d (eval,
+// ATen order) -> ReLU -> max over ALL T slots of the voxel.  Padded slots enter as all-zero rows, so
+// after the norm they hold relu(shift) != 0 and take part in the max; all padded rows of a voxel are
+// identical, so ONE representative row per non-full voxel is evaluated ("useful rows").
+//
+// Rows come from one of two sources:
+//   mode 0  the padded tensor voxels [M, T, C] of the drop-in reader (pv_pfn_forward);
+//   mode 1  the per-voxel POINT LISTS of the list-based voxelizer (voxelize.cu: kept / vox_kg /
+//           vox_c / vox_cell) + the raw point rows -- the [M, T, C] tensor is never materialised;
+//           the kernel also writes coors / num_points and restores the lists (pv_forward_pfn_canvas).
+//
+// One persistent CTA per SM, 13 warps:
+//   warps 0-7   PRODUCERS, two sets of four (set = A-operand stage).  A warp builds one GROUP of <= 32
+//               useful rows out of whole voxels (lane = row): gathers the rows, decorates them, runs
+//               layer 0 (K = C + 5 <= 16, 4 % of the FLOPs) in fp32 FMAs, BatchNorm + ReLU, the
+//               per-voxel maximum by segmented warp scans, and writes its 32 rows of the layer-1
+//               operand [x0 | x_max0(voxel)] into the stage, split into TF32 hi / lo parts, in the
+//               canonical K-major UMMA layout.  Four groups = one 128-row MMA tile.
+//   warp 12     ISSUER: one thread issues the 3 x K/8 tcgen05.mma.kind::tf32 of the tile (3xTF32 split:
+//               lo.hi + hi.lo + hi.hi, fp32-accurate) into one of TWO TMEM accumulator stages and
+//               commits to an mbarrier.
+//   warps 8-11  EPILOGUE: warp e owns TMEM lanes [32 e, 32 e + 32) = the rows of producer e's group:
+//               tcgen05.ld, BatchNorm (ATen order) + ReLU, per-voxel maximum by segmented shuffles
+//               (as many steps as the longest voxel of the group needs), one 128-byte store per
+//               voxel and 32 units.
+// While the tensor core works on tile k of stage s, the other producer set builds tile k + 1 and the
+// epilogue drains tile k - 1: three pipelines (operand full / MMA done / accumulator free) on
+// mbarriers, no block-wide barrier after the prologue.
+#include "tc_common.cuh"
+
+#define P2_THREADS (13 * 32)
+#define P2_EPI_WARP0 8
+#define P2_ISSUER_WARP 12
+#define P2_MC 64               // voxels per mini-chunk (the unit a producer warp fetches)
+#define P2_U0 32               // units of layer 0
+#define P2_K 64                // K of layer 1 = 2 * P2_U0
+#define P2_C0 16               // decorated input width, padded
+
+struct P2Args {
+    int mode;
+    // mode 0: padded tensor
+    const float *voxels; const int32_t *num; const int32_t *coors_in; long long m;
+    // mode 1: point lists of the list-based voxelizer
+    const float *pts; int c_in, cart;
+    const uint32_t *vox_cell, *vox_kg, *vox_c; uint32_t *kept;
+    const int32_t *base; const int32_t *voxel_counts;
+    uint32_t fcap; int32_t nx, ny;
+    int32_t *coors_out; int32_t *num_out;
+    // common
+    int t, c, c0, with_distance;
+    float vx, vy, x_off, y_off, eps;
+    const float *w0, *mean0, *var0, *gamma0, *beta0;
+    const float *w1, *mean1, *var1, *gamma1, *beta1;
+    int n1;
+    uint32_t chunks_per_frame, n_chunks;
+    unsigned int *counter;
+    float *out;
+};
+
+struct P2Meta {                // what the epilogue needs to know about one group
+    int32_t vid[32];           // output row of the voxel whose LAST row this lane holds, else -1
+    uint32_t flags[32];        // bit d: the lane may combine with lane - 2^d (same voxel)
+    uint32_t nsteps;           // scan steps the longest voxel of the group needs
+    uint32_t done;             // the producer ran out of work: nothing to drain
+    uint32_t pad[2];
+};
+
+// Barrier wait with a watchdog: a pipeline bug must not hang the GPU.  After ~0.2 s of waiting the
+// block raises its abort flag, records which wait starved (tag) next to the chunk counter and every
+// role loop drains; the host sees the non-zero diagnostic word and reports PV_ERR_CUDA.
+__device__ __forceinline__ bool p2_mbar_wait(uint32_t bar, uint32_t parity, volatile uint32_t *abort_flag,
+                                             unsigned int *diag, uint32_t tag)
+{
+    uint32_t done;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return true;
+        if (*abort_flag) { if (blockIdx.x == diag[15]) diag[1 + (threadIdx.x >> 5)] = tag; return false; }
+        if (spins == 0) t0 = clock64();
+        else if ((spins & 63u) == 0 && clock64() - t0 > 400000000ll) {
+            if (atomicCAS(diag, 0u, tag) == 0u) diag[15] = blockIdx.x;      // first block to starve: its warps report where they wait
+            __threadfence();
+            *abort_flag = 1u;
+            if (blockIdx.x == diag[15]) diag[1 + (threadIdx.x >> 5)] = tag;
+            return false;
+        }
+    }
+}
+__device__ __forceinline__ void p2_mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// segmented inclusive scan step helpers: flags bit d set <=> lane >= 2^d and lanes (lane - 2^d, lane]
+// hold no first row of a voxel, i.e. lane - 2^d belongs to the same voxel
+__device__ __forceinline__ float p2_seg_max(float v, uint32_t flags, uint32_t nsteps)
+{
+    for (uint32_t d = 0; d < nsteps; ++d) {
+        const float o = __shfl_up_sync(0xffffffffu, v, 1u << d);
+        if ((flags >> d) & 1u) v = fmaxf(v, o);
+    }
+    return v;
+}
+__device__ __forceinline__ float p2_seg_sum(float v, uint32_t flags, uint32_t nsteps)
+{
+    for (uint32_t d = 0; d < nsteps; ++d) {
+        const float o = __shfl_up_sync(0xffffffffu, v, 1u << d);
+        if ((flags >> d) & 1u) v = __fadd_rn(v, o);
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_constant__ P2Args a)
+{
+    extern __shared__ __align__(128) float smem[];
+    const int N = a.n1;
+    float *a_st = smem;                                    // [2 stages][hi | lo][128 x 64] canonical
+    float *b_hi = a_st + 2 * 2 * TC_M * P2_K;              // [N x 64] canonical
+    float *b_lo = b_hi + N * P2_K;
+    float *w0t = b_lo + N * P2_K;                          // [P2_C0][P2_U0]: layer-0 weight, transposed
+    float *bn0 = w0t + P2_C0 * P2_U0;                      // mean, invstd, gamma, beta: 4 x 32
+    float *bn1 = bn0 + 4 * P2_U0;                          // 4 x N
+    P2Meta *meta = reinterpret_cast<P2Meta *>(bn1 + 4 * N);   // [2 stages][2 parities][4 groups]
+    __shared__ __align__(8) unsigned long long s_full[2], s_mma[2], s_free[2], s_rec[2];
+    __shared__ uint32_t s_tmem, s_exit[2];
+    __shared__ uint32_t s_abort;
+    unsigned int *diag = a.counter + 1;     // diagnostic word of the watchdog (0 = healthy)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t ncols = 32;
+    while ((int)ncols < 2 * N) ncols <<= 1;
+
+    // ---- prologue: weights, BatchNorm constants, barriers, TMEM ----
+    if (warp == P2_ISSUER_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc_smem_u32(&s_tmem)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            tc_mbar_init(tc_smem_u32(&s_full[s]), 4);
+            tc_mbar_init(tc_smem_u32(&s_mma[s]), 1);
+            tc_mbar_init(tc_smem_u32(&s_free[s]), 4);
+            tc_mbar_init(tc_smem_u32(&s_rec[s]), 1);
+            s_exit[s] = 0u;
+        }
+        s_abort = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = tid; e < N * P2_K; e += P2_THREADS) {     // linear.weight of layer 1 is [N, 64], K-major already
+        const int r = e / P2_K, k = e - r * P2_K;
+        float hi, lo;
+        tc_split(__ldg(a.w1 + e), hi, lo);
+        const uint32_t o = tc_canon(r, k, N);
+        b_hi[o] = hi; b_lo[o] = lo;
+    }
+    for (int e = tid; e < P2_C0 * P2_U0; e += P2_THREADS) {
+        const int k = e / P2_U0, u = e - k * P2_U0;
+        w0t[e] = k < a.c0 ? __ldg(a.w0 + u * a.c0 + k) : 0.0f;
+    }
+    for (int o = tid; o < P2_U0; o += P2_THREADS) {
+        bn0[o] = a.mean0[o];
+        bn0[P2_U0 + o] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(a.var0[o], a.eps)));
+        bn0[2 * P2_U0 + o] = a.gamma0[o];
+        bn0[3 * P2_U0 + o] = a.beta0[o];
+    }
+    for (int o = tid; o < N; o += P2_THREADS) {
+        bn1[o] = a.mean1[o];
+        bn1[N + o] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(a.var1[o], a.eps)));
+        bn1[2 * N + o] = a.gamma1[o];
+        bn1[3 * N + o] = a.beta1[o];
+    }
+    for (int o = tid; o < 16; o += P2_THREADS) { meta[o].nsteps = 0u; meta[o].done = 1u; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    if (warp < 8) {
+        // =====================================================================================
+        // PRODUCER warp: set = stage, g = group inside the tile
+        // =====================================================================================
+        const int set = warp >> 2, g = warp & 3;
+        float *a_hi = a_st + (size_t)set * 2 * TC_M * P2_K, *a_lo = a_hi + TC_M * P2_K;
+        const uint32_t bar_full = tc_smem_u32(&s_full[set]), bar_mma = tc_smem_u32(&s_mma[set]);
+        const int T = a.t, C = a.c;
+        // the warp's current mini-chunk: voxels [v_next, v_end) of frame b (mode 0: one "frame" of m voxels)
+        int b = 0;
+        uint32_t v_next = 0, v_end = 0;
+        bool out_of_work = false;
+#ifdef P2_DEBUG_ONE_SET
+        if (set == 1) out_of_work = true;
+#endif
+        for (uint32_t round = 0;; ++round) {
+            if (round > 0) {
+                if (!p2_mbar_wait(bar_mma, (round - 1) & 1u, &s_abort, diag, 0x100u | (set << 4) | g | (round << 16))) break;   // the stage's previous tile has been consumed
+                if (*reinterpret_cast<volatile uint32_t *>(&s_exit[set])) break;
+            }
+            P2Meta *mt = meta + ((set * 2 + (round & 1u)) * 4 + g);
+            // ---- next mini-chunk ----
+            while (!out_of_work && v_next >= v_end) {
+                uint32_t id = 0;
+                if (lane == 0) id = atomicAdd(a.counter, 1u);
+                id = __shfl_sync(0xffffffffu, id, 0);
+                if (id >= a.n_chunks) { out_of_work = true; break; }
+                b = (int)(id / a.chunks_per_frame);
+                const uint32_t r0 = (id - (uint32_t)b * a.chunks_per_frame) * P2_MC;
+                const uint32_t cnt = a.mode ? (uint32_t)__ldg(a.voxel_counts + b) : (uint32_t)a.m;
+                v_next = r0;
+                v_end = min(cnt, r0 + P2_MC);
+            }
+            if (out_of_work) {
+                if (lane == 0) mt->done = 1u;
+                __syncwarp();
+                if (lane == 0) p2_mbar_arrive(bar_full);
+                continue;
+            }
+            // ---- pack whole voxels into <= 32 rows: lane i looks at voxel v_next + i ----
+            const uint32_t vi = v_next + lane;
+            int n_i = 0;
+            uint32_t kg_i = 0, cell_i = 0;
+            int4 co_i = make_int4(0, 0, 0, 0);
+            int rows_i = 0;
+            if (vi < v_end) {
+                if (a.mode) {
+                    const size_t v = (size_t)b * a.fcap + vi;
+                    n_i = (int)min(__ldcs(a.vox_c + v), (uint32_t)T);
+                    kg_i = __ldcs(a.vox_kg + v);
+                    cell_i = __ldcs(a.vox_cell + v);
+                    const uint32_t x = cell_i % (uint32_t)a.nx, yz = cell_i / (uint32_t)a.nx;
+                    co_i = make_int4(b, (int)(yz / (uint32_t)a.ny), (int)(yz % (uint32_t)a.ny), (int)x);
+                } else {
+                    n_i = min(max(__ldg(a.num + vi), 0), T);
+                    co_i = __ldg(reinterpret_cast<const int4 *>(a.coors_in) + vi);
+                }
+                rows_i = n_i < T ? n_i + 1 : T;
+            }
+            int incl = rows_i;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const uint32_t fits = __ballot_sync(0xffffffffu, vi < v_end && incl <= 32);
+            const int nv = __popc(fits);                                  // >= 1: a voxel has at most 32 rows
+            const int start_i = incl - rows_i;
+            const uint32_t heads = __reduce_or_sync(0xffffffffu, lane < nv ? 1u << start_i : 0u);
+            const int total = __shfl_sync(0xffffffffu, incl, nv - 1);
+            const int maxlen = __reduce_max_sync(0xffffffffu, lane < nv ? rows_i : 0);
+            uint32_t nsteps = 0;
+            while ((1 << nsteps) < maxlen) ++nsteps;
+            // ---- lane = row: which voxel, which slot ----
+            const bool row_ok = lane < total;
+            const int j = __popc(heads & (0xFFFFFFFFu >> (31 - lane))) - 1;   // voxel ordinal of this row
+            const int jj = row_ok ? j : 0;
+            const int start_j = __shfl_sync(0xffffffffu, start_i, jj);
+            const int n_j = __shfl_sync(0xffffffffu, n_i, jj);
+            const int rows_j = __shfl_sync(0xffffffffu, rows_i, jj);
+            const uint32_t kg_j = __shfl_sync(0xffffffffu, kg_i, jj);
+            const int cx_j = __shfl_sync(0xffffffffu, co_i.w, jj), cy_j = __shfl_sync(0xffffffffu, co_i.z, jj);
+            const int q = lane - start_j;
+            const bool valid = row_ok && q < n_j;                             // a real point (not the padded representative)
+            uint32_t flags = 0;
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                const int dist = 1 << d;
+                // lanes (lane - dist, lane] hold no head <=> lane - dist is in the same voxel
+                const uint32_t span = lane >= dist ? (0xFFFFFFFFu >> (31 - lane)) & ~(0xFFFFFFFFu >> (31 - (lane - dist))) : 0xFFFFFFFFu;
+                if (row_ok && lane >= dist && (heads & span) == 0u) flags |= 1u << d;
+            }
+            const int vid_i = a.mode ? __ldg(a.base + b) + (int)vi : (int)vi;
+            const int vid_j = __shfl_sync(0xffffffffu, vid_i, jj);
+            const bool seg_last = row_ok && q == rows_j - 1;
+            const int last_lane = start_j + rows_j - 1;
+            // ---- the row ----
+            float f[PV_MAX_CHANNELS];
+#pragma unroll
+            for (int k = 0; k < PV_MAX_CHANNELS; ++k) f[k] = 0.0f;
+            if (valid) {
+                if (a.mode) {
+                    const uint32_t idx = __ldcg(a.kept + kg_j + q);
+                    a.kept[kg_j + q] = PV_INF;                               // restore the list for the next call
+                    pv_feature_row(a.pts, idx, a.c_in, a.cart, f);
+                } else {
+                    const float *src = a.voxels + ((size_t)vid_j * T + q) * C;
+#pragma unroll
+                    for (int k = 0; k < PV_MAX_CHANNELS; ++k)
+                        if (k < C) f[k] = __ldg(src + k);
+                }
+            }
+            if (a.mode && lane < nv) {                                        // per-voxel outputs of the voxelizer
+                __stcs(reinterpret_cast<int4 *>(a.coors_out) + vid_i, co_i);
+                __stcs(a.num_out + vid_i, n_i);
+            }
+            // cluster mean (:137-139): sum over the voxel's rows / num
+            float sx = p2_seg_sum(f[0], flags, nsteps), sy = p2_seg_sum(f[1], flags, nsteps), sz = p2_seg_sum(f[2], flags, nsteps);
+            sx = __shfl_sync(0xffffffffu, sx, last_lane & 31); sy = __shfl_sync(0xffffffffu, sy, last_lane & 31);
+            sz = __shfl_sync(0xffffffffu, sz, last_lane & 31);
+            const float nf = (float)n_j;
+            const float mx = __fdiv_rn(sx, nf), my = __fdiv_rn(sy, nf), mz = __fdiv_rn(sz, nf);
+            const float pcx = __fadd_rn(__fmul_rn((float)cx_j, a.vx), a.x_off);   // :146-147
+            const float pcy = __fadd_rn(__fmul_rn((float)cy_j, a.vy), a.y_off);   // :149-150
+            float in[P2_C0];
+#pragma unroll
+            for (int k = 0; k < P2_C0; ++k) {
+                float val = 0.0f;
+                if (k < C) val = f[k < PV_MAX_CHANNELS ? k : 0];
+                else if (k == C) val = __fsub_rn(f[0], mx);                   // :140
+                else if (k == C + 1) val = __fsub_rn(f[1], my);
+                else if (k == C + 2) val = __fsub_rn(f[2], mz);
+                else if (k == C + 3) val = __fsub_rn(f[0], pcx);
+                else if (k == C + 4) val = __fsub_rn(f[1], pcy);
+                else if (k == C + 5 && a.with_distance)
+                    val = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(f[0], f[0]), __fmul_rn(f[1], f[1])), __fmul_rn(f[2], f[2])));   // :155
+                in[k] = valid ? val : 0.0f;                                   // :161-164 mask: padded rows are zero
+            }
+            // ---- layer 0: Linear (fp32 FMA) -> BatchNorm (ATen order) -> ReLU -> per-voxel max ----
+            float x0[P2_U0];
+#pragma unroll
+            for (int u = 0; u < P2_U0; ++u) x0[u] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < P2_C0; ++k) {
+                if (k < a.c0) {
+                    const float4 *wr = reinterpret_cast<const float4 *>(w0t + k * P2_U0);
+#pragma unroll
+                    for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
+                        const float4 w = wr[u4];
+                        x0[4 * u4] = __fmaf_rn(in[k], w.x, x0[4 * u4]); x0[4 * u4 + 1] = __fmaf_rn(in[k], w.y, x0[4 * u4 + 1]);
+                        x0[4 * u4 + 2] = __fmaf_rn(in[k], w.z, x0[4 * u4 + 2]); x0[4 * u4 + 3] = __fmaf_rn(in[k], w.w, x0[4 * u4 + 3]);
+                    }
+                }
+            }
+            const int row = g * 32 + lane;
+#pragma unroll
+            for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
+                float y[4], mxv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int u = 4 * u4 + e;
+                    const float v = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x0[u], bn0[u]), bn0[P2_U0 + u]), bn0[2 * P2_U0 + u]), bn0[3 * P2_U0 + u]);
+                    y[e] = row_ok ? fmaxf(v, 0.0f) : 0.0f;
+                    mxv[e] = __shfl_sync(0xffffffffu, p2_seg_max(y[e], flags, nsteps), last_lane & 31);
+                }
+                // operand row [x0 | x_max0] in the canonical K-major layout, split into TF32 hi / lo
+                float4 hi, lo;
+                tc_split(y[0], hi.x, lo.x); tc_split(y[1], hi.y, lo.y); tc_split(y[2], hi.z, lo.z); tc_split(y[3], hi.w, lo.w);
+                uint32_t o = tc_canon(row, 4 * u4, TC_M);
+                *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
+                tc_split(mxv[0], hi.x, lo.x); tc_split(mxv[1], hi.y, lo.y); tc_split(mxv[2], hi.z, lo.z); tc_split(mxv[3], hi.w, lo.w);
+                o = tc_canon(row, P2_U0 + 4 * u4, TC_M);
+                *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
+            }
+            mt->vid[lane] = seg_last ? vid_j : -1;
+            mt->flags[lane] = flags;
+            if (lane == 0) { mt->nsteps = nsteps; mt->done = 0u; }
+            v_next += (uint32_t)nv;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) p2_mbar_arrive(bar_full);
+        }
+    } else if (warp == P2_ISSUER_WARP) {
+        // =====================================================================================
+        // ISSUER: the whole warp walks the pipeline (barrier waits are warp-wide, the warp stays
+        // converged for the block barrier and the TMEM release at the end); lane 0 issues
+        // =====================================================================================
+        const uint32_t idesc = tc_idesc_tf32(TC_M, N);
+        const uint32_t a_k = (TC_M / 8) * 128, b_k = (N / 8) * 128, mn = 128;
+        bool fin[2] = {false, false};
+        for (uint32_t round = 0; !(fin[0] && fin[1]); ++round) {
+            for (int s = 0; s < 2; ++s) {
+                if (fin[s]) continue;
+                if (!p2_mbar_wait(tc_smem_u32(&s_full[s]), round & 1u, &s_abort, diag, 0x200u | (s << 4) | (round << 16))) { fin[0] = fin[1] = true; break; }
+                const P2Meta *mt = meta + (s * 2 + (round & 1u)) * 4;
+                const uint32_t all_done = *reinterpret_cast<const volatile uint32_t *>(&mt[0].done) &
+                                          *reinterpret_cast<const volatile uint32_t *>(&mt[1].done) &
+                                          *reinterpret_cast<const volatile uint32_t *>(&mt[2].done) &
+                                          *reinterpret_cast<const volatile uint32_t *>(&mt[3].done);
+                // the accumulator stage has been drained.  Also on the way out: a parity wait tells two phases
+                // apart, so no barrier may run two phases ahead of its slowest waiter -- the epilogue must have
+                // passed round - 1 before this round's arrivals (MMA commit or the exit arrivals below)
+                if (round > 0 && !p2_mbar_wait(tc_smem_u32(&s_free[s]), (round - 1) & 1u, &s_abort, diag, 0x300u | (s << 4) | (round << 16))) { fin[0] = fin[1] = true; break; }
+                if (all_done) {                                             // every producer of the set is out of work
+                    fin[s] = true;
+                    if (lane == 0) {
+                        *reinterpret_cast<volatile uint32_t *>(&s_exit[s]) = 1u;
+                        p2_mbar_arrive(tc_smem_u32(&s_rec[s]));
+                        p2_mbar_arrive(tc_smem_u32(&s_mma[s]));
+                    }
+                    __syncwarp();
+                    continue;
+                }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    // hands the producers' group records (acquired with the full barrier) on to the epilogue:
+                    // a plain release / acquire chain, independent of the tensor core's commit
+                    p2_mbar_arrive(tc_smem_u32(&s_rec[s]));
+                    const float *a_hi = a_st + (size_t)s * 2 * TC_M * P2_K, *a_lo = a_hi + TC_M * P2_K;
+                    const uint32_t d_tmem = tmem + (uint32_t)(s * N);
+#pragma unroll 1
+                    for (int ks = 0; ks < P2_K / 8; ++ks) {
+                        const uint32_t a_off = ks * 2 * a_k, b_off = ks * 2 * b_k;
+                        const unsigned long long dah = tc_desc(tc_smem_u32(a_hi) + a_off, a_k, mn), dal = tc_desc(tc_smem_u32(a_lo) + a_off, a_k, mn);
+                        const unsigned long long dbh = tc_desc(tc_smem_u32(b_hi) + b_off, b_k, mn), dbl = tc_desc(tc_smem_u32(b_lo) + b_off, b_k, mn);
+                        tc_mma_tf32(d_tmem, dal, dbh, idesc, ks > 0 ? 1u : 0u);     // small terms first
+                        tc_mma_tf32(d_tmem, dah, dbl, idesc, 1u);
+                        tc_mma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                    }
+                    tc_commit(tc_smem_u32(&s_mma[s]));      // operand stage free + accumulator ready, when the MMAs retire
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // =====================================================================================
+        // EPILOGUE warp e: TMEM lanes [32 e, 32 e + 32)
+        // =====================================================================================
+        const int e = warp - P2_EPI_WARP0;
+        bool fin[2] = {false, false};
+        for (uint32_t round = 0; !(fin[0] && fin[1]); ++round) {
+            for (int s = 0; s < 2; ++s) {
+                if (fin[s]) continue;
+                if (!p2_mbar_wait(tc_smem_u32(&s_rec[s]), round & 1u, &s_abort, diag, 0x500u | (s << 4) | e | (round << 16))) { fin[0] = fin[1] = true; break; }
+                if (!p2_mbar_wait(tc_smem_u32(&s_mma[s]), round & 1u, &s_abort, diag, 0x400u | (s << 4) | e | (round << 16))) { fin[0] = fin[1] = true; break; }
+                if (*reinterpret_cast<volatile uint32_t *>(&s_exit[s])) { fin[s] = true; continue; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const P2Meta *mt = meta + ((s * 2 + (round & 1u)) * 4 + e);
+                const uint32_t done = *reinterpret_cast<const volatile uint32_t *>(&mt->done);
+                if (!done) {
+                    const int vid = mt->vid[lane];
+                    const uint32_t flags = mt->flags[lane], nsteps = min(mt->nsteps, 5u);
+                    for (int c0 = 0; c0 < N; c0 += 32) {
+                        float v[32];
+                        tc_ld_32x32(tmem + ((uint32_t)(e * 32) << 16) + (uint32_t)(s * N + c0), v);
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) {
+                            const int o = c0 + k;
+                            const float y = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v[k], bn1[o]), bn1[N + o]), bn1[2 * N + o]), bn1[3 * N + o]);
+                            v[k] = p2_seg_max(fmaxf(y, 0.0f), flags, nsteps);
+                        }
+                        if (vid >= 0) {
+                            float4 *dst = reinterpret_cast<float4 *>(a.out + (size_t)vid * N + c0);
+#pragma unroll
+                            for (int k4 = 0; k4 < 8; ++k4) __stcs(dst + k4, make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]));
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) p2_mbar_arrive(tc_smem_u32(&s_free[s]));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == P2_ISSUER_WARP)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(ncols) : "memory");
+}
+
+// Shapes the fused kernel covers: two layers, 32 units in the first (K = 64), 32 | units of the last
+// <= 128, decorated width <= 16, T <= 32.
+bool pv_pfn_fused_supported(const pv_pfn_layer *layers, int n_layers, int t, int c, int with_distance)
+{
+    if (n_layers != 2 || t < 1 || t > 32 || c < 3 || c > PV_MAX_CHANNELS) return false;
+    const int c0 = c + 5 + (with_distance ? 1 : 0);
+    if (c0 > P2_C0 || layers[0].in_channels != c0 || layers[0].units != P2_U0) return false;
+    if (layers[1].in_channels != 2 * P2_U0 || layers[1].units % 32 != 0 || layers[1].units < 32 || layers[1].units > 128) return false;
+    return true;
+}
+
+size_t pv_pfn_fused_smem(int n1)
+{
+    return sizeof(float) * (2 * 2 * (size_t)TC_M * P2_K + 2 * (size_t)n1 * P2_K + P2_C0 * P2_U0 + 4 * P2_U0 + 4 * (size_t)n1) +
+           sizeof(P2Meta) * 16 + 128;
+}
+
+// counter: one zeroed 32-bit word in device memory (the dynamic mini-chunk queue); the kernel leaves
+// it non-zero, the caller's memset node precedes every launch.
+int pv_pfn_fused_launch(P2Args &a, const pv_pfn_layer *layers, int batch_frames, long long voxels_per_frame_cap,
+                        cudaStream_t st)
+{
+    a.w0 = layers[0].weight; a.mean0 = layers[0].bn_mean; a.var0 = layers[0].bn_var; a.gamma0 = layers[0].bn_gamma; a.beta0 = layers[0].bn_beta;
+    a.w1 = layers[1].weight; a.mean1 = layers[1].bn_mean; a.var1 = layers[1].bn_var; a.gamma1 = layers[1].bn_gamma; a.beta1 = layers[1].bn_beta;
+    a.n1 = layers[1].units;
+    a.chunks_per_frame = (uint32_t)((voxels_per_frame_cap + P2_MC - 1) / P2_MC);
+    if (a.chunks_per_frame == 0) a.chunks_per_frame = 1;
+    a.n_chunks = a.chunks_per_frame * (uint32_t)batch_frames;
+    const size_t smem = pv_pfn_fused_smem(a.n1);
+    if (cudaMemsetAsync(a.counter, 0, 17 * sizeof(unsigned int), st) != cudaSuccess) return PV_ERR_CUDA;   // queue + watchdog words
+    if (cudaFuncSetAttribute(k_pfn_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
+    const unsigned want = (a.n_chunks + 7) / 8;
+    const unsigned sms = (unsigned)pv_sm_count();
+    k_pfn_fused<<<want < sms ? want : sms, P2_THREADS, smem, st>>>(a);
+    return pv_last_cuda_error();
+}
+
+// mode 0: rows from the padded [m, t, c] tensor of the drop-in reader (pv_pfn_forward)
+int pv_pfn_fused_tensor(const float *voxels, const int32_t *num_points, const int32_t *coors, int64_t m, int32_t t,
+                        int32_t c, int32_t with_distance, float vx, float vy, float x_off, float y_off,
+                        const pv_pfn_layer *layers, float eps, unsigned int *counter, float *out, cudaStream_t st)
+{
+    P2Args a = {};
+    a.mode = 0;
+    a.voxels = voxels; a.num = num_points; a.coors_in = coors; a.m = m;
+    a.t = t; a.c = c; a.with_distance = with_distance ? 1 : 0; a.c0 = c + 5 + a.with_distance;
+    a.vx = vx; a.vy = vy; a.x_off = x_off; a.y_off = y_off; a.eps = eps;
+    a.counter = counter; a.out = out;
+    return pv_pfn_fused_launch(a, layers, 1, m, st);
+}

@@ -246,12 +246,6 @@ struct PtArgs {
     int w_total, xs;                                             // xs = activation row stride (floats)
     const float4 *prep;     // [m][2]: (mean x, mean y, mean z, num) and (pillar centre x, y, -, -)
     unsigned int *chunk_counter;   // dynamic scheduling: next chunk of PT_CHUNK voxels
-    // tensor-core mode: stop after layer 0 and export its rows for pv_pfn_tc_layer
-    int tc_mode;
-    const uint32_t *chunk_base;    // [chunks + 1] first global row of each chunk
-    float *x0_out;                 // [rows][units0]
-    uint32_t *row_vox_out;         // [rows] voxel of each row
-    float *vmax0_out;              // [m][units0]
     float *out;
 };
 
@@ -293,36 +287,6 @@ __global__ void __launch_bounds__(256) k_pfn_prep(const float *__restrict__ voxe
     prep[2 * v] = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __int_as_float(n));
     prep[2 * v + 1] = make_float4(__fadd_rn(__fmul_rn((float)co.w, vx), x_off),
                                   __fadd_rn(__fmul_rn((float)co.z, vy), y_off), 0.0f, 0.0f);
-}
-
-// chunk_base[i] = rows of all earlier chunks (exclusive scan, one block); chunk_base[n] = total.
-__global__ void __launch_bounds__(1024) k_pfn_rows_scan(const uint32_t *__restrict__ chunk_rows, uint32_t n,
-                                                        uint32_t *__restrict__ chunk_base)
-{
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (uint32_t b0 = 0; b0 < n; b0 += 1024) {
-        const uint32_t i = b0 + tid;
-        const uint32_t v = i < n ? chunk_rows[i] : 0u;
-        uint32_t incl = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (unsigned)d) incl += o;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        uint32_t off = s_carry;
-        for (uint32_t k = 0; k < warp; ++k) off += s_warp[k];
-        if (i < n) chunk_base[i] = off + incl - v;
-        __syncthreads();
-        if (tid == 1023) s_carry = off + incl;
-        __syncthreads();
-    }
-    if (tid == 0) chunk_base[n] = s_carry;
 }
 
 // acc[i][j] += sum_k A[row0 + i][k] * Wt[k][J * lane + j]   for the 8 rows of this warp.
@@ -508,7 +472,6 @@ __global__ void __launch_bounds__(PT_THREADS, 2) k_pfn_tiled(const __grid_consta
     // packing info is fetched one tile ahead (warp 0: lane i looks at voxel v_next + i)
     int n_ahead = 0;
     if (warp == 0 && v_next + lane < v_end) n_ahead = __float_as_int(__ldg(&a.prep[2 * (v_next + lane)].w));
-    size_t g_row0 = a.tc_mode ? (size_t)a.chunk_base[s_chunk] : 0;
     while (v_next < v_end) {
         // pack whole voxels greedily into <= PT_ROWS rows (warp 0)
         if (warp == 0) {
@@ -571,8 +534,7 @@ __global__ void __launch_bounds__(PT_THREADS, 2) k_pfn_tiled(const __grid_consta
         // ---- layers ----
         float *xin = s_xa, *xout = s_xb;
         float *vin = s_va, *vout = s_vb;
-        const int run_layers = a.tc_mode ? 1 : a.n_layers;
-        for (int l = 0; l < run_layers; ++l) {
+        for (int l = 0; l < a.n_layers; ++l) {
             switch (a.units[l] >> 5) {
             case 1: pt_layer<1>(a, l, n_rows, n_vox, s_w, s_bn, xin, vin, xout, reinterpret_cast<int *>(vout), s_p, s_row_vox); break;
             case 2: pt_layer<2>(a, l, n_rows, n_vox, s_w, s_bn, xin, vin, xout, reinterpret_cast<int *>(vout), s_p, s_row_vox); break;
@@ -581,21 +543,6 @@ __global__ void __launch_bounds__(PT_THREADS, 2) k_pfn_tiled(const __grid_consta
             }
             float *tmp = xin; xin = xout; xout = tmp;
             tmp = vin; vin = vout; vout = tmp;
-        }
-        if (a.tc_mode) {
-            // export layer 0 for the tensor-core layer: rows (xin after the swap), per-voxel max (vin)
-            const int U0 = a.units[0];
-            for (int r = warp; r < n_rows; r += PT_THREADS / 32) {
-                const size_t g = g_row0 + r;
-                if (lane < U0) a.x0_out[g * U0 + lane] = xin[r * a.xs + lane];
-                if (lane == 0) a.row_vox_out[g] = (uint32_t)(vbase + s_row_vox[r]);
-            }
-            for (int vl = warp; vl < n_vox; vl += PT_THREADS / 32)
-                if (lane < U0) a.vmax0_out[(vbase + vl) * U0 + lane] = vin[vl * PFN_MAX_W + lane];
-            g_row0 += n_rows;
-            __syncthreads();
-            v_next += n_vox;
-            continue;
         }
         // ---- output: max of the last layer (vin after the swap) ----
         const int U = a.units[a.n_layers - 1];
@@ -609,10 +556,12 @@ __global__ void __launch_bounds__(PT_THREADS, 2) k_pfn_tiled(const __grid_consta
     }
 }
 
-// tc_gemm.cu: layer 1 of a two-layer PFN on tcgen05 (3xTF32), BN + ReLU + per-voxel max epilogue.
-int pv_pfn_tc_layer(const float *x0, const uint32_t *row_vox, const float *vmax0, const uint32_t *total_rows,
-                    int u0, int n, const float *w, const float *bn_mean, const float *bn_var, const float *bn_gamma,
-                    const float *bn_beta, float eps, long long m, float *out, cudaStream_t st);
+// pfn_fused.cu: the warp-specialised kernel with the second layer on tcgen05 (default for two-layer nets)
+struct P2Args;
+bool pv_pfn_fused_supported(const pv_pfn_layer *layers, int n_layers, int t, int c, int with_distance);
+int pv_pfn_fused_tensor(const float *voxels, const int32_t *num_points, const int32_t *coors, int64_t m, int32_t t,
+                        int32_t c, int32_t with_distance, float vx, float vy, float x_off, float y_off,
+                        const pv_pfn_layer *layers, float eps, unsigned int *counter, float *out, cudaStream_t st);
 
 static int pfn_tiled_supported(const pv_pfn_layer *layers, int n_layers, int t)
 {
@@ -668,20 +617,16 @@ int pv_scatter(const float *feats, const int32_t *coors, int64_t m, int32_t c, i
     return pv_last_cuda_error();
 }
 
-struct PfnWsLayout { size_t prep, chunk_rows, chunk_base, vmax0, row_vox, x0, total; size_t chunks, rows_cap; };
+struct PfnWsLayout { size_t prep, chunk_rows, total; size_t chunks; };
 static PfnWsLayout pfn_ws_layout(int64_t m, int32_t t)
 {
+    (void)t;
     PfnWsLayout L;
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
     L.chunks = (size_t)(m + PT_CHUNK - 1) / PT_CHUNK;
-    L.rows_cap = (size_t)m * (size_t)t;
     size_t o = 0;
-    L.prep = o;        o = up(o + ((size_t)m * 2 + 1) * sizeof(float4));
+    L.prep = o;        o = up(o + ((size_t)m * 2 + 1) * sizeof(float4));     // also holds the chunk counters (last 16 bytes)
     L.chunk_rows = o;  o = up(o + (L.chunks + 1) * 4);
-    L.chunk_base = o;  o = up(o + (L.chunks + 1) * 4);
-    L.vmax0 = o;       o = up(o + (size_t)m * 32 * 4);
-    L.row_vox = o;     o = up(o + (L.rows_cap + 128) * 4);
-    L.x0 = o;          o = up(o + (L.rows_cap + 128) * 32 * 4);
     L.total = o;
     return L;
 }
@@ -697,6 +642,16 @@ int pv_pfn_forward(const float *voxels, const int32_t *num_points, const int32_t
     if (n_layers > PV_MAX_PFN_LAYERS || t > PFN_MAX_T) return PV_ERR_UNSUPPORTED;
     if (m == 0) return PV_OK;
     if (!voxels || !num_points || !coors || !out) return PV_ERR_BAD_ARGUMENT;
+    for (int l = 0; l < n_layers; ++l)
+        if (!layers[l].weight || !layers[l].bn_mean || !layers[l].bn_var || !layers[l].bn_gamma || !layers[l].bn_beta)
+            return PV_ERR_BAD_ARGUMENT;
+    // two-layer nets (every PFN the reference's configs build): the warp-specialised kernel, second
+    // layer on the tensor cores -- no environment switch, no global state
+    if (pv_pfn_fused_supported(layers, n_layers, t, c, with_distance) && workspace && workspace_bytes >= 256 &&
+        (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0 && (reinterpret_cast<uintptr_t>(coors) & 15u) == 0 &&
+        (reinterpret_cast<uintptr_t>(out) & 15u) == 0)
+        return pv_pfn_fused_tensor(voxels, num_points, coors, m, t, c, with_distance, vx, vy, x_off, y_off, layers, eps,
+                                   reinterpret_cast<unsigned int *>(workspace), out, (cudaStream_t)stream);
     if (pfn_tiled_supported(layers, n_layers, t) && c + 5 + (with_distance ? 1 : 0) <= PT_MAX_IN) {
         PtArgs q;
         q.voxels = voxels; q.num = num_points; q.coors = coors; q.m = m; q.t = t; q.c = c;
@@ -730,31 +685,14 @@ int pv_pfn_forward(const float *voxels, const int32_t *num_points, const int32_t
             q.prep = reinterpret_cast<const float4 *>(ws + W.prep);
             q.chunk_counter = reinterpret_cast<unsigned int *>(reinterpret_cast<float4 *>(ws + W.prep) + 2 * m);
             uint32_t *chunk_rows = reinterpret_cast<uint32_t *>(ws + W.chunk_rows);
-            uint32_t *chunk_base = reinterpret_cast<uint32_t *>(ws + W.chunk_base);
-            // tensor-core path: two layers, layer 1 = [x0 | x_max0] (K = 2 * 32) x N on tcgen05
-            // (opt-in with PV_PFN_TC=1 until the tensor-core layer is software-pipelined: it is parity
-            // green but currently slower end to end than the fused fp32 kernel)
-            const char *env = getenv("PV_PFN_TC");
-            const bool tc = n_layers == 2 && layers[0].units == 32 && layers[1].units % 32 == 0 &&
-                            layers[1].units <= 128 && env && env[0] == '1';
-            q.tc_mode = tc ? 1 : 0;
-            q.chunk_base = chunk_base;
-            q.x0_out = reinterpret_cast<float *>(ws + W.x0);
-            q.row_vox_out = reinterpret_cast<uint32_t *>(ws + W.row_vox);
-            q.vmax0_out = reinterpret_cast<float *>(ws + W.vmax0);
             k_pfn_prep<<<(unsigned)W.chunks, PT_CHUNK, 0, st>>>(
                 voxels, num_points, coors, m, t, c, vx, vy, x_off, y_off, reinterpret_cast<float4 *>(ws + W.prep), chunk_rows);
-            if (tc) k_pfn_rows_scan<<<1, 1024, 0, st>>>(chunk_rows, (uint32_t)W.chunks, chunk_base);
             if (cudaFuncSetAttribute(k_pfn_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                 return PV_ERR_CUDA;
             const long long want = (m + PT_CHUNK - 1) / PT_CHUNK;
-            const unsigned grid = (unsigned)(want < 296 ? want : 296);
+            const long long cap = 2ll * pv_sm_count();            // two resident blocks per SM
+            const unsigned grid = (unsigned)(want < cap ? want : cap);
             k_pfn_tiled<<<grid, PT_THREADS, smem, st>>>(q);
-            if (tc) {
-                const pv_pfn_layer &L1 = layers[1];
-                return pv_pfn_tc_layer(q.x0_out, q.row_vox_out, q.vmax0_out, chunk_base + W.chunks, 32, L1.units,
-                                       L1.weight, L1.bn_mean, L1.bn_var, L1.bn_gamma, L1.bn_beta, eps, m, out, st);
-            }
             return pv_last_cuda_error();
         }
     }
@@ -783,7 +721,7 @@ int pv_pfn_forward(const float *voxels, const int32_t *num_points, const int32_t
     if (smem > 200 * 1024) return PV_ERR_UNSUPPORTED;
     if (cudaFuncSetAttribute(k_pfn_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return PV_ERR_CUDA;
-    const unsigned grid = (unsigned)min((long long)148 * 3, (long long)m);
+    const unsigned grid = (unsigned)min((long long)pv_sm_count() * 3, (long long)m);
     k_pfn_simt<<<grid, PFN_THREADS, smem, (cudaStream_t)stream>>>(a);
     return pv_last_cuda_error();
 }

@@ -55,8 +55,11 @@ def _need(t, dtype, name, ndim=None):
 
 
 def workspace(nbytes, device, tag="main"):
-    """Grow-only byte buffer per (device, tag); the library itself never allocates."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    """Grow-only byte buffer per (device, current stream, tag); the library itself never allocates.
+    Keyed by the stream so that callers working concurrently on different streams never share (or,
+    when one of them grows it, free) each other's scratch memory."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream, tag)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)

@@ -53,16 +53,34 @@ def test_pillar_feature_net_matches_reference(g, tag, filters, dist):
     assert_close_fp32(out, g[f"{tag}_out"], tag + " vs reference")
 
 
-@pytest.mark.parametrize("tag,filters", [("pfn64_128", (64, 128))])
-def test_pillar_feature_net_tensor_core_path_matches_reference(g, tag, filters, monkeypatch):
-    """Second layer on tcgen05 (3xTF32, accumulators in TMEM): same 1e-5 gate as the fp32 kernel."""
-    monkeypatch.setenv("PV_PFN_TC", "1")
-    net = _load_pfn(g, tag, filters, False)
-    out = net(_cuda(g["voxels"]), _cuda(g["num_points"]), _cuda(g["coors"])).cpu().numpy()
-    assert_close_fp32(out, g[f"{tag}_out"], tag + " (tcgen05) vs reference")
-    monkeypatch.setenv("PV_PFN_TC", "0")
-    ref = net(_cuda(g["voxels"]), _cuda(g["num_points"]), _cuda(g["coors"])).cpu().numpy()
-    assert_close_fp32(out, ref, "tcgen05 vs fp32 kernel")
+@pytest.mark.parametrize("filters,dist,t,c", [((64, 128), False, 20, 7), ((64, 64), False, 20, 7), ((64, 128), True, 20, 7),
+                                              ((64, 96), False, 5, 8), ((64, 128), False, 32, 5), ((64, 32), True, 1, 9)])
+def test_pfn_tensor_core_kernel_vs_oracle(filters, dist, t, c):
+    """The default two-layer path (pfn_fused.cu: second layer on tcgen05, 3xTF32, accumulators in TMEM) on
+    random padded tensors: every fill level (full voxels, single points, padded-slot quirk), M not a
+    multiple of anything, same 1e-5 gate as the fp32 kernels."""
+    import torch
+    from partner_b200 import functional as F
+    rng = np.random.default_rng(hash((filters, dist, t, c)) % 2 ** 31)
+    m = 20011
+    num = rng.integers(1, t + 1, m).astype(np.int32)
+    num[::7] = t
+    vox = rng.normal(0, 3, (m, t, c)).astype(np.float32) * (np.arange(t)[None, :, None] < num[:, None, None])
+    coors = np.stack([np.zeros(m), np.zeros(m), rng.integers(0, 512, m), rng.integers(0, 512, m)], 1).astype(np.int32)
+    vs, rg = [0.098, 0.0123, 8.0], [0.3, -3.1488, -5.0, 50.476, 3.1488, 3.0]
+    width, layers, dev_layers = c + 5 + (1 if dist else 0), [], []
+    for i, fo in enumerate(filters):
+        u = fo if i == len(filters) - 1 else fo // 2
+        L = dict(weight=rng.normal(0, 0.3, (u, width)).astype(np.float32), mean=rng.normal(0, 1, u).astype(np.float32),
+                 var=rng.uniform(0.5, 2, u).astype(np.float32), gamma=rng.normal(0, 1, u).astype(np.float32),
+                 beta=rng.normal(0, 1, u).astype(np.float32))
+        layers.append(L)
+        dev_layers.append(tuple(torch.from_numpy(L[k]).cuda() for k in ("weight", "mean", "var", "gamma", "beta")))
+        width = 2 * u
+    ref = oracle.pfn_forward(vox, num, coors, layers, vs, rg, with_distance=dist, eps=1e-3)
+    out = F.pfn_forward(_cuda(vox), _cuda(num), _cuda(coors), dev_layers, vs[0], vs[1], vs[0] / 2 + rg[0], vs[1] / 2 + rg[1],
+                        dist, 1e-3)
+    assert_close_fp32(out.cpu().numpy(), ref, "tcgen05 PFN %s dist=%s t=%d c=%d" % (filters, dist, t, c))
 
 
 def test_pfn_training_mode_is_refused(g):
