@@ -141,6 +141,32 @@ int pv_forward_mean_canvas(const pv_config *cfg, const float *points, const int3
                            int32_t *voxel_counts, float *mean_feats, float *canvas,
                            pv_stream_t stream);
 
+/* Fused PILLAR-FEATURE-NET front end (BASELINE config 3): replaces, for a batch of frames,
+ *   VoxelGenerator.generate + collate (as pv_voxelize)  ->  PillarFeatureNet.forward in eval mode
+ *   (det3d/models/readers/pillar_encoder.py:131-169, PFNLayer.forward_static :49-61)  ->
+ *   PointPillarsScatter.forward (:189-225),
+ * i.e. PointPillars.extract_feat_static (det3d/models/detectors/point_pillars.py:28-35) on raw points.
+ * The padded voxels tensor [M, T, C] is never materialised: the PFN kernel gathers the kept points of
+ * every voxel through the voxelizer's point lists (fused cylinder transform for Cartesian input), runs
+ * layer 0 in fp32 FMAs and layer 1 on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split, fp32
+ * accumulators in TMEM), BatchNorm (eval, ATen order) + ReLU + the per-voxel maximum over all T slots
+ * (padded-slot quirk included) in the epilogue.
+ *   layers (HOST array), vx, vy, x_off, y_off, eps as for pv_pfn_forward; two layers, 32 units in the
+ *   first, 32 | units of the last <= 128 (every PillarFeatureNet the reference's configs build),
+ *   C + 5 (+1 with_distance) <= 16, max_points <= 32; PV_ERR_UNSUPPORTED otherwise.
+ * Outputs: coors [SM, 4], num_points [SM], voxel_counts [batch] as pv_voxelize; pfn_feats f32 [SM, U]
+ * (capacity min(batch * V, n_total) rows); canvas f32 [batch, U, ny, nx] or NULL (pillar grids).
+ * aux_workspace: pv_pfn_canvas_workspace_bytes(batch, ny, nx) bytes, 256-byte aligned (chunk queue,
+ * watchdog words, BEV index map); workspace as for pv_voxelize. */
+size_t pv_pfn_canvas_workspace_bytes(int32_t batch, int32_t ny, int32_t nx);
+int pv_forward_pfn_canvas(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
+                          int32_t batch, int64_t n_total, int32_t c_in, int32_t is_cartesian,
+                          int64_t max_points_total, int64_t frame_capacity, void *workspace,
+                          size_t workspace_bytes, void *aux_workspace, size_t aux_bytes,
+                          const pv_pfn_layer *layers, int32_t n_layers, int32_t with_distance, float vx, float vy,
+                          float x_off, float y_off, float eps, int32_t *coors, int32_t *num_points,
+                          int32_t *voxel_counts, float *pfn_feats, float *canvas, pv_stream_t stream);
+
 /* Measurement aid for bench.py: runs pv_forward_mean_canvas (canvas may be NULL for 3-D grids)
  * `iters` times with CUDA events recorded on `stream` between the stages and returns the average
  * milliseconds per stage in stage_ms (HOST, PV_PROFILE_STAGES floats).  List-free pipeline:

@@ -8,7 +8,7 @@ Drop-in classes (same names / signatures as the reference):
     DynamicPFNet, DynamicPPScatter         det3d/models/readers/pillar_encoder.py
     Voxelization                           det3d/datasets/pipelines/voxelization.py (hard + double flip, dynamic)
     transform_points                       det3d/datasets/pipelines/utils.py
-and the fused batched path ``PolarFrontEnd``.  All compute runs in hand-written CUDA kernels
+and the fused batched paths ``PolarFrontEnd`` (mean VFE + canvas) and ``PillarFrontEnd`` (PFN + canvas).  All compute runs in hand-written CUDA kernels
 reached through the C ABI of include/polar_voxel_b200.h; importing the package does not need a
 GPU, calling anything does.
 """
@@ -30,7 +30,7 @@ def __getattr__(name):
                 "DynamicVoxelEncoderV1", "DynamicPFNet", "DynamicPPScatter"):
         from . import readers
         return getattr(readers, name)
-    if name in ("PolarFrontEnd", "shard_range"):
+    if name in ("PolarFrontEnd", "PillarFrontEnd", "shard_range"):
         from . import frontend
         return getattr(frontend, name)
     if name == "transform_points":

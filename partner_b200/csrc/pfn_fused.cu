@@ -32,35 +32,15 @@
 // epilogue drains tile k - 1: three pipelines (operand full / MMA done / accumulator free) on
 // mbarriers, no block-wide barrier after the prologue.
 #include "tc_common.cuh"
+#include "pfn_fused.cuh"
 
-#define P2_THREADS (13 * 32)
-#define P2_EPI_WARP0 8
-#define P2_ISSUER_WARP 12
+#define P2_THREADS (17 * 32)
+#define P2_EPI_WARP0 8         // warps 8-15: epilogue (TMEM quarter = warp & 3, column half = (warp - 8) >> 2)
+#define P2_ISSUER_WARP 16
 #define P2_MC 64               // voxels per mini-chunk (the unit a producer warp fetches)
 #define P2_U0 32               // units of layer 0
 #define P2_K 64                // K of layer 1 = 2 * P2_U0
 #define P2_C0 16               // decorated input width, padded
-
-struct P2Args {
-    int mode;
-    // mode 0: padded tensor
-    const float *voxels; const int32_t *num; const int32_t *coors_in; long long m;
-    // mode 1: point lists of the list-based voxelizer
-    const float *pts; int c_in, cart;
-    const uint32_t *vox_cell, *vox_kg, *vox_c; uint32_t *kept;
-    const int32_t *base; const int32_t *voxel_counts;
-    uint32_t fcap; int32_t nx, ny;
-    int32_t *coors_out; int32_t *num_out;
-    // common
-    int t, c, c0, with_distance;
-    float vx, vy, x_off, y_off, eps;
-    const float *w0, *mean0, *var0, *gamma0, *beta0;
-    const float *w1, *mean1, *var1, *gamma1, *beta1;
-    int n1;
-    uint32_t chunks_per_frame, n_chunks;
-    unsigned int *counter;
-    float *out;
-};
 
 struct P2Meta {                // what the epilogue needs to know about one group
     int32_t vid[32];           // output row of the voxel whose LAST row this lane holds, else -1
@@ -83,13 +63,13 @@ __device__ __forceinline__ bool p2_mbar_wait(uint32_t bar, uint32_t parity, vola
                      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return true;
-        if (*abort_flag) { if (blockIdx.x == diag[15]) diag[1 + (threadIdx.x >> 5)] = tag; return false; }
+        if (*abort_flag) { if (blockIdx.x == diag[1]) diag[2 + (threadIdx.x >> 5)] = tag; return false; }
         if (spins == 0) t0 = clock64();
         else if ((spins & 63u) == 0 && clock64() - t0 > 400000000ll) {
-            if (atomicCAS(diag, 0u, tag) == 0u) diag[15] = blockIdx.x;      // first block to starve: its warps report where they wait
+            if (atomicCAS(diag, 0u, tag) == 0u) diag[1] = blockIdx.x;      // first block to starve: its warps report where they wait
             __threadfence();
             *abort_flag = 1u;
-            if (blockIdx.x == diag[15]) diag[1 + (threadIdx.x >> 5)] = tag;
+            if (blockIdx.x == diag[1]) diag[2 + (threadIdx.x >> 5)] = tag;
             return false;
         }
     }
@@ -101,21 +81,30 @@ __device__ __forceinline__ void p2_mbar_arrive(uint32_t bar)
 
 // segmented inclusive scan step helpers: flags bit d set <=> lane >= 2^d and lanes (lane - 2^d, lane]
 // hold no first row of a voxel, i.e. lane - 2^d belongs to the same voxel
-__device__ __forceinline__ float p2_seg_max(float v, uint32_t flags, uint32_t nsteps)
+// (whole arrays at a time: the NV shuffles of a step are independent, so they pipeline)
+template <int NV>
+__device__ __forceinline__ void p2_seg_max(float (&v)[NV], uint32_t flags, uint32_t nsteps)
 {
     for (uint32_t d = 0; d < nsteps; ++d) {
-        const float o = __shfl_up_sync(0xffffffffu, v, 1u << d);
-        if ((flags >> d) & 1u) v = fmaxf(v, o);
+        const bool take = (flags >> d) & 1u;
+        float o[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) o[k] = __shfl_up_sync(0xffffffffu, v[k], 1u << d);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v[k] = take ? fmaxf(v[k], o[k]) : v[k];
     }
-    return v;
 }
-__device__ __forceinline__ float p2_seg_sum(float v, uint32_t flags, uint32_t nsteps)
+template <int NV>
+__device__ __forceinline__ void p2_seg_sum(float (&v)[NV], uint32_t flags, uint32_t nsteps)
 {
     for (uint32_t d = 0; d < nsteps; ++d) {
-        const float o = __shfl_up_sync(0xffffffffu, v, 1u << d);
-        if ((flags >> d) & 1u) v = __fadd_rn(v, o);
+        const bool take = (flags >> d) & 1u;
+        float o[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) o[k] = __shfl_up_sync(0xffffffffu, v[k], 1u << d);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v[k] = take ? __fadd_rn(v[k], o[k]) : v[k];
     }
-    return v;
 }
 
 __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_constant__ P2Args a)
@@ -146,7 +135,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
         for (int s = 0; s < 2; ++s) {
             tc_mbar_init(tc_smem_u32(&s_full[s]), 4);
             tc_mbar_init(tc_smem_u32(&s_mma[s]), 1);
-            tc_mbar_init(tc_smem_u32(&s_free[s]), 4);
+            tc_mbar_init(tc_smem_u32(&s_free[s]), 8);
             tc_mbar_init(tc_smem_u32(&s_rec[s]), 1);
             s_exit[s] = 0u;
         }
@@ -300,9 +289,10 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                 __stcs(a.num_out + vid_i, n_i);
             }
             // cluster mean (:137-139): sum over the voxel's rows / num
-            float sx = p2_seg_sum(f[0], flags, nsteps), sy = p2_seg_sum(f[1], flags, nsteps), sz = p2_seg_sum(f[2], flags, nsteps);
-            sx = __shfl_sync(0xffffffffu, sx, last_lane & 31); sy = __shfl_sync(0xffffffffu, sy, last_lane & 31);
-            sz = __shfl_sync(0xffffffffu, sz, last_lane & 31);
+            float sm[3] = {f[0], f[1], f[2]};
+            p2_seg_sum<3>(sm, flags, nsteps);
+            const float sx = __shfl_sync(0xffffffffu, sm[0], last_lane & 31), sy = __shfl_sync(0xffffffffu, sm[1], last_lane & 31),
+                        sz = __shfl_sync(0xffffffffu, sm[2], last_lane & 31);
             const float nf = (float)n_j;
             const float mx = __fdiv_rn(sx, nf), my = __fdiv_rn(sy, nf), mz = __fdiv_rn(sz, nf);
             const float pcx = __fadd_rn(__fmul_rn((float)cx_j, a.vx), a.x_off);   // :146-147
@@ -338,22 +328,24 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                 }
             }
             const int row = g * 32 + lane;
+            float xm[P2_U0];
+#pragma unroll
+            for (int u = 0; u < P2_U0; ++u) {
+                const float v = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x0[u], bn0[u]), bn0[P2_U0 + u]), bn0[2 * P2_U0 + u]), bn0[3 * P2_U0 + u]);
+                x0[u] = row_ok ? fmaxf(v, 0.0f) : 0.0f;
+                xm[u] = x0[u];
+            }
+            p2_seg_max<P2_U0>(xm, flags, nsteps);
+#pragma unroll
+            for (int u = 0; u < P2_U0; ++u) xm[u] = __shfl_sync(0xffffffffu, xm[u], last_lane & 31);
+            // operand row [x0 | x_max0] in the canonical K-major layout, split into TF32 hi / lo
 #pragma unroll
             for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
-                float y[4], mxv[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int u = 4 * u4 + e;
-                    const float v = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x0[u], bn0[u]), bn0[P2_U0 + u]), bn0[2 * P2_U0 + u]), bn0[3 * P2_U0 + u]);
-                    y[e] = row_ok ? fmaxf(v, 0.0f) : 0.0f;
-                    mxv[e] = __shfl_sync(0xffffffffu, p2_seg_max(y[e], flags, nsteps), last_lane & 31);
-                }
-                // operand row [x0 | x_max0] in the canonical K-major layout, split into TF32 hi / lo
                 float4 hi, lo;
-                tc_split(y[0], hi.x, lo.x); tc_split(y[1], hi.y, lo.y); tc_split(y[2], hi.z, lo.z); tc_split(y[3], hi.w, lo.w);
+                tc_split(x0[4 * u4], hi.x, lo.x); tc_split(x0[4 * u4 + 1], hi.y, lo.y); tc_split(x0[4 * u4 + 2], hi.z, lo.z); tc_split(x0[4 * u4 + 3], hi.w, lo.w);
                 uint32_t o = tc_canon(row, 4 * u4, TC_M);
                 *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
-                tc_split(mxv[0], hi.x, lo.x); tc_split(mxv[1], hi.y, lo.y); tc_split(mxv[2], hi.z, lo.z); tc_split(mxv[3], hi.w, lo.w);
+                tc_split(xm[4 * u4], hi.x, lo.x); tc_split(xm[4 * u4 + 1], hi.y, lo.y); tc_split(xm[4 * u4 + 2], hi.z, lo.z); tc_split(xm[4 * u4 + 3], hi.w, lo.w);
                 o = tc_canon(row, P2_U0 + 4 * u4, TC_M);
                 *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
             }
@@ -421,13 +413,14 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
         // =====================================================================================
         // EPILOGUE warp e: TMEM lanes [32 e, 32 e + 32)
         // =====================================================================================
-        const int e = warp - P2_EPI_WARP0;
+        const int e = warp & 3, half = (warp - P2_EPI_WARP0) >> 2;
+        const int n_chunks = N / 32, c_lo = half ? (n_chunks + 1) / 2 * 32 : 0, c_hi = half ? N : (n_chunks + 1) / 2 * 32;
         bool fin[2] = {false, false};
         for (uint32_t round = 0; !(fin[0] && fin[1]); ++round) {
             for (int s = 0; s < 2; ++s) {
                 if (fin[s]) continue;
-                if (!p2_mbar_wait(tc_smem_u32(&s_rec[s]), round & 1u, &s_abort, diag, 0x500u | (s << 4) | e | (round << 16))) { fin[0] = fin[1] = true; break; }
-                if (!p2_mbar_wait(tc_smem_u32(&s_mma[s]), round & 1u, &s_abort, diag, 0x400u | (s << 4) | e | (round << 16))) { fin[0] = fin[1] = true; break; }
+                if (!p2_mbar_wait(tc_smem_u32(&s_rec[s]), round & 1u, &s_abort, diag, 0x500u | (s << 4) | (warp - P2_EPI_WARP0) | (round << 16))) { fin[0] = fin[1] = true; break; }
+                if (!p2_mbar_wait(tc_smem_u32(&s_mma[s]), round & 1u, &s_abort, diag, 0x400u | (s << 4) | (warp - P2_EPI_WARP0) | (round << 16))) { fin[0] = fin[1] = true; break; }
                 if (*reinterpret_cast<volatile uint32_t *>(&s_exit[s])) { fin[s] = true; continue; }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const P2Meta *mt = meta + ((s * 2 + (round & 1u)) * 4 + e);
@@ -435,15 +428,16 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                 if (!done) {
                     const int vid = mt->vid[lane];
                     const uint32_t flags = mt->flags[lane], nsteps = min(mt->nsteps, 5u);
-                    for (int c0 = 0; c0 < N; c0 += 32) {
+                    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
                         float v[32];
                         tc_ld_32x32(tmem + ((uint32_t)(e * 32) << 16) + (uint32_t)(s * N + c0), v);
 #pragma unroll
                         for (int k = 0; k < 32; ++k) {
                             const int o = c0 + k;
                             const float y = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v[k], bn1[o]), bn1[N + o]), bn1[2 * N + o]), bn1[3 * N + o]);
-                            v[k] = p2_seg_max(fmaxf(y, 0.0f), flags, nsteps);
+                            v[k] = fmaxf(y, 0.0f);
                         }
+                        p2_seg_max<32>(v, flags, nsteps);
                         if (vid >= 0) {
                             float4 *dst = reinterpret_cast<float4 *>(a.out + (size_t)vid * N + c0);
 #pragma unroll
@@ -480,8 +474,8 @@ size_t pv_pfn_fused_smem(int n1)
            sizeof(P2Meta) * 16 + 128;
 }
 
-// counter: one zeroed 32-bit word in device memory (the dynamic mini-chunk queue); the kernel leaves
-// it non-zero, the caller's memset node precedes every launch.
+// counter: 24 words of device scratch: [0] the dynamic mini-chunk queue, [1] watchdog tag (0 = healthy),
+// [2] the block that starved first, [3..] where each of its warps was waiting; zeroed before every launch.
 int pv_pfn_fused_launch(P2Args &a, const pv_pfn_layer *layers, int batch_frames, long long voxels_per_frame_cap,
                         cudaStream_t st)
 {
@@ -492,7 +486,7 @@ int pv_pfn_fused_launch(P2Args &a, const pv_pfn_layer *layers, int batch_frames,
     if (a.chunks_per_frame == 0) a.chunks_per_frame = 1;
     a.n_chunks = a.chunks_per_frame * (uint32_t)batch_frames;
     const size_t smem = pv_pfn_fused_smem(a.n1);
-    if (cudaMemsetAsync(a.counter, 0, 17 * sizeof(unsigned int), st) != cudaSuccess) return PV_ERR_CUDA;   // queue + watchdog words
+    if (cudaMemsetAsync(a.counter, 0, 24 * sizeof(unsigned int), st) != cudaSuccess) return PV_ERR_CUDA;   // queue + watchdog words
     if (cudaFuncSetAttribute(k_pfn_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
     const unsigned want = (a.n_chunks + 7) / 8;
     const unsigned sms = (unsigned)pv_sm_count();

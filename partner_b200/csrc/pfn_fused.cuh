@@ -1,0 +1,32 @@
+// pfn_fused.cuh -- host-side interface of the warp-specialised tensor-core PFN kernel (pfn_fused.cu).
+#pragma once
+#include "pv_common.cuh"
+
+struct P2Args {
+    int mode;
+    // mode 0: padded tensor
+    const float *voxels; const int32_t *num; const int32_t *coors_in; long long m;
+    // mode 1: point lists of the list-based voxelizer
+    const float *pts; int c_in, cart;
+    const uint32_t *vox_cell, *vox_kg, *vox_c; uint32_t *kept;
+    const int32_t *base; const int32_t *voxel_counts;
+    uint32_t fcap; int32_t nx, ny;
+    int32_t *coors_out; int32_t *num_out;
+    // common
+    int t, c, c0, with_distance;
+    float vx, vy, x_off, y_off, eps;
+    const float *w0, *mean0, *var0, *gamma0, *beta0;
+    const float *w1, *mean1, *var1, *gamma1, *beta1;
+    int n1;
+    uint32_t chunks_per_frame, n_chunks;
+    unsigned int *counter;
+    float *out;
+};
+
+
+// Shapes the kernel covers: two layers, 32 units in the first, 32 | units of the last <= 128,
+// decorated width <= 16, T <= 32.
+bool pv_pfn_fused_supported(const pv_pfn_layer *layers, int n_layers, int t, int c, int with_distance);
+// counter: 24 words of device scratch (chunk queue + watchdog diagnostics), zeroed by the launch.
+int pv_pfn_fused_launch(P2Args &a, const pv_pfn_layer *layers, int batch_frames, long long voxels_per_frame_cap,
+                        cudaStream_t st);

@@ -44,6 +44,17 @@ __global__ void __launch_bounds__(256) k_bev_index(const int32_t *__restrict__ c
     atomicMax(map + (size_t)c.x * ny * nx + idx, (int32_t)v);
 }
 
+// the same with the number of valid rows read on the device (fused front ends: no host sync)
+__global__ void __launch_bounds__(256) k_bev_index_dev(const int32_t *__restrict__ coors, const int32_t *__restrict__ total_rows,
+                                                       long long cap, int batch, int ny, int nx, int32_t *__restrict__ map)
+{
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= cap || v >= (long long)__ldg(total_rows)) return;
+    const int4 c = reinterpret_cast<const int4 *>(coors)[v];          // (b, z, y, x)
+    if (c.x < 0 || c.x >= batch || c.z < 0 || c.z >= ny || c.w < 0 || c.w >= nx) return;
+    atomicMax(map + (size_t)c.x * ny * nx + (size_t)c.z * nx + c.w, (int32_t)v);
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256) k_canvas_from_index(const float *__restrict__ feats,
                                                            const int32_t *__restrict__ map, int c,
@@ -569,6 +580,23 @@ static int pfn_tiled_supported(const pv_pfn_layer *layers, int n_layers, int t)
     for (int l = 0; l < n_layers; ++l)
         if (layers[l].units % 32 != 0 || layers[l].units > PFN_MAX_W) return 0;
     return 1;
+}
+
+extern "C" size_t pv_scatter_workspace_bytes(int32_t batch, int32_t ny, int32_t nx);
+
+// PointPillarsScatter for a fused front end: rows [0, *total_rows) of feats / coors are valid.
+int pv_scatter_dev(const float *feats, const int32_t *coors, const int32_t *total_rows, int64_t cap, int32_t c,
+                   int32_t batch, int32_t ny, int32_t nx, void *workspace, float *canvas, cudaStream_t st)
+{
+    const size_t need = pv_scatter_workspace_bytes(batch, ny, nx);
+    int32_t *map = (int32_t *)workspace;
+    if (cudaMemsetAsync(map, 0xFF, need, st) != cudaSuccess) return PV_ERR_CUDA;
+    if (cap > 0) k_bev_index_dev<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(coors, total_rows, cap, batch, ny, nx, map);
+    const uint32_t cells = (uint32_t)ny * (uint32_t)nx;
+    const bool vec = (cells % 4 == 0) && ((reinterpret_cast<uintptr_t>(canvas) & 15u) == 0);
+    if (vec) k_canvas_from_index<4><<<dim3((cells / 4 + 255) / 256, (unsigned)batch), 256, 0, st>>>(feats, map, c, cells, canvas);
+    else k_canvas_from_index<1><<<dim3((cells + 255) / 256, (unsigned)batch), 256, 0, st>>>(feats, map, c, cells, canvas);
+    return pv_last_cuda_error();
 }
 
 extern "C" {

@@ -22,7 +22,10 @@
 // voxels with rank >= V dropped -- the three order-dependent behaviours of the reference loop.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "pv_common.cuh"
+#include "pfn_fused.cuh"
 
 #define K1_THREADS 256
 #define SCAN_THREADS 256
@@ -768,7 +771,9 @@ static void launch_emit(const PvParams &p, cudaStream_t st)
 #define PV_STAGES 5
 #define PV_MARK(k) do { if (ev && cudaEventRecord(ev[k], st) != cudaSuccess) return PV_ERR_CUDA; } while (0)
 
-static int run_voxelize(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev = nullptr)
+// emit == false: stop after the point lists are in place (K1-K4); the caller's own kernel consumes the
+// lists (and restores them) instead of k_emit -- the fused PFN front end.
+static int run_voxelize(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev = nullptr, bool emit = true)
 {
     const PvWs &w = p.ws;
     if (p.density &&
@@ -794,6 +799,7 @@ static int run_voxelize(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev = 
     PV_MARK(3);
     if (p.n > 0) k_place<<<(p.n + 255) / 256, 256, 0, st>>>(p);
     PV_MARK(4);
+    if (!emit) return pv_last_cuda_error();
     switch (p.C) {
     case 3: case 4: case 5: launch_emit<5>(p, st); break;
     case 6: launch_emit<6>(p, st); break;
@@ -805,6 +811,10 @@ static int run_voxelize(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev = 
     PV_MARK(5);
     return pv_last_cuda_error();
 }
+
+// readers.cu
+int pv_scatter_dev(const float *feats, const int32_t *coors, const int32_t *total_rows, int64_t cap, int32_t c,
+                   int32_t batch, int32_t ny, int32_t nx, void *workspace, float *canvas, cudaStream_t st);
 
 extern "C" {
 
@@ -987,6 +997,59 @@ int pv_dynamic_voxelize(const pv_config *cfg, const float *points, const int32_t
     p.coors = unq; p.num_points = unq_cnt; p.unq_inv = unq_inv; p.voxel_counts = voxel_counts;
     p.feats = mean_feats; p.canvas = canvas;
     return pvf_run_dynamic(p, f, (cudaStream_t)stream);
+}
+
+size_t pv_pfn_canvas_workspace_bytes(int32_t batch, int32_t ny, int32_t nx)
+{
+    const size_t map = pv_scatter_workspace_bytes(batch, ny, nx);
+    return map ? 256 + map : 0;                          // [chunk queue + watchdog words | BEV index map]
+}
+
+int pv_forward_pfn_canvas(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
+                          int32_t batch, int64_t n_total, int32_t c_in, int32_t is_cartesian,
+                          int64_t max_points_total, int64_t frame_capacity, void *workspace,
+                          size_t workspace_bytes, void *aux_workspace, size_t aux_bytes,
+                          const pv_pfn_layer *layers, int32_t n_layers, int32_t with_distance, float vx, float vy,
+                          float x_off, float y_off, float eps, int32_t *coors, int32_t *num_points,
+                          int32_t *voxel_counts, float *pfn_feats, float *canvas, pv_stream_t stream)
+{
+    PvParams p;
+    PvF f;
+    int rc = fill_params(&p, &f, cfg, points, frame_offsets, batch, n_total, c_in, is_cartesian,
+                         max_points_total, frame_capacity, workspace, workspace_bytes);
+    if (rc) return rc;
+    if (!coors || !num_points || !voxel_counts || !pfn_feats || !layers || !aux_workspace) return PV_ERR_BAD_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(coors) & 15u) != 0 || (reinterpret_cast<uintptr_t>(pfn_feats) & 15u) != 0 ||
+        (reinterpret_cast<uintptr_t>(aux_workspace) & 255u) != 0)
+        return PV_ERR_BAD_ARGUMENT;
+    if (canvas && (cfg->grid[2] != 1 || (reinterpret_cast<uintptr_t>(canvas) & 15u) != 0)) return PV_ERR_BAD_CONFIG;
+    if (aux_bytes < pv_pfn_canvas_workspace_bytes(batch, cfg->grid[1], cfg->grid[0])) return PV_ERR_WORKSPACE;
+    if (n_layers <= 0 || n_layers > PV_MAX_PFN_LAYERS) return PV_ERR_BAD_ARGUMENT;
+    for (int l = 0; l < n_layers; ++l)
+        if (!layers[l].weight || !layers[l].bn_mean || !layers[l].bn_var || !layers[l].bn_gamma || !layers[l].bn_beta)
+            return PV_ERR_BAD_ARGUMENT;
+    if (!pv_pfn_fused_supported(layers, n_layers, cfg->max_points, p.C, with_distance)) return PV_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    p.coors = coors; p.num_points = num_points; p.voxel_counts = voxel_counts;
+    rc = run_voxelize(p, f, st, nullptr, false);         // point lists only: no [M, T, C] tensor, no k_emit
+    if (rc) return rc;
+    P2Args a = {};
+    a.mode = 1;
+    a.pts = points; a.c_in = c_in; a.cart = is_cartesian ? 1 : 0;
+    a.vox_cell = p.ws.vox_cell; a.vox_kg = p.ws.vox_kg; a.vox_c = p.ws.vox_c; a.kept = p.ws.kept;
+    a.base = p.ws.base; a.voxel_counts = voxel_counts; a.fcap = p.ws.fcap;
+    a.nx = cfg->grid[0]; a.ny = cfg->grid[1];
+    a.coors_out = coors; a.num_out = num_points;
+    a.t = cfg->max_points; a.c = p.C; a.with_distance = with_distance ? 1 : 0; a.c0 = p.C + 5 + a.with_distance;
+    a.vx = vx; a.vy = vy; a.x_off = x_off; a.y_off = y_off; a.eps = eps;
+    a.counter = reinterpret_cast<unsigned int *>(aux_workspace);
+    a.out = pfn_feats;
+    const long long vcap = std::min<long long>(cfg->max_voxels, (long long)p.ws.fcap);
+    rc = pv_pfn_fused_launch(a, layers, batch, vcap, st);
+    if (rc || !canvas) return rc;
+    const int64_t cap = std::min<int64_t>((int64_t)batch * cfg->max_voxels, n_total);
+    return pv_scatter_dev(pfn_feats, coors, p.ws.base + batch, cap, layers[n_layers - 1].units, batch, cfg->grid[1], cfg->grid[0],
+                          reinterpret_cast<char *>(aux_workspace) + 256, canvas, st);
 }
 
 int pv_read_status(const void *workspace, pv_stream_t stream)

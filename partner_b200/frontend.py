@@ -131,3 +131,59 @@ class PolarFrontEnd:
         if self.canvas:
             out["canvas"] = canvas
         return out
+
+
+class PillarFrontEnd:
+    """PointPillars.extract_feat_static (det3d/models/detectors/point_pillars.py:28-35) on raw sweeps:
+    voxelize (+ fused cylinder transform) -> PillarFeatureNet (eval) -> PointPillarsScatter, as ONE
+    launch sequence per batch (pv_forward_pfn_canvas).  The padded voxels tensor is never built; the
+    PFN's second layer runs on the tensor cores.
+
+    ``reader`` is a ``partner_b200.PillarFeatureNet`` (reference checkpoints load into it unchanged)
+    with two PFN layers, e.g. ``num_filters=(64, 128)`` or ``(64, 64)``."""
+
+    def __init__(self, voxel_size, point_cloud_range, max_points_in_voxel, max_voxel_num, reader, cartesian=True,
+                 canvas=True, device=None, workspace_tag=0):
+        self.cfg, self.voxel_size, self.point_cloud_range, self.grid_size = F.make_config(
+            voxel_size, point_cloud_range, max_points_in_voxel, max_voxel_num)
+        if int(self.grid_size[2]) != 1:
+            raise ValueError("the pillar front end needs a pillar grid (nz == 1)")
+        if reader.training:
+            raise RuntimeError("PillarFrontEnd implements eval-mode BatchNorm only; call reader.eval() first")
+        self.reader = reader
+        self.cartesian, self.canvas = bool(cartesian), bool(canvas)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.workspace_tag = workspace_tag
+
+    def _layers(self):
+        eps = {l.norm.eps for l in self.reader.pfn_layers}
+        if len(eps) != 1:
+            raise ValueError("all PFN layers must share one BatchNorm eps")
+        return [(l.linear.weight.detach().contiguous(), l.norm.running_mean, l.norm.running_var,
+                 l.norm.weight.detach(), l.norm.bias.detach()) for l in self.reader.pfn_layers], eps.pop()
+
+    def forward_device(self, points, frame_offsets, batch, frame_capacity, out=None):
+        """points [N, c_in] f32 CUDA, frame_offsets [batch+1] int32 CUDA -> VoxelBatch (no sync):
+        ``mean_feats`` holds the PFN features [capacity, U], ``canvas`` the BEV canvas [B, U, ny, nx]."""
+        layers, eps = self._layers()
+        rd = self.reader
+        return F.forward_pfn_canvas(self.cfg, points, frame_offsets, batch, frame_capacity, self.cartesian, layers,
+                                    rd.vx, rd.vy, rd.x_offset, rd.y_offset, rd._with_distance, eps,
+                                    canvas=self.canvas, out=out, ws_tag=self.workspace_tag)
+
+    def __call__(self, frames):
+        """List of float32 numpy frames -> dict(coordinates, num_points, num_voxels, features, canvas) (syncs)."""
+        sizes = [int(f.shape[0]) for f in frames]
+        offsets = np.zeros(len(frames) + 1, dtype=np.int32)
+        np.cumsum(sizes, out=offsets[1:])
+        pts = torch.from_numpy(np.ascontiguousarray(np.concatenate(frames, axis=0), dtype=np.float32)).to(self.device)
+        vb = self.forward_device(pts, torch.from_numpy(offsets).to(self.device), len(frames), max(sizes))
+        counts = vb.voxel_counts.cpu().numpy()
+        F.read_status(vb)
+        m = int(counts.sum())
+        coors, num, feats, canvas = F.to_numpy(vb.coors[:m], vb.num_points[:m], vb.mean_feats[:m],
+                                               vb.canvas if self.canvas else None)
+        out = dict(coordinates=coors, num_points=num, num_voxels=counts.astype(np.int64), features=feats)
+        if self.canvas:
+            out["canvas"] = canvas
+        return out

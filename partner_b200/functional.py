@@ -177,6 +177,55 @@ def voxelize(cfg, points, frame_offsets, batch, frame_capacity, is_cartesian, wa
     return r
 
 
+def _pfn_layer_array(layers):
+    arr = (PvPfnLayer * len(layers))()
+    for i, (w, mean, var, gamma, beta) in enumerate(layers):
+        for nm, x in (("weight", w), ("mean", mean), ("var", var), ("gamma", gamma), ("beta", beta)):
+            _need(x, torch.float32, "pfn_layers.%d.%s" % (i, nm))
+        arr[i].weight, arr[i].bn_mean, arr[i].bn_var = w.data_ptr(), mean.data_ptr(), var.data_ptr()
+        arr[i].bn_gamma, arr[i].bn_beta = gamma.data_ptr(), beta.data_ptr()
+        arr[i].units, arr[i].in_channels = w.shape[0], w.shape[1]
+    return arr
+
+
+def forward_pfn_canvas(cfg, points, frame_offsets, batch, frame_capacity, is_cartesian, layers, vx, vy, x_off, y_off,
+                       with_distance, eps, canvas=True, out=None, ws_tag=0):
+    """pv_forward_pfn_canvas: voxelize -> PillarFeatureNet (eval) -> PointPillarsScatter in one launch
+    sequence, without the padded [M, T, C] tensor.  layers as for pfn_forward.  Returns a VoxelBatch
+    whose ``mean_feats`` slot holds the PFN features [capacity, U] and ``canvas`` [B, U, ny, nx]."""
+    _need(points, torch.float32, "points", 2)
+    _need(frame_offsets, torch.int32, "frame_offsets", 1)
+    if frame_offsets.numel() != batch + 1:
+        raise ValueError("frame_offsets must have batch+1 entries")
+    n, c_in = points.shape
+    C = c_in + 2 if is_cartesian else c_in
+    dev = points.device
+    lib = _lib.load()
+    n_cap = _bucket(n)
+    f_cap = min(n_cap, _bucket(frame_capacity))
+    ws = voxel_workspace(cfg, n_cap, batch, f_cap, C, dev, ws_tag)
+    rows = max(1, min(batch * cfg.max_voxels, n))
+    units = layers[-1][0].shape[0]
+    ny, nx = int(cfg.grid[1]), int(cfg.grid[0])
+    r = out if out is not None else VoxelBatch()
+    if out is None:
+        r.coors = torch.empty((rows, 4), dtype=torch.int32, device=dev)
+        r.num_points = torch.empty((rows,), dtype=torch.int32, device=dev)
+        r.voxel_counts = torch.empty((batch,), dtype=torch.int32, device=dev)
+        r.voxels = r.pc_grid_ind = r.density = None
+        r.mean_feats = torch.empty((rows, units), dtype=torch.float32, device=dev)
+        r.canvas = torch.empty((batch, units, ny, nx), dtype=torch.float32, device=dev) if canvas else None
+    r.ws, r.cfg, r.n_cap, r.f_cap = ws, cfg, n_cap, f_cap
+    aux = workspace(lib.pv_pfn_canvas_workspace_bytes(batch, ny, nx), dev, ("pfn_canvas", ws_tag))
+    arr = _pfn_layer_array(layers)
+    check(lib.pv_forward_pfn_canvas(cfg, ptr(points), ptr(frame_offsets), batch, n, c_in, 1 if is_cartesian else 0,
+                                    n_cap, f_cap, ptr(ws), ws.numel(), ptr(aux), aux.numel(), arr, len(layers),
+                                    1 if with_distance else 0, vx, vy, x_off, y_off, eps, ptr(r.coors), ptr(r.num_points),
+                                    ptr(r.voxel_counts), ptr(r.mean_feats), ptr(r.canvas), current_stream(dev)),
+          "pv_forward_pfn_canvas")
+    return r
+
+
 class DynamicBatch:
     """Outputs of pv_dynamic_voxelize in capacity layout (rows [0, sum(voxel_counts)) are valid)."""
 
@@ -384,13 +433,7 @@ def pfn_forward(features, num_voxels, coors, layers, vx, vy, x_off, y_off, with_
     m, t, c = features.shape
     if coors.shape != (m, 4) or num_voxels.numel() != m:
         raise ValueError("coors must be [M,4] and num_voxels [M]")
-    arr = (PvPfnLayer * len(layers))()
-    for i, (w, mean, var, gamma, beta) in enumerate(layers):
-        for nm, x in (("weight", w), ("mean", mean), ("var", var), ("gamma", gamma), ("beta", beta)):
-            _need(x, torch.float32, "pfn_layers.%d.%s" % (i, nm))
-        arr[i].weight, arr[i].bn_mean, arr[i].bn_var = w.data_ptr(), mean.data_ptr(), var.data_ptr()
-        arr[i].bn_gamma, arr[i].bn_beta = gamma.data_ptr(), beta.data_ptr()
-        arr[i].units, arr[i].in_channels = w.shape[0], w.shape[1]
+    arr = _pfn_layer_array(layers)
     out = torch.empty((m, layers[-1][0].shape[0]), dtype=torch.float32, device=features.device)
     lib = _lib.load()
     ws = workspace(max(256, lib.pv_pfn_workspace_bytes(m, t)), features.device, "pfn")

@@ -179,3 +179,34 @@ def test_static_pfn_full_size_vs_oracle():
     got = canvas.cpu().numpy()
     assert got.shape == rc.shape == (2, 128, 512, 512)
     assert_close_fp32(got, rc, "PFN canvas, full size")
+
+
+def test_fused_pillar_front_end_vs_oracle():
+    """pv_forward_pfn_canvas (raw Cartesian sweeps -> voxelize -> PFN [64, 128] -> scatter, no [M, T, C]
+    tensor, second layer on tcgen05) on three frames -- one full nuScenes 10-sweep frame with max_voxels
+    binding, one sparse, one empty -- vs the oracle chain transform_points -> VoxelGenerator.generate ->
+    pfn_forward -> scatter.  Integers bit-exact, features / canvas within the 1e-5 gate."""
+    import torch
+    from partner_b200 import PillarFeatureNet, PillarFrontEnd, synth
+    g = synth.GRIDS["NUSC-PILLAR"]
+    frames = [synth.nusc_frame(3200), synth.nusc_frame(3201, nsweeps=1), np.zeros((0, 5), np.float32)]
+    torch.manual_seed(1)
+    net = _random_pfn_state(PillarFeatureNet(7, (64, 128), False, tuple(g["voxel_size"]), tuple(g["range"])), seed=1).cuda().eval()
+    fe = PillarFrontEnd(g["voxel_size"], g["range"], g["max_points"], g["max_voxels"], net, cartesian=True)
+    got = fe(frames)
+    ref_gen = oracle.VoxelGenerator(g["voxel_size"], g["range"], g["max_points"], g["max_voxels"])
+    outs = [ref_gen.generate(oracle.transform_points(f))[:3] for f in frames]
+    vox, coor, num, nv = oracle.collate(outs)
+    assert np.array_equal(got["num_voxels"], nv)
+    assert np.array_equal(got["coordinates"], coor)
+    assert np.array_equal(got["num_points"], num)
+    layers = [dict(weight=L.linear.weight.detach().cpu().numpy(), mean=L.norm.running_mean.cpu().numpy(),
+                   var=L.norm.running_var.cpu().numpy(), gamma=L.norm.weight.detach().cpu().numpy(),
+                   beta=L.norm.bias.detach().cpu().numpy()) for L in net.pfn_layers]
+    ref = oracle.pfn_forward(vox, num, coor, layers, g["voxel_size"], g["range"], with_distance=False, eps=1e-3)
+    assert_close_fp32(got["features"], ref, "fused PFN features")
+    rc, _ = oracle.scatter(ref, coor, len(frames), [512, 512, 1])
+    assert_close_fp32(got["canvas"], rc, "fused PFN canvas")
+    again = fe(frames)                      # the point lists and the map were restored: a second call is identical
+    assert np.array_equal(again["coordinates"], coor) and np.array_equal(again["num_points"], num)
+    assert_close_fp32(again["features"], ref, "fused PFN features, second call")
