@@ -14,20 +14,23 @@
 //           vox_c / vox_cell) + the raw point rows -- the [M, T, C] tensor is never materialised;
 //           the kernel also writes coors / num_points and restores the lists (pv_forward_pfn_canvas).
 //
-// One persistent CTA per SM, 13 warps:
+// One persistent CTA per SM, 17 warps:
 //   warps 0-7   PRODUCERS, two sets of four (set = A-operand stage).  A warp builds one GROUP of <= 32
 //               useful rows out of whole voxels (lane = row): gathers the rows, decorates them, runs
 //               layer 0 (K = C + 5 <= 16, 4 % of the FLOPs) in fp32 FMAs, BatchNorm + ReLU, the
 //               per-voxel maximum by segmented warp scans, and writes its 32 rows of the layer-1
 //               operand [x0 | x_max0(voxel)] into the stage, split into TF32 hi / lo parts, in the
 //               canonical K-major UMMA layout.  Four groups = one 128-row MMA tile.
-//   warp 12     ISSUER: one thread issues the 3 x K/8 tcgen05.mma.kind::tf32 of the tile (3xTF32 split:
+//   warp 16     ISSUER: one thread issues the 3 x K/8 tcgen05.mma.kind::tf32 of the tile (3xTF32 split:
 //               lo.hi + hi.lo + hi.hi, fp32-accurate) into one of TWO TMEM accumulator stages and
-//               commits to an mbarrier.
-//   warps 8-11  EPILOGUE: warp e owns TMEM lanes [32 e, 32 e + 32) = the rows of producer e's group:
-//               tcgen05.ld, BatchNorm (ATen order) + ReLU, per-voxel maximum by segmented shuffles
-//               (as many steps as the longest voxel of the group needs), one 128-byte store per
-//               voxel and 32 units.
+//               commits to an mbarrier.  The GEMM is issued TRANSPOSED, D[unit, row] = W1 . X^T (the
+//               weight is the M-side operand), so that TMEM lane = output unit, column = row.
+//   warps 8-15  EPILOGUE: warp (e, half) owns TMEM lanes [32 e, 32 e + 32) = 32 units, and the 64 rows
+//               (two producer groups) of row half `half`.  A thread holds ONE unit: its BatchNorm
+//               scale / shift sit in two registers, the rows of a voxel are consecutive columns, so
+//               the per-voxel maximum is a running FMNMX down the row -- and because x -> relu(s x + b)
+//               is monotone, the running op is max (s >= 0) or min (s < 0) on the RAW accumulators and
+//               BatchNorm + ReLU are applied once per voxel.  One coalesced 128-byte store per voxel.
 // While the tensor core works on tile k of stage s, the other producer set builds tile k + 1 and the
 // epilogue drains tile k - 1: three pipelines (operand full / MMA done / accumulator free) on
 // mbarriers, no block-wide barrier after the prologue.
@@ -35,17 +38,16 @@
 #include "pfn_fused.cuh"
 
 #define P2_THREADS (17 * 32)
-#define P2_EPI_WARP0 8         // warps 8-15: epilogue (TMEM quarter = warp & 3, column half = (warp - 8) >> 2)
-#define P2_ISSUER_WARP 16
+#define P2_EPI_WARP0 8         // warps 8-15: epilogue (TMEM quarter = warp & 3, row half = (warp - 8) >> 2)
+#define P2_ISSUER_WARP 16      // (measured: 4 epilogue warps and 128 registers per thread: 1.60 ms vs 1.26 ms)
 #define P2_MC 64               // voxels per mini-chunk (the unit a producer warp fetches)
 #define P2_U0 32               // units of layer 0
 #define P2_K 64                // K of layer 1 = 2 * P2_U0
 #define P2_C0 16               // decorated input width, padded
 
 struct P2Meta {                // what the epilogue needs to know about one group
-    int32_t vid[32];           // output row of the voxel whose LAST row this lane holds, else -1
-    uint32_t flags[32];        // bit d: the lane may combine with lane - 2^d (same voxel)
-    uint32_t nsteps;           // scan steps the longest voxel of the group needs
+    int32_t vid[32];           // output row of the voxel whose LAST row is row k of the group, else -1
+    uint32_t lasts;            // bit k: row k is the last row of its voxel
     uint32_t done;             // the producer ran out of work: nothing to drain
     uint32_t pad[2];
 };
@@ -57,20 +59,29 @@ __device__ __forceinline__ bool p2_mbar_wait(uint32_t bar, uint32_t parity, vola
                                              unsigned int *diag, uint32_t tag)
 {
     uint32_t done;
-    long long t0 = 0;
-    for (uint32_t spins = 0;; ++spins) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return true;
+    // not there yet: sleep between polls (a spinning warp costs the other roles of the SM their issue
+    // slots: 41 % of all executed instructions in the first profile); the watchdog looks at the clock
+    // every 256 polls
+    const long long t0 = clock64();
+    for (uint32_t spins = 1;; ++spins) {
+        __nanosleep(100);
         asm volatile("{\n\t.reg .pred p;\n\t"
                      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return true;
-        if (*abort_flag) { if (blockIdx.x == diag[1]) diag[2 + (threadIdx.x >> 5)] = tag; return false; }
-        if (spins == 0) t0 = clock64();
-        else if ((spins & 63u) == 0 && clock64() - t0 > 400000000ll) {
-            if (atomicCAS(diag, 0u, tag) == 0u) diag[1] = blockIdx.x;      // first block to starve: its warps report where they wait
-            __threadfence();
-            *abort_flag = 1u;
-            if (blockIdx.x == diag[1]) diag[2 + (threadIdx.x >> 5)] = tag;
-            return false;
+        if ((spins & 255u) == 0) {
+            if (*abort_flag) { if (blockIdx.x == diag[1]) diag[2 + (threadIdx.x >> 5)] = tag; return false; }
+            if (clock64() - t0 > 400000000ll) {
+                if (atomicCAS(diag, 0u, tag) == 0u) diag[1] = blockIdx.x;      // first block to starve: its warps report where they wait
+                __threadfence();
+                *abort_flag = 1u;
+                if (blockIdx.x == diag[1]) diag[2 + (threadIdx.x >> 5)] = tag;
+                return false;
+            }
         }
     }
 }
@@ -112,9 +123,9 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
     extern __shared__ __align__(128) float smem[];
     const int N = a.n1;
     float *a_st = smem;                                    // [2 stages][hi | lo][128 x 64] canonical
-    float *b_hi = a_st + 2 * 2 * TC_M * P2_K;              // [N x 64] canonical
-    float *b_lo = b_hi + N * P2_K;
-    float *w0t = b_lo + N * P2_K;                          // [P2_C0][P2_U0]: layer-0 weight, transposed
+    float *b_hi = a_st + 2 * 2 * TC_M * P2_K;              // [128 x 64] canonical: layer-1 weight, units >= N are zero
+    float *b_lo = b_hi + TC_M * P2_K;
+    float *w0t = b_lo + TC_M * P2_K;                       // [P2_C0][P2_U0]: layer-0 weight, transposed
     float *bn0 = w0t + P2_C0 * P2_U0;                      // mean, invstd, gamma, beta: 4 x 32
     float *bn1 = bn0 + 4 * P2_U0;                          // 4 x N
     P2Meta *meta = reinterpret_cast<P2Meta *>(bn1 + 4 * N);   // [2 stages][2 parities][4 groups]
@@ -123,8 +134,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
     __shared__ uint32_t s_abort;
     unsigned int *diag = a.counter + 1;     // diagnostic word of the watchdog (0 = healthy)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint32_t ncols = 32;
-    while ((int)ncols < 2 * N) ncols <<= 1;
+    const uint32_t ncols = 256;                             // two accumulator stages x 128 rows (columns)
 
     // ---- prologue: weights, BatchNorm constants, barriers, TMEM ----
     if (warp == P2_ISSUER_WARP) {
@@ -142,11 +152,11 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
         s_abort = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int e = tid; e < N * P2_K; e += P2_THREADS) {     // linear.weight of layer 1 is [N, 64], K-major already
+    for (int e = tid; e < TC_M * P2_K; e += P2_THREADS) {  // linear.weight of layer 1 is [N, 64], K-major already
         const int r = e / P2_K, k = e - r * P2_K;
-        float hi, lo;
-        tc_split(__ldg(a.w1 + e), hi, lo);
-        const uint32_t o = tc_canon(r, k, N);
+        float hi = 0.0f, lo = 0.0f;
+        if (r < N) tc_split(__ldg(a.w1 + e), hi, lo);
+        const uint32_t o = tc_canon(r, k, TC_M);
         b_hi[o] = hi; b_lo[o] = lo;
     }
     for (int e = tid; e < P2_C0 * P2_U0; e += P2_THREADS) {
@@ -159,13 +169,14 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
         bn0[2 * P2_U0 + o] = a.gamma0[o];
         bn0[3 * P2_U0 + o] = a.beta0[o];
     }
+    // layer 1's BatchNorm is folded to one FMA per element, y = x * s + b with s = invstd * gamma and
+    // b = beta - mean * s: the GEMM in front of it is accurate to ~1e-6 (3xTF32), the fold moves y by ulps
     for (int o = tid; o < N; o += P2_THREADS) {
-        bn1[o] = a.mean1[o];
-        bn1[N + o] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(a.var1[o], a.eps)));
-        bn1[2 * N + o] = a.gamma1[o];
-        bn1[3 * N + o] = a.beta1[o];
+        const float sc = __fmul_rn(__fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(a.var1[o], a.eps))), a.gamma1[o]);
+        bn1[2 * o] = sc;
+        bn1[2 * o + 1] = __fsub_rn(a.beta1[o], __fmul_rn(a.mean1[o], sc));
     }
-    for (int o = tid; o < 16; o += P2_THREADS) { meta[o].nsteps = 0u; meta[o].done = 1u; }
+    for (int o = tid; o < 16; o += P2_THREADS) { meta[o].lasts = 0u; meta[o].done = 1u; }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -179,7 +190,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
         const int set = warp >> 2, g = warp & 3;
         float *a_hi = a_st + (size_t)set * 2 * TC_M * P2_K, *a_lo = a_hi + TC_M * P2_K;
         const uint32_t bar_full = tc_smem_u32(&s_full[set]), bar_mma = tc_smem_u32(&s_mma[set]);
-        const int T = a.t, C = a.c;
+        const int T = a.t, C = a.c, c0r = (a.c0 + 3) & ~3;
         // the warp's current mini-chunk: voxels [v_next, v_end) of frame b (mode 0: one "frame" of m voxels)
         int b = 0;
         uint32_t v_next = 0, v_end = 0;
@@ -187,6 +198,28 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
 #ifdef P2_DEBUG_ONE_SET
         if (set == 1) out_of_work = true;
 #endif
+        // record of the voxel this lane looks at in the next packing step, loaded one iteration ahead
+        int w_n = 0;
+        uint32_t w_kg = 0;
+        int4 w_co = make_int4(0, 0, 0, 0);
+        bool win_valid = false;
+        auto load_window = [&]() {
+            const uint32_t vi = v_next + lane;
+            w_n = 0; w_kg = 0; w_co = make_int4(0, 0, 0, 0);
+            if (vi < v_end) {
+                if (a.mode) {
+                    const size_t v = (size_t)b * a.fcap + vi;
+                    w_n = (int)min(__ldcs(a.vox_c + v), (uint32_t)T);
+                    w_kg = __ldcs(a.vox_kg + v);
+                    const uint32_t cell = __ldcs(a.vox_cell + v);
+                    const uint32_t x = cell % (uint32_t)a.nx, yz = cell / (uint32_t)a.nx;
+                    w_co = make_int4(b, (int)(yz / (uint32_t)a.ny), (int)(yz % (uint32_t)a.ny), (int)x);
+                } else {
+                    w_n = min(max(__ldg(a.num + vi), 0), T);
+                    w_co = __ldg(reinterpret_cast<const int4 *>(a.coors_in) + vi);
+                }
+            }
+        };
         for (uint32_t round = 0;; ++round) {
             if (round > 0) {
                 if (!p2_mbar_wait(bar_mma, (round - 1) & 1u, &s_abort, diag, 0x100u | (set << 4) | g | (round << 16))) break;   // the stage's previous tile has been consumed
@@ -204,6 +237,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                 const uint32_t cnt = a.mode ? (uint32_t)__ldg(a.voxel_counts + b) : (uint32_t)a.m;
                 v_next = r0;
                 v_end = min(cnt, r0 + P2_MC);
+                win_valid = false;
             }
             if (out_of_work) {
                 if (lane == 0) mt->done = 1u;
@@ -211,26 +245,15 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                 if (lane == 0) p2_mbar_arrive(bar_full);
                 continue;
             }
-            // ---- pack whole voxels into <= 32 rows: lane i looks at voxel v_next + i ----
+            // ---- pack whole voxels into <= 32 rows: lane i looks at voxel v_next + i (its record was
+            // requested at the end of the previous iteration, or just now after a chunk change) ----
+            if (!win_valid) load_window();
+            win_valid = false;
             const uint32_t vi = v_next + lane;
-            int n_i = 0;
-            uint32_t kg_i = 0, cell_i = 0;
-            int4 co_i = make_int4(0, 0, 0, 0);
-            int rows_i = 0;
-            if (vi < v_end) {
-                if (a.mode) {
-                    const size_t v = (size_t)b * a.fcap + vi;
-                    n_i = (int)min(__ldcs(a.vox_c + v), (uint32_t)T);
-                    kg_i = __ldcs(a.vox_kg + v);
-                    cell_i = __ldcs(a.vox_cell + v);
-                    const uint32_t x = cell_i % (uint32_t)a.nx, yz = cell_i / (uint32_t)a.nx;
-                    co_i = make_int4(b, (int)(yz / (uint32_t)a.ny), (int)(yz % (uint32_t)a.ny), (int)x);
-                } else {
-                    n_i = min(max(__ldg(a.num + vi), 0), T);
-                    co_i = __ldg(reinterpret_cast<const int4 *>(a.coors_in) + vi);
-                }
-                rows_i = n_i < T ? n_i + 1 : T;
-            }
+            const int n_i = w_n;
+            const uint32_t kg_i = w_kg;
+            const int4 co_i = w_co;
+            const int rows_i = vi < v_end ? (n_i < T ? n_i + 1 : T) : 0;
             int incl = rows_i;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -317,7 +340,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
             for (int u = 0; u < P2_U0; ++u) x0[u] = 0.0f;
 #pragma unroll
             for (int k = 0; k < P2_C0; ++k) {
-                if (k < a.c0) {
+                if (k < c0r) {                              // warp-uniform: whole groups of four inputs are skipped
                     const float4 *wr = reinterpret_cast<const float4 *>(w0t + k * P2_U0);
 #pragma unroll
                     for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
@@ -350,9 +373,11 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                 *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
             }
             mt->vid[lane] = seg_last ? vid_j : -1;
-            mt->flags[lane] = flags;
-            if (lane == 0) { mt->nsteps = nsteps; mt->done = 0u; }
+            const uint32_t lasts = __ballot_sync(0xffffffffu, seg_last);
+            if (lane == 0) { mt->lasts = lasts; mt->done = 0u; }
             v_next += (uint32_t)nv;
+            // (requesting the next group's records here, one hand-off ahead, measured SLOWER -- 1.34 vs 1.26 ms:
+            // at 96 registers per thread the extra live values spill)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> the tensor core's async proxy
             __syncwarp();
             if (lane == 0) p2_mbar_arrive(bar_full);
@@ -362,8 +387,8 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
         // ISSUER: the whole warp walks the pipeline (barrier waits are warp-wide, the warp stays
         // converged for the block barrier and the TMEM release at the end); lane 0 issues
         // =====================================================================================
-        const uint32_t idesc = tc_idesc_tf32(TC_M, N);
-        const uint32_t a_k = (TC_M / 8) * 128, b_k = (N / 8) * 128, mn = 128;
+        const uint32_t idesc = tc_idesc_tf32(TC_M, TC_M);     // D[unit (M = 128, padded), row (N = 128)]
+        const uint32_t a_k = (TC_M / 8) * 128, mn = 128;
         bool fin[2] = {false, false};
         for (uint32_t round = 0; !(fin[0] && fin[1]); ++round) {
             for (int s = 0; s < 2; ++s) {
@@ -394,15 +419,15 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                     // a plain release / acquire chain, independent of the tensor core's commit
                     p2_mbar_arrive(tc_smem_u32(&s_rec[s]));
                     const float *a_hi = a_st + (size_t)s * 2 * TC_M * P2_K, *a_lo = a_hi + TC_M * P2_K;
-                    const uint32_t d_tmem = tmem + (uint32_t)(s * N);
+                    const uint32_t d_tmem = tmem + (uint32_t)(s * TC_M);
 #pragma unroll 1
                     for (int ks = 0; ks < P2_K / 8; ++ks) {
-                        const uint32_t a_off = ks * 2 * a_k, b_off = ks * 2 * b_k;
-                        const unsigned long long dah = tc_desc(tc_smem_u32(a_hi) + a_off, a_k, mn), dal = tc_desc(tc_smem_u32(a_lo) + a_off, a_k, mn);
-                        const unsigned long long dbh = tc_desc(tc_smem_u32(b_hi) + b_off, b_k, mn), dbl = tc_desc(tc_smem_u32(b_lo) + b_off, b_k, mn);
-                        tc_mma_tf32(d_tmem, dal, dbh, idesc, ks > 0 ? 1u : 0u);     // small terms first
-                        tc_mma_tf32(d_tmem, dah, dbl, idesc, 1u);
-                        tc_mma_tf32(d_tmem, dah, dbh, idesc, 1u);
+                        const uint32_t off = ks * 2 * a_k;
+                        const unsigned long long dxh = tc_desc(tc_smem_u32(a_hi) + off, a_k, mn), dxl = tc_desc(tc_smem_u32(a_lo) + off, a_k, mn);
+                        const unsigned long long dwh = tc_desc(tc_smem_u32(b_hi) + off, a_k, mn), dwl = tc_desc(tc_smem_u32(b_lo) + off, a_k, mn);
+                        tc_mma_tf32(d_tmem, dwl, dxh, idesc, ks > 0 ? 1u : 0u);     // small terms first
+                        tc_mma_tf32(d_tmem, dwh, dxl, idesc, 1u);
+                        tc_mma_tf32(d_tmem, dwh, dxh, idesc, 1u);
                     }
                     tc_commit(tc_smem_u32(&s_mma[s]));      // operand stage free + accumulator ready, when the MMAs retire
                 }
@@ -414,7 +439,11 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
         // EPILOGUE warp e: TMEM lanes [32 e, 32 e + 32)
         // =====================================================================================
         const int e = warp & 3, half = (warp - P2_EPI_WARP0) >> 2;
-        const int n_chunks = N / 32, c_lo = half ? (n_chunks + 1) / 2 * 32 : 0, c_hi = half ? N : (n_chunks + 1) / 2 * 32;
+        const int unit = e * 32 + lane;
+        const bool has_units = e * 32 < N;                                   // warp-uniform
+        const float sc = unit < N ? bn1[2 * unit] : 0.0f, sh = unit < N ? bn1[2 * unit + 1] : 0.0f;
+        const bool neg = sc < 0.0f;                                          // relu(s x + b) decreases in x: track the minimum
+        const float neutral = neg ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
         bool fin[2] = {false, false};
         for (uint32_t round = 0; !(fin[0] && fin[1]); ++round) {
             for (int s = 0; s < 2; ++s) {
@@ -423,25 +452,20 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                 if (!p2_mbar_wait(tc_smem_u32(&s_mma[s]), round & 1u, &s_abort, diag, 0x400u | (s << 4) | (warp - P2_EPI_WARP0) | (round << 16))) { fin[0] = fin[1] = true; break; }
                 if (*reinterpret_cast<volatile uint32_t *>(&s_exit[s])) { fin[s] = true; continue; }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const P2Meta *mt = meta + ((s * 2 + (round & 1u)) * 4 + e);
-                const uint32_t done = *reinterpret_cast<const volatile uint32_t *>(&mt->done);
-                if (!done) {
-                    const int vid = mt->vid[lane];
-                    const uint32_t flags = mt->flags[lane], nsteps = min(mt->nsteps, 5u);
-                    for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
-                        float v[32];
-                        tc_ld_32x32(tmem + ((uint32_t)(e * 32) << 16) + (uint32_t)(s * N + c0), v);
+                for (int gg = 2 * half; gg < 2 * half + 2 && has_units; ++gg) {
+                    const P2Meta *mt = meta + ((s * 2 + (round & 1u)) * 4 + gg);
+                    if (*reinterpret_cast<const volatile uint32_t *>(&mt->done)) continue;
+                    const uint32_t lasts = mt->lasts;
+                    float v[32];
+                    tc_ld_32x32(tmem + ((uint32_t)(e * 32) << 16) + (uint32_t)(s * TC_M + gg * 32), v);
+                    float run = neutral;
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) {
-                            const int o = c0 + k;
-                            const float y = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v[k], bn1[o]), bn1[N + o]), bn1[2 * N + o]), bn1[3 * N + o]);
-                            v[k] = fmaxf(y, 0.0f);
-                        }
-                        p2_seg_max<32>(v, flags, nsteps);
-                        if (vid >= 0) {
-                            float4 *dst = reinterpret_cast<float4 *>(a.out + (size_t)vid * N + c0);
-#pragma unroll
-                            for (int k4 = 0; k4 < 8; ++k4) __stcs(dst + k4, make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]));
+                    for (int k = 0; k < 32; ++k) {
+                        run = neg ? fminf(run, v[k]) : fmaxf(run, v[k]);
+                        if ((lasts >> k) & 1u) {                             // warp-uniform: the voxel ends at row k
+                            const int vid = mt->vid[k];
+                            if (unit < N) __stcs(a.out + (size_t)vid * N + unit, fmaxf(__fmaf_rn(run, sc, sh), 0.0f));
+                            run = neutral;
                         }
                     }
                 }
@@ -470,7 +494,7 @@ bool pv_pfn_fused_supported(const pv_pfn_layer *layers, int n_layers, int t, int
 
 size_t pv_pfn_fused_smem(int n1)
 {
-    return sizeof(float) * (2 * 2 * (size_t)TC_M * P2_K + 2 * (size_t)n1 * P2_K + P2_C0 * P2_U0 + 4 * P2_U0 + 4 * (size_t)n1) +
+    return sizeof(float) * (2 * 2 * (size_t)TC_M * P2_K + 2 * (size_t)TC_M * P2_K + P2_C0 * P2_U0 + 4 * P2_U0 + 4 * (size_t)n1) +
            sizeof(P2Meta) * 16 + 128;
 }
 
