@@ -685,6 +685,25 @@ def main():
     e2e_ms = timed(e2e_step, e2e_steps, n_streams)
     e2e_wall = (time.perf_counter() - t0) * 1e3
     h2d, d2h = traffic
+    # copy-only floor: the SAME pinned buffers and streams, no kernels -- what the host link alone allows.
+    # The two directions are also timed on their own (they share the PCIe root complex of the box).
+    def copies(k, h2d_on=True, d2h_on=True):
+        io = ios[k % N_SETS]
+        if h2d_on:
+            io["d_points"].copy_(io["h_points"], non_blocking=True)
+            io["d_offsets"].copy_(io["h_offsets"], non_blocking=True)
+        if d2h_on:
+            vb = io["vb"]
+            io["h_counts"].copy_(vb.voxel_counts, non_blocking=True)
+            io["h_coors"].copy_(vb.coors, non_blocking=True)
+            io["h_num"].copy_(vb.num_points, non_blocking=True)
+            io["h_feats"].copy_(vb.mean_feats, non_blocking=True)
+            if io["h_canvas"] is not None:
+                io["h_canvas"].copy_(vb.canvas, non_blocking=True)
+    timed(copies, 4, n_streams)
+    copy_ms = timed(copies, e2e_steps, n_streams) / e2e_steps
+    h2d_ms = timed(lambda k: copies(k, True, False), e2e_steps, n_streams) / e2e_steps
+    d2h_ms = timed(lambda k: copies(k, False, True), e2e_steps, n_streams) / e2e_steps
     # fully synchronous variant (one step at a time, slices copied after reading the counts)
     t0 = time.perf_counter()
     for k in range(8):
@@ -724,13 +743,15 @@ def main():
             extra["ref_eager_gpu"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
 
     # ---- reduce over ranks: max time, sum of work ------------------------------------------
-    vec = torch.tensor([ms_total, e2e_ms, float(pts_done), float(e2e_pts), ms_single], dtype=torch.float64, device=dev)
+    vec = torch.tensor([ms_total, e2e_ms, float(pts_done), float(e2e_pts), ms_single, copy_ms, h2d_ms, d2h_ms],
+                       dtype=torch.float64, device=dev)
     if dist is not None:
         mx = vec.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vec.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms_total, e2e_ms, ms_single = float(mx[0]), float(mx[1]), float(mx[4])
+        copy_ms, h2d_ms, d2h_ms = float(mx[5]), float(mx[6]), float(mx[7])
         pts_all, e2e_pts_all = float(sm[2]), float(sm[3])
     else:
         pts_all, e2e_pts_all = float(pts_done), float(e2e_pts)
@@ -778,7 +799,13 @@ def main():
             "e2e": {"value": e2e_pts_all / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                     "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                     "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": e2e_wall / e2e_steps, "steps": e2e_steps,
-                    "streams": n_streams, "synchronous_ms_per_step": e2e_sync_ms},
+                    "streams": n_streams, "synchronous_ms_per_step": e2e_sync_ms,
+                    "copy_floor_ms_per_step": copy_ms,
+                    "copy_floor_note": "same pinned buffers and streams with the kernels removed (max over ranks): "
+                                       "the part of e2e.ms_per_step that belongs to the host link, not to this code",
+                    "h2d_only_ms_per_step": h2d_ms, "d2h_only_ms_per_step": d2h_ms,
+                    "h2d_GBps_per_rank": (h2d // e2e_steps) / (h2d_ms * 1e-3) / 1e9,
+                    "d2h_GBps_per_rank": (d2h // e2e_steps) / (d2h_ms * 1e-3) / 1e9},
             "gpu_launches": LAUNCHES_PER_STEP[pipeline] * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": (ach / peak) if ach else None, "traffic": traffic, "traffic_source": traffic_src,

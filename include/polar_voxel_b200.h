@@ -199,8 +199,11 @@ int pv_profile_mean_canvas(const pv_config *cfg, const float *points, const int3
  *   unq_inv      int32 [n]   or NULL       unq_cnt  int32 [M]  or NULL
  *   voxel_counts int32 [batch]  required   mean_feats f32 [M, C] or NULL
  *   canvas       f32 [batch, C, ny, nx] or NULL (pillar grids)
- * Direct-map grids only (<= 2^20 cells per frame: the pillar grids the dynamic configs use);
- * PV_ERR_UNSUPPORTED otherwise.  Integer outputs are bit-exact; means as in the list-free pipeline.
+ * Grids up to 2^26 cells per frame: direct maps (<= 2^20 cells, the pillar grids) keep the rows per cell,
+ * larger grids (the reference's 3-D cylinder grids of voxelnet_det_cylinder_singlehead.py /
+ * voxelnet_seg_cylinder.py: 1024 x 1024 x 40, 640 x 640 x 40) keep them in the hash map while the voxel
+ * order still comes from a cell-order occupancy bitmap (no canvas there); PV_ERR_UNSUPPORTED beyond.
+ * Integer outputs are bit-exact; means as in the list-free pipeline.
  */
 int pv_dynamic_voxelize(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
                         const int32_t *grid_ind_in, int32_t batch, int64_t n_total, int32_t c_in,
@@ -208,6 +211,12 @@ int pv_dynamic_voxelize(const pv_config *cfg, const float *points, const int32_t
                         void *workspace, size_t workspace_bytes, int32_t *grid_ind_out, int32_t *unq,
                         int32_t *unq_inv, int32_t *unq_cnt, int32_t *voxel_counts, float *mean_feats,
                         float *canvas, pv_stream_t stream);
+
+/* Binning only: the grid index of Voxelization.voxelize_dynamic (voxelization.py:169-172) with the batch
+ * column of collate_kitti, grid_ind_out int32 [n, 4] (b, z, y, x) = floor(clip((p - lo) / vs, 0, grid - 1))
+ * for every point -- on ANY grid (no map is built), no workspace. */
+int pv_dynamic_grid_ind(const pv_config *cfg, const float *points, const int32_t *frame_offsets, int32_t batch,
+                        int64_t n_total, int32_t c_in, int32_t is_cartesian, int32_t *grid_ind_out, pv_stream_t stream);
 
 /*
  * DynamicPFNet.forward (det3d/models/readers/pillar_encoder.py:262-411; PFNLayer.forward_dynamic :63-71)

@@ -103,6 +103,7 @@ EXPORTS = {
                                               P, SZ, P, P, P, P, P, P, I32, ctypes.POINTER(F32)]),
     "pv_dynamic_voxelize": (ctypes.c_int, [ctypes.POINTER(PvConfig), P, P, P, I32, I64, I32, I32, I64, I64, P, SZ,
                                            P, P, P, P, P, P, P, P]),
+    "pv_dynamic_grid_ind": (ctypes.c_int, [ctypes.POINTER(PvConfig), P, P, I32, I64, I32, I32, P, P]),
     "pv_dynamic_pfn_workspace_bytes": (SZ, [I64, I64]),
     "pv_dynamic_pfn": (ctypes.c_int, [P, P, P, P, P, I64, I64, I32, I32, I32, F32, F32, F32, F32,
                                       ctypes.POINTER(PvPfnLayer), I32, P, SZ, P, P]),

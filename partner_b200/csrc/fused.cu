@@ -303,7 +303,13 @@ __global__ void __launch_bounds__(PF_THREADS, PF_INSERT_MIN_BLOCKS) kf_insert(co
             }
             sa = s;
         } else if (DYN) {
-            s = (uint32_t)b * f.capf + cell;
+            if (DENSE) s = (uint32_t)b * f.capf + cell;
+            else {                                               // 3-D grids: rows live in the hash map, the bitmap stays in cell order
+                const uint32_t h = pf_claim(f.keys + (size_t)b * f.capf, f.capf - 1, cell,
+                                          pv_slot_home(cx, cy, cz, nx, ny, f.capf - 1), p.ws.ctrl + 1);
+                if (h == PV_INF) continue;
+                s = (uint32_t)b * f.capf + h;
+            }
             sa = (uint32_t)b * (f.wcap * 32u) + cell;            // bit address in the occupancy bitmap
         } else if (DENSE) {
             // direct map, PHI FASTEST: consecutive points of a LiDAR ring are azimuth neighbours, so
@@ -1382,6 +1388,43 @@ __global__ void __launch_bounds__(256) kf_dyn_finalize(const __grid_constant__ P
     }
 }
 
+// The same for hash-map grids: one thread per map slot; the voxel's row = popcount prefix of its CELL in
+// the cell-order bitmap (so rows are still in torch.unique order), its sums sit in the slot's row.
+template <int NV, int CC>
+__global__ void __launch_bounds__(256) kf_dyn_finalize_hash(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
+{
+    constexpr int CT = NV * 4;
+    pf_pdl_trigger();
+    pf_pdl_wait();
+    const int C = CC ? CC : p.C;
+    const int b = blockIdx.y;
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= f.capf) return;
+    const uint32_t s = (uint32_t)b * f.capf + l;
+    const uint32_t cell = __ldcs(f.keys + s);
+    if (cell == PV_INF) return;
+    const uint2 wv = __ldg(f.wb + (size_t)b * f.wcap + (cell >> 5));
+    const uint32_t rank = wv.x + __popc(wv.y & ((1u << (cell & 31u)) - 1u));
+    const int32_t vid = __ldg(f.base + b) + (int32_t)rank;
+    float *rowp = f.acc + (size_t)s * f.rowf;
+    float r[CT];
+    pf_ld_row<NV>(rowp, r);
+    float cntf = 0.0f;
+#pragma unroll
+    for (int k = 0; k < CT; ++k) cntf = k == C ? r[k] : cntf;
+    const uint32_t nx = p.grid[0], ny = p.grid[1];
+    const uint32_t x = cell % nx, yz = cell / nx, cz = yz / ny, cy = yz - cz * ny;
+    reinterpret_cast<int4 *>(p.coors)[vid] = make_int4(b, (int)cz, (int)cy, (int)x);   // unq row
+    if (p.num_points) p.num_points[vid] = (int32_t)cntf;                               // unq_cnt
+    const float inv = __frcp_rn(cntf);
+    float mean[CT];
+#pragma unroll
+    for (int k = 0; k < CT; ++k) mean[k] = k < C ? pv_div_count(r[k], cntf, inv) : 0.0f;   // scatter_mean: sum / count
+    if (p.feats) pv_store_feats<CT>(p.feats, vid, C, mean);
+    pf_st_row_clean<NV>(rowp, 0.0f);
+    f.keys[s] = PV_INF;
+}
+
 // unq_inv[i] = row of point i's voxel (torch.unique's return_inverse)
 __global__ void __launch_bounds__(PF_THREADS) kf_dyn_inverse(const __grid_constant__ PvParams p, const __grid_constant__ PvF f)
 {
@@ -1402,6 +1445,32 @@ __global__ void __launch_bounds__(PF_THREADS) kf_dyn_inverse(const __grid_consta
         }
         p.unq_inv[i] = v;
     }
+}
+
+// Binning only (Voxelization.voxelize_dynamic, voxelization.py:169-172, + the batch column of collate):
+// grid_ind[i] = (b, z, y, x) = floor(clip((p - lo) / vs, 0, grid - 1)) for EVERY point, on any grid --
+// no map, no bitmap, so the 3-D Waymo grid (94 M cells) is as good as a pillar grid.
+__global__ void __launch_bounds__(256) kf_dyn_grid_ind(const __grid_constant__ PvParams p)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    float v[PV_MAX_CHANNELS];
+    pv_feature_row(p.pts, i, p.c_in, p.cart, v);
+    const int b = pv_frame_of(p.offsets, p.B, i);
+    float c[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float q = pv_bin(v[d], p.lo[d], p.vs[d], p.inv_vs[d]);       // floor of the IEEE quotient
+        c[d] = fminf(fmaxf(q, 0.0f), p.gridf[d] - 1.0f);                   // clip (NaN -> 0)
+    }
+    reinterpret_cast<int4 *>(p.grid_ind)[i] = make_int4(b, (int)c[2], (int)c[1], (int)c[0]);
+}
+
+int pvf_run_grid_ind(PvParams &p, cudaStream_t st)
+{
+    if (p.n == 0) return PV_OK;
+    kf_dyn_grid_ind<<<(p.n + 255) / 256, 256, 0, st>>>(p);
+    return pv_last_cuda_error();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1433,7 +1502,11 @@ int pvf_make_layout(const pv_config *cfg, int64_t n_cap, int32_t batch, int64_t 
     w->capf = (uint32_t)capf;
     w->dense = dense ? 1u : 0u;
     // bitmap words per frame: one bit per point (static path) or per cell (dynamic path, direct maps)
-    const size_t bit_items = dense && capf > fcap ? (size_t)capf : fcap;
+    // dynamic voxelization keeps a CELL-order occupancy bitmap: direct maps always, hash-map grids up to
+    // PV_DYN_MAX_CELLS cells per frame (the reference's 3-D cylinder grids: 640 x 640 x 40, 1024 x 1024 x 40)
+    const bool dyn_cells = dense || cells <= PV_DYN_MAX_CELLS;
+    w->dyn_ok = dyn_cells ? 1u : 0u;
+    const size_t bit_items = dyn_cells && cells > fcap ? (size_t)cells : fcap;
     w->wcap = (uint32_t)(((bit_items + 31) / 32 + 3) / 4 * 4);
     w->rowf_cap = (uint32_t)((max_channels + 1 + 3) / 4 * 4);
     w->rowf = w->rowf_cap;
@@ -1605,6 +1678,23 @@ int pvf_insert_lists(PvParams &p, PvF &f, cudaStream_t st)
     return p.ws.dense ? pf_dispatch_insert_lists<true>(p, f, st) : pf_dispatch_insert_lists<false>(p, f, st);
 }
 
+static int pf_dispatch_insert_dyn_hash(const PvParams &p, const PvF &f, cudaStream_t st)
+{
+    switch ((int)f.rowf / 4) {
+    case 1: return pf_launch_insert<false, 0, false, 1, PF_MODE_DYN>(p, f, st);
+    case 2: return pf_launch_insert<false, 0, false, 2, PF_MODE_DYN>(p, f, st);
+    case 3: return pf_launch_insert<false, 0, false, 3, PF_MODE_DYN>(p, f, st);
+    case 4: return pf_launch_insert<false, 0, false, 4, PF_MODE_DYN>(p, f, st);
+    default: return pf_launch_insert<false, 0, false, 5, PF_MODE_DYN>(p, f, st);
+    }
+}
+
+template <int NV>
+static int pf_launch_dyn_finalize_hash(const PvParams &p, const PvF &f, cudaStream_t st)
+{
+    return pf_launch_pdl(kf_dyn_finalize_hash<NV, 0>, dim3((f.capf + 255) / 256, (unsigned)p.B), dim3(256), 0, st, p, f);
+}
+
 static int pf_dispatch_insert_dyn(const PvParams &p, const PvF &f, cudaStream_t st)
 {
     if (p.cart && p.c_in == 5) return pf_launch_insert<true, 5, true, 2, PF_MODE_DYN>(p, f, st);
@@ -1631,8 +1721,31 @@ int pvf_run_dynamic(PvParams &p, PvF &f, cudaStream_t st)
 {
     f.rowf = (uint32_t)((p.C + 1 + 3) / 4 * 4);
     if (f.rowf > f.rowf_cap) return PV_ERR_WORKSPACE;
-    if (!f.dense || (unsigned)p.grid[1] * (unsigned)p.grid[2] > 65535u || p.B > 65535) return PV_ERR_UNSUPPORTED;
+    if (!f.dyn_ok || p.B > 65535) return PV_ERR_UNSUPPORTED;            // more than PV_DYN_MAX_CELLS cells per frame
     if ((unsigned long long)p.B * f.wcap * 32ull >= 0xFFFFFF00ull) return PV_ERR_BAD_ARGUMENT;   // bit addresses are 32-bit
+    if (!f.dense) {
+        // 3-D cylinder grids (voxelnet_det_cylinder_singlehead.py, voxelnet_seg_cylinder.py): rows in the hash
+        // map, voxel order from the cell-order bitmap; no dense canvas on these grids
+        if (p.canvas) return PV_ERR_BAD_CONFIG;
+        if (p.n > 0) {
+            const int rc = pf_dispatch_insert_dyn_hash(p, f, st);
+            if (rc) return rc;
+        }
+        if (pf_launch_pdl(kf_scan, dim3((unsigned)p.B), dim3(PF_SCAN_THREADS), 0, st, p, f)) return PV_ERR_CUDA;
+        int rc;
+        switch ((int)f.rowf / 4) {
+        case 1: rc = pf_launch_dyn_finalize_hash<1>(p, f, st); break;
+        case 2: rc = pf_launch_dyn_finalize_hash<2>(p, f, st); break;
+        case 3: rc = pf_launch_dyn_finalize_hash<3>(p, f, st); break;
+        case 4: rc = pf_launch_dyn_finalize_hash<4>(p, f, st); break;
+        default: rc = pf_launch_dyn_finalize_hash<5>(p, f, st); break;
+        }
+        if (rc) return rc;
+        if (p.unq_inv && p.n > 0 &&
+            pf_launch_pdl(kf_dyn_inverse, dim3((p.n + PF_TILE - 1) / PF_TILE), dim3(PF_THREADS), 0, st, p, f)) return PV_ERR_CUDA;
+        return pv_last_cuda_error();
+    }
+    if ((unsigned)p.grid[1] * (unsigned)p.grid[2] > 65535u) return PV_ERR_UNSUPPORTED;
     if (p.n > 0) {
         const int rc = pf_dispatch_insert_dyn(p, f, st);
         if (rc) return rc;

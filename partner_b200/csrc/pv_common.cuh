@@ -7,6 +7,7 @@
 
 #define PV_INF 0xFFFFFFFFu
 #define PV_DENSE_MAX_CELLS (1u << 20)  // grids up to this many cells/frame use a direct map
+#define PV_DYN_MAX_CELLS (1u << 26)    // dynamic voxelization: cell-order bitmap up to this many cells/frame
 
 // One voxel-map entry (one per grid cell in dense mode, one per hash slot otherwise).
 // CLEAN state = all bits set.  The workspace is self-cleaning: k_cell_flags, the only reader,
@@ -69,6 +70,7 @@ struct PvF {
     uint32_t rowf_cap;     // floats per accumulator row the workspace was sized for
     uint32_t rowf;         // floats per row in THIS call: C + 1 rounded up to 4
     uint32_t dense;
+    uint32_t dyn_ok;       // the bitmap covers every cell of a frame: dynamic voxelization available
     uint32_t hmax;
     uint32_t max_chunks;
     size_t total_bytes;
@@ -332,4 +334,5 @@ int pvf_init(const PvF &f, int32_t batch, int64_t n_cap, cudaStream_t st);
 // list-free front end; ev (optional) = PV_PROFILE_STAGES + 1 events recorded at the stage boundaries
 int pvf_run(PvParams &p, PvF &f, cudaStream_t st, cudaEvent_t *ev);
 int pvf_run_dynamic(PvParams &p, PvF &f, cudaStream_t st);
+int pvf_run_grid_ind(PvParams &p, cudaStream_t st);           // binning only: p.grid_ind [n, 4]
 int pvf_insert_lists(PvParams &p, PvF &f, cudaStream_t st);     // binning front end of the list-based pipeline

@@ -1052,6 +1052,28 @@ int pv_forward_pfn_canvas(const pv_config *cfg, const float *points, const int32
                           reinterpret_cast<char *>(aux_workspace) + 256, canvas, st);
 }
 
+int pv_dynamic_grid_ind(const pv_config *cfg, const float *points, const int32_t *frame_offsets, int32_t batch,
+                        int64_t n_total, int32_t c_in, int32_t is_cartesian, int32_t *grid_ind_out, pv_stream_t stream)
+{
+    int rc = pv_check_config(cfg);
+    if (rc) return rc;
+    if (!frame_offsets || !grid_ind_out || batch <= 0 || n_total < 0 || n_total >= (1ll << 31) || (!points && n_total > 0))
+        return PV_ERR_BAD_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(grid_ind_out) & 15u) != 0) return PV_ERR_BAD_ARGUMENT;
+    const int C = is_cartesian ? c_in + 2 : c_in;
+    if (c_in < 3 || C > PV_MAX_CHANNELS) return PV_ERR_BAD_ARGUMENT;
+    PvParams p = {};
+    for (int j = 0; j < 3; ++j) {
+        p.lo[j] = cfg->lo[j]; p.vs[j] = cfg->vs[j]; p.grid[j] = cfg->grid[j];
+        p.gridf[j] = (float)cfg->grid[j];
+        p.inv_vs[j] = 1.0f / cfg->vs[j];
+    }
+    p.pts = points; p.offsets = frame_offsets; p.B = batch; p.n = (uint32_t)n_total;
+    p.c_in = c_in; p.cart = is_cartesian ? 1 : 0; p.C = C;
+    p.grid_ind = grid_ind_out;
+    return pvf_run_grid_ind(p, (cudaStream_t)stream);
+}
+
 int pv_read_status(const void *workspace, pv_stream_t stream)
 {
     if (!workspace) return PV_ERR_BAD_ARGUMENT;

@@ -277,6 +277,19 @@ def dynamic_voxelize(cfg, points, frame_offsets, batch, frame_capacity, is_carte
     return r
 
 
+def dynamic_grid_ind(cfg, points, frame_offsets, batch, is_cartesian=False):
+    """pv_dynamic_grid_ind: [N, 4] int32 (b, z, y, x) clamped grid index of every point, on any grid."""
+    _need(points, torch.float32, "points", 2)
+    _need(frame_offsets, torch.int32, "frame_offsets", 1)
+    if frame_offsets.numel() != batch + 1:
+        raise ValueError("frame_offsets must have batch+1 entries")
+    n, c_in = points.shape
+    gi = torch.empty((max(n, 1), 4), dtype=torch.int32, device=points.device)
+    check(_lib.load().pv_dynamic_grid_ind(cfg, ptr(points), ptr(frame_offsets), batch, n, c_in, 1 if is_cartesian else 0,
+                                          ptr(gi), current_stream(points.device)), "pv_dynamic_grid_ind")
+    return gi[:n]
+
+
 def dynamic_pfn(points, batch, m, weights, vx, vy, x_off, y_off, cylinder, xyz_cluster, raz_cluster, xy_center,
                 ra_center):
     """pv_dynamic_pfn on a DynamicBatch (`batch`) with `m` valid voxel rows; weights: list of [U, K] CUDA f32."""

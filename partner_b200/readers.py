@@ -147,8 +147,10 @@ def _dynamic_from_grid_ind(features, grid_ind, grid_size, batch_size, want_inver
             grid_size = (mx[3] + 1, mx[2] + 1, mx[1] + 1)
     nx, ny, nz = (int(v) for v in grid_size)
     cfg, _, _, _ = F.make_config([1.0, 1.0, 1.0], [0.0, 0.0, 0.0, float(nx), float(ny), float(nz)], 1, 1)
-    return F.dynamic_voxelize(cfg, features.contiguous(), None, int(batch_size), 0, False, grid_ind=gi,
-                              want_inverse=want_inverse)
+    r = F.dynamic_voxelize(cfg, features.contiguous(), None, int(batch_size), 0, False, grid_ind=gi,
+                           want_inverse=want_inverse)
+    F.read_status(r)      # a row outside grid_size / batch_size raises instead of silently dropping out of the means
+    return r              # (torch.unique keeps every row); the readers synchronise on the voxel count anyway
 
 
 @READERS.register_module

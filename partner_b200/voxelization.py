@@ -123,10 +123,9 @@ class Voxelization(object):
         n = points.shape[0]
         dev = torch.device("cuda", torch.cuda.current_device())
         off = torch.tensor([0, n], dtype=torch.int32, device=dev)
-        r = F.dynamic_voxelize(vg._cfg, torch.from_numpy(points).to(dev), off, 1, n, False, want_inverse=False,
-                               want_counts=False, want_grid_ind=True, want_mean=False)
-        F.read_status(r)
-        pc_grid_ind = F.to_numpy(r.grid_ind[:, 1:].contiguous())[0].astype(np.int64)   # (z, y, x), np.int of the reference
+        # only the clamped grid index is needed here (:169-172): the binning-only kernel, any grid size
+        gi = F.dynamic_grid_ind(vg._cfg, torch.from_numpy(points).to(dev), off, 1, False)
+        pc_grid_ind = F.to_numpy(gi[:, 1:].contiguous())[0].astype(np.int64)           # (z, y, x), np.int of the reference
         res["lidar"]["voxels"] = dict(grid_ind=pc_grid_ind.copy(), shape=vg.grid_size, range=vg.point_cloud_range,
                                       size=vg.voxel_size)
         if ("seg" in self.super_tasks) and kwargs.get("seg", True):

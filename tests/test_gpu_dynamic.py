@@ -116,7 +116,7 @@ def test_dynamic_rejects_bad_rows_and_large_grids():
     assert r.unq_inv.cpu().tolist() == [0, -1, 1]
     with pytest.raises(ValueError):
         F.read_status(r)
-    big, _ = _cfg("WAYMO-PARTNER")                         # 1152 x 2048 x 40 cells: no direct map
+    big, _ = _cfg("WAYMO-PARTNER")                         # 1152 x 2048 x 40 = 94 M cells: beyond the 2^26-cell bitmap
     with pytest.raises(ValueError):
         F.dynamic_voxelize(big, pts, torch.tensor([0, 3], dtype=torch.int32).cuda(), 1, 3, False)
 
@@ -297,3 +297,61 @@ def test_voxelization_sweep_streaming_bidirectional_vs_oracle():
         assert got.shape == rp.shape
         assert np.allclose(got, rp, rtol=1e-6, atol=2e-5)          # float64 warp / cos / sin: last-bit differences
         assert (cur["lidar"]["voxels"]["grid_ind"] != gi).sum() <= 2   # a warped coordinate within an ulp of a bin edge
+
+
+@pytest.mark.parametrize("tag,vs", [("NUSC-CYL 1024x1024x40", [0.049, 0.00615, 0.2]),
+                                    ("seg cylinder 640x640x40", [0.0784, 0.00984, 0.2])])
+def test_dynamic_voxelize_on_3d_cylinder_grids(tag, vs):
+    """The reference's dynamic=True configs on 3-D cylinder grids (voxelnet_det_cylinder_singlehead.py:8-18,68-74:
+    1024 x 1024 x 40; voxelnet_seg_cylinder.py: 640 x 640 x 40) -- tens of millions of cells per frame, so the
+    rows live in the hash map while the torch.unique order still comes from the cell-order bitmap.  Two full
+    nuScenes frames (fused Cartesian input) + the drop-in DynamicVoxelEncoderV1 on a caller-made grid_ind,
+    twice on the same workspace; integers bit-exact vs the oracle."""
+    import torch
+    from partner_b200 import DynamicVoxelEncoderV1
+    from partner_b200 import functional as F
+    rng = [0.3, -3.1488, -5.0, 50.476, 3.1488, 3.0]
+    cfg, _, _, grid = F.make_config(vs, rng, 30, 120000)
+    assert int(grid[0]) * int(grid[1]) * int(grid[2]) > (1 << 20)
+    frames = synth.make_batch("nusc", 2, 2)
+    sizes = [f.shape[0] for f in frames]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    polars = [oracle.transform_points(f) for f in frames]
+    gi = np.concatenate([np.pad(oracle.dynamic_grid_ind(p, vs, rng), ((0, 0), (1, 0)), constant_values=b)
+                         for b, p in enumerate(polars)])
+    mean, unq, inv, cnt = oracle.dynamic_mean(gi, np.concatenate(polars))
+    pts = torch.from_numpy(np.concatenate(frames)).cuda()
+    for _ in range(2):
+        r = F.dynamic_voxelize(cfg, pts, torch.from_numpy(off).cuda(), len(frames), max(sizes), True, want_grid_ind=True)
+        F.read_status(r)
+        m = r.total()
+        assert m == unq.shape[0], tag
+        assert np.array_equal(r.grid_ind.cpu().numpy(), gi)
+        assert np.array_equal(r.unq[:m].cpu().numpy(), unq)
+        assert np.array_equal(r.unq_inv.cpu().numpy(), inv)
+        assert np.array_equal(r.unq_cnt[:m].cpu().numpy(), cnt)
+        assert_close_fp32(r.mean_feats[:m].cpu().numpy(), mean, "features")
+    # binning only (Voxelization.voxelize_dynamic): any grid, no map
+    gi_dev = F.dynamic_grid_ind(cfg, pts, torch.from_numpy(off).cuda(), len(frames), True)
+    assert np.array_equal(gi_dev.cpu().numpy(), gi)
+    # drop-in reader on the reference's dict (grid_ind made by the caller), grid size given or inferred
+    polar_dev = torch.from_numpy(np.concatenate(polars)).cuda()
+    for gs in ((int(grid[0]), int(grid[1]), int(grid[2])), None):
+        enc = DynamicVoxelEncoderV1(num_input_features=7, grid_size=gs, batch_size=2 if gs else None)
+        feats, u = enc(dict(points=polar_dev, grid_ind=torch.from_numpy(gi).cuda().long()))
+        assert np.array_equal(u.cpu().numpy(), unq)
+        assert_close_fp32(feats.cpu().numpy(), mean, "DynamicVoxelEncoderV1 features")
+
+
+def test_dynamic_grid_ind_on_the_waymo_grid():
+    """Binning only works where no map fits at all: the 1152 x 2048 x 40 Waymo grid (94 M cells)."""
+    import torch
+    from partner_b200 import functional as F
+    g = synth.GRIDS["WAYMO-PARTNER"]
+    cfg, _, _, _ = F.make_config(g["voxel_size"], g["range"], g["max_points"], g["max_voxels"])
+    f = synth.waymo_frame(77, nsweeps=1, time_column=True)
+    polar = oracle.transform_points(f)
+    ref = np.pad(oracle.dynamic_grid_ind(polar, g["voxel_size"], g["range"]), ((0, 0), (1, 0)))
+    off = torch.tensor([0, f.shape[0]], dtype=torch.int32).cuda()
+    assert np.array_equal(F.dynamic_grid_ind(cfg, torch.from_numpy(f).cuda(), off, 1, True).cpu().numpy(), ref)
+    assert np.array_equal(F.dynamic_grid_ind(cfg, torch.from_numpy(polar).cuda(), off, 1, False).cpu().numpy(), ref)
