@@ -313,6 +313,25 @@ int pv_pfn_forward(const float *voxels, const int32_t *num_points, const int32_t
                    float y_off, const pv_pfn_layer *layers, int32_t n_layers, float eps,
                    void *workspace, size_t workspace_bytes, float *out, pv_stream_t stream);
 
+/* PillarFeatureNet in TRAINING mode (pillar_encoder.py:37-38,49-61 with self.norm in training mode, and the
+ * backward pass torch.autograd derives from it).  BatchNorm1d uses the batch statistics over ALL m * t rows,
+ * padded slots included, and updates running_mean / running_var IN PLACE through layers[l].bn_mean / bn_var
+ * (momentum `momentum`, unbiased variance); the maximum runs over all t slots.
+ *   forward : out [m, units of the last layer]; everything the backward pass needs stays in `workspace`
+ *             (pv_pfn_train_workspace_bytes), which the caller keeps until pv_pfn_train_backward.
+ *   backward: d_out [m, units of last layer] -> d_weight[l] [units, in_channels], d_gamma[l], d_beta[l] [units]
+ *             (HOST arrays of device pointers, overwritten).  No gradient flows to the point features.
+ * Units must divide 256; `layers` is a HOST array (same layout as pv_pfn_forward). */
+size_t pv_pfn_train_workspace_bytes(int64_t m, int32_t t, int32_t c, int32_t with_distance, const pv_pfn_layer *layers,
+                                    int32_t n_layers);
+int pv_pfn_train_forward(const float *voxels, const int32_t *num_points, const int32_t *coors, int64_t m, int32_t t,
+                         int32_t c, int32_t with_distance, float vx, float vy, float x_off, float y_off,
+                         const pv_pfn_layer *layers, int32_t n_layers, float eps, float momentum, void *workspace,
+                         size_t workspace_bytes, float *out, pv_stream_t stream);
+int pv_pfn_train_backward(const float *d_out, int64_t m, int32_t t, int32_t c, int32_t with_distance,
+                          const pv_pfn_layer *layers, int32_t n_layers, void *workspace, size_t workspace_bytes,
+                          float *const *d_weight, float *const *d_gamma, float *const *d_beta, pv_stream_t stream);
+
 /* Scratch bytes pv_pfn_forward needs for m voxels of t slots (per-voxel statistics and, for
  * two-layer nets whose second layer runs on tcgen05, the layer-0 rows). */
 size_t pv_pfn_workspace_bytes(int64_t m, int32_t t);

@@ -118,6 +118,11 @@ EXPORTS = {
     "pv_pfn_forward": (ctypes.c_int, [P, P, P, I64, I32, I32, I32, F32, F32, F32, F32,
                                       ctypes.POINTER(PvPfnLayer), I32, F32, P, SZ, P, P]),
     "pv_pfn_workspace_bytes": (SZ, [I64, I32]),
+    "pv_pfn_train_workspace_bytes": (SZ, [I64, I32, I32, I32, ctypes.POINTER(PvPfnLayer), I32]),
+    "pv_pfn_train_forward": (ctypes.c_int, [P, P, P, I64, I32, I32, I32, F32, F32, F32, F32, ctypes.POINTER(PvPfnLayer), I32,
+                                            F32, F32, P, SZ, P, P]),
+    "pv_pfn_train_backward": (ctypes.c_int, [P, I64, I32, I32, I32, ctypes.POINTER(PvPfnLayer), I32, P, SZ,
+                                             ctypes.POINTER(P), ctypes.POINTER(P), ctypes.POINTER(P), P]),
     "pv_tc_gemm_tf32x3": (ctypes.c_int, [P, P, I32, I32, I32, P, I32, P]),
     "pv_scatter_workspace_bytes": (SZ, [I32, I32, I32]),
     "pv_scatter": (ctypes.c_int, [P, P, I64, I32, I32, I32, I32, P, SZ, P, P, P]),

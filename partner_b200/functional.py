@@ -456,6 +456,45 @@ def pfn_forward(features, num_voxels, coors, layers, vx, vy, x_off, y_off, with_
     return out
 
 
+def pfn_train_forward(features, num_voxels, coors, layers, vx, vy, x_off, y_off, with_distance, eps, momentum):
+    """pv_pfn_train_forward.  layers as for pfn_forward (running_mean / running_var are UPDATED in place).
+    Returns (out [M, U], saved) where ``saved`` holds what pfn_train_backward needs."""
+    _need(features, torch.float32, "features", 3)
+    _need(num_voxels, torch.int32, "num_voxels", 1)
+    _need(coors, torch.int32, "coors", 2)
+    m, t, c = features.shape
+    if coors.shape != (m, 4) or num_voxels.numel() != m:
+        raise ValueError("coors must be [M,4] and num_voxels [M]")
+    arr = _pfn_layer_array(layers)
+    lib = _lib.load()
+    nbytes = lib.pv_pfn_train_workspace_bytes(m, t, c, 1 if with_distance else 0, arr, len(layers))
+    if nbytes == 0:
+        raise ValueError("PFN training kernels: unsupported layer shapes (units must divide 256)")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=features.device)      # lives until the backward pass
+    out = torch.empty((m, layers[-1][0].shape[0]), dtype=torch.float32, device=features.device)
+    check(lib.pv_pfn_train_forward(ptr(features), ptr(num_voxels), ptr(coors), m, t, c, 1 if with_distance else 0,
+                                   vx, vy, x_off, y_off, arr, len(layers), eps, momentum, ptr(ws), ws.numel(), ptr(out),
+                                   current_stream(features.device)), "pv_pfn_train_forward")
+    return out, (ws, m, t, c, bool(with_distance))
+
+
+def pfn_train_backward(d_out, saved, layers):
+    """pv_pfn_train_backward -> lists (d_weight, d_gamma, d_beta), one entry per layer."""
+    import ctypes
+    ws, m, t, c, with_distance = saved
+    _need(d_out, torch.float32, "d_out", 2)
+    arr = _pfn_layer_array(layers)
+    dev = d_out.device
+    dw = [torch.empty_like(l[0]) for l in layers]
+    dg = [torch.empty_like(l[3]) for l in layers]
+    db = [torch.empty_like(l[4]) for l in layers]
+    vec = lambda ts: (ctypes.c_void_p * len(ts))(*[x.data_ptr() for x in ts])      # noqa: E731
+    check(_lib.load().pv_pfn_train_backward(ptr(d_out), m, t, c, 1 if with_distance else 0, arr, len(layers), ptr(ws),
+                                            ws.numel(), vec(dw), vec(dg), vec(db), current_stream(dev)),
+          "pv_pfn_train_backward")
+    return dw, dg, db
+
+
 def scatter(voxel_features, coords, batch_size, ny, nx, want_bev_index=False):
     _need(voxel_features, torch.float32, "voxel_features", 2)
     _need(coords, torch.int32, "coords", 2)

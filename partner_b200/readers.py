@@ -5,8 +5,8 @@ det3d/models/readers/voxel_encoder.py:7-22 and det3d/models/readers/pillar_encod
 reference configs (``type="PillarFeatureNet"`` ...) and checkpoints
 (``reader.pfn_layers.{i}.linear.weight``, ``...norm.{weight,bias,running_mean,running_var}``)
 load unchanged.  Forward runs the CUDA kernels; there is no eager-PyTorch or CPU fallback.
-Training-mode batch statistics are a "next" row: forward() in training
-mode raises instead of silently using running statistics.
+PillarFeatureNet also trains: in ``.train()`` mode forward() uses batch statistics over all padded
+rows and is differentiable with respect to its parameters (pv_pfn_train_forward / _backward).
 """
 import torch
 from torch import nn
@@ -81,8 +81,7 @@ class PillarFeatureNet(nn.Module):
 
     def forward(self, features, num_voxels, coors):
         if self.training:
-            raise RuntimeError("PillarFeatureNet (B200 kernels) implements eval-mode BatchNorm only; "
-                               "call .eval() first")
+            return self._forward_train(features, num_voxels, coors)
         eps = {l.norm.eps for l in self.pfn_layers}
         if len(eps) != 1:
             raise ValueError("all PFN layers must share one BatchNorm eps")
@@ -92,6 +91,46 @@ class PillarFeatureNet(nn.Module):
                             layers, self.vx, self.vy, self.x_offset, self.y_offset,
                             self._with_distance, eps.pop())
         return out.squeeze()                      # pillar_encoder.py:169 (M == 1 collapses)
+
+
+    def _forward_train(self, features, num_voxels, coors):
+        """Training mode (pillar_encoder.py:49-61 with the norm in training mode): batch statistics over all
+        M * T rows, running statistics updated in place, gradients for linear.weight / norm.weight / norm.bias
+        through ``pv_pfn_train_backward`` (torch.autograd.Function, no eager fallback)."""
+        eps = {l.norm.eps for l in self.pfn_layers}
+        mom = {l.norm.momentum for l in self.pfn_layers}
+        if len(eps) != 1 or len(mom) != 1:
+            raise ValueError("all PFN layers must share one BatchNorm eps / momentum")
+        params = []
+        for l in self.pfn_layers:
+            params += [l.linear.weight, l.norm.weight, l.norm.bias]
+        out = _PfnTrain.apply(self, features.contiguous(), _as_i32(num_voxels),
+                              coors if coors.dtype == torch.int32 else coors.int(), eps.pop(), mom.pop(), *params)
+        with torch.no_grad():
+            for l in self.pfn_layers:
+                l.norm.num_batches_tracked += 1
+        return out.squeeze()
+
+
+class _PfnTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net, features, num_voxels, coors, eps, momentum, *params):
+        layers = [(params[3 * i].detach().contiguous(), l.norm.running_mean, l.norm.running_var,
+                   params[3 * i + 1].detach().contiguous(), params[3 * i + 2].detach().contiguous())
+                  for i, l in enumerate(net.pfn_layers)]
+        out, saved = F.pfn_train_forward(features, num_voxels, coors, layers, net.vx, net.vy, net.x_offset, net.y_offset,
+                                         net._with_distance, eps, momentum)
+        ctx.saved, ctx.layers = saved, layers
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        dw, dg, db = F.pfn_train_backward(d_out.contiguous(), ctx.saved, ctx.layers)
+        grads = []
+        for a, b, c in zip(dw, dg, db):
+            grads += [a, b, c]
+        ctx.saved = None                       # release the activations
+        return (None, None, None, None, None, None, *grads)
 
 
 @BACKBONES.register_module

@@ -83,10 +83,46 @@ def test_pfn_tensor_core_kernel_vs_oracle(filters, dist, t, c):
     assert_close_fp32(out.cpu().numpy(), ref, "tcgen05 PFN %s dist=%s t=%d c=%d" % (filters, dist, t, c))
 
 
-def test_pfn_training_mode_is_refused(g):
-    net = _load_pfn(g, "pfn64", (64,), False).train()
-    with pytest.raises(RuntimeError):
-        net(_cuda(g["voxels"][:4]), _cuda(g["num_points"][:4]), _cuda(g["coors"][:4]))
+@pytest.mark.parametrize("tag,filters,dist", [("t64_128", (64, 128), False), ("t32_32_64_dist", (32, 32, 64), True)])
+def test_pfn_training_mode_matches_reference_autograd(tag, filters, dist, golden_dir):
+    """PillarFeatureNet.train(): forward with batch statistics over all M * T rows (padded slots included),
+    running statistics after the step, and the gradients of every parameter, against the REFERENCE module
+    run in .train() mode under torch.autograd (tests/golden/make_golden_train.py)."""
+    import torch
+    from partner_b200 import PillarFeatureNet
+    t = np.load(os.path.join(golden_dir, "pfn_train.npz"))
+    net = PillarFeatureNet(7, filters, dist, tuple(t["voxel_size"]), tuple(t["pc_range"]))
+    sd = {}
+    for i in range(len(filters)):
+        sd[f"pfn_layers.{i}.linear.weight"] = torch.from_numpy(t[f"{tag}_w{i}"])
+        sd[f"pfn_layers.{i}.norm.running_mean"] = torch.from_numpy(t[f"{tag}_mean{i}"])
+        sd[f"pfn_layers.{i}.norm.running_var"] = torch.from_numpy(t[f"{tag}_var{i}"])
+        sd[f"pfn_layers.{i}.norm.weight"] = torch.from_numpy(t[f"{tag}_gamma{i}"])
+        sd[f"pfn_layers.{i}.norm.bias"] = torch.from_numpy(t[f"{tag}_beta{i}"])
+        sd[f"pfn_layers.{i}.norm.num_batches_tracked"] = torch.tensor(0)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().train()
+    out = net(_cuda(t["voxels"]), _cuda(t["num_points"]), _cuda(t["coors"]))
+    assert_close_fp32(out.detach().cpu().numpy(), t[f"{tag}_out"], tag + " forward (batch statistics)")
+    (out * _cuda(t[f"{tag}_G"])).sum().backward()
+
+    def close(a, b, what, tol=2e-4):
+        # gradients are sums over 30 000 rows in a different order than torch's: relative to the tensor's scale
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        err = np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+        assert err < tol, "%s: max error %.3g of the largest entry" % (what, err)
+
+    for i, l in enumerate(net.pfn_layers):
+        close(l.norm.running_mean.cpu().numpy(), t[f"{tag}_mean{i}_after"], f"running_mean {i}", 1e-5)
+        close(l.norm.running_var.cpu().numpy(), t[f"{tag}_var{i}_after"], f"running_var {i}", 1e-5)
+        assert int(l.norm.num_batches_tracked) == 1
+        close(l.linear.weight.grad.cpu().numpy(), t[f"{tag}_dw{i}"], f"d weight {i}")
+        close(l.norm.weight.grad.cpu().numpy(), t[f"{tag}_dgamma{i}"], f"d gamma {i}")
+        close(l.norm.bias.grad.cpu().numpy(), t[f"{tag}_dbeta{i}"], f"d beta {i}")
+    # eval mode afterwards uses the updated running statistics through the inference kernels
+    net.eval()
+    ev = net(_cuda(t["voxels"]), _cuda(t["num_points"]), _cuda(t["coors"]))
+    assert tuple(ev.shape) == tuple(out.shape) and bool(torch.isfinite(ev).all())
 
 
 def test_pfn_single_voxel_squeeze(g):
