@@ -7,9 +7,11 @@ The four voxelizations of a double-flip sample run as ONE batched launch sequenc
 Polar azimuth-sector streaming (``nsectors > 1``, :305-371) runs as one stable GPU partition
 (evaluation path); sweep streaming with bidirectional padding (``transform_type == 'feature'``,
 cylinder branch of :393-460) composes the GPU warp, cylinder transform and sector partition.
-Cartesian sector / sweep streaming (:183-303, :404-422) and the training-time label assignment of
-``get_grid_ind`` (:40-60) are "next" rows and raise ``NotImplementedError``; training-time ``filter_gt`` is the caller's job (it edits
-annotations, not points).
+Training mode is covered as well: ``filter_gt`` (polar branch, utils.py:11-27), the per-sector ground truth of
+the streaming paths (filter + rotation into the first wedge, :332-349), the per-sector point labels (:374-377),
+the label hand-over of sweep streaming (:451-453) and the label assignment of ``get_grid_ind`` (:40-60, on the
+GPU).  Cartesian sector / sweep streaming (:183-303, :404-422) and ``AssignLabel.assign_part_2d`` are outside the
+polar front end and raise ``NotImplementedError``.
 """
 import numpy as np
 
@@ -25,6 +27,60 @@ def _get(cfg, key, default=None, required=False):
     if required:
         return getattr(cfg, key)
     return getattr(cfg, key, default) if not hasattr(cfg, "get") else cfg.get(key, default)
+
+
+def _dict_select(dict_, inds):
+    """det3d/datasets/pipelines/utils.py:3-8."""
+    for k, v in dict_.items():
+        if isinstance(v, dict):
+            _dict_select(v, inds)
+        else:
+            dict_[k] = v[inds]
+
+
+def filter_gt(res, pc_range):
+    """Ground-truth boxes outside the (polar) range are dropped from every annotation array --
+    det3d/datasets/pipelines/utils.py:11-27, the branch for voxel_shape != 'cuboid' (box centre radius in
+    [rho_lo, rho_hi], azimuth in [phi_lo, phi_hi]; the reference multiplies the box diagonal by 0).  The cuboid
+    branch (a numba polygon test on Cartesian ranges) is outside the polar front end."""
+    gt_dict = res["lidar"]["annotations"]
+    if len(gt_dict["gt_boxes"]) > 0:
+        bv_range = np.asarray(pc_range)[[0, 1, 3, 4]]
+        if res.get("voxel_shape", "cylinder") == "cuboid":
+            raise NotImplementedError("filter_gt on Cartesian ranges (cuboid voxels) is outside the polar front end")
+        boxes = gt_dict["gt_boxes"]
+        gt_rho = np.linalg.norm(boxes[:, :2], axis=1)
+        gt_diag = np.linalg.norm(boxes[:, 3:5], axis=1)
+        gt_diag *= 0
+        gt_az = np.arctan2(boxes[:, 1], boxes[:, 0])
+        mask = ((gt_rho - gt_diag) >= bv_range[0]) & ((gt_rho + gt_diag) <= bv_range[2]) & (
+            gt_az >= bv_range[1]) & (gt_az <= bv_range[3])
+        _dict_select(gt_dict, mask)
+        res["lidar"]["annotations"] = gt_dict
+
+
+def rotation_points_single_angle(points, angle, axis=2):
+    """det3d/core/bbox/box_np_ops.py:182-204, rotation about z (the only axis the streaming path uses)."""
+    if axis not in (2, -1):
+        raise ValueError("only the z axis is used by the polar front end")
+    rot_sin, rot_cos = np.sin(angle), np.cos(angle)
+    rot_mat_T = np.array([[rot_cos, -rot_sin, 0], [rot_sin, rot_cos, 0], [0, 0, 1]], dtype=points.dtype)
+    return points @ rot_mat_T
+
+
+def sector_annotations(cur_res, cur_pc_range, pc_range):
+    """Training-time ground truth of one azimuth sector (voxelization.py:332-349): boxes outside the wedge are
+    dropped, the rest are rotated into the first wedge (centres, heading and -- if present -- velocities)."""
+    filter_gt(cur_res, cur_pc_range)
+    gt_boxes = cur_res["lidar"]["annotations"]["gt_boxes"]
+    if len(gt_boxes):
+        angle = cur_pc_range[1] - pc_range[1]
+        gt_boxes[:, :3] = rotation_points_single_angle(gt_boxes[:, :3], angle, axis=2)
+        gt_boxes[:, -1] += angle
+        if gt_boxes.shape[1] > 7:
+            gt_boxes[:, 6:8] = rotation_points_single_angle(
+                np.hstack([gt_boxes[:, 6:8], np.zeros((gt_boxes.shape[0], 1))]), angle, axis=2)[:, :2]
+        cur_res["lidar"]["annotations"]["gt_boxes"] = gt_boxes
 
 
 class Voxelization(object):
@@ -88,6 +144,8 @@ class Voxelization(object):
 
     def voxelize_hard(self, res, info):
         vg = self.voxel_generator
+        if res["mode"] in ["train", "debug_gt"]:
+            filter_gt(res, vg.point_cloud_range)                        # voxelization.py:67-68
         max_voxels = self.max_voxel_num[0] if res["mode"] in ["train", "debug_gt"] else self.max_voxel_num[1]
         double_flip = self.double_flip and (res["mode"] != "train")
         if not double_flip:
@@ -119,6 +177,14 @@ class Voxelization(object):
     def voxelize_dynamic(self, res, info, **kwargs):
         import torch
         vg = self.voxel_generator
+        if res["mode"] in ["train", "debug_gt"]:                        # voxelization.py:156-163
+            if res.get("voxel_shape", "cylinder") != "cuboid":
+                cur_pc_range = vg.point_cloud_range.copy()
+                cur_pc_range[1] = -np.pi
+                cur_pc_range[5] = np.pi                                 # (sic: index 5, as the reference writes it)
+                filter_gt(res, cur_pc_range)
+            else:
+                filter_gt(res, vg.point_cloud_range)
         points = np.ascontiguousarray(res["lidar"]["points"], dtype=np.float32)
         n = points.shape[0]
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -133,11 +199,11 @@ class Voxelization(object):
         return res, info
 
     def voxelize_streaming_polar(self, res, info, **kwargs):
-        """voxelization.py:305-371, evaluation path: all sectors in one stable GPU partition."""
+        """voxelization.py:305-392: all sectors in one stable GPU partition; in training the per-sector ground
+        truth (filter + rotation into the first wedge, :332-349) and point labels (:374-377) as the reference."""
         import copy
         import torch
-        if res["mode"] in ["train", "debug_gt"]:
-            raise NotImplementedError("training-time sector streaming (ground-truth filtering / rotation) is a 'next' row")
+        train = res["mode"] in ["train", "debug_gt"]
         vg = self.voxel_generator
         grid_size, pc_range, voxel_size = vg.grid_size, vg.point_cloud_range, vg.voxel_size
         nsectors = self.nsectors
@@ -160,16 +226,26 @@ class Voxelization(object):
             lo, hi = int(offs[i]), int(offs[i + 1])
             cur_res = {k: copy.deepcopy(v) for k, v in res.items() if k != "lidar"}
             cur_res["lidar"] = copy.deepcopy(lidar_rest)
+            if train:
+                cur_pc_range = pc_range.copy()                          # :328-331
+                cur_pc_range[1] = min_az + i * interval
+                cur_pc_range[4] = min_az + (i + 1) * interval
+                sector_annotations(cur_res, cur_pc_range, pc_range)
             cur_res["lidar"]["points"] = out[lo:hi].copy()
             pc_grid_ind = gi[lo:hi]
             cur_res["lidar"]["voxels"] = dict(grid_ind=pc_grid_ind.copy(), shape=cur_grid_size, range=ref_pc_range,
                                               size=voxel_size)
             if ("seg" in self.super_tasks) and kwargs.get("seg", True):
                 points_index = idx[lo:hi]
-                key_points_index = points_index[points_index < res["lidar"]["n_key_points"]]
-                cur_res["lidar"]["n_key_points"] = len(key_points_index)
-                cur_res["lidar"]["key_points_index"] = key_points_index
+                if train:                                               # :374-380
+                    cur_res["lidar"]["pc_label"] = cur_res["lidar"]["pc_label"][points_index]
+                if (not train) or res["mode"] == "debug_gt":
+                    key_points_index = points_index[points_index < res["lidar"]["n_key_points"]]
+                    cur_res["lidar"]["n_key_points"] = len(key_points_index)
+                    cur_res["lidar"]["key_points_index"] = key_points_index
                 cur_res = self.get_grid_ind(cur_res, pc_grid_ind, cur_grid_size)
+                if ("part" in self.super_tasks) and train:
+                    raise NotImplementedError("AssignLabel.assign_part_2d is outside the front end")
             sectors.append(cur_res)
         return {"sectors": sectors}, info
 
@@ -181,8 +257,7 @@ class Voxelization(object):
         import torch
         if res.get("voxel_shape", "cylinder") == "cuboid":
             raise NotImplementedError("Cartesian sweep streaming is outside the polar front end")
-        if res["mode"] in ["train", "debug_gt"]:
-            raise NotImplementedError("training-time sweep streaming is a 'next' row")
+        train = res["mode"] in ["train", "debug_gt"]
         dev = torch.device("cuda", torch.cuda.current_device())
         npoints_sweep = np.cumsum(res["lidar"]["npoints_sweep"])
         nsweeps = len(npoints_sweep)
@@ -210,6 +285,9 @@ class Voxelization(object):
         t0 = prev[0, -1] if prev.shape[0] else np.float32(0)
         warped = F.affine_points(torch.from_numpy(np.ascontiguousarray(prev)).to(dev), tm, t0)
         earlier = run(warped, False, extra={"transform_matrix": tm[:2, :2]})
+        if ("seg" in self.super_tasks) and train:                       # :451-453 the earlier sweeps reuse the labels
+            for i in range(len(earlier)):
+                earlier[i]["lidar"]["voxels"]["labels"] = later[i]["lidar"]["voxels"]["labels"].copy()
         sweeps = earlier + later
         return {"sweeps": sweeps, "nsweeps": 2, "nsectors": len(earlier)}, info
 

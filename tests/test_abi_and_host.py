@@ -138,3 +138,29 @@ def test_dynamic_reader_state_dict_keys_match_reference():
         for name in ("linear.weight", "norm.weight", "norm.bias", "norm.running_mean", "norm.running_var"):
             assert f"pfn_layers.{i}.{name}" in keys
     assert net.voxel_shape == "cuboid"                 # the reference's default, which its configs rely on
+
+
+@pytest.mark.parametrize("nsec", [1, 4, 8])
+def test_sector_ground_truth_matches_reference_golden(nsec, golden_dir):
+    """Training-time sector streaming, annotation side (host numpy): filter_gt + rotation into the first wedge
+    vs the reference's own statements (voxelization.py:332-349, utils.py:11-27; tests/golden/make_golden_stream_train.py)."""
+    import copy
+    import os
+    from partner_b200.voxelization import sector_annotations
+    g = np.load(os.path.join(golden_dir, "stream_train.npz"))
+    pc_range = g["pc_range"]
+    interval = (pc_range[4] - pc_range[1]) / nsec
+    n = g["gt_boxes"].shape[0]
+    for i in range(nsec):
+        cur = pc_range.copy()
+        cur[1] = pc_range[1] + i * interval
+        cur[4] = pc_range[1] + (i + 1) * interval
+        res = {"mode": "train", "voxel_shape": "cylinder",
+               "lidar": {"annotations": {"gt_boxes": g["gt_boxes"].copy(), "gt_names": g["gt_names"].copy(),
+                                         "gt_index": np.arange(n)}}}
+        cur_res = copy.deepcopy(res)
+        sector_annotations(cur_res, cur, pc_range)
+        ann = cur_res["lidar"]["annotations"]
+        assert np.array_equal(ann["gt_index"], g[f"n{nsec}_s{i}_index"])
+        assert np.array_equal(ann["gt_boxes"], g[f"n{nsec}_s{i}_boxes"])          # same numpy statements: bit for bit
+        assert ann["gt_names"].shape[0] == ann["gt_boxes"].shape[0]

@@ -355,3 +355,58 @@ def test_dynamic_grid_ind_on_the_waymo_grid():
     off = torch.tensor([0, f.shape[0]], dtype=torch.int32).cuda()
     assert np.array_equal(F.dynamic_grid_ind(cfg, torch.from_numpy(f).cuda(), off, 1, True).cpu().numpy(), ref)
     assert np.array_equal(F.dynamic_grid_ind(cfg, torch.from_numpy(polar).cuda(), off, 1, False).cpu().numpy(), ref)
+
+
+def test_voxelization_streaming_polar_training_mode():
+    """mode == 'train' through Voxelization(nsectors=4): per-sector ground truth (filtered + rotated into the
+    first wedge, voxelization.py:332-349), per-sector point labels (:374-377) and the voxel labels of
+    get_grid_ind / assign_voxel_labels, checked against the oracle composition; and the sweep-streaming variant
+    hands the labels of the later sweeps to the earlier ones (:451-453)."""
+    import copy
+    from partner_b200 import Voxelization
+    from partner_b200.voxelization import sector_annotations
+    g = synth.GRIDS["NUSC-PILLAR"]
+    cart = synth.nusc_frame(36, nsweeps=3)
+    polar = oracle.transform_points(cart)
+    rng = np.random.default_rng(5)
+    labels = rng.integers(-1, 17, (polar.shape[0], 1)).astype(np.int64)          # -1 = unlabelled (dropped)
+    nb = 40
+    rho, az = rng.uniform(0, 60, nb), rng.uniform(-np.pi, np.pi, nb)
+    boxes = np.zeros((nb, 9), np.float32)
+    boxes[:, 0], boxes[:, 1], boxes[:, 3:6], boxes[:, 8] = rho * np.cos(az), rho * np.sin(az), 2.0, rng.uniform(-3, 3, nb)
+    boxes[:, 6:8] = rng.normal(0, 2, (nb, 2))
+    ann = dict(gt_boxes=boxes, gt_names=np.array(["car"] * nb))
+    cfg = dict(range=g["range"], voxel_size=g["voxel_size"], max_points_in_voxel=20, max_voxel_num=[30000, 60000],
+               dynamic=True, nsectors=4)
+    step = Voxelization(cfg=cfg, super_tasks=["det", "seg"])
+    res_in = dict(mode="train", voxel_shape="cylinder",
+                  lidar=dict(points=polar, pc_label=labels, annotations=copy.deepcopy(ann), transform_type="point"))
+    res, _ = step(copy.deepcopy(res_in), {})
+    secs = oracle.stream_polar(polar, g["voxel_size"], g["range"], 4)
+    pc_range = step.voxel_generator.point_cloud_range
+    interval = (pc_range[4] - pc_range[1]) / 4
+    total_boxes = 0
+    for i, (cur, (pts, gi, idx)) in enumerate(zip(res["sectors"], secs)):
+        assert np.array_equal(cur["lidar"]["voxels"]["grid_ind"], gi)
+        assert np.array_equal(cur["lidar"]["pc_label"], labels[idx])
+        vl, valid = oracle.seg_voxel_labels(gi, labels[idx].reshape(-1), [512, 128, 1])
+        assert np.array_equal(cur["lidar"]["voxels"]["labels"].reshape(vl.shape), vl)
+        assert np.array_equal(cur["lidar"]["voxels"]["valid_grid_ind"], valid)
+        ref = {"mode": "train", "voxel_shape": "cylinder", "lidar": {"annotations": copy.deepcopy(ann)}}
+        cr = pc_range.copy()
+        cr[1], cr[4] = pc_range[1] + i * interval, pc_range[1] + (i + 1) * interval
+        sector_annotations(ref, cr, pc_range)
+        assert np.array_equal(cur["lidar"]["annotations"]["gt_boxes"], ref["lidar"]["annotations"]["gt_boxes"])
+        total_boxes += cur["lidar"]["annotations"]["gt_boxes"].shape[0]
+    assert 0 < total_boxes <= nb
+    # sweep streaming in training mode
+    counts = [int((cart[:, 4] == np.float32(0.05 * s)).sum()) for s in range(3)]
+    th = 0.02
+    tm1 = np.array([[np.cos(th), -np.sin(th), 0, 0.3], [np.sin(th), np.cos(th), 0, 0.1], [0, 0, 1, 0], [0, 0, 0, 1]])
+    sw, _ = step(dict(mode="train", voxel_shape="cylinder",
+                      lidar=dict(points=cart, pc_label=labels, annotations=copy.deepcopy(ann), npoints_sweep=counts,
+                                 transform_matrices=[np.eye(4), tm1, tm1 @ tm1], transform_type="feature")), {})
+    assert sw["nsweeps"] == 2 and len(sw["sweeps"]) == 8
+    for i in range(4):
+        assert np.array_equal(sw["sweeps"][i]["lidar"]["voxels"]["labels"], sw["sweeps"][4 + i]["lidar"]["voxels"]["labels"])
+        assert "valid_grid_ind" in sw["sweeps"][4 + i]["lidar"]["voxels"]

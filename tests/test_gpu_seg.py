@@ -119,8 +119,17 @@ def test_voxelization_step_train_seg_labels():
     polar = oracle.transform_points(synth.nusc_frame(63, nsweeps=2))
     rng = np.random.default_rng(3)
     label = rng.integers(-1, 17, (polar.shape[0], 1)).astype(np.int64)
-    res = {"mode": "train", "lidar": {"points": polar, "pc_label": label}}
+    # training mode filters the ground truth first (voxelization.py:67-68), so the sample carries annotations:
+    # three boxes, one of them beyond the 50.476 m range
+    boxes = np.zeros((3, 9), np.float32)
+    boxes[:, 0] = [10.0, 60.0, -20.0]
+    boxes[:, 3:6] = 2.0
+    res = {"mode": "train", "voxel_shape": "cylinder",
+           "lidar": {"points": polar, "pc_label": label,
+                     "annotations": {"gt_boxes": boxes, "gt_names": np.array(["car", "car", "bus"])}}}
     res, _ = step(res, {})
+    assert res["lidar"]["annotations"]["gt_names"].tolist() == ["car", "bus"]          # utils.py:11-27
+    assert np.array_equal(res["lidar"]["annotations"]["gt_boxes"][:, 0], [10.0, -20.0])
     vg = oracle.VoxelGenerator(g["voxel_size"], g["range"], g["max_points"], g["max_voxels"])
     _, _, _, ind, _ = vg.generate(polar, return_pc_grid_ind=True)
     want_l, want_v = oracle.seg_voxel_labels(ind, label, vg.grid_size)
