@@ -40,6 +40,9 @@
 #define P2_THREADS (17 * 32)
 #define P2_EPI_WARP0 8         // warps 8-15: epilogue (TMEM quarter = warp & 3, row half = (warp - 8) >> 2)
 #define P2_ISSUER_WARP 16      // (measured: 4 epilogue warps and 128 registers per thread: 1.60 ms vs 1.26 ms)
+#define P2_PROD_REGS 128
+#define P2_EPI_REGS 64
+#define P2_ISSUE_REGS 40
 #define P2_MC 64               // voxels per mini-chunk (the unit a producer warp fetches)
 #define P2_U0 32               // units of layer 0
 #define P2_K 64                // K of layer 1 = 2 * P2_U0
@@ -183,7 +186,14 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
 
+    // register budget per role (warpgroups 0-1 = producers, 2-3 = epilogue, 4 = issuer): the kernel is
+    // launched at 96 registers per thread (17 warps allocate like 20); the epilogue and the issuer hand
+    // theirs back so that the producers can take 128 (1.26 -> 1.20 ms).  Tried on top of that and slower
+    // (1.51 ms): a software pipeline inside the producer warp (records of group k + 2, list entries and
+    // rows of group k + 1 in flight while group k is evaluated) -- the kernel is bound by issue slots
+    // (46 % busy with every role resident), not by the producers' load latency.
     if (warp < 8) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(P2_PROD_REGS));
         // =====================================================================================
         // PRODUCER warp: set = stage, g = group inside the tile
         // =====================================================================================
@@ -383,6 +393,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
             if (lane == 0) p2_mbar_arrive(bar_full);
         }
     } else if (warp == P2_ISSUER_WARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P2_ISSUE_REGS));
         // =====================================================================================
         // ISSUER: the whole warp walks the pipeline (barrier waits are warp-wide, the warp stays
         // converged for the block barrier and the TMEM release at the end); lane 0 issues
@@ -438,6 +449,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
         // =====================================================================================
         // EPILOGUE warp e: TMEM lanes [32 e, 32 e + 32)
         // =====================================================================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P2_EPI_REGS));
         const int e = warp & 3, half = (warp - P2_EPI_WARP0) >> 2;
         const int unit = e * 32 + lane;
         const bool has_units = e * 32 < N;                                   // warp-uniform
