@@ -43,6 +43,9 @@
 #define P2_PROD_REGS 128
 #define P2_EPI_REGS 64
 #define P2_ISSUE_REGS 40
+#ifndef P2_MAX_NAP
+#define P2_MAX_NAP 1024
+#endif
 #define P2_MC 64               // voxels per mini-chunk (the unit a producer warp fetches)
 #define P2_U0 32               // units of layer 0
 #define P2_K 64                // K of layer 1 = 2 * P2_U0
@@ -67,16 +70,18 @@ __device__ __forceinline__ bool p2_mbar_wait(uint32_t bar, uint32_t parity, vola
                  "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) return true;
     // not there yet: sleep between polls (a spinning warp costs the other roles of the SM their issue
-    // slots: 41 % of all executed instructions in the first profile); the watchdog looks at the clock
-    // every 256 polls
+    // slots: 41 % of all executed instructions in the first profiles, also with a fixed 100 ns nap); the
+    // watchdog looks at the clock every 64 polls
     const long long t0 = clock64();
+    uint32_t nap = 128;
     for (uint32_t spins = 1;; ++spins) {
-        __nanosleep(100);
+        __nanosleep(nap);                                   // exponential back-off, capped: a tile takes microseconds
+        nap = min(nap * 2u, (uint32_t)P2_MAX_NAP);
         asm volatile("{\n\t.reg .pred p;\n\t"
                      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return true;
-        if ((spins & 255u) == 0) {
+        if ((spins & 63u) == 0) {
             if (*abort_flag) { if (blockIdx.x == diag[1]) diag[2 + (threadIdx.x >> 5)] = tag; return false; }
             if (clock64() - t0 > 400000000ll) {
                 if (atomicCAS(diag, 0u, tag) == 0u) diag[1] = blockIdx.x;      // first block to starve: its warps report where they wait

@@ -10,6 +10,9 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from partner_b200 import _lib  # noqa: E402
+if os.environ.get("PV_LIB"):                     # development aid: time another build of the library
+    _lib.SO_PATH = os.path.abspath(os.environ["PV_LIB"])
 from partner_b200 import PillarFeatureNet, PointPillarsScatter, synth  # noqa: E402
 from partner_b200 import functional as F  # noqa: E402
 
