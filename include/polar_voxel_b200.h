@@ -47,6 +47,7 @@ typedef struct CUstream_st *pv_stream_t; /* == cudaStream_t */
 #define PV_ERR_CUDA (-4)          /* a CUDA runtime call failed (cudaGetLastError)     */
 #define PV_ERR_TABLE_FULL (-5)    /* device status: a frame had more points than frame_capacity */
 #define PV_ERR_UNSUPPORTED (-6)   /* layer shape outside what the kernels cover        */
+#define PV_ERR_INTERNAL (-7)      /* device status: a pipeline wait of the tensor-core PFN kernel starved (watchdog) */
 
 #define PV_MAX_CHANNELS 16        /* C (after the transform) <= 16                     */
 #define PV_MAX_PFN_LAYERS 4
@@ -293,8 +294,10 @@ int pv_seg_gather_points(const int64_t *pred_labels, int32_t nz_pred, int32_t ny
                          const int32_t *valid_grid_ind, const int32_t *valid_offsets, int32_t batch,
                          int64_t n_valid, int64_t *out, int32_t *status, pv_stream_t stream);
 
-/* Copies the device status word of the last pv_voxelize on `workspace` to the host
- * (synchronises `stream`).  Returns PV_OK or PV_ERR_TABLE_FULL / PV_ERR_CUDA. */
+/* Copies the device status word of the last call on `workspace` to the host (synchronises
+ * `stream`).  Returns PV_OK or PV_ERR_TABLE_FULL / PV_ERR_BAD_ARGUMENT / PV_ERR_CUDA, and
+ * PV_ERR_INTERNAL when the barrier watchdog of the tensor-core PFN kernel fired (its results are
+ * then undefined).  Also accepts the workspace of pv_pfn_forward. */
 int pv_read_status(const void *workspace, pv_stream_t stream);
 
 /* VoxelFeatureExtractorV3.forward (det3d/models/readers/voxel_encoder.py:15-22):

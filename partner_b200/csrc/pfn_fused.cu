@@ -60,7 +60,7 @@ struct P2Meta {                // what the epilogue needs to know about one grou
 
 // Barrier wait with a watchdog: a pipeline bug must not hang the GPU.  After ~0.2 s of waiting the
 // block raises its abort flag, records which wait starved (tag) next to the chunk counter and every
-// role loop drains; the host sees the non-zero diagnostic word and reports PV_ERR_CUDA.
+// role loop drains; the block sets bit 2 of the status word, which pv_read_status reports as PV_ERR_INTERNAL.
 __device__ __forceinline__ bool p2_mbar_wait(uint32_t bar, uint32_t parity, volatile uint32_t *abort_flag,
                                              unsigned int *diag, uint32_t tag)
 {
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
     __shared__ __align__(8) unsigned long long s_full[2], s_mma[2], s_free[2], s_rec[2];
     __shared__ uint32_t s_tmem, s_exit[2];
     __shared__ uint32_t s_abort;
-    unsigned int *diag = a.counter + 1;     // diagnostic word of the watchdog (0 = healthy)
+    unsigned int *diag = a.counter + 2;     // diagnostic words of the watchdog (0 = healthy)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t ncols = 256;                             // two accumulator stages x 128 rows (columns)
 
@@ -494,6 +494,10 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0 && s_abort) {                       // a wait starved: tell the host (pv_read_status)
+        atomicOr(a.counter + 1, 4u);
+        if (a.status) atomicOr(a.status, 4u);
+    }
     if (warp == P2_ISSUER_WARP)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(ncols) : "memory");
 }
@@ -515,8 +519,9 @@ size_t pv_pfn_fused_smem(int n1)
            sizeof(P2Meta) * 16 + 128;
 }
 
-// counter: 24 words of device scratch: [0] the dynamic mini-chunk queue, [1] watchdog tag (0 = healthy),
-// [2] the block that starved first, [3..] where each of its warps was waiting; zeroed before every launch.
+// counter: 24 words of device scratch: [0] the dynamic mini-chunk queue, [1] status bits in the layout
+// pv_read_status expects (bit 2: the watchdog fired), [2] watchdog tag (0 = healthy), [3] the block that
+// starved first, [4..] where each of its warps was waiting; zeroed before every launch.
 int pv_pfn_fused_launch(P2Args &a, const pv_pfn_layer *layers, int batch_frames, long long voxels_per_frame_cap,
                         cudaStream_t st)
 {

@@ -20,6 +20,7 @@ struct P2Args {
     int n1;
     uint32_t chunks_per_frame, n_chunks;
     unsigned int *counter;
+    unsigned int *status;      // optional second status word (the voxelizer workspace's, fused front end); may be null
     float *out;
 };
 

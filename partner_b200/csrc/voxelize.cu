@@ -839,6 +839,7 @@ const char *pv_error_string(int code)
     case PV_ERR_CUDA: return "CUDA runtime error";
     case PV_ERR_TABLE_FULL: return "a frame holds more points than frame_capacity";
     case PV_ERR_UNSUPPORTED: return "unsupported layer shape";
+    case PV_ERR_INTERNAL: return "a pipeline wait of the tensor-core PFN kernel starved (watchdog)";
     default: return "unknown error";
     }
 }
@@ -1043,6 +1044,7 @@ int pv_forward_pfn_canvas(const pv_config *cfg, const float *points, const int32
     a.t = cfg->max_points; a.c = p.C; a.with_distance = with_distance ? 1 : 0; a.c0 = p.C + 5 + a.with_distance;
     a.vx = vx; a.vy = vy; a.x_off = x_off; a.y_off = y_off; a.eps = eps;
     a.counter = reinterpret_cast<unsigned int *>(aux_workspace);
+    a.status = p.ws.ctrl + 1;
     a.out = pfn_feats;
     const long long vcap = std::min<long long>(cfg->max_voxels, (long long)p.ws.fcap);
     rc = pv_pfn_fused_launch(a, layers, batch, vcap, st);
@@ -1081,6 +1083,7 @@ int pv_read_status(const void *workspace, pv_stream_t stream)
     if (cudaMemcpyAsync(ctrl, workspace, sizeof(ctrl), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess)
         return PV_ERR_CUDA;
     if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return PV_ERR_CUDA;
+    if (ctrl[1] & 4u) return PV_ERR_INTERNAL;                 // the tensor-core PFN's barrier watchdog fired
     if (ctrl[1] & 1u) return PV_ERR_TABLE_FULL;
     return (ctrl[1] & 2u) ? PV_ERR_BAD_ARGUMENT : PV_OK;     // bit 1: a caller-provided grid_ind row was outside the grid
 }
