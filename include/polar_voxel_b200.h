@@ -157,9 +157,12 @@ int pv_forward_mean_canvas(const pv_config *cfg, const float *points, const int3
  *   C + 5 (+1 with_distance) <= 16, max_points <= 32; PV_ERR_UNSUPPORTED otherwise.
  * Outputs: coors [SM, 4], num_points [SM], voxel_counts [batch] as pv_voxelize; pfn_feats f32 [SM, U]
  * (capacity min(batch * V, n_total) rows); canvas f32 [batch, U, ny, nx] or NULL (pillar grids).
- * aux_workspace: pv_pfn_canvas_workspace_bytes(batch, ny, nx) bytes, 256-byte aligned (chunk queue,
- * watchdog words, BEV index map); workspace as for pv_voxelize. */
-size_t pv_pfn_canvas_workspace_bytes(int32_t batch, int32_t ny, int32_t nx);
+ * aux_workspace: pv_pfn_canvas_workspace_bytes(batch, ny, nx, max_points_total, cfg->max_voxels) bytes,
+ * 256-byte aligned (chunk queues, watchdog words, BEV index map, and the decorated rows the gather
+ * pre-pass hands to the tensor-core kernel: 64 B per kept point + 64 B per voxel); workspace as for
+ * pv_voxelize. */
+size_t pv_pfn_canvas_workspace_bytes(int32_t batch, int32_t ny, int32_t nx, int64_t max_points_total,
+                                     int32_t max_voxels);
 int pv_forward_pfn_canvas(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
                           int32_t batch, int64_t n_total, int32_t c_in, int32_t is_cartesian,
                           int64_t max_points_total, int64_t frame_capacity, void *workspace,

@@ -95,7 +95,7 @@ EXPORTS = {
                                    P, P, P, P, P, P, P, P]),
     "pv_forward_mean_canvas": (ctypes.c_int, [ctypes.POINTER(PvConfig), P, P, I32, I64, I32, I32, I64, I64,
                                               P, SZ, P, P, P, P, P, P]),
-    "pv_pfn_canvas_workspace_bytes": (SZ, [I32, I32, I32]),
+    "pv_pfn_canvas_workspace_bytes": (SZ, [I32, I32, I32, I64, I32]),
     "pv_forward_pfn_canvas": (ctypes.c_int, [ctypes.POINTER(PvConfig), P, P, I32, I64, I32, I32, I64, I64, P, SZ, P, SZ,
                                              ctypes.POINTER(PvPfnLayer), I32, I32, F32, F32, F32, F32, F32,
                                              P, P, P, P, P, P]),

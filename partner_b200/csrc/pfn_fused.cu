@@ -126,6 +126,155 @@ __device__ __forceinline__ void p2_seg_sum(float (&v)[NV], uint32_t flags, uint3
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_pfn_rows -- the gather half of the fused front end (pv_forward_pfn_canvas), at full occupancy.
+// The dependent chain voxel record -> list entry -> point row -> cluster mean -> decoration took the
+// eight producer warps of k_pfn_fused ~11 us per 128 rows (one block per SM, nothing to hide the
+// three round trips behind); here every SM runs 48 warps of it.  A warp takes a mini-chunk of 64
+// voxels, packs whole voxels into groups of <= 32 rows (lane = row) exactly as the tensor-core
+// kernel wants them, and writes per group
+//   drows[row_start + lane]  the decorated row, (C + 5 (+1)) floats padded to a 64-byte slot; the
+//                            representative padded row of a non-full voxel is all zeros (:161-164)
+//   desc[chunk * 64 + g]     {row_start, first output row, head mask, total | scan steps << 8}
+// and per chunk ngroups[chunk].  Rows are allocated per chunk with one atomic on counter[22].
+// Also writes coors / num_points of the voxelizer and restores its point lists.
+// ---------------------------------------------------------------------------------------------
+#define P2_ROWS_THREADS 256
+__global__ void __launch_bounds__(P2_ROWS_THREADS) k_pfn_rows(const __grid_constant__ P2Args a)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_warps = gridDim.x * (P2_ROWS_THREADS / 32);
+    const int T = a.t, C = a.c, c0q = (a.c0 + 3) >> 2;
+    for (uint32_t id = blockIdx.x * (P2_ROWS_THREADS / 32) + (threadIdx.x >> 5); id < a.n_chunks; id += n_warps) {
+        const int b = (int)(id / a.chunks_per_frame);
+        const uint32_t r0 = (id - (uint32_t)b * a.chunks_per_frame) * P2_MC;
+        const uint32_t cnt = (uint32_t)__ldg(a.voxel_counts + b);
+        const uint32_t v_end = min(cnt, r0 + P2_MC);
+        uint32_t v_next = r0, ng = 0;
+        if (v_next >= v_end) {
+            if (lane == 0) a.ngroups_out[id] = 0u;
+            continue;
+        }
+        // records of the chunk's 64 voxels (two windows), rows of the chunk -> one allocation
+        int n_w[2];
+        uint32_t kg_w[2], cell_w[2];
+        int rows_chunk = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t vi = r0 + 32u * h + lane;
+            n_w[h] = 0; kg_w[h] = 0; cell_w[h] = 0;
+            if (vi < v_end) {
+                const size_t v = (size_t)b * a.fcap + vi;
+                n_w[h] = (int)min(__ldcs(a.vox_c + v), (uint32_t)T);
+                kg_w[h] = __ldcs(a.vox_kg + v);
+                cell_w[h] = __ldcs(a.vox_cell + v);
+                rows_chunk += n_w[h] < T ? n_w[h] + 1 : T;
+            }
+        }
+        rows_chunk = __reduce_add_sync(0xffffffffu, rows_chunk);
+        uint32_t row_cursor = 0;
+        if (lane == 0) row_cursor = atomicAdd(a.counter + 22, (uint32_t)rows_chunk);
+        row_cursor = __shfl_sync(0xffffffffu, row_cursor, 0);
+        const int vid0_chunk = __ldg(a.base + b) + (int)r0;
+        while (v_next < v_end) {
+            // ---- pack whole voxels into <= 32 rows: lane i looks at voxel v_next + i ----
+            const uint32_t rel = v_next - r0 + lane;                          // < 64 + 31
+            const int n_lo = __shfl_sync(0xffffffffu, n_w[0], rel & 31u), n_hi = __shfl_sync(0xffffffffu, n_w[1], rel & 31u);
+            const uint32_t kg_lo = __shfl_sync(0xffffffffu, kg_w[0], rel & 31u), kg_hi = __shfl_sync(0xffffffffu, kg_w[1], rel & 31u);
+            const uint32_t ce_lo = __shfl_sync(0xffffffffu, cell_w[0], rel & 31u), ce_hi = __shfl_sync(0xffffffffu, cell_w[1], rel & 31u);
+            const uint32_t vi = v_next + lane;
+            const bool in_chunk = vi < v_end;
+            const int n_i = in_chunk ? (rel < 32u ? n_lo : n_hi) : 0;
+            const uint32_t kg_i = rel < 32u ? kg_lo : kg_hi, cell_i = rel < 32u ? ce_lo : ce_hi;
+            const uint32_t cxi = cell_i % (uint32_t)a.nx, yz = cell_i / (uint32_t)a.nx;
+            const int4 co_i = make_int4(b, (int)(yz / (uint32_t)a.ny), (int)(yz % (uint32_t)a.ny), (int)cxi);
+            const int rows_i = in_chunk ? (n_i < T ? n_i + 1 : T) : 0;
+            int incl = rows_i;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const uint32_t fits = __ballot_sync(0xffffffffu, in_chunk && incl <= 32);
+            const int nv = __popc(fits);                                      // >= 1: a voxel has at most 32 rows
+            const int start_i = incl - rows_i;
+            const uint32_t heads = __reduce_or_sync(0xffffffffu, lane < nv ? 1u << start_i : 0u);
+            const int total = __shfl_sync(0xffffffffu, incl, nv - 1);
+            const int maxlen = __reduce_max_sync(0xffffffffu, lane < nv ? rows_i : 0);
+            uint32_t nsteps = 0;
+            while ((1 << nsteps) < maxlen) ++nsteps;
+            // ---- lane = row: which voxel, which slot ----
+            const bool row_ok = lane < total;
+            const int j = __popc(heads & (0xFFFFFFFFu >> (31 - lane))) - 1;
+            const int jj = row_ok ? j : 0;
+            const int start_j = __shfl_sync(0xffffffffu, start_i, jj);
+            const int n_j = __shfl_sync(0xffffffffu, n_i, jj);
+            const int rows_j = __shfl_sync(0xffffffffu, rows_i, jj);
+            const uint32_t kg_j = __shfl_sync(0xffffffffu, kg_i, jj);
+            const int cx_j = __shfl_sync(0xffffffffu, co_i.w, jj), cy_j = __shfl_sync(0xffffffffu, co_i.z, jj);
+            const int q = lane - start_j;
+            const bool valid = row_ok && q < n_j;                             // a real point (not the padded representative)
+            uint32_t flags = 0;
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                const int dist = 1 << d;
+                const uint32_t span = lane >= dist ? (0xFFFFFFFFu >> (31 - lane)) & ~(0xFFFFFFFFu >> (31 - (lane - dist))) : 0xFFFFFFFFu;
+                if (row_ok && lane >= dist && (heads & span) == 0u) flags |= 1u << d;
+            }
+            const int vid_i = vid0_chunk + (int)(v_next - r0) + lane;
+            const int last_lane = start_j + rows_j - 1;
+            float f[PV_MAX_CHANNELS];
+#pragma unroll
+            for (int k = 0; k < PV_MAX_CHANNELS; ++k) f[k] = 0.0f;
+            if (valid) {
+                const uint32_t idx = __ldcg(a.kept + kg_j + q);
+                a.kept[kg_j + q] = PV_INF;                                    // restore the list for the next call
+                pv_feature_row(a.pts, idx, a.c_in, a.cart, f);
+            }
+            if (lane < nv) {                                                  // per-voxel outputs of the voxelizer
+                __stcs(reinterpret_cast<int4 *>(a.coors_out) + vid_i, co_i);
+                __stcs(a.num_out + vid_i, n_i);
+            }
+            // cluster mean (:137-139): sum over the voxel's rows / num
+            float sm[3] = {f[0], f[1], f[2]};
+            p2_seg_sum<3>(sm, flags, nsteps);
+            const float sx = __shfl_sync(0xffffffffu, sm[0], last_lane & 31), sy = __shfl_sync(0xffffffffu, sm[1], last_lane & 31),
+                        sz = __shfl_sync(0xffffffffu, sm[2], last_lane & 31);
+            const float nf = (float)n_j;
+            const float mx = __fdiv_rn(sx, nf), my = __fdiv_rn(sy, nf), mz = __fdiv_rn(sz, nf);
+            const float pcx = __fadd_rn(__fmul_rn((float)cx_j, a.vx), a.x_off);   // :146-147
+            const float pcy = __fadd_rn(__fmul_rn((float)cy_j, a.vy), a.y_off);   // :149-150
+            float in[P2_C0];
+#pragma unroll
+            for (int k = 0; k < P2_C0; ++k) {
+                float val = 0.0f;
+                if (k < C) val = f[k < PV_MAX_CHANNELS ? k : 0];
+                else if (k == C) val = __fsub_rn(f[0], mx);                   // :140
+                else if (k == C + 1) val = __fsub_rn(f[1], my);
+                else if (k == C + 2) val = __fsub_rn(f[2], mz);
+                else if (k == C + 3) val = __fsub_rn(f[0], pcx);
+                else if (k == C + 4) val = __fsub_rn(f[1], pcy);
+                else if (k == C + 5 && a.with_distance)
+                    val = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(f[0], f[0]), __fmul_rn(f[1], f[1])), __fmul_rn(f[2], f[2])));   // :155
+                in[k] = valid ? val : 0.0f;                                   // :161-164 mask: padded rows are zero
+            }
+            if (row_ok) {
+                float4 *dst = a.drows_out + ((size_t)row_cursor + lane) * (P2_C0 / 4);
+#pragma unroll
+                for (int k4 = 0; k4 < P2_C0 / 4; ++k4)
+                    if (k4 < c0q) __stcg(dst + k4, make_float4(in[4 * k4], in[4 * k4 + 1], in[4 * k4 + 2], in[4 * k4 + 3]));
+            }
+            if (lane == 0)
+                __stcg(a.desc_out + (size_t)id * P2_MC + ng, make_uint4(row_cursor, (uint32_t)vid_i, heads, (uint32_t)total | (nsteps << 8)));
+            row_cursor += (uint32_t)total;
+            ++ng;
+            v_next += (uint32_t)nv;
+        }
+        if (lane == 0) a.ngroups_out[id] = ng;
+    }
+}
+
+template <int MODE>          // 0: rows gathered from the padded tensor inside the producers; 2: rows pre-decorated by k_pfn_rows
 __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_constant__ P2Args a)
 {
     extern __shared__ __align__(128) float smem[];
@@ -205,7 +354,120 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
         const int set = warp >> 2, g = warp & 3;
         float *a_hi = a_st + (size_t)set * 2 * TC_M * P2_K, *a_lo = a_hi + TC_M * P2_K;
         const uint32_t bar_full = tc_smem_u32(&s_full[set]), bar_mma = tc_smem_u32(&s_mma[set]);
+        if constexpr (MODE == 2) {
+            // ---------------------------------------------------------------------------------
+            // rows were gathered and decorated by k_pfn_rows: a group is a descriptor {first row in
+            // drows, first output row, head mask, total | scan steps << 8} and <= 32 consecutive
+            // 64-byte rows -- one coalesced load, no dependent gather left in this kernel
+            // ---------------------------------------------------------------------------------
+            const int c0q = (a.c0 + 3) >> 2;                 // float4s per decorated row
+            uint4 d_lo = make_uint4(0, 0, 0, 0), d_hi = d_lo; // descriptors of the warp's chunk: groups lane and 32 + lane
+            uint32_t ng = 0, gi = 0;
+            bool out_of_work = false;
+            for (uint32_t round = 0;; ++round) {
+                // ---- next group: descriptor and rows are requested BEFORE the stage is waited for ----
+                while (!out_of_work && gi >= ng) {
+                    uint32_t id = 0;
+                    if (lane == 0) id = atomicAdd(a.counter, 1u);
+                    id = __shfl_sync(0xffffffffu, id, 0);
+                    if (id >= a.n_chunks) { out_of_work = true; break; }
+                    ng = __ldcs(a.ngroups + id);
+                    d_lo = __ldcs(a.desc + (size_t)id * P2_MC + lane);
+                    d_hi = __ldcs(a.desc + (size_t)id * P2_MC + 32 + lane);
+                    gi = 0;
+                }
+                uint4 dsc = make_uint4(0, 0, 0, 0);
+                float4 in4[P2_C0 / 4];
+#pragma unroll
+                for (int k4 = 0; k4 < P2_C0 / 4; ++k4) in4[k4] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (!out_of_work) {
+                    const uint4 src = gi < 32u ? d_lo : d_hi;
+                    dsc.x = __shfl_sync(0xffffffffu, src.x, gi & 31u); dsc.y = __shfl_sync(0xffffffffu, src.y, gi & 31u);
+                    dsc.z = __shfl_sync(0xffffffffu, src.z, gi & 31u); dsc.w = __shfl_sync(0xffffffffu, src.w, gi & 31u);
+                    ++gi;
+                    if ((uint32_t)lane < (dsc.w & 0xffu)) {
+                        const float4 *src4 = a.drows + ((size_t)dsc.x + lane) * (P2_C0 / 4);
+#pragma unroll
+                        for (int k4 = 0; k4 < P2_C0 / 4; ++k4)
+                            if (k4 < c0q) in4[k4] = __ldcs(src4 + k4);
+                    }
+                }
+                if (round > 0) {
+                    if (!p2_mbar_wait(bar_mma, (round - 1) & 1u, &s_abort, diag, 0x100u | (set << 4) | g | (round << 16))) break;   // the stage's previous tile has been consumed
+                    if (*reinterpret_cast<volatile uint32_t *>(&s_exit[set])) break;
+                }
+                P2Meta *mt = meta + ((set * 2 + (round & 1u)) * 4 + g);
+                if (out_of_work) {
+                    if (lane == 0) mt->done = 1u;
+                    __syncwarp();
+                    if (lane == 0) p2_mbar_arrive(bar_full);
+                    continue;
+                }
+                const uint32_t heads = dsc.z, total = dsc.w & 0xffu, nsteps = (dsc.w >> 8) & 0xffu;
+                const bool row_ok = (uint32_t)lane < total;
+                const int j = __popc(heads & (0xFFFFFFFFu >> (31 - lane))) - 1;   // voxel ordinal of this row
+                const int vid_j = (int)dsc.y + (row_ok ? j : 0);
+                const uint32_t above = lane < 31 ? heads & (0xFFFFFFFEu << lane) : 0u;   // heads in lanes > lane
+                const int last_lane = (above ? __ffs(above) - 1 : (int)total) - 1;
+                const bool seg_last = row_ok && lane == last_lane;
+                uint32_t flags = 0;
+#pragma unroll
+                for (int d = 0; d < 5; ++d) {
+                    const int dist = 1 << d;
+                    const uint32_t span = lane >= dist ? (0xFFFFFFFFu >> (31 - lane)) & ~(0xFFFFFFFFu >> (31 - (lane - dist))) : 0xFFFFFFFFu;
+                    if (row_ok && lane >= dist && (heads & span) == 0u) flags |= 1u << d;
+                }
+                // ---- layer 0: Linear (fp32 FMA) -> BatchNorm (ATen order) -> ReLU -> per-voxel max ----
+                float x0[P2_U0];
+#pragma unroll
+                for (int u = 0; u < P2_U0; ++u) x0[u] = 0.0f;
+#pragma unroll
+                for (int k4 = 0; k4 < P2_C0 / 4; ++k4) {
+                    if (k4 < c0q) {                              // warp-uniform: whole groups of four inputs are skipped
+                        const float in[4] = {in4[k4].x, in4[k4].y, in4[k4].z, in4[k4].w};
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const float4 *wr = reinterpret_cast<const float4 *>(w0t + (4 * k4 + kk) * P2_U0);
+#pragma unroll
+                            for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
+                                const float4 w = wr[u4];
+                                x0[4 * u4] = __fmaf_rn(in[kk], w.x, x0[4 * u4]); x0[4 * u4 + 1] = __fmaf_rn(in[kk], w.y, x0[4 * u4 + 1]);
+                                x0[4 * u4 + 2] = __fmaf_rn(in[kk], w.z, x0[4 * u4 + 2]); x0[4 * u4 + 3] = __fmaf_rn(in[kk], w.w, x0[4 * u4 + 3]);
+                            }
+                        }
+                    }
+                }
+                const int row = g * 32 + lane;
+                float xm[P2_U0];
+#pragma unroll
+                for (int u = 0; u < P2_U0; ++u) {
+                    const float v = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x0[u], bn0[u]), bn0[P2_U0 + u]), bn0[2 * P2_U0 + u]), bn0[3 * P2_U0 + u]);
+                    x0[u] = row_ok ? fmaxf(v, 0.0f) : 0.0f;
+                    xm[u] = x0[u];
+                }
+                p2_seg_max<P2_U0>(xm, flags, nsteps);
+#pragma unroll
+                for (int u = 0; u < P2_U0; ++u) xm[u] = __shfl_sync(0xffffffffu, xm[u], last_lane & 31);
+#pragma unroll
+                for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
+                    float4 hi, lo;
+                    tc_split(x0[4 * u4], hi.x, lo.x); tc_split(x0[4 * u4 + 1], hi.y, lo.y); tc_split(x0[4 * u4 + 2], hi.z, lo.z); tc_split(x0[4 * u4 + 3], hi.w, lo.w);
+                    uint32_t o = tc_canon(row, 4 * u4, TC_M);
+                    *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
+                    tc_split(xm[4 * u4], hi.x, lo.x); tc_split(xm[4 * u4 + 1], hi.y, lo.y); tc_split(xm[4 * u4 + 2], hi.z, lo.z); tc_split(xm[4 * u4 + 3], hi.w, lo.w);
+                    o = tc_canon(row, P2_U0 + 4 * u4, TC_M);
+                    *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
+                }
+                mt->vid[lane] = seg_last ? vid_j : -1;
+                const uint32_t lasts = __ballot_sync(0xffffffffu, seg_last);
+                if (lane == 0) { mt->lasts = lasts; mt->done = 0u; }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) p2_mbar_arrive(bar_full);
+            }
+        } else {
         const int T = a.t, C = a.c, c0r = (a.c0 + 3) & ~3;
+        constexpr bool LISTS = false;         // the point-list source moved to k_pfn_rows (MODE 2)
         // the warp's current mini-chunk: voxels [v_next, v_end) of frame b (mode 0: one "frame" of m voxels)
         int b = 0;
         uint32_t v_next = 0, v_end = 0;
@@ -222,7 +484,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
             const uint32_t vi = v_next + lane;
             w_n = 0; w_kg = 0; w_co = make_int4(0, 0, 0, 0);
             if (vi < v_end) {
-                if (a.mode) {
+                if (LISTS) {
                     const size_t v = (size_t)b * a.fcap + vi;
                     w_n = (int)min(__ldcs(a.vox_c + v), (uint32_t)T);
                     w_kg = __ldcs(a.vox_kg + v);
@@ -249,7 +511,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                 if (id >= a.n_chunks) { out_of_work = true; break; }
                 b = (int)(id / a.chunks_per_frame);
                 const uint32_t r0 = (id - (uint32_t)b * a.chunks_per_frame) * P2_MC;
-                const uint32_t cnt = a.mode ? (uint32_t)__ldg(a.voxel_counts + b) : (uint32_t)a.m;
+                const uint32_t cnt = LISTS ? (uint32_t)__ldg(a.voxel_counts + b) : (uint32_t)a.m;
                 v_next = r0;
                 v_end = min(cnt, r0 + P2_MC);
                 win_valid = false;
@@ -302,7 +564,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                 const uint32_t span = lane >= dist ? (0xFFFFFFFFu >> (31 - lane)) & ~(0xFFFFFFFFu >> (31 - (lane - dist))) : 0xFFFFFFFFu;
                 if (row_ok && lane >= dist && (heads & span) == 0u) flags |= 1u << d;
             }
-            const int vid_i = a.mode ? __ldg(a.base + b) + (int)vi : (int)vi;
+            const int vid_i = LISTS ? __ldg(a.base + b) + (int)vi : (int)vi;
             const int vid_j = __shfl_sync(0xffffffffu, vid_i, jj);
             const bool seg_last = row_ok && q == rows_j - 1;
             const int last_lane = start_j + rows_j - 1;
@@ -311,7 +573,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
 #pragma unroll
             for (int k = 0; k < PV_MAX_CHANNELS; ++k) f[k] = 0.0f;
             if (valid) {
-                if (a.mode) {
+                if (LISTS) {
                     const uint32_t idx = __ldcg(a.kept + kg_j + q);
                     a.kept[kg_j + q] = PV_INF;                               // restore the list for the next call
                     pv_feature_row(a.pts, idx, a.c_in, a.cart, f);
@@ -322,7 +584,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                         if (k < C) f[k] = __ldg(src + k);
                 }
             }
-            if (a.mode && lane < nv) {                                        // per-voxel outputs of the voxelizer
+            if (LISTS && lane < nv) {                                        // per-voxel outputs of the voxelizer
                 __stcs(reinterpret_cast<int4 *>(a.coors_out) + vid_i, co_i);
                 __stcs(a.num_out + vid_i, n_i);
             }
@@ -397,6 +659,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
             __syncwarp();
             if (lane == 0) p2_mbar_arrive(bar_full);
         }
+        }   // MODE == 0
     } else if (warp == P2_ISSUER_WARP) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P2_ISSUE_REGS));
         // =====================================================================================
@@ -519,7 +782,7 @@ size_t pv_pfn_fused_smem(int n1)
            sizeof(P2Meta) * 16 + 128;
 }
 
-// counter: 24 words of device scratch: [0] the dynamic mini-chunk queue, [1] status bits in the layout
+// counter: 24 words of device scratch: [0] the dynamic mini-chunk queue ([22]: row allocator of k_pfn_rows), [1] status bits in the layout
 // pv_read_status expects (bit 2: the watchdog fired), [2] watchdog tag (0 = healthy), [3] the block that
 // starved first, [4..] where each of its warps was waiting; zeroed before every launch.
 int pv_pfn_fused_launch(P2Args &a, const pv_pfn_layer *layers, int batch_frames, long long voxels_per_frame_cap,
@@ -532,12 +795,34 @@ int pv_pfn_fused_launch(P2Args &a, const pv_pfn_layer *layers, int batch_frames,
     if (a.chunks_per_frame == 0) a.chunks_per_frame = 1;
     a.n_chunks = a.chunks_per_frame * (uint32_t)batch_frames;
     const size_t smem = pv_pfn_fused_smem(a.n1);
-    if (cudaMemsetAsync(a.counter, 0, 24 * sizeof(unsigned int), st) != cudaSuccess) return PV_ERR_CUDA;   // queue + watchdog words
-    if (cudaFuncSetAttribute(k_pfn_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
+    if (cudaMemsetAsync(a.counter, 0, 24 * sizeof(unsigned int), st) != cudaSuccess) return PV_ERR_CUDA;   // queues + watchdog words
     const unsigned want = (a.n_chunks + 7) / 8;
     const unsigned sms = (unsigned)pv_sm_count();
-    k_pfn_fused<<<want < sms ? want : sms, P2_THREADS, smem, st>>>(a);
+    if (a.mode == 1) {                                       // point lists: gather + decorate first, at full occupancy
+        a.drows = a.drows_out; a.desc = a.desc_out; a.ngroups = a.ngroups_out;
+        const unsigned blocks = (a.n_chunks + P2_ROWS_THREADS / 32 - 1) / (P2_ROWS_THREADS / 32);
+        k_pfn_rows<<<blocks < sms * 6 ? blocks : sms * 6, P2_ROWS_THREADS, 0, st>>>(a);
+        if (cudaFuncSetAttribute(k_pfn_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
+        k_pfn_fused<2><<<want < sms ? want : sms, P2_THREADS, smem, st>>>(a);
+    } else {
+        if (cudaFuncSetAttribute(k_pfn_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
+        k_pfn_fused<0><<<want < sms ? want : sms, P2_THREADS, smem, st>>>(a);
+    }
     return pv_last_cuda_error();
+}
+
+// Rows / descriptors of the pre-pass (mode 1): bytes for `rows` decorated rows and `voxel_cap` voxels in `batch` frames.
+size_t pv_pfn_rows_bytes(long long rows, long long voxels_per_frame_cap, int batch_frames, size_t *desc_off, size_t *ng_off)
+{
+    size_t chunks = (size_t)((voxels_per_frame_cap + P2_MC - 1) / P2_MC);
+    if (chunks == 0) chunks = 1;
+    chunks *= (size_t)batch_frames;
+    size_t o = ((size_t)(rows + 64) * P2_C0 * sizeof(float) + 255) & ~(size_t)255;
+    if (desc_off) *desc_off = o;
+    o += (chunks * P2_MC * sizeof(uint4) + 255) & ~(size_t)255;
+    if (ng_off) *ng_off = o;
+    o += (chunks * sizeof(uint32_t) + 255) & ~(size_t)255;
+    return o;
 }
 
 // mode 0: rows from the padded [m, t, c] tensor of the drop-in reader (pv_pfn_forward)

@@ -1000,10 +1000,13 @@ int pv_dynamic_voxelize(const pv_config *cfg, const float *points, const int32_t
     return pvf_run_dynamic(p, f, (cudaStream_t)stream);
 }
 
-size_t pv_pfn_canvas_workspace_bytes(int32_t batch, int32_t ny, int32_t nx)
+size_t pv_pfn_canvas_workspace_bytes(int32_t batch, int32_t ny, int32_t nx, int64_t max_points_total, int32_t max_voxels)
 {
     const size_t map = pv_scatter_workspace_bytes(batch, ny, nx);
-    return map ? 256 + map : 0;                          // [chunk queue + watchdog words | BEV index map]
+    if (!map || max_points_total < 0 || max_voxels <= 0) return 0;
+    // [chunk queues + watchdog words | BEV index map | decorated rows, group descriptors, groups per chunk]
+    const long long rows = (long long)max_points_total + std::min<long long>((long long)batch * max_voxels, (long long)max_points_total);
+    return 256 + ((map + 255) & ~(size_t)255) + pv_pfn_rows_bytes(rows, max_voxels, batch, nullptr, nullptr);
 }
 
 int pv_forward_pfn_canvas(const pv_config *cfg, const float *points, const int32_t *frame_offsets,
@@ -1024,7 +1027,7 @@ int pv_forward_pfn_canvas(const pv_config *cfg, const float *points, const int32
         (reinterpret_cast<uintptr_t>(aux_workspace) & 255u) != 0)
         return PV_ERR_BAD_ARGUMENT;
     if (canvas && (cfg->grid[2] != 1 || (reinterpret_cast<uintptr_t>(canvas) & 15u) != 0)) return PV_ERR_BAD_CONFIG;
-    if (aux_bytes < pv_pfn_canvas_workspace_bytes(batch, cfg->grid[1], cfg->grid[0])) return PV_ERR_WORKSPACE;
+    if (aux_bytes < pv_pfn_canvas_workspace_bytes(batch, cfg->grid[1], cfg->grid[0], max_points_total, cfg->max_voxels)) return PV_ERR_WORKSPACE;
     if (n_layers <= 0 || n_layers > PV_MAX_PFN_LAYERS) return PV_ERR_BAD_ARGUMENT;
     for (int l = 0; l < n_layers; ++l)
         if (!layers[l].weight || !layers[l].bn_mean || !layers[l].bn_var || !layers[l].bn_gamma || !layers[l].bn_beta)
@@ -1047,6 +1050,16 @@ int pv_forward_pfn_canvas(const pv_config *cfg, const float *points, const int32
     a.status = p.ws.ctrl + 1;
     a.out = pfn_feats;
     const long long vcap = std::min<long long>(cfg->max_voxels, (long long)p.ws.fcap);
+    {
+        const size_t map = (pv_scatter_workspace_bytes(batch, cfg->grid[1], cfg->grid[0]) + 255) & ~(size_t)255;
+        char *rows0 = reinterpret_cast<char *>(aux_workspace) + 256 + map;
+        size_t desc_off = 0, ng_off = 0;
+        const long long rows = (long long)max_points_total + std::min<long long>((long long)batch * cfg->max_voxels, (long long)max_points_total);
+        pv_pfn_rows_bytes(rows, vcap, batch, &desc_off, &ng_off);
+        a.drows_out = reinterpret_cast<float4 *>(rows0);
+        a.desc_out = reinterpret_cast<uint4 *>(rows0 + desc_off);
+        a.ngroups_out = reinterpret_cast<uint32_t *>(rows0 + ng_off);
+    }
     rc = pv_pfn_fused_launch(a, layers, batch, vcap, st);
     if (rc || !canvas) return rc;
     const int64_t cap = std::min<int64_t>((int64_t)batch * cfg->max_voxels, n_total);

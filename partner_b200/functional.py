@@ -216,7 +216,7 @@ def forward_pfn_canvas(cfg, points, frame_offsets, batch, frame_capacity, is_car
         r.mean_feats = torch.empty((rows, units), dtype=torch.float32, device=dev)
         r.canvas = torch.empty((batch, units, ny, nx), dtype=torch.float32, device=dev) if canvas else None
     r.ws, r.cfg, r.n_cap, r.f_cap = ws, cfg, n_cap, f_cap
-    aux = workspace(lib.pv_pfn_canvas_workspace_bytes(batch, ny, nx), dev, ("pfn_canvas", ws_tag))
+    aux = workspace(lib.pv_pfn_canvas_workspace_bytes(batch, ny, nx, n_cap, int(cfg.max_voxels)), dev, ("pfn_canvas", ws_tag))
     arr = _pfn_layer_array(layers)
     check(lib.pv_forward_pfn_canvas(cfg, ptr(points), ptr(frame_offsets), batch, n, c_in, 1 if is_cartesian else 0,
                                     n_cap, f_cap, ptr(ws), ws.numel(), ptr(aux), aux.numel(), arr, len(layers),

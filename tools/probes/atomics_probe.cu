@@ -64,6 +64,45 @@ static float run(const char *name, const uint32_t *slot, uint32_t n, uint32_t *f
     return us;
 }
 
+// Sector-pairing probes: the same 2 x 16-byte reductions per point as MODE 4, but both halves of a
+// point's 32-byte row leave in ONE warp instruction from two different lanes.
+//   PAIR 0: lanes 0-15 carry the first halves of 16 points, lanes 16-31 the second halves
+//   PAIR 1: adjacent lanes carry the two halves of one point
+//   PAIR 2: control -- 16 points per instruction, first halves only (half the reductions)
+//   PAIR 3: 32-byte plain store per lane (st.v8 as two float4 halves by lane pairs), control for request cost
+template <int PAIR>
+__global__ void kp(const uint32_t *__restrict__ slot, uint32_t n, float *acc)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = t & 31u, wbase = (t >> 5) * 16u;
+    uint32_t i, half;
+    if (PAIR == 1) { i = wbase + (lane >> 1); half = lane & 1u; }
+    else { i = wbase + (lane & 15u); half = lane >> 4; }
+    if (i >= n) return;
+    const uint32_t s = slot[i];
+    if (s == 0xFFFFFFFFu) return;
+    if (PAIR == 2 && half) return;
+    red_v4(acc + (size_t)s * 8 + 4 * half, 1.f, 2.f, 3.f, 4.f);
+}
+template <int PAIR>
+static float runp(const char *name, const uint32_t *slot, uint32_t n, float *acc, int lanes)
+{
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const uint32_t threads = 2 * n;
+    for (int w = 0; w < 3; ++w) kp<PAIR><<<(threads + 255) / 256, 256>>>(slot, n, acc);
+    CK(cudaDeviceSynchronize());
+    const int it = 20;
+    CK(cudaEventRecord(e0));
+    for (int w = 0; w < it; ++w) kp<PAIR><<<(threads + 255) / 256, 256>>>(slot, n, acc);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    const float us = ms * 1000.f / it;
+    printf("%-44s %8.2f us   %7.2f G points/s\n", name, us, (double)lanes * 1e-3 / us);
+    return us;
+}
+
 int main(int argc, char **argv)
 {
     const uint32_t B = 8, cells = 512 * 512, per = 295000, occupied = 76650;
@@ -107,6 +146,9 @@ int main(int argc, char **argv)
         run<7>("match_any aggregated RED.MIN + RED.ADD", slot, n, first, cnt, acc, out, live);
         run<8>("8 x RED.ADD.f32", slot, n, first, cnt, acc, out, live);
         run<13>("ATOM.MIN.u64 (return)", slot, n, first, cnt, acc, out, live);
+        runp<0>("row halves from lanes l / l+16, 1 instr", slot, n, acc, live);
+        runp<1>("row halves from adjacent lanes, 1 instr", slot, n, acc, live);
+        runp<2>("control: first halves only, 16 pts / instr", slot, n, acc, live);
         cudaFree(slot); cudaFree(out); cudaFree(first); cudaFree(cnt); cudaFree(acc);
     }
     return 0;
