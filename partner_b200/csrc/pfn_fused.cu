@@ -43,8 +43,8 @@
 #define P2_PROD_REGS 128
 #define P2_EPI_REGS 64
 #define P2_ISSUE_REGS 40
-#ifndef P2_MAX_NAP
-#define P2_MAX_NAP 1024
+#ifndef P2_WAIT_HINT_NS
+#define P2_WAIT_HINT_NS 20000
 #endif
 #define P2_MC 64               // voxels per mini-chunk (the unit a producer warp fetches)
 #define P2_U0 32               // units of layer 0
@@ -73,15 +73,14 @@ __device__ __forceinline__ bool p2_mbar_wait(uint32_t bar, uint32_t parity, vola
     // slots: 41 % of all executed instructions in the first profiles, also with a fixed 100 ns nap); the
     // watchdog looks at the clock every 64 polls
     const long long t0 = clock64();
-    uint32_t nap = 128;
     for (uint32_t spins = 1;; ++spins) {
-        __nanosleep(nap);                                   // exponential back-off, capped: a tile takes microseconds
-        nap = min(nap * 2u, (uint32_t)P2_MAX_NAP);
+        // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or the
+        // hint runs out, instead of polling (polls were 27-41 % of all executed instructions)
         asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity), "r"((uint32_t)P2_WAIT_HINT_NS) : "memory");
         if (done) return true;
-        if ((spins & 63u) == 0) {
+        if ((spins & 15u) == 0) {
             if (*abort_flag) { if (blockIdx.x == diag[1]) diag[2 + (threadIdx.x >> 5)] = tag; return false; }
             if (clock64() - t0 > 400000000ll) {
                 if (atomicCAS(diag, 0u, tag) == 0u) diag[1] = blockIdx.x;      // first block to starve: its warps report where they wait
@@ -133,14 +132,21 @@ __device__ __forceinline__ void p2_seg_sum(float (&v)[NV], uint32_t flags, uint3
 // three round trips behind); here every SM runs 48 warps of it.  A warp takes a mini-chunk of 64
 // voxels, packs whole voxels into groups of <= 32 rows (lane = row) exactly as the tensor-core
 // kernel wants them, and writes per group
-//   drows[row_start + lane]  the decorated row, (C + 5 (+1)) floats padded to a 64-byte slot; the
-//                            representative padded row of a non-full voxel is all zeros (:161-164)
+//   drows[k4][row_start + lane]  the decorated row, (C + 5 (+1)) floats as up to four float4 PLANES (a
+//                            warp's store / load covers 512 contiguous bytes); the representative
+//                            padded row of a non-full voxel is all zeros (:161-164)
 //   desc[chunk * 64 + g]     {row_start, first output row, head mask, total | scan steps << 8}
 // and per chunk ngroups[chunk].  Rows are allocated per chunk with one atomic on counter[22].
 // Also writes coors / num_points of the voxelizer and restores its point lists.
 // ---------------------------------------------------------------------------------------------
 #define P2_ROWS_THREADS 256
-__global__ void __launch_bounds__(P2_ROWS_THREADS) k_pfn_rows(const __grid_constant__ P2Args a)
+#ifndef P2R_EXP
+#define P2R_EXP 0      // timing experiments (never defined in product builds)
+#endif
+#ifndef P2_ROWS_BLOCKS
+#define P2_ROWS_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(P2_ROWS_THREADS, P2_ROWS_BLOCKS) k_pfn_rows(const __grid_constant__ P2Args a)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t n_warps = gridDim.x * (P2_ROWS_THREADS / 32);
@@ -227,8 +233,8 @@ __global__ void __launch_bounds__(P2_ROWS_THREADS) k_pfn_rows(const __grid_const
 #pragma unroll
             for (int k = 0; k < PV_MAX_CHANNELS; ++k) f[k] = 0.0f;
             if (valid) {
-                const uint32_t idx = __ldcg(a.kept + kg_j + q);
-                a.kept[kg_j + q] = PV_INF;                                    // restore the list for the next call
+                uint32_t idx = __ldcg(a.kept + kg_j + q);
+                if (P2R_EXP == 1) idx = kg_j + q;                             // experiment: no random gather
                 pv_feature_row(a.pts, idx, a.c_in, a.cart, f);
             }
             if (lane < nv) {                                                  // per-voxel outputs of the voxelizer
@@ -258,12 +264,16 @@ __global__ void __launch_bounds__(P2_ROWS_THREADS) k_pfn_rows(const __grid_const
                     val = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(f[0], f[0]), __fmul_rn(f[1], f[1])), __fmul_rn(f[2], f[2])));   // :155
                 in[k] = valid ? val : 0.0f;                                   // :161-164 mask: padded rows are zero
             }
-            if (row_ok) {
-                float4 *dst = a.drows_out + ((size_t)row_cursor + lane) * (P2_C0 / 4);
+            if (row_ok && P2R_EXP != 2) {
+                // four planes of float4 columns: the 32 lanes of a store write 512 contiguous bytes
+                float4 *dst = a.drows_out + (size_t)row_cursor + lane;
 #pragma unroll
                 for (int k4 = 0; k4 < P2_C0 / 4; ++k4)
-                    if (k4 < c0q) __stcg(dst + k4, make_float4(in[4 * k4], in[4 * k4 + 1], in[4 * k4 + 2], in[4 * k4 + 3]));
+                    if (k4 < c0q) __stcg(dst + (size_t)k4 * a.drow_stride, make_float4(in[4 * k4], in[4 * k4 + 1], in[4 * k4 + 2], in[4 * k4 + 3]));
             }
+            // restore the list for the next call -- only now: a store to an address whose load is still in
+            // flight stalls the load/store unit for the whole round trip (measured here: 440 -> 240 us)
+            if (valid && P2R_EXP != 3) a.kept[kg_j + q] = PV_INF;
             if (lane == 0)
                 __stcg(a.desc_out + (size_t)id * P2_MC + ng, make_uint4(row_cursor, (uint32_t)vid_i, heads, (uint32_t)total | (nsteps << 8)));
             row_cursor += (uint32_t)total;
@@ -312,7 +322,9 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
     for (int e = tid; e < TC_M * P2_K; e += P2_THREADS) {  // linear.weight of layer 1 is [N, 64], K-major already
         const int r = e / P2_K, k = e - r * P2_K;
         float hi = 0.0f, lo = 0.0f;
-        if (r < N) tc_split(__ldg(a.w1 + e), hi, lo);
+        // units whose folded BatchNorm scale is negative get their weight row negated: the epilogue then
+        // always tracks the MAXIMUM of the raw accumulator (relu(s a + b) = relu(|s| (-a) + b) for s < 0)
+        if (r < N) tc_split(__ldg(a.gamma1 + r) < 0.0f ? -__ldg(a.w1 + e) : __ldg(a.w1 + e), hi, lo);
         const uint32_t o = tc_canon(r, k, TC_M);
         b_hi[o] = hi; b_lo[o] = lo;
     }
@@ -330,7 +342,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
     // b = beta - mean * s: the GEMM in front of it is accurate to ~1e-6 (3xTF32), the fold moves y by ulps
     for (int o = tid; o < N; o += P2_THREADS) {
         const float sc = __fmul_rn(__fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(a.var1[o], a.eps))), a.gamma1[o]);
-        bn1[2 * o] = sc;
+        bn1[2 * o] = fabsf(sc);                              // the sign went into the weight row
         bn1[2 * o + 1] = __fsub_rn(a.beta1[o], __fmul_rn(a.mean1[o], sc));
     }
     for (int o = tid; o < 16; o += P2_THREADS) { meta[o].lasts = 0u; meta[o].done = 1u; }
@@ -386,10 +398,10 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                     dsc.z = __shfl_sync(0xffffffffu, src.z, gi & 31u); dsc.w = __shfl_sync(0xffffffffu, src.w, gi & 31u);
                     ++gi;
                     if ((uint32_t)lane < (dsc.w & 0xffu)) {
-                        const float4 *src4 = a.drows + ((size_t)dsc.x + lane) * (P2_C0 / 4);
+                        const float4 *src4 = a.drows + (size_t)dsc.x + lane;
 #pragma unroll
                         for (int k4 = 0; k4 < P2_C0 / 4; ++k4)
-                            if (k4 < c0q) in4[k4] = __ldcs(src4 + k4);
+                            if (k4 < c0q) in4[k4] = __ldcs(src4 + (size_t)k4 * a.drow_stride);
                     }
                 }
                 if (round > 0) {
@@ -722,8 +734,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
         const int unit = e * 32 + lane;
         const bool has_units = e * 32 < N;                                   // warp-uniform
         const float sc = unit < N ? bn1[2 * unit] : 0.0f, sh = unit < N ? bn1[2 * unit + 1] : 0.0f;
-        const bool neg = sc < 0.0f;                                          // relu(s x + b) decreases in x: track the minimum
-        const float neutral = neg ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+        const float neutral = __int_as_float(0xff800000);                    // -inf: sc >= 0 here, so the maximum of the raw accumulator decides
         bool fin[2] = {false, false};
         for (uint32_t round = 0; !(fin[0] && fin[1]); ++round) {
             for (int s = 0; s < 2; ++s) {
@@ -741,7 +752,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                     float run = neutral;
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
-                        run = neg ? fminf(run, v[k]) : fmaxf(run, v[k]);
+                        run = fmaxf(run, v[k]);
                         if ((lasts >> k) & 1u) {                             // warp-uniform: the voxel ends at row k
                             const int vid = mt->vid[k];
                             if (unit < N) __stcs(a.out + (size_t)vid * N + unit, fmaxf(__fmaf_rn(run, sc, sh), 0.0f));
@@ -801,7 +812,7 @@ int pv_pfn_fused_launch(P2Args &a, const pv_pfn_layer *layers, int batch_frames,
     if (a.mode == 1) {                                       // point lists: gather + decorate first, at full occupancy
         a.drows = a.drows_out; a.desc = a.desc_out; a.ngroups = a.ngroups_out;
         const unsigned blocks = (a.n_chunks + P2_ROWS_THREADS / 32 - 1) / (P2_ROWS_THREADS / 32);
-        k_pfn_rows<<<blocks < sms * 6 ? blocks : sms * 6, P2_ROWS_THREADS, 0, st>>>(a);
+        k_pfn_rows<<<blocks < sms * 2 * P2_ROWS_BLOCKS ? blocks : sms * 2 * P2_ROWS_BLOCKS, P2_ROWS_THREADS, 0, st>>>(a);
         if (cudaFuncSetAttribute(k_pfn_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
         k_pfn_fused<2><<<want < sms ? want : sms, P2_THREADS, smem, st>>>(a);
     } else {
@@ -811,13 +822,16 @@ int pv_pfn_fused_launch(P2Args &a, const pv_pfn_layer *layers, int batch_frames,
     return pv_last_cuda_error();
 }
 
+// rows per float4 plane of the pre-pass's row store (a multiple of 16 rows = 256 bytes)
+long long pv_pfn_rows_stride(long long rows) { return (rows + 64 + 15) & ~15ll; }
+
 // Rows / descriptors of the pre-pass (mode 1): bytes for `rows` decorated rows and `voxel_cap` voxels in `batch` frames.
 size_t pv_pfn_rows_bytes(long long rows, long long voxels_per_frame_cap, int batch_frames, size_t *desc_off, size_t *ng_off)
 {
     size_t chunks = (size_t)((voxels_per_frame_cap + P2_MC - 1) / P2_MC);
     if (chunks == 0) chunks = 1;
     chunks *= (size_t)batch_frames;
-    size_t o = ((size_t)(rows + 64) * P2_C0 * sizeof(float) + 255) & ~(size_t)255;
+    size_t o = (size_t)pv_pfn_rows_stride(rows) * P2_C0 * sizeof(float);
     if (desc_off) *desc_off = o;
     o += (chunks * P2_MC * sizeof(uint4) + 255) & ~(size_t)255;
     if (ng_off) *ng_off = o;

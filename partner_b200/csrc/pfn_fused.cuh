@@ -13,7 +13,7 @@ struct P2Args {
     uint32_t fcap; int32_t nx, ny;
     int32_t *coors_out; int32_t *num_out;
     // mode 1: decorated rows + group descriptors written by k_pfn_rows, read by k_pfn_fused<2>
-    float4 *drows_out; uint4 *desc_out; uint32_t *ngroups_out;
+    float4 *drows_out; uint4 *desc_out; uint32_t *ngroups_out; long long drow_stride;   // rows per float4 plane
     const float4 *drows; const uint4 *desc; const uint32_t *ngroups;
     // common
     int t, c, c0, with_distance;
@@ -33,6 +33,7 @@ struct P2Args {
 bool pv_pfn_fused_supported(const pv_pfn_layer *layers, int n_layers, int t, int c, int with_distance);
 // counter: 24 words of device scratch (chunk queue + watchdog diagnostics), zeroed by the launch.
 // workspace of the pre-pass: [rows x 64 B | descriptors | groups per chunk]; offsets of the last two are returned
+long long pv_pfn_rows_stride(long long rows);
 size_t pv_pfn_rows_bytes(long long rows, long long voxels_per_frame_cap, int batch_frames, size_t *desc_off, size_t *ng_off);
 int pv_pfn_fused_launch(P2Args &a, const pv_pfn_layer *layers, int batch_frames, long long voxels_per_frame_cap,
                         cudaStream_t st);

@@ -1057,6 +1057,7 @@ int pv_forward_pfn_canvas(const pv_config *cfg, const float *points, const int32
         const long long rows = (long long)max_points_total + std::min<long long>((long long)batch * cfg->max_voxels, (long long)max_points_total);
         pv_pfn_rows_bytes(rows, vcap, batch, &desc_off, &ng_off);
         a.drows_out = reinterpret_cast<float4 *>(rows0);
+        a.drow_stride = pv_pfn_rows_stride(rows);
         a.desc_out = reinterpret_cast<uint4 *>(rows0 + desc_off);
         a.ngroups_out = reinterpret_cast<uint32_t *>(rows0 + ng_off);
     }

@@ -20,6 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--filters", default="64,128")
+ap.add_argument("--fused-only", action="store_true", help="skip the three-call path (for ncu launch lists of the fused front end)")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 g = synth.GRIDS["NUSC-PILLAR"]
@@ -43,7 +44,7 @@ scat = PointPillarsScatter(num_input_features=filters[-1])
 
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 tot = np.zeros(3)
-for it in range(args.iters + 2):
+for it in range(0 if args.fused_only else args.iters + 2):
     ev[0].record()
     vb = F.voxelize(cfg, pts, d_off, args.batch, max(sizes), True, want_voxels=True)
     ev[1].record()
@@ -57,6 +58,8 @@ for it in range(args.iters + 2):
         tot += [ev[k].elapsed_time(ev[k + 1]) for k in range(3)]
     del canvas
 tot /= args.iters
+if args.fused_only:
+    tot[:] = 1.0
 # fused front end: pv_forward_pfn_canvas (no [M, T, C] tensor), CUDA-graph replay on rotating input sets
 from partner_b200 import PillarFrontEnd  # noqa: E402
 n_sets = 3
@@ -92,8 +95,13 @@ fused_ms = e0.elapsed_time(e1) / reps
 fused_pts = float(np.mean([int(s_[1][-1].item()) for s_ in fused_sets]))
 fused_m = float(np.mean([int(o.voxel_counts.sum().item()) for o in outs]))
 n = int(off[-1])
-K = int(vb.num_points[:m].sum().item())
-nonfull = int((vb.num_points[:m] < g["max_points"]).sum().item())
+if args.fused_only:
+    m = int(outs[0].voxel_counts.sum().item())
+    K = int(outs[0].num_points[:m].sum().item())
+    nonfull = int((outs[0].num_points[:m] < g["max_points"]).sum().item())
+else:
+    K = int(vb.num_points[:m].sum().item())
+    nonfull = int((vb.num_points[:m] < g["max_points"]).sum().item())
 macs = sum(a * b for a, b in zip([12] + [f for f in filters[:-1]], [f // 2 for f in filters[:-1]] + [filters[-1]]))
 print(json.dumps({"workload": "nusc_pillar_pfn_canvas_b%d" % args.batch, "points": n, "voxels": m, "kept_points": K,
                   "useful_rows": K + nonfull, "ms": {"voxelize_with_voxels_tensor": tot[0], "pfn": tot[1], "scatter": tot[2]},
