@@ -37,9 +37,30 @@
 #include "tc_common.cuh"
 #include "pfn_fused.cuh"
 
-#define P2_THREADS (17 * 32)
-#define P2_EPI_WARP0 8         // warps 8-15: epilogue (TMEM quarter = warp & 3, row half = (warp - 8) >> 2)
-#define P2_ISSUER_WARP 16      // (measured: 4 epilogue warps and 128 registers per thread: 1.60 ms vs 1.26 ms)
+// warps: NPROD producers | 8 epilogue (TMEM quarter = warp & 3, row half = (warp - first) >> 2) | 1 issuer.
+// MODE 0: 8 producers, one per group of 32 rows.  MODE 2: 16 producers, TWO per group, each computing half of
+// layer 0's units for the group's rows: a producer warp is one serial instruction stream (~1350 dependent
+// instructions per group), and with two of them per scheduler the stream's own latency set the pace.
+#ifdef P2_TRACE          // development builds only: per-warp time stamps of block 0 (tools/pfn_trace.py)
+__device__ long long g_p2_trace[32 * 64 * 2 * 3];
+__device__ long long g_p2_trace2[8 * 64 * 2 * 4];
+#define P2_STAMP2(round, s, k) do { if (blockIdx.x == 0 && lane == 0 && (round) < 64u) g_p2_trace2[(((warp - P2_EPI_WARP0) * 64 + (round)) * 2 + (s)) * 4 + (k)] = clock64(); } while (0)
+#define P2_STAMP(round, s, k) do { if (blockIdx.x == 0 && lane == 0 && (round) < 64u) g_p2_trace[((warp * 64 + (round)) * 2 + (s)) * 3 + (k)] = clock64(); } while (0)
+extern "C" int pv_debug_p2_trace(void *dst, size_t bytes)
+{
+    return cudaMemcpyFromSymbol(dst, g_p2_trace, bytes < sizeof(g_p2_trace) ? bytes : sizeof(g_p2_trace)) == cudaSuccess ? 0 : -4;
+}
+extern "C" int pv_debug_p2_trace2(void *dst, size_t bytes)
+{
+    return cudaMemcpyFromSymbol(dst, g_p2_trace2, bytes < sizeof(g_p2_trace2) ? bytes : sizeof(g_p2_trace2)) == cudaSuccess ? 0 : -4;
+}
+#else
+#define P2_STAMP(round, s, k) do { } while (0)
+#define P2_STAMP2(round, s, k) do { } while (0)
+#endif
+#define P2_NPROD(MODE) ((MODE) == 2 ? 16 : 8)
+#define P2_NTHREADS(MODE) ((P2_NPROD(MODE) + 9) * 32)
+// (measured: 4 epilogue warps and 128 registers per thread: 1.60 ms vs 1.26 ms)
 #define P2_PROD_REGS 128
 #define P2_EPI_REGS 64
 #define P2_ISSUE_REGS 40
@@ -52,7 +73,8 @@
 #define P2_C0 16               // decorated input width, padded
 
 struct P2Meta {                // what the epilogue needs to know about one group
-    int32_t vid[32];           // output row of the voxel whose LAST row is row k of the group, else -1
+    int32_t vid0;              // output row of the group's first voxel (the following voxels take the following rows)
+    int32_t pad0[3];
     uint32_t lasts;            // bit k: row k is the last row of its voxel
     uint32_t done;             // the producer ran out of work: nothing to drain
     uint32_t pad[2];
@@ -285,8 +307,10 @@ __global__ void __launch_bounds__(P2_ROWS_THREADS, P2_ROWS_BLOCKS) k_pfn_rows(co
 }
 
 template <int MODE>          // 0: rows gathered from the padded tensor inside the producers; 2: rows pre-decorated by k_pfn_rows
-__global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_constant__ P2Args a)
+__global__ void __launch_bounds__(P2_NTHREADS(MODE), 1) k_pfn_fused(const __grid_constant__ P2Args a)
 {
+    constexpr int P2_THREADS = P2_NTHREADS(MODE), P2_EPI_WARP0 = P2_NPROD(MODE), P2_ISSUER_WARP = P2_NPROD(MODE) + 8;
+    constexpr int UH = MODE == 2 ? P2_U0 / 2 : P2_U0;     // layer-0 units per producer warp
     extern __shared__ __align__(128) float smem[];
     const int N = a.n1;
     float *a_st = smem;                                    // [2 stages][hi | lo][128 x 64] canonical
@@ -310,7 +334,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
     }
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            tc_mbar_init(tc_smem_u32(&s_full[s]), 4);
+            tc_mbar_init(tc_smem_u32(&s_full[s]), MODE == 2 ? 8 : 4);
             tc_mbar_init(tc_smem_u32(&s_mma[s]), 1);
             tc_mbar_init(tc_smem_u32(&s_free[s]), 8);
             tc_mbar_init(tc_smem_u32(&s_rec[s]), 1);
@@ -358,12 +382,13 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
     // (1.51 ms): a software pipeline inside the producer warp (records of group k + 2, list entries and
     // rows of group k + 1 in flight while group k is evaluated) -- the kernel is bound by issue slots
     // (46 % busy with every role resident), not by the producers' load latency.
-    if (warp < 8) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(P2_PROD_REGS));
+    if (warp < P2_EPI_WARP0) {
+        if constexpr (MODE != 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(P2_PROD_REGS));
         // =====================================================================================
         // PRODUCER warp: set = stage, g = group inside the tile
         // =====================================================================================
-        const int set = warp >> 2, g = warp & 3;
+        const int set = MODE == 2 ? warp >> 3 : warp >> 2, g = MODE == 2 ? (warp >> 1) & 3 : warp & 3;
+        const int uh = MODE == 2 ? (warp & 1) * UH : 0;       // first layer-0 unit of this warp
         float *a_hi = a_st + (size_t)set * 2 * TC_M * P2_K, *a_lo = a_hi + TC_M * P2_K;
         const uint32_t bar_full = tc_smem_u32(&s_full[set]), bar_mma = tc_smem_u32(&s_mma[set]);
         if constexpr (MODE == 2) {
@@ -376,12 +401,13 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
             uint4 d_lo = make_uint4(0, 0, 0, 0), d_hi = d_lo; // descriptors of the warp's chunk: groups lane and 32 + lane
             uint32_t ng = 0, gi = 0;
             bool out_of_work = false;
+            uint32_t next_chunk = blockIdx.x * 8u + (uint32_t)(warp >> 1);   // pair index
             for (uint32_t round = 0;; ++round) {
                 // ---- next group: descriptor and rows are requested BEFORE the stage is waited for ----
                 while (!out_of_work && gi >= ng) {
-                    uint32_t id = 0;
-                    if (lane == 0) id = atomicAdd(a.counter, 1u);
-                    id = __shfl_sync(0xffffffffu, id, 0);
+                    // the two warps of a pair walk the same chunks: a static stride instead of the queue
+                    const uint32_t id = next_chunk;
+                    next_chunk += gridDim.x * 8u;
                     if (id >= a.n_chunks) { out_of_work = true; break; }
                     ng = __ldcs(a.ngroups + id);
                     d_lo = __ldcs(a.desc + (size_t)id * P2_MC + lane);
@@ -401,16 +427,18 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                         const float4 *src4 = a.drows + (size_t)dsc.x + lane;
 #pragma unroll
                         for (int k4 = 0; k4 < P2_C0 / 4; ++k4)
-                            if (k4 < c0q) in4[k4] = __ldcs(src4 + (size_t)k4 * a.drow_stride);
+                            if (k4 < c0q) in4[k4] = __ldg(src4 + (size_t)k4 * a.drow_stride);   // the pair's other warp reads the same rows
                     }
                 }
+                P2_STAMP(round, 0, 0);
                 if (round > 0) {
                     if (!p2_mbar_wait(bar_mma, (round - 1) & 1u, &s_abort, diag, 0x100u | (set << 4) | g | (round << 16))) break;   // the stage's previous tile has been consumed
                     if (*reinterpret_cast<volatile uint32_t *>(&s_exit[set])) break;
                 }
+                P2_STAMP(round, 0, 1);
                 P2Meta *mt = meta + ((set * 2 + (round & 1u)) * 4 + g);
                 if (out_of_work) {
-                    if (lane == 0) mt->done = 1u;
+                    if (lane == 0 && uh == 0) mt->done = 1u;
                     __syncwarp();
                     if (lane == 0) p2_mbar_arrive(bar_full);
                     continue;
@@ -418,7 +446,6 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                 const uint32_t heads = dsc.z, total = dsc.w & 0xffu, nsteps = (dsc.w >> 8) & 0xffu;
                 const bool row_ok = (uint32_t)lane < total;
                 const int j = __popc(heads & (0xFFFFFFFFu >> (31 - lane))) - 1;   // voxel ordinal of this row
-                const int vid_j = (int)dsc.y + (row_ok ? j : 0);
                 const uint32_t above = lane < 31 ? heads & (0xFFFFFFFEu << lane) : 0u;   // heads in lanes > lane
                 const int last_lane = (above ? __ffs(above) - 1 : (int)total) - 1;
                 const bool seg_last = row_ok && lane == last_lane;
@@ -430,18 +457,18 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                     if (row_ok && lane >= dist && (heads & span) == 0u) flags |= 1u << d;
                 }
                 // ---- layer 0: Linear (fp32 FMA) -> BatchNorm (ATen order) -> ReLU -> per-voxel max ----
-                float x0[P2_U0];
+                float x0[UH];
 #pragma unroll
-                for (int u = 0; u < P2_U0; ++u) x0[u] = 0.0f;
+                for (int u = 0; u < UH; ++u) x0[u] = 0.0f;
 #pragma unroll
                 for (int k4 = 0; k4 < P2_C0 / 4; ++k4) {
                     if (k4 < c0q) {                              // warp-uniform: whole groups of four inputs are skipped
                         const float in[4] = {in4[k4].x, in4[k4].y, in4[k4].z, in4[k4].w};
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
-                            const float4 *wr = reinterpret_cast<const float4 *>(w0t + (4 * k4 + kk) * P2_U0);
+                            const float4 *wr = reinterpret_cast<const float4 *>(w0t + (4 * k4 + kk) * P2_U0 + uh);
 #pragma unroll
-                            for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
+                            for (int u4 = 0; u4 < UH / 4; ++u4) {
                                 const float4 w = wr[u4];
                                 x0[4 * u4] = __fmaf_rn(in[kk], w.x, x0[4 * u4]); x0[4 * u4 + 1] = __fmaf_rn(in[kk], w.y, x0[4 * u4 + 1]);
                                 x0[4 * u4 + 2] = __fmaf_rn(in[kk], w.z, x0[4 * u4 + 2]); x0[4 * u4 + 3] = __fmaf_rn(in[kk], w.w, x0[4 * u4 + 3]);
@@ -450,32 +477,34 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                     }
                 }
                 const int row = g * 32 + lane;
-                float xm[P2_U0];
+                float xm[UH];
 #pragma unroll
-                for (int u = 0; u < P2_U0; ++u) {
-                    const float v = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x0[u], bn0[u]), bn0[P2_U0 + u]), bn0[2 * P2_U0 + u]), bn0[3 * P2_U0 + u]);
+                for (int u = 0; u < UH; ++u) {
+                    const float v = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x0[u], bn0[uh + u]), bn0[P2_U0 + uh + u]), bn0[2 * P2_U0 + uh + u]), bn0[3 * P2_U0 + uh + u]);
                     x0[u] = row_ok ? fmaxf(v, 0.0f) : 0.0f;
                     xm[u] = x0[u];
                 }
-                p2_seg_max<P2_U0>(xm, flags, nsteps);
+                p2_seg_max<UH>(xm, flags, nsteps);
 #pragma unroll
-                for (int u = 0; u < P2_U0; ++u) xm[u] = __shfl_sync(0xffffffffu, xm[u], last_lane & 31);
+                for (int u = 0; u < UH; ++u) xm[u] = __shfl_sync(0xffffffffu, xm[u], last_lane & 31);
 #pragma unroll
-                for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
+                for (int u4 = 0; u4 < UH / 4; ++u4) {
                     float4 hi, lo;
                     tc_split(x0[4 * u4], hi.x, lo.x); tc_split(x0[4 * u4 + 1], hi.y, lo.y); tc_split(x0[4 * u4 + 2], hi.z, lo.z); tc_split(x0[4 * u4 + 3], hi.w, lo.w);
-                    uint32_t o = tc_canon(row, 4 * u4, TC_M);
+                    uint32_t o = tc_canon(row, uh + 4 * u4, TC_M);
                     *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
                     tc_split(xm[4 * u4], hi.x, lo.x); tc_split(xm[4 * u4 + 1], hi.y, lo.y); tc_split(xm[4 * u4 + 2], hi.z, lo.z); tc_split(xm[4 * u4 + 3], hi.w, lo.w);
-                    o = tc_canon(row, P2_U0 + 4 * u4, TC_M);
+                    o = tc_canon(row, P2_U0 + uh + 4 * u4, TC_M);
                     *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
                 }
-                mt->vid[lane] = seg_last ? vid_j : -1;
-                const uint32_t lasts = __ballot_sync(0xffffffffu, seg_last);
-                if (lane == 0) { mt->lasts = lasts; mt->done = 0u; }
+                if (uh == 0) {                                  // the group's record is written by the pair's first warp
+                    const uint32_t lasts = __ballot_sync(0xffffffffu, seg_last);
+                    if (lane == 0) { mt->vid0 = (int)dsc.y; mt->lasts = lasts; mt->done = 0u; }
+                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) p2_mbar_arrive(bar_full);
+                P2_STAMP(round, 0, 2);
             }
         } else {
         const int T = a.t, C = a.c, c0r = (a.c0 + 3) & ~3;
@@ -661,9 +690,8 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                 o = tc_canon(row, P2_U0 + 4 * u4, TC_M);
                 *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
             }
-            mt->vid[lane] = seg_last ? vid_j : -1;
             const uint32_t lasts = __ballot_sync(0xffffffffu, seg_last);
-            if (lane == 0) { mt->lasts = lasts; mt->done = 0u; }
+            if (lane == 0) { mt->vid0 = vid_j; mt->lasts = lasts; mt->done = 0u; }   // lane 0 = first row of the first voxel
             v_next += (uint32_t)nv;
             // (requesting the next group's records here, one hand-off ahead, measured SLOWER -- 1.34 vs 1.26 ms:
             // at 96 registers per thread the extra live values spill)
@@ -673,7 +701,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
         }
         }   // MODE == 0
     } else if (warp == P2_ISSUER_WARP) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P2_ISSUE_REGS));
+        if constexpr (MODE != 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P2_ISSUE_REGS));
         // =====================================================================================
         // ISSUER: the whole warp walks the pipeline (barrier waits are warp-wide, the warp stays
         // converged for the block barrier and the TMEM release at the end); lane 0 issues
@@ -685,6 +713,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
             for (int s = 0; s < 2; ++s) {
                 if (fin[s]) continue;
                 if (!p2_mbar_wait(tc_smem_u32(&s_full[s]), round & 1u, &s_abort, diag, 0x200u | (s << 4) | (round << 16))) { fin[0] = fin[1] = true; break; }
+                P2_STAMP(round, s, 0);
                 const P2Meta *mt = meta + (s * 2 + (round & 1u)) * 4;
                 const uint32_t all_done = *reinterpret_cast<const volatile uint32_t *>(&mt[0].done) &
                                           *reinterpret_cast<const volatile uint32_t *>(&mt[1].done) &
@@ -694,6 +723,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                 // apart, so no barrier may run two phases ahead of its slowest waiter -- the epilogue must have
                 // passed round - 1 before this round's arrivals (MMA commit or the exit arrivals below)
                 if (round > 0 && !p2_mbar_wait(tc_smem_u32(&s_free[s]), (round - 1) & 1u, &s_abort, diag, 0x300u | (s << 4) | (round << 16))) { fin[0] = fin[1] = true; break; }
+                P2_STAMP(round, s, 1);
                 if (all_done) {                                             // every producer of the set is out of work
                     fin[s] = true;
                     if (lane == 0) {
@@ -723,13 +753,14 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                     tc_commit(tc_smem_u32(&s_mma[s]));      // operand stage free + accumulator ready, when the MMAs retire
                 }
                 __syncwarp();
+                P2_STAMP(round, s, 2);
             }
         }
     } else {
         // =====================================================================================
         // EPILOGUE warp e: TMEM lanes [32 e, 32 e + 32)
         // =====================================================================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P2_EPI_REGS));
+        if constexpr (MODE != 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P2_EPI_REGS));
         const int e = warp & 3, half = (warp - P2_EPI_WARP0) >> 2;
         const int unit = e * 32 + lane;
         const bool has_units = e * 32 < N;                                   // warp-uniform
@@ -742,6 +773,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                 if (!p2_mbar_wait(tc_smem_u32(&s_rec[s]), round & 1u, &s_abort, diag, 0x500u | (s << 4) | (warp - P2_EPI_WARP0) | (round << 16))) { fin[0] = fin[1] = true; break; }
                 if (!p2_mbar_wait(tc_smem_u32(&s_mma[s]), round & 1u, &s_abort, diag, 0x400u | (s << 4) | (warp - P2_EPI_WARP0) | (round << 16))) { fin[0] = fin[1] = true; break; }
                 if (*reinterpret_cast<volatile uint32_t *>(&s_exit[s])) { fin[s] = true; continue; }
+                P2_STAMP(round, s, 0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int gg = 2 * half; gg < 2 * half + 2 && has_units; ++gg) {
                     const P2Meta *mt = meta + ((s * 2 + (round & 1u)) * 4 + gg);
@@ -749,20 +781,27 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                     const uint32_t lasts = mt->lasts;
                     float v[32];
                     tc_ld_32x32(tmem + ((uint32_t)(e * 32) << 16) + (uint32_t)(s * TC_M + gg * 32), v);
+                    P2_STAMP2(round, s, 2 * (gg & 1));
+                    // branch-free: the voxels of a group take consecutive output rows (first one = vid0), so the
+                    // store address just advances at every voxel end; BatchNorm + ReLU are evaluated for every
+                    // column (two instructions) instead of branching 32 times, the store is predicated
                     float run = neutral;
+                    float *dst = a.out + (size_t)mt->vid0 * N + unit;
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
+                        const bool last = (lasts >> k) & 1u;                 // warp-uniform: the voxel ends at row k
                         run = fmaxf(run, v[k]);
-                        if ((lasts >> k) & 1u) {                             // warp-uniform: the voxel ends at row k
-                            const int vid = mt->vid[k];
-                            if (unit < N) __stcs(a.out + (size_t)vid * N + unit, fmaxf(__fmaf_rn(run, sc, sh), 0.0f));
-                            run = neutral;
-                        }
+                        const float y = fmaxf(__fmaf_rn(run, sc, sh), 0.0f);
+                        if (last && unit < N) __stcs(dst, y);
+                        dst += last ? N : 0;
+                        run = last ? neutral : run;
                     }
+                    P2_STAMP2(round, s, 2 * (gg & 1) + 1);
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) p2_mbar_arrive(tc_smem_u32(&s_free[s]));
+                P2_STAMP(round, s, 1);
             }
         }
     }
@@ -814,10 +853,10 @@ int pv_pfn_fused_launch(P2Args &a, const pv_pfn_layer *layers, int batch_frames,
         const unsigned blocks = (a.n_chunks + P2_ROWS_THREADS / 32 - 1) / (P2_ROWS_THREADS / 32);
         k_pfn_rows<<<blocks < sms * 2 * P2_ROWS_BLOCKS ? blocks : sms * 2 * P2_ROWS_BLOCKS, P2_ROWS_THREADS, 0, st>>>(a);
         if (cudaFuncSetAttribute(k_pfn_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
-        k_pfn_fused<2><<<want < sms ? want : sms, P2_THREADS, smem, st>>>(a);
+        k_pfn_fused<2><<<want < sms ? want : sms, P2_NTHREADS(2), smem, st>>>(a);
     } else {
         if (cudaFuncSetAttribute(k_pfn_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
-        k_pfn_fused<0><<<want < sms ? want : sms, P2_THREADS, smem, st>>>(a);
+        k_pfn_fused<0><<<want < sms ? want : sms, P2_NTHREADS(0), smem, st>>>(a);
     }
     return pv_last_cuda_error();
 }
