@@ -37,15 +37,18 @@
 #include "tc_common.cuh"
 #include "pfn_fused.cuh"
 
-// warps: NPROD producers | 8 epilogue (TMEM quarter = warp & 3, row half = (warp - first) >> 2) | 1 issuer.
-// MODE 0: 8 producers, one per group of 32 rows.  MODE 2: 16 producers, TWO per group, each computing half of
-// layer 0's units for the group's rows: a producer warp is one serial instruction stream (~1350 dependent
-// instructions per group), and with two of them per scheduler the stream's own latency set the pace.
+// warps 0-7 producers (two sets of four: set = operand stage, one warp per group of 32 rows) | warps 8-23
+// epilogue in two TEAMS of eight (team = round parity; TMEM quarter = warp & 3, row half = bit 2) | warp 24 issuer.
+// Four TMEM accumulator stages (acc = 2 * (round & 1) + set) against two operand stages in shared memory:
+// an operand stage is free again when its MMAs retire, an accumulator stage only when an epilogue team has
+// drained it -- and a lone warp retires an instruction every ~8 cycles, so a tile's epilogue takes ~3 us.
+// With two accumulator stages that time was on the critical path of every tile (traced: issue 1.4 us ->
+// MMA + wake-up 2.0 us -> epilogue 3.0 us -> next issue); with four, two teams drain two tiles at once.
 #ifdef P2_TRACE          // development builds only: per-warp time stamps of block 0 (tools/pfn_trace.py)
 __device__ long long g_p2_trace[32 * 64 * 2 * 3];
-__device__ long long g_p2_trace2[8 * 64 * 2 * 4];
-#define P2_STAMP2(round, s, k) do { if (blockIdx.x == 0 && lane == 0 && (round) < 64u) g_p2_trace2[(((warp - P2_EPI_WARP0) * 64 + (round)) * 2 + (s)) * 4 + (k)] = clock64(); } while (0)
+__device__ long long g_p2_trace2[16 * 64 * 2 * 4];
 #define P2_STAMP(round, s, k) do { if (blockIdx.x == 0 && lane == 0 && (round) < 64u) g_p2_trace[((warp * 64 + (round)) * 2 + (s)) * 3 + (k)] = clock64(); } while (0)
+#define P2_STAMP2(round, s, k) do { if (blockIdx.x == 0 && lane == 0 && (round) < 64u) g_p2_trace2[(((warp - P2_EPI_WARP0) * 64 + (round)) * 2 + (s)) * 4 + (k)] = clock64(); } while (0)
 extern "C" int pv_debug_p2_trace(void *dst, size_t bytes)
 {
     return cudaMemcpyFromSymbol(dst, g_p2_trace, bytes < sizeof(g_p2_trace) ? bytes : sizeof(g_p2_trace)) == cudaSuccess ? 0 : -4;
@@ -58,12 +61,14 @@ extern "C" int pv_debug_p2_trace2(void *dst, size_t bytes)
 #define P2_STAMP(round, s, k) do { } while (0)
 #define P2_STAMP2(round, s, k) do { } while (0)
 #endif
-#define P2_NPROD(MODE) ((MODE) == 2 ? 16 : 8)
-#define P2_NTHREADS(MODE) ((P2_NPROD(MODE) + 9) * 32)
+#define P2_NPROD 8
+#define P2_EPI_WARP0 8
+#define P2_ISSUER_WARP 24
+#define P2_THREADS (25 * 32)
 // (measured: 4 epilogue warps and 128 registers per thread: 1.60 ms vs 1.26 ms)
-#define P2_PROD_REGS 128
-#define P2_EPI_REGS 64
-#define P2_ISSUE_REGS 40
+// (No setmaxnreg: it moves registers inside the pool the CTA was LAUNCHED with -- threads x the kernel's register
+// count -- and an .inc that pool cannot satisfy blocks for ever.  Every role fits the launch count since the
+// producers keep one live array of 32 values.)
 #ifndef P2_WAIT_HINT_NS
 #define P2_WAIT_HINT_NS 20000
 #endif
@@ -117,6 +122,24 @@ __device__ __forceinline__ bool p2_mbar_wait(uint32_t bar, uint32_t parity, vola
 __device__ __forceinline__ void p2_mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// packed fp32 pairs (sm_100: FFMA2 -- two IEEE fp32 FMAs per instruction, bit-identical to two scalar FMAs)
+__device__ __forceinline__ unsigned long long p2_pack(float a, float b)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void p2_unpack(unsigned long long v, float &a, float &b)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long p2_fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
 }
 
 // segmented inclusive scan step helpers: flags bit d set <=> lane >= 2^d and lanes (lane - 2^d, lane]
@@ -306,11 +329,11 @@ __global__ void __launch_bounds__(P2_ROWS_THREADS, P2_ROWS_BLOCKS) k_pfn_rows(co
     }
 }
 
-template <int MODE>          // 0: rows gathered from the padded tensor inside the producers; 2: rows pre-decorated by k_pfn_rows
-__global__ void __launch_bounds__(P2_NTHREADS(MODE), 1) k_pfn_fused(const __grid_constant__ P2Args a)
+template <int MODE, int C0Q>  // MODE 0: rows gathered from the padded tensor inside the producers (C0Q unused); MODE 2: rows pre-decorated by
+                             // k_pfn_rows, C0Q = float4s per decorated row (compile-time: the row registers are live across a hand-off)
+__global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_constant__ P2Args a)
 {
-    constexpr int P2_THREADS = P2_NTHREADS(MODE), P2_EPI_WARP0 = P2_NPROD(MODE), P2_ISSUER_WARP = P2_NPROD(MODE) + 8;
-    constexpr int UH = MODE == 2 ? P2_U0 / 2 : P2_U0;     // layer-0 units per producer warp
+    constexpr int UH = P2_U0;
     extern __shared__ __align__(128) float smem[];
     const int N = a.n1;
     float *a_st = smem;                                    // [2 stages][hi | lo][128 x 64] canonical
@@ -319,13 +342,14 @@ __global__ void __launch_bounds__(P2_NTHREADS(MODE), 1) k_pfn_fused(const __grid
     float *w0t = b_lo + TC_M * P2_K;                       // [P2_C0][P2_U0]: layer-0 weight, transposed
     float *bn0 = w0t + P2_C0 * P2_U0;                      // mean, invstd, gamma, beta: 4 x 32
     float *bn1 = bn0 + 4 * P2_U0;                          // 4 x N
-    P2Meta *meta = reinterpret_cast<P2Meta *>(bn1 + 4 * N);   // [2 stages][2 parities][4 groups]
-    __shared__ __align__(8) unsigned long long s_full[2], s_mma[2], s_free[2], s_rec[2];
+    P2Meta *meta = reinterpret_cast<P2Meta *>(bn1 + 4 * N);   // [2 sets][4 rounds in flight][4 groups]
+    uint4 *s_desc = reinterpret_cast<uint4 *>(meta + 32);      // [8 producer warps][64]: group descriptors of the warp's chunk
+    __shared__ __align__(8) unsigned long long s_full[2], s_mma[2], s_acc[4], s_free[4], s_rec[4];
     __shared__ uint32_t s_tmem, s_exit[2];
     __shared__ uint32_t s_abort;
     unsigned int *diag = a.counter + 2;     // diagnostic words of the watchdog (0 = healthy)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t ncols = 256;                             // two accumulator stages x 128 rows (columns)
+    const uint32_t ncols = 512;                             // four accumulator stages x 128 rows (columns): all of TMEM
 
     // ---- prologue: weights, BatchNorm constants, barriers, TMEM ----
     if (warp == P2_ISSUER_WARP) {
@@ -334,11 +358,14 @@ __global__ void __launch_bounds__(P2_NTHREADS(MODE), 1) k_pfn_fused(const __grid
     }
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            tc_mbar_init(tc_smem_u32(&s_full[s]), MODE == 2 ? 8 : 4);
+            tc_mbar_init(tc_smem_u32(&s_full[s]), 4);
             tc_mbar_init(tc_smem_u32(&s_mma[s]), 1);
-            tc_mbar_init(tc_smem_u32(&s_free[s]), 8);
-            tc_mbar_init(tc_smem_u32(&s_rec[s]), 1);
             s_exit[s] = 0u;
+        }
+        for (int q = 0; q < 4; ++q) {
+            tc_mbar_init(tc_smem_u32(&s_acc[q]), 1);
+            tc_mbar_init(tc_smem_u32(&s_free[q]), 8);
+            tc_mbar_init(tc_smem_u32(&s_rec[q]), 1);
         }
         s_abort = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -356,20 +383,19 @@ __global__ void __launch_bounds__(P2_NTHREADS(MODE), 1) k_pfn_fused(const __grid
         const int k = e / P2_U0, u = e - k * P2_U0;
         w0t[e] = k < a.c0 ? __ldg(a.w0 + u * a.c0 + k) : 0.0f;
     }
+    // both BatchNorms are folded to one FMA per element, y = x * s + b with s = invstd * gamma and
+    // b = beta - mean * s (moves y by ulps against ATen's (x - mean) * invstd * gamma + beta)
     for (int o = tid; o < P2_U0; o += P2_THREADS) {
-        bn0[o] = a.mean0[o];
-        bn0[P2_U0 + o] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(a.var0[o], a.eps)));
-        bn0[2 * P2_U0 + o] = a.gamma0[o];
-        bn0[3 * P2_U0 + o] = a.beta0[o];
+        const float sc = __fmul_rn(__fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(a.var0[o], a.eps))), a.gamma0[o]);
+        bn0[o] = sc;
+        bn0[P2_U0 + o] = __fsub_rn(a.beta0[o], __fmul_rn(a.mean0[o], sc));
     }
-    // layer 1's BatchNorm is folded to one FMA per element, y = x * s + b with s = invstd * gamma and
-    // b = beta - mean * s: the GEMM in front of it is accurate to ~1e-6 (3xTF32), the fold moves y by ulps
     for (int o = tid; o < N; o += P2_THREADS) {
         const float sc = __fmul_rn(__fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(a.var1[o], a.eps))), a.gamma1[o]);
         bn1[2 * o] = fabsf(sc);                              // the sign went into the weight row
         bn1[2 * o + 1] = __fsub_rn(a.beta1[o], __fmul_rn(a.mean1[o], sc));
     }
-    for (int o = tid; o < 16; o += P2_THREADS) { meta[o].lasts = 0u; meta[o].done = 1u; }
+    for (int o = tid; o < 32; o += P2_THREADS) { meta[o].lasts = 0u; meta[o].done = 1u; }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -383,12 +409,11 @@ __global__ void __launch_bounds__(P2_NTHREADS(MODE), 1) k_pfn_fused(const __grid
     // rows of group k + 1 in flight while group k is evaluated) -- the kernel is bound by issue slots
     // (46 % busy with every role resident), not by the producers' load latency.
     if (warp < P2_EPI_WARP0) {
-        if constexpr (MODE != 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(P2_PROD_REGS));
         // =====================================================================================
         // PRODUCER warp: set = stage, g = group inside the tile
         // =====================================================================================
-        const int set = MODE == 2 ? warp >> 3 : warp >> 2, g = MODE == 2 ? (warp >> 1) & 3 : warp & 3;
-        const int uh = MODE == 2 ? (warp & 1) * UH : 0;       // first layer-0 unit of this warp
+        const int set = warp >> 2, g = warp & 3;
+        constexpr int uh = 0;
         float *a_hi = a_st + (size_t)set * 2 * TC_M * P2_K, *a_lo = a_hi + TC_M * P2_K;
         const uint32_t bar_full = tc_smem_u32(&s_full[set]), bar_mma = tc_smem_u32(&s_mma[set]);
         if constexpr (MODE == 2) {
@@ -397,55 +422,49 @@ __global__ void __launch_bounds__(P2_NTHREADS(MODE), 1) k_pfn_fused(const __grid
             // drows, first output row, head mask, total | scan steps << 8} and <= 32 consecutive
             // 64-byte rows -- one coalesced load, no dependent gather left in this kernel
             // ---------------------------------------------------------------------------------
-            const int c0q = (a.c0 + 3) >> 2;                 // float4s per decorated row
-            uint4 d_lo = make_uint4(0, 0, 0, 0), d_hi = d_lo; // descriptors of the warp's chunk: groups lane and 32 + lane
+            constexpr int c0q = C0Q;                          // float4s per decorated row
+            uint4 *my_desc = s_desc + warp * P2_MC;           // descriptors of the warp's chunk
             uint32_t ng = 0, gi = 0;
-            bool out_of_work = false;
-            uint32_t next_chunk = blockIdx.x * 8u + (uint32_t)(warp >> 1);   // pair index
-            for (uint32_t round = 0;; ++round) {
-                // ---- next group: descriptor and rows are requested BEFORE the stage is waited for ----
-                while (!out_of_work && gi >= ng) {
-                    // the two warps of a pair walk the same chunks: a static stride instead of the queue
-                    const uint32_t id = next_chunk;
-                    next_chunk += gridDim.x * 8u;
-                    if (id >= a.n_chunks) { out_of_work = true; break; }
+            // the NEXT group's descriptor and rows: requested one group ahead, right after layer 0 of the current
+            // group has consumed the row registers, so that the loads travel while the warp waits for its operand
+            // stage and writes it (traced: 1-2 us of exposed load latency per group without this)
+            uint4 dsc_n = make_uint4(0, 0, 0, 0);
+            float4 in4[C0Q];
+            bool oow_n = false;
+            auto fetch_next = [&]() {
+                while (!oow_n && gi >= ng) {
+                    uint32_t id = 0;
+                    if (lane == 0) id = atomicAdd(a.counter, 1u);
+                    id = __shfl_sync(0xffffffffu, id, 0);
+                    if (id >= a.n_chunks) { oow_n = true; break; }
                     ng = __ldcs(a.ngroups + id);
-                    d_lo = __ldcs(a.desc + (size_t)id * P2_MC + lane);
-                    d_hi = __ldcs(a.desc + (size_t)id * P2_MC + 32 + lane);
+                    __syncwarp();
+                    my_desc[lane] = __ldcs(a.desc + (size_t)id * P2_MC + lane);
+                    my_desc[32 + lane] = __ldcs(a.desc + (size_t)id * P2_MC + 32 + lane);
+                    __syncwarp();
                     gi = 0;
                 }
-                uint4 dsc = make_uint4(0, 0, 0, 0);
-                float4 in4[P2_C0 / 4];
+                dsc_n = make_uint4(0, 0, 0, 0);
 #pragma unroll
-                for (int k4 = 0; k4 < P2_C0 / 4; ++k4) in4[k4] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (!out_of_work) {
-                    const uint4 src = gi < 32u ? d_lo : d_hi;
-                    dsc.x = __shfl_sync(0xffffffffu, src.x, gi & 31u); dsc.y = __shfl_sync(0xffffffffu, src.y, gi & 31u);
-                    dsc.z = __shfl_sync(0xffffffffu, src.z, gi & 31u); dsc.w = __shfl_sync(0xffffffffu, src.w, gi & 31u);
+                for (int k4 = 0; k4 < C0Q; ++k4) in4[k4] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (!oow_n) {
+                    dsc_n = my_desc[gi];
                     ++gi;
-                    if ((uint32_t)lane < (dsc.w & 0xffu)) {
-                        const float4 *src4 = a.drows + (size_t)dsc.x + lane;
+                    if ((uint32_t)lane < (dsc_n.w & 0xffu)) {
+                        const float4 *src4 = a.drows + (size_t)dsc_n.x + lane;
 #pragma unroll
-                        for (int k4 = 0; k4 < P2_C0 / 4; ++k4)
-                            if (k4 < c0q) in4[k4] = __ldg(src4 + (size_t)k4 * a.drow_stride);   // the pair's other warp reads the same rows
+                        for (int k4 = 0; k4 < C0Q; ++k4) in4[k4] = __ldcs(src4 + (size_t)k4 * a.drow_stride);
                     }
                 }
-                P2_STAMP(round, 0, 0);
-                if (round > 0) {
-                    if (!p2_mbar_wait(bar_mma, (round - 1) & 1u, &s_abort, diag, 0x100u | (set << 4) | g | (round << 16))) break;   // the stage's previous tile has been consumed
-                    if (*reinterpret_cast<volatile uint32_t *>(&s_exit[set])) break;
-                }
-                P2_STAMP(round, 0, 1);
-                P2Meta *mt = meta + ((set * 2 + (round & 1u)) * 4 + g);
-                if (out_of_work) {
-                    if (lane == 0 && uh == 0) mt->done = 1u;
-                    __syncwarp();
-                    if (lane == 0) p2_mbar_arrive(bar_full);
-                    continue;
-                }
+            };
+            fetch_next();
+            for (uint32_t round = 0;; ++round) {
+                const uint4 dsc = dsc_n;
+                const bool out_of_work = oow_n;
+                // ---- everything that does not touch the operand stage comes BEFORE the wait for it: the group's
+                // segment structure and layer 0 (Linear as packed FFMA2 pairs -> folded BatchNorm -> ReLU) ----
                 const uint32_t heads = dsc.z, total = dsc.w & 0xffu, nsteps = (dsc.w >> 8) & 0xffu;
                 const bool row_ok = (uint32_t)lane < total;
-                const int j = __popc(heads & (0xFFFFFFFFu >> (31 - lane))) - 1;   // voxel ordinal of this row
                 const uint32_t above = lane < 31 ? heads & (0xFFFFFFFEu << lane) : 0u;   // heads in lanes > lane
                 const int last_lane = (above ? __ffs(above) - 1 : (int)total) - 1;
                 const bool seg_last = row_ok && lane == last_lane;
@@ -456,45 +475,71 @@ __global__ void __launch_bounds__(P2_NTHREADS(MODE), 1) k_pfn_fused(const __grid
                     const uint32_t span = lane >= dist ? (0xFFFFFFFFu >> (31 - lane)) & ~(0xFFFFFFFFu >> (31 - (lane - dist))) : 0xFFFFFFFFu;
                     if (row_ok && lane >= dist && (heads & span) == 0u) flags |= 1u << d;
                 }
-                // ---- layer 0: Linear (fp32 FMA) -> BatchNorm (ATen order) -> ReLU -> per-voxel max ----
                 float x0[UH];
+                {
+                    unsigned long long acc[UH / 2];
 #pragma unroll
-                for (int u = 0; u < UH; ++u) x0[u] = 0.0f;
+                    for (int u = 0; u < UH / 2; ++u) acc[u] = 0ull;
 #pragma unroll
-                for (int k4 = 0; k4 < P2_C0 / 4; ++k4) {
-                    if (k4 < c0q) {                              // warp-uniform: whole groups of four inputs are skipped
-                        const float in[4] = {in4[k4].x, in4[k4].y, in4[k4].z, in4[k4].w};
+                    for (int k4 = 0; k4 < C0Q; ++k4) {
+                        {
+                            const float in[4] = {in4[k4].x, in4[k4].y, in4[k4].z, in4[k4].w};
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const float4 *wr = reinterpret_cast<const float4 *>(w0t + (4 * k4 + kk) * P2_U0 + uh);
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const ulonglong2 *wr = reinterpret_cast<const ulonglong2 *>(w0t + (4 * k4 + kk) * P2_U0);
+                                const unsigned long long xin = p2_pack(in[kk], in[kk]);
 #pragma unroll
-                            for (int u4 = 0; u4 < UH / 4; ++u4) {
-                                const float4 w = wr[u4];
-                                x0[4 * u4] = __fmaf_rn(in[kk], w.x, x0[4 * u4]); x0[4 * u4 + 1] = __fmaf_rn(in[kk], w.y, x0[4 * u4 + 1]);
-                                x0[4 * u4 + 2] = __fmaf_rn(in[kk], w.z, x0[4 * u4 + 2]); x0[4 * u4 + 3] = __fmaf_rn(in[kk], w.w, x0[4 * u4 + 3]);
+                                for (int u4 = 0; u4 < UH / 4; ++u4) {
+                                    const ulonglong2 w = wr[u4];
+                                    acc[2 * u4] = p2_fma2(xin, w.x, acc[2 * u4]);
+                                    acc[2 * u4 + 1] = p2_fma2(xin, w.y, acc[2 * u4 + 1]);
+                                }
                             }
                         }
                     }
+                    const ulonglong2 *bsc = reinterpret_cast<const ulonglong2 *>(bn0), *bsh = reinterpret_cast<const ulonglong2 *>(bn0 + P2_U0);
+#pragma unroll
+                    for (int u4 = 0; u4 < UH / 4; ++u4) {
+                        const ulonglong2 sc2 = bsc[u4], sh2 = bsh[u4];
+                        float y0, y1, y2, y3;
+                        p2_unpack(p2_fma2(acc[2 * u4], sc2.x, sh2.x), y0, y1);
+                        p2_unpack(p2_fma2(acc[2 * u4 + 1], sc2.y, sh2.y), y2, y3);
+                        x0[4 * u4] = row_ok ? fmaxf(y0, 0.0f) : 0.0f; x0[4 * u4 + 1] = row_ok ? fmaxf(y1, 0.0f) : 0.0f;
+                        x0[4 * u4 + 2] = row_ok ? fmaxf(y2, 0.0f) : 0.0f; x0[4 * u4 + 3] = row_ok ? fmaxf(y3, 0.0f) : 0.0f;
+                    }
+                }
+                if (!out_of_work) fetch_next();                  // the row registers are free again
+                P2_STAMP(round, 0, 0);
+                if (round > 0) {
+                    if (!p2_mbar_wait(bar_mma, (round - 1) & 1u, &s_abort, diag, 0x100u | (set << 4) | g | (round << 16))) break;   // the stage's previous tile has been consumed
+                    if (*reinterpret_cast<volatile uint32_t *>(&s_exit[set])) break;
+                }
+                P2_STAMP(round, 0, 1);
+                P2Meta *mt = meta + ((set * 4 + (round & 3u)) * 4 + g);
+                if (out_of_work) {
+                    if (lane == 0) mt->done = 1u;
+                    __syncwarp();
+                    if (lane == 0) p2_mbar_arrive(bar_full);
+                    continue;
                 }
                 const int row = g * 32 + lane;
-                float xm[UH];
-#pragma unroll
-                for (int u = 0; u < UH; ++u) {
-                    const float v = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x0[u], bn0[uh + u]), bn0[P2_U0 + uh + u]), bn0[2 * P2_U0 + uh + u]), bn0[3 * P2_U0 + uh + u]);
-                    x0[u] = row_ok ? fmaxf(v, 0.0f) : 0.0f;
-                    xm[u] = x0[u];
-                }
-                p2_seg_max<UH>(xm, flags, nsteps);
-#pragma unroll
-                for (int u = 0; u < UH; ++u) xm[u] = __shfl_sync(0xffffffffu, xm[u], last_lane & 31);
+                // the x0 half of the operand row leaves BEFORE the per-voxel maximum is taken in the same registers:
+                // one live array of 32 values
 #pragma unroll
                 for (int u4 = 0; u4 < UH / 4; ++u4) {
                     float4 hi, lo;
                     tc_split(x0[4 * u4], hi.x, lo.x); tc_split(x0[4 * u4 + 1], hi.y, lo.y); tc_split(x0[4 * u4 + 2], hi.z, lo.z); tc_split(x0[4 * u4 + 3], hi.w, lo.w);
-                    uint32_t o = tc_canon(row, uh + 4 * u4, TC_M);
+                    const uint32_t o = tc_canon(row, uh + 4 * u4, TC_M);
                     *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
-                    tc_split(xm[4 * u4], hi.x, lo.x); tc_split(xm[4 * u4 + 1], hi.y, lo.y); tc_split(xm[4 * u4 + 2], hi.z, lo.z); tc_split(xm[4 * u4 + 3], hi.w, lo.w);
-                    o = tc_canon(row, P2_U0 + uh + 4 * u4, TC_M);
+                }
+                p2_seg_max<UH>(x0, flags, nsteps);
+#pragma unroll
+                for (int u = 0; u < UH; ++u) x0[u] = __shfl_sync(0xffffffffu, x0[u], last_lane & 31);
+#pragma unroll
+                for (int u4 = 0; u4 < UH / 4; ++u4) {
+                    float4 hi, lo;
+                    tc_split(x0[4 * u4], hi.x, lo.x); tc_split(x0[4 * u4 + 1], hi.y, lo.y); tc_split(x0[4 * u4 + 2], hi.z, lo.z); tc_split(x0[4 * u4 + 3], hi.w, lo.w);
+                    const uint32_t o = tc_canon(row, P2_U0 + uh + 4 * u4, TC_M);
                     *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
                 }
                 if (uh == 0) {                                  // the group's record is written by the pair's first warp
@@ -543,7 +588,7 @@ __global__ void __launch_bounds__(P2_NTHREADS(MODE), 1) k_pfn_fused(const __grid
                 if (!p2_mbar_wait(bar_mma, (round - 1) & 1u, &s_abort, diag, 0x100u | (set << 4) | g | (round << 16))) break;   // the stage's previous tile has been consumed
                 if (*reinterpret_cast<volatile uint32_t *>(&s_exit[set])) break;
             }
-            P2Meta *mt = meta + ((set * 2 + (round & 1u)) * 4 + g);
+            P2Meta *mt = meta + ((set * 4 + (round & 3u)) * 4 + g);
             // ---- next mini-chunk ----
             while (!out_of_work && v_next >= v_end) {
                 uint32_t id = 0;
@@ -669,25 +714,28 @@ __global__ void __launch_bounds__(P2_NTHREADS(MODE), 1) k_pfn_fused(const __grid
                 }
             }
             const int row = g * 32 + lane;
-            float xm[P2_U0];
 #pragma unroll
             for (int u = 0; u < P2_U0; ++u) {
-                const float v = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x0[u], bn0[u]), bn0[P2_U0 + u]), bn0[2 * P2_U0 + u]), bn0[3 * P2_U0 + u]);
+                const float v = __fmaf_rn(x0[u], bn0[u], bn0[P2_U0 + u]);
                 x0[u] = row_ok ? fmaxf(v, 0.0f) : 0.0f;
-                xm[u] = x0[u];
             }
-            p2_seg_max<P2_U0>(xm, flags, nsteps);
-#pragma unroll
-            for (int u = 0; u < P2_U0; ++u) xm[u] = __shfl_sync(0xffffffffu, xm[u], last_lane & 31);
-            // operand row [x0 | x_max0] in the canonical K-major layout, split into TF32 hi / lo
+            // operand row [x0 | x_max0] in the canonical K-major layout, split into TF32 hi / lo; the x0 half leaves
+            // before the per-voxel maximum is taken in the same registers
 #pragma unroll
             for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
                 float4 hi, lo;
                 tc_split(x0[4 * u4], hi.x, lo.x); tc_split(x0[4 * u4 + 1], hi.y, lo.y); tc_split(x0[4 * u4 + 2], hi.z, lo.z); tc_split(x0[4 * u4 + 3], hi.w, lo.w);
-                uint32_t o = tc_canon(row, 4 * u4, TC_M);
+                const uint32_t o = tc_canon(row, 4 * u4, TC_M);
                 *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
-                tc_split(xm[4 * u4], hi.x, lo.x); tc_split(xm[4 * u4 + 1], hi.y, lo.y); tc_split(xm[4 * u4 + 2], hi.z, lo.z); tc_split(xm[4 * u4 + 3], hi.w, lo.w);
-                o = tc_canon(row, P2_U0 + 4 * u4, TC_M);
+            }
+            p2_seg_max<P2_U0>(x0, flags, nsteps);
+#pragma unroll
+            for (int u = 0; u < P2_U0; ++u) x0[u] = __shfl_sync(0xffffffffu, x0[u], last_lane & 31);
+#pragma unroll
+            for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
+                float4 hi, lo;
+                tc_split(x0[4 * u4], hi.x, lo.x); tc_split(x0[4 * u4 + 1], hi.y, lo.y); tc_split(x0[4 * u4 + 2], hi.z, lo.z); tc_split(x0[4 * u4 + 3], hi.w, lo.w);
+                const uint32_t o = tc_canon(row, P2_U0 + 4 * u4, TC_M);
                 *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
             }
             const uint32_t lasts = __ballot_sync(0xffffffffu, seg_last);
@@ -701,7 +749,6 @@ __global__ void __launch_bounds__(P2_NTHREADS(MODE), 1) k_pfn_fused(const __grid
         }
         }   // MODE == 0
     } else if (warp == P2_ISSUER_WARP) {
-        if constexpr (MODE != 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P2_ISSUE_REGS));
         // =====================================================================================
         // ISSUER: the whole warp walks the pipeline (barrier waits are warp-wide, the warp stays
         // converged for the block barrier and the TMEM release at the end); lane 0 issues
@@ -712,24 +759,31 @@ __global__ void __launch_bounds__(P2_NTHREADS(MODE), 1) k_pfn_fused(const __grid
         for (uint32_t round = 0; !(fin[0] && fin[1]); ++round) {
             for (int s = 0; s < 2; ++s) {
                 if (fin[s]) continue;
+                const uint32_t acc = ((round & 1u) << 1) | (uint32_t)s;       // accumulator stage of tile (round, s)
                 if (!p2_mbar_wait(tc_smem_u32(&s_full[s]), round & 1u, &s_abort, diag, 0x200u | (s << 4) | (round << 16))) { fin[0] = fin[1] = true; break; }
                 P2_STAMP(round, s, 0);
-                const P2Meta *mt = meta + (s * 2 + (round & 1u)) * 4;
+                const P2Meta *mt = meta + (s * 4 + (round & 3u)) * 4;
                 const uint32_t all_done = *reinterpret_cast<const volatile uint32_t *>(&mt[0].done) &
                                           *reinterpret_cast<const volatile uint32_t *>(&mt[1].done) &
                                           *reinterpret_cast<const volatile uint32_t *>(&mt[2].done) &
                                           *reinterpret_cast<const volatile uint32_t *>(&mt[3].done);
-                // the accumulator stage has been drained.  Also on the way out: a parity wait tells two phases
-                // apart, so no barrier may run two phases ahead of its slowest waiter -- the epilogue must have
-                // passed round - 1 before this round's arrivals (MMA commit or the exit arrivals below)
-                if (round > 0 && !p2_mbar_wait(tc_smem_u32(&s_free[s]), (round - 1) & 1u, &s_abort, diag, 0x300u | (s << 4) | (round << 16))) { fin[0] = fin[1] = true; break; }
+                // the accumulator stage has been drained by its team (tile (round - 2, s)).  A parity wait tells
+                // two phases apart, so no barrier may run two phases ahead of its slowest waiter: every arrival
+                // on s_acc / s_rec [acc] below comes after this wait
+                if (round >= 2 && !p2_mbar_wait(tc_smem_u32(&s_free[acc]), ((round >> 1) - 1u) & 1u, &s_abort, diag, 0x300u | (acc << 4) | (round << 16))) { fin[0] = fin[1] = true; break; }
                 P2_STAMP(round, s, 1);
                 if (all_done) {                                             // every producer of the set is out of work
                     fin[s] = true;
+                    // the OTHER team must have finished the set's last real tile (round - 1) before the exit flag
+                    // goes up (it reads the flag after its waits), and before its barriers see one more phase
+                    const uint32_t acc2 = acc ^ 2u;
+                    if (round >= 1 && !p2_mbar_wait(tc_smem_u32(&s_free[acc2]), (((round + 1u) >> 1) - 1u) & 1u, &s_abort, diag, 0x600u | (acc2 << 4) | (round << 16))) { fin[0] = fin[1] = true; break; }
                     if (lane == 0) {
                         *reinterpret_cast<volatile uint32_t *>(&s_exit[s]) = 1u;
-                        p2_mbar_arrive(tc_smem_u32(&s_rec[s]));
-                        p2_mbar_arrive(tc_smem_u32(&s_mma[s]));
+                        __threadfence_block();
+                        p2_mbar_arrive(tc_smem_u32(&s_rec[acc]));  p2_mbar_arrive(tc_smem_u32(&s_acc[acc]));    // team of this round
+                        p2_mbar_arrive(tc_smem_u32(&s_rec[acc2])); p2_mbar_arrive(tc_smem_u32(&s_acc[acc2]));   // team of the next round
+                        p2_mbar_arrive(tc_smem_u32(&s_mma[s]));                                                  // the set's producers
                     }
                     __syncwarp();
                     continue;
@@ -738,9 +792,9 @@ __global__ void __launch_bounds__(P2_NTHREADS(MODE), 1) k_pfn_fused(const __grid
                 if (lane == 0) {
                     // hands the producers' group records (acquired with the full barrier) on to the epilogue:
                     // a plain release / acquire chain, independent of the tensor core's commit
-                    p2_mbar_arrive(tc_smem_u32(&s_rec[s]));
+                    p2_mbar_arrive(tc_smem_u32(&s_rec[acc]));
                     const float *a_hi = a_st + (size_t)s * 2 * TC_M * P2_K, *a_lo = a_hi + TC_M * P2_K;
-                    const uint32_t d_tmem = tmem + (uint32_t)(s * TC_M);
+                    const uint32_t d_tmem = tmem + acc * (uint32_t)TC_M;
 #pragma unroll 1
                     for (int ks = 0; ks < P2_K / 8; ++ks) {
                         const uint32_t off = ks * 2 * a_k;
@@ -750,7 +804,8 @@ __global__ void __launch_bounds__(P2_NTHREADS(MODE), 1) k_pfn_fused(const __grid
                         tc_mma_tf32(d_tmem, dwh, dxl, idesc, 1u);
                         tc_mma_tf32(d_tmem, dwh, dxh, idesc, 1u);
                     }
-                    tc_commit(tc_smem_u32(&s_mma[s]));      // operand stage free + accumulator ready, when the MMAs retire
+                    tc_commit(tc_smem_u32(&s_mma[s]));      // operand stage free (producers) ...
+                    tc_commit(tc_smem_u32(&s_acc[acc]));    // ... and accumulator ready (epilogue team), when the MMAs retire
                 }
                 __syncwarp();
                 P2_STAMP(round, s, 2);
@@ -758,49 +813,50 @@ __global__ void __launch_bounds__(P2_NTHREADS(MODE), 1) k_pfn_fused(const __grid
         }
     } else {
         // =====================================================================================
-        // EPILOGUE warp e: TMEM lanes [32 e, 32 e + 32)
+        // EPILOGUE warp: team = round parity it serves, e = TMEM quarter (lanes [32 e, 32 e + 32) = 32 units),
+        // half = which two groups of the tile
         // =====================================================================================
-        if constexpr (MODE != 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(P2_EPI_REGS));
-        const int e = warp & 3, half = (warp - P2_EPI_WARP0) >> 2;
+        const int ew = warp - P2_EPI_WARP0, team = ew >> 3, e = warp & 3, half = (ew >> 2) & 1;
         const int unit = e * 32 + lane;
         const bool has_units = e * 32 < N;                                   // warp-uniform
         const float sc = unit < N ? bn1[2 * unit] : 0.0f, sh = unit < N ? bn1[2 * unit + 1] : 0.0f;
         const float neutral = __int_as_float(0xff800000);                    // -inf: sc >= 0 here, so the maximum of the raw accumulator decides
         bool fin[2] = {false, false};
-        for (uint32_t round = 0; !(fin[0] && fin[1]); ++round) {
+        for (uint32_t round = (uint32_t)team; !(fin[0] && fin[1]); round += 2) {
             for (int s = 0; s < 2; ++s) {
                 if (fin[s]) continue;
-                if (!p2_mbar_wait(tc_smem_u32(&s_rec[s]), round & 1u, &s_abort, diag, 0x500u | (s << 4) | (warp - P2_EPI_WARP0) | (round << 16))) { fin[0] = fin[1] = true; break; }
-                if (!p2_mbar_wait(tc_smem_u32(&s_mma[s]), round & 1u, &s_abort, diag, 0x400u | (s << 4) | (warp - P2_EPI_WARP0) | (round << 16))) { fin[0] = fin[1] = true; break; }
+                const uint32_t acc = ((round & 1u) << 1) | (uint32_t)s, par = (round >> 1) & 1u;
+                if (!p2_mbar_wait(tc_smem_u32(&s_rec[acc]), par, &s_abort, diag, 0x500u | (acc << 4) | (ew & 7) | (round << 16))) { fin[0] = fin[1] = true; break; }
+                if (!p2_mbar_wait(tc_smem_u32(&s_acc[acc]), par, &s_abort, diag, 0x400u | (acc << 4) | (ew & 7) | (round << 16))) { fin[0] = fin[1] = true; break; }
                 if (*reinterpret_cast<volatile uint32_t *>(&s_exit[s])) { fin[s] = true; continue; }
                 P2_STAMP(round, s, 0);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int gg = 2 * half; gg < 2 * half + 2 && has_units; ++gg) {
-                    const P2Meta *mt = meta + ((s * 2 + (round & 1u)) * 4 + gg);
+                    const P2Meta *mt = meta + ((s * 4 + (round & 3u)) * 4 + gg);
                     if (*reinterpret_cast<const volatile uint32_t *>(&mt->done)) continue;
                     const uint32_t lasts = mt->lasts;
                     float v[32];
-                    tc_ld_32x32(tmem + ((uint32_t)(e * 32) << 16) + (uint32_t)(s * TC_M + gg * 32), v);
+                    tc_ld_32x32(tmem + ((uint32_t)(e * 32) << 16) + acc * (uint32_t)TC_M + (uint32_t)(gg * 32), v);
                     P2_STAMP2(round, s, 2 * (gg & 1));
                     // branch-free: the voxels of a group take consecutive output rows (first one = vid0), so the
                     // store address just advances at every voxel end; BatchNorm + ReLU are evaluated for every
                     // column (two instructions) instead of branching 32 times, the store is predicated
                     float run = neutral;
-                    float *dst = a.out + (size_t)mt->vid0 * N + unit;
+                    float *const dst = a.out + (size_t)mt->vid0 * N + unit;   // units are a multiple of 32: every lane of the warp owns one
+                    uint32_t off = 0;                                        // 32-bit element offset: advances by N at every voxel end
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
                         const bool last = (lasts >> k) & 1u;                 // warp-uniform: the voxel ends at row k
                         run = fmaxf(run, v[k]);
-                        const float y = fmaxf(__fmaf_rn(run, sc, sh), 0.0f);
-                        if (last && unit < N) __stcs(dst, y);
-                        dst += last ? N : 0;
+                        if (last) __stcs(dst + off, fmaxf(__fmaf_rn(run, sc, sh), 0.0f));
+                        off += last ? (uint32_t)N : 0u;
                         run = last ? neutral : run;
                     }
                     P2_STAMP2(round, s, 2 * (gg & 1) + 1);
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) p2_mbar_arrive(tc_smem_u32(&s_free[s]));
+                if (lane == 0) p2_mbar_arrive(tc_smem_u32(&s_free[acc]));
                 P2_STAMP(round, s, 1);
             }
         }
@@ -829,7 +885,7 @@ bool pv_pfn_fused_supported(const pv_pfn_layer *layers, int n_layers, int t, int
 size_t pv_pfn_fused_smem(int n1)
 {
     return sizeof(float) * (2 * 2 * (size_t)TC_M * P2_K + 2 * (size_t)TC_M * P2_K + P2_C0 * P2_U0 + 4 * P2_U0 + 4 * (size_t)n1) +
-           sizeof(P2Meta) * 16 + 128;
+           sizeof(P2Meta) * 32 + 8 * P2_MC * sizeof(uint4) + 128;
 }
 
 // counter: 24 words of device scratch: [0] the dynamic mini-chunk queue ([22]: row allocator of k_pfn_rows), [1] status bits in the layout
@@ -852,11 +908,21 @@ int pv_pfn_fused_launch(P2Args &a, const pv_pfn_layer *layers, int batch_frames,
         a.drows = a.drows_out; a.desc = a.desc_out; a.ngroups = a.ngroups_out;
         const unsigned blocks = (a.n_chunks + P2_ROWS_THREADS / 32 - 1) / (P2_ROWS_THREADS / 32);
         k_pfn_rows<<<blocks < sms * 2 * P2_ROWS_BLOCKS ? blocks : sms * 2 * P2_ROWS_BLOCKS, P2_ROWS_THREADS, 0, st>>>(a);
-        if (cudaFuncSetAttribute(k_pfn_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
-        k_pfn_fused<2><<<want < sms ? want : sms, P2_NTHREADS(2), smem, st>>>(a);
+        const unsigned grid = want < sms ? want : sms;
+        const int c0q = (a.c0 + 3) >> 2;
+        if (c0q <= 2) {
+            if (cudaFuncSetAttribute(k_pfn_fused<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
+            k_pfn_fused<2, 2><<<grid, P2_THREADS, smem, st>>>(a);
+        } else if (c0q == 3) {
+            if (cudaFuncSetAttribute(k_pfn_fused<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
+            k_pfn_fused<2, 3><<<grid, P2_THREADS, smem, st>>>(a);
+        } else {
+            if (cudaFuncSetAttribute(k_pfn_fused<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
+            k_pfn_fused<2, 4><<<grid, P2_THREADS, smem, st>>>(a);
+        }
     } else {
-        if (cudaFuncSetAttribute(k_pfn_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
-        k_pfn_fused<0><<<want < sms ? want : sms, P2_NTHREADS(0), smem, st>>>(a);
+        if (cudaFuncSetAttribute(k_pfn_fused<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
+        k_pfn_fused<0, 4><<<want < sms ? want : sms, P2_THREADS, smem, st>>>(a);
     }
     return pv_last_cuda_error();
 }

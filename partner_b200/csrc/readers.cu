@@ -678,8 +678,11 @@ int pv_pfn_forward(const float *voxels, const int32_t *num_points, const int32_t
     if (pv_pfn_fused_supported(layers, n_layers, t, c, with_distance) && workspace && workspace_bytes >= 256 &&
         (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0 && (reinterpret_cast<uintptr_t>(coors) & 15u) == 0 &&
         (reinterpret_cast<uintptr_t>(out) & 15u) == 0)
-        return pv_pfn_fused_tensor(voxels, num_points, coors, m, t, c, with_distance, vx, vy, x_off, y_off, layers, eps,
-                                   reinterpret_cast<unsigned int *>(workspace), out, (cudaStream_t)stream);
+    {
+        const int rc = pv_pfn_fused_tensor(voxels, num_points, coors, m, t, c, with_distance, vx, vy, x_off, y_off, layers, eps,
+                                           reinterpret_cast<unsigned int *>(workspace), out, (cudaStream_t)stream);
+        if (rc != PV_ERR_UNSUPPORTED) return rc;             // (unsupported: this build's register budget, see pv_pfn_fused_launch)
+    }
     if (pfn_tiled_supported(layers, n_layers, t) && c + 5 + (with_distance ? 1 : 0) <= PT_MAX_IN) {
         PtArgs q;
         q.voxels = voxels; q.num = num_points; q.coors = coors; q.m = m; q.t = t; q.c = c;
