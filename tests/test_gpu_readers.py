@@ -246,3 +246,40 @@ def test_fused_pillar_front_end_vs_oracle():
     again = fe(frames)                      # the point lists and the map were restored: a second call is identical
     assert np.array_equal(again["coordinates"], coor) and np.array_equal(again["num_points"], num)
     assert_close_fp32(again["features"], ref, "fused PFN features, second call")
+
+
+@pytest.mark.parametrize("name,cartesian,c_in,with_distance,filters", [
+    ("cartesian5_distance_64", True, 5, True, (64, 64)),     # C = 7, decorated width 13: four float4 planes per row
+    ("polar3_96", False, 3, False, (64, 96)),                # C = 3, decorated width 8: two planes
+    ("polar4_32", False, 4, False, (64, 32)),                # C = 4, decorated width 9: three planes, one TMEM quarter
+])
+def test_fused_pillar_front_end_row_widths(name, cartesian, c_in, with_distance, filters):
+    """pv_forward_pfn_canvas on the other decorated-row widths (the tensor-core kernel is instantiated per
+    number of float4 planes), with and without the distance channel, Cartesian and polar input, several
+    last-layer widths; two 1-sweep frames + one 2-sweep frame.  Same gates as the full-size test."""
+    import torch
+    from partner_b200 import PillarFeatureNet, PillarFrontEnd, synth
+    g = synth.GRIDS["NUSC-PILLAR"]
+    cart = [synth.nusc_frame(3300, nsweeps=1), synth.nusc_frame(3301, nsweeps=2), synth.nusc_frame(3302, nsweeps=1)[:777]]
+    if cartesian:
+        frames = [np.ascontiguousarray(f[:, :c_in]) for f in cart]
+        polar = [oracle.transform_points(f) for f in frames]
+    else:
+        polar = [np.ascontiguousarray(oracle.transform_points(f)[:, :c_in]) for f in cart]
+        frames = polar
+    C = polar[0].shape[1]
+    net = _random_pfn_state(PillarFeatureNet(C, filters, with_distance, tuple(g["voxel_size"]), tuple(g["range"])), seed=7).cuda().eval()
+    fe = PillarFrontEnd(g["voxel_size"], g["range"], g["max_points"], g["max_voxels"], net, cartesian=cartesian)
+    got = fe(frames)
+    ref_gen = oracle.VoxelGenerator(g["voxel_size"], g["range"], g["max_points"], g["max_voxels"])
+    vox, coor, num, nv = oracle.collate([ref_gen.generate(p)[:3] for p in polar])
+    assert np.array_equal(got["num_voxels"], nv)
+    assert np.array_equal(got["coordinates"], coor)
+    assert np.array_equal(got["num_points"], num)
+    layers = [dict(weight=L.linear.weight.detach().cpu().numpy(), mean=L.norm.running_mean.cpu().numpy(),
+                   var=L.norm.running_var.cpu().numpy(), gamma=L.norm.weight.detach().cpu().numpy(),
+                   beta=L.norm.bias.detach().cpu().numpy()) for L in net.pfn_layers]
+    ref = oracle.pfn_forward(vox, num, coor, layers, g["voxel_size"], g["range"], with_distance=with_distance, eps=1e-3)
+    assert_close_fp32(got["features"], ref, "fused PFN features " + name)
+    rc, _ = oracle.scatter(ref, coor, len(frames), [512, 512, 1])
+    assert_close_fp32(got["canvas"], rc, "fused PFN canvas " + name)
