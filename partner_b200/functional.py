@@ -127,6 +127,25 @@ class VoxelBatch:
         return int(self.voxel_counts.sum().item())
 
 
+def _check_out(r, dev, rows, batch, want):
+    """``out=`` reuses a previous call's buffers: they must fit THIS call (rows = min(batch * V, n), batch,
+    channel counts, the outputs asked for) -- the kernels write `rows` rows whatever the tensors hold."""
+    def fits(t, shape, dtype, what):
+        if t is None:
+            raise ValueError("out= has no %s buffer, but this call produces one" % what)
+        if t.device != dev or t.dtype != dtype or not t.is_contiguous():
+            raise ValueError("out.%s must be a contiguous %s tensor on %s" % (what, dtype, dev))
+        if t.dim() != len(shape) or t.shape[0] < shape[0] or tuple(t.shape[1:]) != tuple(shape[1:]):
+            raise ValueError("out.%s has shape %s, this call needs at least %s" % (what, tuple(t.shape), tuple(shape)))
+    fits(r.coors, (rows, 4), torch.int32, "coors")
+    fits(r.num_points, (rows,), torch.int32, "num_points")
+    fits(r.voxel_counts, (batch,), torch.int32, "voxel_counts")
+    if r.voxel_counts.shape[0] != batch:
+        raise ValueError("out.voxel_counts has %d entries, this call has %d frames" % (r.voxel_counts.shape[0], batch))
+    for name, (shape, dtype) in want.items():
+        fits(getattr(r, name), shape, dtype, name)
+
+
 def voxelize(cfg, points, frame_offsets, batch, frame_capacity, is_cartesian, want_voxels=False,
              want_mean=False, want_grid_ind=False, want_density=False, canvas=False, out=None, ws_tag=0):
     """pv_voxelize / pv_forward_mean_canvas on CUDA tensors.
@@ -160,6 +179,21 @@ def voxelize(cfg, points, frame_offsets, batch, frame_capacity, is_cartesian, wa
                      if want_density else None)
         r.canvas = (torch.empty((batch, C, cfg.grid[1], cfg.grid[0]), dtype=torch.float32, device=dev)
                     if canvas else None)
+    else:
+        want = {}
+        if want_voxels:
+            want["voxels"] = ((rows, T, C), torch.float32)
+        if want_mean or canvas:
+            want["mean_feats"] = ((rows, C), torch.float32)
+        if want_grid_ind:
+            want["pc_grid_ind"] = ((n, 3), torch.int32)
+        if want_density:
+            want["density"] = ((batch, int(cfg.grid[2]), int(cfg.grid[1]), int(cfg.grid[0])), torch.int32)
+        if canvas:
+            want["canvas"] = ((batch, C, int(cfg.grid[1]), int(cfg.grid[0])), torch.float32)
+        _check_out(r, dev, rows, batch, want)
+        if not want_voxels:
+            r.voxels = None
     r.ws = ws
     r.cfg = cfg
     r.n_cap, r.f_cap = n_cap, f_cap
@@ -215,6 +249,11 @@ def forward_pfn_canvas(cfg, points, frame_offsets, batch, frame_capacity, is_car
         r.voxels = r.pc_grid_ind = r.density = None
         r.mean_feats = torch.empty((rows, units), dtype=torch.float32, device=dev)
         r.canvas = torch.empty((batch, units, ny, nx), dtype=torch.float32, device=dev) if canvas else None
+    else:
+        want = {"mean_feats": ((rows, units), torch.float32)}
+        if canvas:
+            want["canvas"] = ((batch, units, ny, nx), torch.float32)
+        _check_out(r, dev, rows, batch, want)
     r.ws, r.cfg, r.n_cap, r.f_cap = ws, cfg, n_cap, f_cap
     aux = workspace(lib.pv_pfn_canvas_workspace_bytes(batch, ny, nx, n_cap, int(cfg.max_voxels)), dev, ("pfn_canvas", ws_tag))
     arr = _pfn_layer_array(layers)

@@ -164,3 +164,27 @@ def test_sector_ground_truth_matches_reference_golden(nsec, golden_dir):
         assert np.array_equal(ann["gt_index"], g[f"n{nsec}_s{i}_index"])
         assert np.array_equal(ann["gt_boxes"], g[f"n{nsec}_s{i}_boxes"])          # same numpy statements: bit for bit
         assert ann["gt_names"].shape[0] == ann["gt_boxes"].shape[0]
+
+
+def test_out_buffers_are_validated():
+    """`out=` reuses a previous call's tensors: buffers that do not fit the current call are refused on the host
+    instead of being overrun on the device (functional._check_out)."""
+    import torch
+    from partner_b200 import functional as F
+    dev = torch.device("cpu")
+    r = F.VoxelBatch()
+    r.coors = torch.empty((100, 4), dtype=torch.int32)
+    r.num_points = torch.empty((100,), dtype=torch.int32)
+    r.voxel_counts = torch.empty((2,), dtype=torch.int32)
+    r.mean_feats = torch.empty((100, 7), dtype=torch.float32)
+    r.canvas = None
+    F._check_out(r, dev, 100, 2, {"mean_feats": ((100, 7), torch.float32)})
+    F._check_out(r, dev, 60, 2, {"mean_feats": ((60, 7), torch.float32)})          # larger buffers are fine
+    with pytest.raises(ValueError):
+        F._check_out(r, dev, 101, 2, {})                                          # more rows than the buffers hold
+    with pytest.raises(ValueError):
+        F._check_out(r, dev, 100, 3, {})                                          # another batch size
+    with pytest.raises(ValueError):
+        F._check_out(r, dev, 100, 2, {"mean_feats": ((100, 8), torch.float32)})   # another channel count
+    with pytest.raises(ValueError):
+        F._check_out(r, dev, 100, 2, {"canvas": ((2, 7, 8, 8), torch.float32)})   # an output the old call did not produce
