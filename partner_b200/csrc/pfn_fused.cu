@@ -439,8 +439,8 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                     if (id >= a.n_chunks) { oow_n = true; break; }
                     ng = __ldcs(a.ngroups + id);
                     __syncwarp();
-                    my_desc[lane] = __ldcs(a.desc + (size_t)id * P2_MC + lane);
-                    my_desc[32 + lane] = __ldcs(a.desc + (size_t)id * P2_MC + 32 + lane);
+                    if ((uint32_t)lane < ng) my_desc[lane] = __ldcs(a.desc + (size_t)id * P2_MC + lane);       // (only what k_pfn_rows wrote)
+                    if (32u + lane < ng) my_desc[32 + lane] = __ldcs(a.desc + (size_t)id * P2_MC + 32 + lane);
                     __syncwarp();
                     gi = 0;
                 }
