@@ -501,6 +501,7 @@ def main():
     ap.add_argument("--graph-steps", type=int, default=20, help="steps captured per CUDA graph")
     ap.add_argument("--ws-per-stream", type=int, default=0, help="1: one workspace per stream instead of per input set")
     ap.add_argument("--lib", default=None, help="development aid: time another build of the C-ABI library (A/B runs)")
+    ap.add_argument("--pipeline", type=int, default=0, choices=[0, 1, 2], help="development aid: force the list-based (1) / list-free (2) pipeline")
     args = ap.parse_args()
     N_SETS = max(1, args.sets)
     rank = int(os.environ.get("RANK", "0"))
@@ -525,6 +526,8 @@ def main():
     from partner_b200 import functional as F
     from partner_b200._lib import ptr, current_stream
     import ctypes
+    if args.pipeline:
+        F.set_default_pipeline(args.pipeline)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU (there is no CPU fallback)")
     torch.cuda.set_device(local)

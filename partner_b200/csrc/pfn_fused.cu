@@ -181,7 +181,7 @@ __device__ __forceinline__ void p2_seg_sum(float (&v)[NV], uint32_t flags, uint3
 //                            warp's store / load covers 512 contiguous bytes); the representative
 //                            padded row of a non-full voxel is all zeros (:161-164)
 //   desc[chunk * 64 + g]     {row_start, first output row, head mask, total | scan steps << 8}
-// and per chunk ngroups[chunk].  Rows are allocated per chunk with one atomic on counter[22].
+// and per chunk ngroups[chunk].  Rows are allocated per chunk with one atomic on counter[40].
 // Also writes coors / num_points of the voxelizer and restores its point lists.
 // ---------------------------------------------------------------------------------------------
 #define P2_ROWS_THREADS 256
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(P2_ROWS_THREADS, P2_ROWS_BLOCKS) k_pfn_rows(co
         }
         rows_chunk = __reduce_add_sync(0xffffffffu, rows_chunk);
         uint32_t row_cursor = 0;
-        if (lane == 0) row_cursor = atomicAdd(a.counter + 22, (uint32_t)rows_chunk);
+        if (lane == 0) row_cursor = atomicAdd(a.counter + 40, (uint32_t)rows_chunk);
         row_cursor = __shfl_sync(0xffffffffu, row_cursor, 0);
         const int vid0_chunk = __ldg(a.base + b) + (int)r0;
         while (v_next < v_end) {
@@ -888,9 +888,9 @@ size_t pv_pfn_fused_smem(int n1)
            sizeof(P2Meta) * 32 + 8 * P2_MC * sizeof(uint4) + 128;
 }
 
-// counter: 24 words of device scratch: [0] the dynamic mini-chunk queue ([22]: row allocator of k_pfn_rows), [1] status bits in the layout
-// pv_read_status expects (bit 2: the watchdog fired), [2] watchdog tag (0 = healthy), [3] the block that
-// starved first, [4..] where each of its warps was waiting; zeroed before every launch.
+// counter: 64 words (256 bytes) of device scratch, zeroed before every launch: [0] the dynamic mini-chunk queue,
+// [1] status bits in the layout pv_read_status expects (bit 2: the watchdog fired), [2] watchdog tag (0 = healthy),
+// [3] the block that starved first, [4 .. 28] where each of its 25 warps was waiting, [40] row allocator of k_pfn_rows.
 int pv_pfn_fused_launch(P2Args &a, const pv_pfn_layer *layers, int batch_frames, long long voxels_per_frame_cap,
                         cudaStream_t st)
 {
@@ -901,7 +901,7 @@ int pv_pfn_fused_launch(P2Args &a, const pv_pfn_layer *layers, int batch_frames,
     if (a.chunks_per_frame == 0) a.chunks_per_frame = 1;
     a.n_chunks = a.chunks_per_frame * (uint32_t)batch_frames;
     const size_t smem = pv_pfn_fused_smem(a.n1);
-    if (cudaMemsetAsync(a.counter, 0, 24 * sizeof(unsigned int), st) != cudaSuccess) return PV_ERR_CUDA;   // queues + watchdog words
+    if (cudaMemsetAsync(a.counter, 0, 64 * sizeof(unsigned int), st) != cudaSuccess) return PV_ERR_CUDA;   // queues + watchdog words
     const unsigned want = (a.n_chunks + 7) / 8;
     const unsigned sms = (unsigned)pv_sm_count();
     if (a.mode == 1) {                                       // point lists: gather + decorate first, at full occupancy

@@ -31,7 +31,7 @@ struct P2Args {
 // Shapes the kernel covers: two layers, 32 units in the first, 32 | units of the last <= 128,
 // decorated width <= 16, T <= 32.
 bool pv_pfn_fused_supported(const pv_pfn_layer *layers, int n_layers, int t, int c, int with_distance);
-// counter: 24 words of device scratch (chunk queue + watchdog diagnostics), zeroed by the launch.
+// counter: 64 words (256 bytes) of device scratch (chunk queue, status, watchdog diagnostics, row allocator), zeroed by the launch.
 // workspace of the pre-pass: [rows x 64 B | descriptors | groups per chunk]; offsets of the last two are returned
 long long pv_pfn_rows_stride(long long rows);
 size_t pv_pfn_rows_bytes(long long rows, long long voxels_per_frame_cap, int batch_frames, size_t *desc_off, size_t *ng_off);
