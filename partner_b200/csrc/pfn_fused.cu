@@ -8,32 +8,32 @@
 // after the norm they hold relu(shift) != 0 and take part in the max; all padded rows of a voxel are
 // identical, so ONE representative row per non-full voxel is evaluated ("useful rows").
 //
-// Rows come from one of two sources:
-//   mode 0  the padded tensor voxels [M, T, C] of the drop-in reader (pv_pfn_forward);
-//   mode 1  the per-voxel POINT LISTS of the list-based voxelizer (voxelize.cu: kept / vox_kg /
-//           vox_c / vox_cell) + the raw point rows -- the [M, T, C] tensor is never materialised;
-//           the kernel also writes coors / num_points and restores the lists (pv_forward_pfn_canvas).
-//
-// One persistent CTA per SM, 17 warps:
-//   warps 0-7   PRODUCERS, two sets of four (set = A-operand stage).  A warp builds one GROUP of <= 32
-//               useful rows out of whole voxels (lane = row): gathers the rows, decorates them, runs
-//               layer 0 (K = C + 5 <= 16, 4 % of the FLOPs) in fp32 FMAs, BatchNorm + ReLU, the
-//               per-voxel maximum by segmented warp scans, and writes its 32 rows of the layer-1
-//               operand [x0 | x_max0(voxel)] into the stage, split into TF32 hi / lo parts, in the
+// Two kernels.  k_pfn_rows<SRC> (full occupancy) gathers and decorates the useful rows from one of two sources and
+// writes them as float4 planes + one descriptor per group of <= 32 rows:
+//   SRC 0  the padded tensor voxels [M, T, C] of the drop-in reader (pv_pfn_forward), in slices of P2_SLICE voxels;
+//   SRC 1  the per-voxel POINT LISTS of the list-based voxelizer (voxelize.cu: kept / vox_kg / vox_c / vox_cell)
+//          + the raw point rows -- the [M, T, C] tensor is never materialised; also writes coors / num_points
+//          and restores the lists (pv_forward_pfn_canvas).
+// k_pfn_fused<C0Q>: one persistent CTA per SM, 25 warps:
+//   warps 0-7   PRODUCERS, two sets of four (set = A-operand stage).  A warp takes one GROUP (lane = row): loads its
+//               decorated rows (requested one group ahead), runs layer 0 (K = C + 5 <= 16, 4 % of the FLOPs) as
+//               packed fp32 FMAs with the folded BatchNorm + ReLU -- all before it needs the operand stage --, then
+//               writes the x0 half of the layer-1 operand row, takes the per-voxel maximum by segmented warp scans
+//               in the same registers and writes the x_max0 half; both split into TF32 hi / lo parts, in the
 //               canonical K-major UMMA layout.  Four groups = one 128-row MMA tile.
-//   warp 16     ISSUER: one thread issues the 3 x K/8 tcgen05.mma.kind::tf32 of the tile (3xTF32 split:
-//               lo.hi + hi.lo + hi.hi, fp32-accurate) into one of TWO TMEM accumulator stages and
-//               commits to an mbarrier.  The GEMM is issued TRANSPOSED, D[unit, row] = W1 . X^T (the
-//               weight is the M-side operand), so that TMEM lane = output unit, column = row.
-//   warps 8-15  EPILOGUE: warp (e, half) owns TMEM lanes [32 e, 32 e + 32) = 32 units, and the 64 rows
-//               (two producer groups) of row half `half`.  A thread holds ONE unit: its BatchNorm
-//               scale / shift sit in two registers, the rows of a voxel are consecutive columns, so
-//               the per-voxel maximum is a running FMNMX down the row -- and because x -> relu(s x + b)
-//               is monotone, the running op is max (s >= 0) or min (s < 0) on the RAW accumulators and
-//               BatchNorm + ReLU are applied once per voxel.  One coalesced 128-byte store per voxel.
-// While the tensor core works on tile k of stage s, the other producer set builds tile k + 1 and the
-// epilogue drains tile k - 1: three pipelines (operand full / MMA done / accumulator free) on
-// mbarriers, no block-wide barrier after the prologue.
+//   warp 24     ISSUER: one thread issues the 3 x K/8 tcgen05.mma.kind::tf32 of the tile (3xTF32 split:
+//               lo.hi + hi.lo + hi.hi, fp32-accurate) into one of FOUR TMEM accumulator stages and commits to two
+//               mbarriers (operand stage -> producers, accumulator -> epilogue team).  The GEMM is issued
+//               TRANSPOSED, D[unit, row] = W1 . X^T (the weight is the M-side operand), so that TMEM lane = output
+//               unit, column = row.
+//   warps 8-23  EPILOGUE, two teams of eight (a team serves every other round): warp (e, half) owns TMEM lanes
+//               [32 e, 32 e + 32) = 32 units and two groups of the tile.  A thread holds ONE unit: its BatchNorm
+//               scale / shift sit in two registers, the rows of a voxel are consecutive columns, so the per-voxel
+//               maximum is a running FMNMX down the row -- x -> relu(|s| x + b) is monotone (the sign of s went
+//               into the weight row) -- and BatchNorm + ReLU are applied once per voxel.  One coalesced 128-byte
+//               store per voxel.
+// Pipelines on mbarriers (operand full / operand consumed / accumulator ready / records valid / accumulator free),
+// no block-wide barrier after the prologue; see the barrier protocol in DESIGN.md section 3.5.
 #include "tc_common.cuh"
 #include "pfn_fused.cuh"
 
@@ -72,7 +72,9 @@ extern "C" int pv_debug_p2_trace2(void *dst, size_t bytes)
 #ifndef P2_WAIT_HINT_NS
 #define P2_WAIT_HINT_NS 20000
 #endif
-#define P2_MC 64               // voxels per mini-chunk (the unit a producer warp fetches)
+#ifndef P2_MC
+#define P2_MC 64               // voxels per mini-chunk (the unit a producer warp fetches); <= 64
+#endif
 #define P2_U0 32               // units of layer 0
 #define P2_K 64                // K of layer 1 = 2 * P2_U0
 #define P2_C0 16               // decorated input width, padded
@@ -191,15 +193,17 @@ __device__ __forceinline__ void p2_seg_sum(float (&v)[NV], uint32_t flags, uint3
 #ifndef P2_ROWS_BLOCKS
 #define P2_ROWS_BLOCKS 5
 #endif
+template <int SRC>          // 1: point lists of the list-based voxelizer (fused front end); 0: the padded tensor [M, T, C] (pv_pfn_forward)
 __global__ void __launch_bounds__(P2_ROWS_THREADS, P2_ROWS_BLOCKS) k_pfn_rows(const __grid_constant__ P2Args a)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t n_warps = gridDim.x * (P2_ROWS_THREADS / 32);
     const int T = a.t, C = a.c, c0q = (a.c0 + 3) >> 2;
     for (uint32_t id = blockIdx.x * (P2_ROWS_THREADS / 32) + (threadIdx.x >> 5); id < a.n_chunks; id += n_warps) {
-        const int b = (int)(id / a.chunks_per_frame);
-        const uint32_t r0 = (id - (uint32_t)b * a.chunks_per_frame) * P2_MC;
-        const uint32_t cnt = (uint32_t)__ldg(a.voxel_counts + b);
+        // SRC 1: chunk id -> (frame b, voxels [r0, r0 + 64) of the frame); SRC 0: one "frame" = voxels [v0, v0 + m) of the tensor
+        const int b = SRC ? (int)(id / a.chunks_per_frame) : 0;
+        const uint32_t r0 = SRC ? (id - (uint32_t)b * a.chunks_per_frame) * P2_MC : (uint32_t)a.v0 + id * P2_MC;
+        const uint32_t cnt = SRC ? (uint32_t)__ldg(a.voxel_counts + b) : (uint32_t)(a.v0 + a.m);
         const uint32_t v_end = min(cnt, r0 + P2_MC);
         uint32_t v_next = r0, ng = 0;
         if (v_next >= v_end) {
@@ -215,10 +219,16 @@ __global__ void __launch_bounds__(P2_ROWS_THREADS, P2_ROWS_BLOCKS) k_pfn_rows(co
             const uint32_t vi = r0 + 32u * h + lane;
             n_w[h] = 0; kg_w[h] = 0; cell_w[h] = 0;
             if (vi < v_end) {
-                const size_t v = (size_t)b * a.fcap + vi;
-                n_w[h] = (int)min(__ldcs(a.vox_c + v), (uint32_t)T);
-                kg_w[h] = __ldcs(a.vox_kg + v);
-                cell_w[h] = __ldcs(a.vox_cell + v);
+                if (SRC) {
+                    const size_t v = (size_t)b * a.fcap + vi;
+                    n_w[h] = (int)min(__ldcs(a.vox_c + v), (uint32_t)T);
+                    kg_w[h] = __ldcs(a.vox_kg + v);
+                    cell_w[h] = __ldcs(a.vox_cell + v);
+                } else {                                   // kg_w / cell_w carry the pillar's (y, x) of coors (b, z, y, x)
+                    n_w[h] = min(max(__ldg(a.num + vi), 0), T);
+                    const int4 co = __ldg(reinterpret_cast<const int4 *>(a.coors_in) + vi);
+                    kg_w[h] = (uint32_t)co.z; cell_w[h] = (uint32_t)co.w;
+                }
                 rows_chunk += n_w[h] < T ? n_w[h] + 1 : T;
             }
         }
@@ -226,7 +236,7 @@ __global__ void __launch_bounds__(P2_ROWS_THREADS, P2_ROWS_BLOCKS) k_pfn_rows(co
         uint32_t row_cursor = 0;
         if (lane == 0) row_cursor = atomicAdd(a.counter + 40, (uint32_t)rows_chunk);
         row_cursor = __shfl_sync(0xffffffffu, row_cursor, 0);
-        const int vid0_chunk = __ldg(a.base + b) + (int)r0;
+        const int vid0_chunk = SRC ? __ldg(a.base + b) + (int)r0 : (int)r0;
         while (v_next < v_end) {
             // ---- pack whole voxels into <= 32 rows: lane i looks at voxel v_next + i ----
             const uint32_t rel = v_next - r0 + lane;                          // < 64 + 31
@@ -237,8 +247,11 @@ __global__ void __launch_bounds__(P2_ROWS_THREADS, P2_ROWS_BLOCKS) k_pfn_rows(co
             const bool in_chunk = vi < v_end;
             const int n_i = in_chunk ? (rel < 32u ? n_lo : n_hi) : 0;
             const uint32_t kg_i = rel < 32u ? kg_lo : kg_hi, cell_i = rel < 32u ? ce_lo : ce_hi;
-            const uint32_t cxi = cell_i % (uint32_t)a.nx, yz = cell_i / (uint32_t)a.nx;
-            const int4 co_i = make_int4(b, (int)(yz / (uint32_t)a.ny), (int)(yz % (uint32_t)a.ny), (int)cxi);
+            int4 co_i;
+            if (SRC) {
+                const uint32_t cxi = cell_i % (uint32_t)a.nx, yz = cell_i / (uint32_t)a.nx;
+                co_i = make_int4(b, (int)(yz / (uint32_t)a.ny), (int)(yz % (uint32_t)a.ny), (int)cxi);
+            } else co_i = make_int4(0, 0, (int)kg_i, (int)cell_i);
             const int rows_i = in_chunk ? (n_i < T ? n_i + 1 : T) : 0;
             int incl = rows_i;
 #pragma unroll
@@ -278,11 +291,18 @@ __global__ void __launch_bounds__(P2_ROWS_THREADS, P2_ROWS_BLOCKS) k_pfn_rows(co
 #pragma unroll
             for (int k = 0; k < PV_MAX_CHANNELS; ++k) f[k] = 0.0f;
             if (valid) {
-                uint32_t idx = __ldcg(a.kept + kg_j + q);
-                if (P2R_EXP == 1) idx = kg_j + q;                             // experiment: no random gather
-                pv_feature_row(a.pts, idx, a.c_in, a.cart, f);
+                if (SRC) {
+                    uint32_t idx = __ldcg(a.kept + kg_j + q);
+                    if (P2R_EXP == 1) idx = kg_j + q;                         // experiment: no random gather
+                    pv_feature_row(a.pts, idx, a.c_in, a.cart, f);
+                } else {
+                    const float *src = a.voxels + ((size_t)(vid_i - lane + j) * T + q) * C;   // voxel of this row = first voxel of the group + j
+#pragma unroll
+                    for (int k = 0; k < PV_MAX_CHANNELS; ++k)
+                        if (k < C) f[k] = __ldg(src + k);
+                }
             }
-            if (lane < nv) {                                                  // per-voxel outputs of the voxelizer
+            if (SRC && lane < nv) {                                           // per-voxel outputs of the voxelizer
                 __stcs(reinterpret_cast<int4 *>(a.coors_out) + vid_i, co_i);
                 __stcs(a.num_out + vid_i, n_i);
             }
@@ -318,7 +338,7 @@ __global__ void __launch_bounds__(P2_ROWS_THREADS, P2_ROWS_BLOCKS) k_pfn_rows(co
             }
             // restore the list for the next call -- only now: a store to an address whose load is still in
             // flight stalls the load/store unit for the whole round trip (measured here: 440 -> 240 us)
-            if (valid && P2R_EXP != 3) a.kept[kg_j + q] = PV_INF;
+            if (SRC && valid && P2R_EXP != 3) a.kept[kg_j + q] = PV_INF;
             if (lane == 0)
                 __stcg(a.desc_out + (size_t)id * P2_MC + ng, make_uint4(row_cursor, (uint32_t)vid_i, heads, (uint32_t)total | (nsteps << 8)));
             row_cursor += (uint32_t)total;
@@ -329,11 +349,11 @@ __global__ void __launch_bounds__(P2_ROWS_THREADS, P2_ROWS_BLOCKS) k_pfn_rows(co
     }
 }
 
-template <int MODE, int C0Q>  // MODE 0: rows gathered from the padded tensor inside the producers (C0Q unused); MODE 2: rows pre-decorated by
-                             // k_pfn_rows, C0Q = float4s per decorated row (compile-time: the row registers are live across a hand-off)
+template <int C0Q>          // float4s per decorated row (compile-time: the row registers are live across a hand-off)
 __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_constant__ P2Args a)
 {
     constexpr int UH = P2_U0;
+    constexpr int uh = 0;
     extern __shared__ __align__(128) float smem[];
     const int N = a.n1;
     float *a_st = smem;                                    // [2 stages][hi | lo][128 x 64] canonical
@@ -413,16 +433,14 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
         // PRODUCER warp: set = stage, g = group inside the tile
         // =====================================================================================
         const int set = warp >> 2, g = warp & 3;
-        constexpr int uh = 0;
         float *a_hi = a_st + (size_t)set * 2 * TC_M * P2_K, *a_lo = a_hi + TC_M * P2_K;
         const uint32_t bar_full = tc_smem_u32(&s_full[set]), bar_mma = tc_smem_u32(&s_mma[set]);
-        if constexpr (MODE == 2) {
+        {
             // ---------------------------------------------------------------------------------
             // rows were gathered and decorated by k_pfn_rows: a group is a descriptor {first row in
             // drows, first output row, head mask, total | scan steps << 8} and <= 32 consecutive
             // 64-byte rows -- one coalesced load, no dependent gather left in this kernel
             // ---------------------------------------------------------------------------------
-            constexpr int c0q = C0Q;                          // float4s per decorated row
             uint4 *my_desc = s_desc + warp * P2_MC;           // descriptors of the warp's chunk
             uint32_t ng = 0, gi = 0;
             // the NEXT group's descriptor and rows: requested one group ahead, right after layer 0 of the current
@@ -551,203 +569,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                 if (lane == 0) p2_mbar_arrive(bar_full);
                 P2_STAMP(round, 0, 2);
             }
-        } else {
-        const int T = a.t, C = a.c, c0r = (a.c0 + 3) & ~3;
-        constexpr bool LISTS = false;         // the point-list source moved to k_pfn_rows (MODE 2)
-        // the warp's current mini-chunk: voxels [v_next, v_end) of frame b (mode 0: one "frame" of m voxels)
-        int b = 0;
-        uint32_t v_next = 0, v_end = 0;
-        bool out_of_work = false;
-#ifdef P2_DEBUG_ONE_SET
-        if (set == 1) out_of_work = true;
-#endif
-        // record of the voxel this lane looks at in the next packing step, loaded one iteration ahead
-        int w_n = 0;
-        uint32_t w_kg = 0;
-        int4 w_co = make_int4(0, 0, 0, 0);
-        bool win_valid = false;
-        auto load_window = [&]() {
-            const uint32_t vi = v_next + lane;
-            w_n = 0; w_kg = 0; w_co = make_int4(0, 0, 0, 0);
-            if (vi < v_end) {
-                if (LISTS) {
-                    const size_t v = (size_t)b * a.fcap + vi;
-                    w_n = (int)min(__ldcs(a.vox_c + v), (uint32_t)T);
-                    w_kg = __ldcs(a.vox_kg + v);
-                    const uint32_t cell = __ldcs(a.vox_cell + v);
-                    const uint32_t x = cell % (uint32_t)a.nx, yz = cell / (uint32_t)a.nx;
-                    w_co = make_int4(b, (int)(yz / (uint32_t)a.ny), (int)(yz % (uint32_t)a.ny), (int)x);
-                } else {
-                    w_n = min(max(__ldg(a.num + vi), 0), T);
-                    w_co = __ldg(reinterpret_cast<const int4 *>(a.coors_in) + vi);
-                }
-            }
-        };
-        for (uint32_t round = 0;; ++round) {
-            if (round > 0) {
-                if (!p2_mbar_wait(bar_mma, (round - 1) & 1u, &s_abort, diag, 0x100u | (set << 4) | g | (round << 16))) break;   // the stage's previous tile has been consumed
-                if (*reinterpret_cast<volatile uint32_t *>(&s_exit[set])) break;
-            }
-            P2Meta *mt = meta + ((set * 4 + (round & 3u)) * 4 + g);
-            // ---- next mini-chunk ----
-            while (!out_of_work && v_next >= v_end) {
-                uint32_t id = 0;
-                if (lane == 0) id = atomicAdd(a.counter, 1u);
-                id = __shfl_sync(0xffffffffu, id, 0);
-                if (id >= a.n_chunks) { out_of_work = true; break; }
-                b = (int)(id / a.chunks_per_frame);
-                const uint32_t r0 = (id - (uint32_t)b * a.chunks_per_frame) * P2_MC;
-                const uint32_t cnt = LISTS ? (uint32_t)__ldg(a.voxel_counts + b) : (uint32_t)a.m;
-                v_next = r0;
-                v_end = min(cnt, r0 + P2_MC);
-                win_valid = false;
-            }
-            if (out_of_work) {
-                if (lane == 0) mt->done = 1u;
-                __syncwarp();
-                if (lane == 0) p2_mbar_arrive(bar_full);
-                continue;
-            }
-            // ---- pack whole voxels into <= 32 rows: lane i looks at voxel v_next + i (its record was
-            // requested at the end of the previous iteration, or just now after a chunk change) ----
-            if (!win_valid) load_window();
-            win_valid = false;
-            const uint32_t vi = v_next + lane;
-            const int n_i = w_n;
-            const uint32_t kg_i = w_kg;
-            const int4 co_i = w_co;
-            const int rows_i = vi < v_end ? (n_i < T ? n_i + 1 : T) : 0;
-            int incl = rows_i;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += o;
-            }
-            const uint32_t fits = __ballot_sync(0xffffffffu, vi < v_end && incl <= 32);
-            const int nv = __popc(fits);                                  // >= 1: a voxel has at most 32 rows
-            const int start_i = incl - rows_i;
-            const uint32_t heads = __reduce_or_sync(0xffffffffu, lane < nv ? 1u << start_i : 0u);
-            const int total = __shfl_sync(0xffffffffu, incl, nv - 1);
-            const int maxlen = __reduce_max_sync(0xffffffffu, lane < nv ? rows_i : 0);
-            uint32_t nsteps = 0;
-            while ((1 << nsteps) < maxlen) ++nsteps;
-            // ---- lane = row: which voxel, which slot ----
-            const bool row_ok = lane < total;
-            const int j = __popc(heads & (0xFFFFFFFFu >> (31 - lane))) - 1;   // voxel ordinal of this row
-            const int jj = row_ok ? j : 0;
-            const int start_j = __shfl_sync(0xffffffffu, start_i, jj);
-            const int n_j = __shfl_sync(0xffffffffu, n_i, jj);
-            const int rows_j = __shfl_sync(0xffffffffu, rows_i, jj);
-            const uint32_t kg_j = __shfl_sync(0xffffffffu, kg_i, jj);
-            const int cx_j = __shfl_sync(0xffffffffu, co_i.w, jj), cy_j = __shfl_sync(0xffffffffu, co_i.z, jj);
-            const int q = lane - start_j;
-            const bool valid = row_ok && q < n_j;                             // a real point (not the padded representative)
-            uint32_t flags = 0;
-#pragma unroll
-            for (int d = 0; d < 5; ++d) {
-                const int dist = 1 << d;
-                // lanes (lane - dist, lane] hold no head <=> lane - dist is in the same voxel
-                const uint32_t span = lane >= dist ? (0xFFFFFFFFu >> (31 - lane)) & ~(0xFFFFFFFFu >> (31 - (lane - dist))) : 0xFFFFFFFFu;
-                if (row_ok && lane >= dist && (heads & span) == 0u) flags |= 1u << d;
-            }
-            const int vid_i = LISTS ? __ldg(a.base + b) + (int)vi : (int)vi;
-            const int vid_j = __shfl_sync(0xffffffffu, vid_i, jj);
-            const bool seg_last = row_ok && q == rows_j - 1;
-            const int last_lane = start_j + rows_j - 1;
-            // ---- the row ----
-            float f[PV_MAX_CHANNELS];
-#pragma unroll
-            for (int k = 0; k < PV_MAX_CHANNELS; ++k) f[k] = 0.0f;
-            if (valid) {
-                if (LISTS) {
-                    const uint32_t idx = __ldcg(a.kept + kg_j + q);
-                    a.kept[kg_j + q] = PV_INF;                               // restore the list for the next call
-                    pv_feature_row(a.pts, idx, a.c_in, a.cart, f);
-                } else {
-                    const float *src = a.voxels + ((size_t)vid_j * T + q) * C;
-#pragma unroll
-                    for (int k = 0; k < PV_MAX_CHANNELS; ++k)
-                        if (k < C) f[k] = __ldg(src + k);
-                }
-            }
-            if (LISTS && lane < nv) {                                        // per-voxel outputs of the voxelizer
-                __stcs(reinterpret_cast<int4 *>(a.coors_out) + vid_i, co_i);
-                __stcs(a.num_out + vid_i, n_i);
-            }
-            // cluster mean (:137-139): sum over the voxel's rows / num
-            float sm[3] = {f[0], f[1], f[2]};
-            p2_seg_sum<3>(sm, flags, nsteps);
-            const float sx = __shfl_sync(0xffffffffu, sm[0], last_lane & 31), sy = __shfl_sync(0xffffffffu, sm[1], last_lane & 31),
-                        sz = __shfl_sync(0xffffffffu, sm[2], last_lane & 31);
-            const float nf = (float)n_j;
-            const float mx = __fdiv_rn(sx, nf), my = __fdiv_rn(sy, nf), mz = __fdiv_rn(sz, nf);
-            const float pcx = __fadd_rn(__fmul_rn((float)cx_j, a.vx), a.x_off);   // :146-147
-            const float pcy = __fadd_rn(__fmul_rn((float)cy_j, a.vy), a.y_off);   // :149-150
-            float in[P2_C0];
-#pragma unroll
-            for (int k = 0; k < P2_C0; ++k) {
-                float val = 0.0f;
-                if (k < C) val = f[k < PV_MAX_CHANNELS ? k : 0];
-                else if (k == C) val = __fsub_rn(f[0], mx);                   // :140
-                else if (k == C + 1) val = __fsub_rn(f[1], my);
-                else if (k == C + 2) val = __fsub_rn(f[2], mz);
-                else if (k == C + 3) val = __fsub_rn(f[0], pcx);
-                else if (k == C + 4) val = __fsub_rn(f[1], pcy);
-                else if (k == C + 5 && a.with_distance)
-                    val = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(f[0], f[0]), __fmul_rn(f[1], f[1])), __fmul_rn(f[2], f[2])));   // :155
-                in[k] = valid ? val : 0.0f;                                   // :161-164 mask: padded rows are zero
-            }
-            // ---- layer 0: Linear (fp32 FMA) -> BatchNorm (ATen order) -> ReLU -> per-voxel max ----
-            float x0[P2_U0];
-#pragma unroll
-            for (int u = 0; u < P2_U0; ++u) x0[u] = 0.0f;
-#pragma unroll
-            for (int k = 0; k < P2_C0; ++k) {
-                if (k < c0r) {                              // warp-uniform: whole groups of four inputs are skipped
-                    const float4 *wr = reinterpret_cast<const float4 *>(w0t + k * P2_U0);
-#pragma unroll
-                    for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
-                        const float4 w = wr[u4];
-                        x0[4 * u4] = __fmaf_rn(in[k], w.x, x0[4 * u4]); x0[4 * u4 + 1] = __fmaf_rn(in[k], w.y, x0[4 * u4 + 1]);
-                        x0[4 * u4 + 2] = __fmaf_rn(in[k], w.z, x0[4 * u4 + 2]); x0[4 * u4 + 3] = __fmaf_rn(in[k], w.w, x0[4 * u4 + 3]);
-                    }
-                }
-            }
-            const int row = g * 32 + lane;
-#pragma unroll
-            for (int u = 0; u < P2_U0; ++u) {
-                const float v = __fmaf_rn(x0[u], bn0[u], bn0[P2_U0 + u]);
-                x0[u] = row_ok ? fmaxf(v, 0.0f) : 0.0f;
-            }
-            // operand row [x0 | x_max0] in the canonical K-major layout, split into TF32 hi / lo; the x0 half leaves
-            // before the per-voxel maximum is taken in the same registers
-#pragma unroll
-            for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
-                float4 hi, lo;
-                tc_split(x0[4 * u4], hi.x, lo.x); tc_split(x0[4 * u4 + 1], hi.y, lo.y); tc_split(x0[4 * u4 + 2], hi.z, lo.z); tc_split(x0[4 * u4 + 3], hi.w, lo.w);
-                const uint32_t o = tc_canon(row, 4 * u4, TC_M);
-                *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
-            }
-            p2_seg_max<P2_U0>(x0, flags, nsteps);
-#pragma unroll
-            for (int u = 0; u < P2_U0; ++u) x0[u] = __shfl_sync(0xffffffffu, x0[u], last_lane & 31);
-#pragma unroll
-            for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
-                float4 hi, lo;
-                tc_split(x0[4 * u4], hi.x, lo.x); tc_split(x0[4 * u4 + 1], hi.y, lo.y); tc_split(x0[4 * u4 + 2], hi.z, lo.z); tc_split(x0[4 * u4 + 3], hi.w, lo.w);
-                const uint32_t o = tc_canon(row, P2_U0 + 4 * u4, TC_M);
-                *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
-            }
-            const uint32_t lasts = __ballot_sync(0xffffffffu, seg_last);
-            if (lane == 0) { mt->vid0 = vid_j; mt->lasts = lasts; mt->done = 0u; }   // lane 0 = first row of the first voxel
-            v_next += (uint32_t)nv;
-            // (requesting the next group's records here, one hand-off ahead, measured SLOWER -- 1.34 vs 1.26 ms:
-            // at 96 registers per thread the extra live values spill)
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> the tensor core's async proxy
-            __syncwarp();
-            if (lane == 0) p2_mbar_arrive(bar_full);
         }
-        }   // MODE == 0
     } else if (warp == P2_ISSUER_WARP) {
         // =====================================================================================
         // ISSUER: the whole warp walks the pipeline (barrier waits are warp-wide, the warp stays
@@ -904,25 +726,23 @@ int pv_pfn_fused_launch(P2Args &a, const pv_pfn_layer *layers, int batch_frames,
     if (cudaMemsetAsync(a.counter, 0, 64 * sizeof(unsigned int), st) != cudaSuccess) return PV_ERR_CUDA;   // queues + watchdog words
     const unsigned want = (a.n_chunks + 7) / 8;
     const unsigned sms = (unsigned)pv_sm_count();
-    if (a.mode == 1) {                                       // point lists: gather + decorate first, at full occupancy
-        a.drows = a.drows_out; a.desc = a.desc_out; a.ngroups = a.ngroups_out;
-        const unsigned blocks = (a.n_chunks + P2_ROWS_THREADS / 32 - 1) / (P2_ROWS_THREADS / 32);
-        k_pfn_rows<<<blocks < sms * 2 * P2_ROWS_BLOCKS ? blocks : sms * 2 * P2_ROWS_BLOCKS, P2_ROWS_THREADS, 0, st>>>(a);
-        const unsigned grid = want < sms ? want : sms;
-        const int c0q = (a.c0 + 3) >> 2;
-        if (c0q <= 2) {
-            if (cudaFuncSetAttribute(k_pfn_fused<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
-            k_pfn_fused<2, 2><<<grid, P2_THREADS, smem, st>>>(a);
-        } else if (c0q == 3) {
-            if (cudaFuncSetAttribute(k_pfn_fused<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
-            k_pfn_fused<2, 3><<<grid, P2_THREADS, smem, st>>>(a);
-        } else {
-            if (cudaFuncSetAttribute(k_pfn_fused<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
-            k_pfn_fused<2, 4><<<grid, P2_THREADS, smem, st>>>(a);
-        }
+    // gather + decorate first, at full occupancy; then layer 0 / tcgen05 layer 1 / per-voxel max
+    a.drows = a.drows_out; a.desc = a.desc_out; a.ngroups = a.ngroups_out;
+    const unsigned blocks = (a.n_chunks + P2_ROWS_THREADS / 32 - 1) / (P2_ROWS_THREADS / 32);
+    const unsigned rgrid = blocks < sms * 2 * P2_ROWS_BLOCKS ? blocks : sms * 2 * P2_ROWS_BLOCKS;
+    if (a.mode == 1) k_pfn_rows<1><<<rgrid, P2_ROWS_THREADS, 0, st>>>(a);
+    else k_pfn_rows<0><<<rgrid, P2_ROWS_THREADS, 0, st>>>(a);
+    const unsigned grid = want < sms ? want : sms;
+    const int c0q = (a.c0 + 3) >> 2;
+    if (c0q <= 2) {
+        if (cudaFuncSetAttribute(k_pfn_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
+        k_pfn_fused<2><<<grid, P2_THREADS, smem, st>>>(a);
+    } else if (c0q == 3) {
+        if (cudaFuncSetAttribute(k_pfn_fused<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
+        k_pfn_fused<3><<<grid, P2_THREADS, smem, st>>>(a);
     } else {
-        if (cudaFuncSetAttribute(k_pfn_fused<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
-        k_pfn_fused<0, 4><<<want < sms ? want : sms, P2_THREADS, smem, st>>>(a);
+        if (cudaFuncSetAttribute(k_pfn_fused<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PV_ERR_CUDA;
+        k_pfn_fused<4><<<grid, P2_THREADS, smem, st>>>(a);
     }
     return pv_last_cuda_error();
 }
@@ -944,16 +764,38 @@ size_t pv_pfn_rows_bytes(long long rows, long long voxels_per_frame_cap, int bat
     return o;
 }
 
-// mode 0: rows from the padded [m, t, c] tensor of the drop-in reader (pv_pfn_forward)
+// The drop-in call on the padded tensor runs in slices of P2_SLICE voxels, so that the decorated rows of a slice
+// (at most T per voxel, 64 bytes each) fit a bounded scratch whatever M is.
+#define P2_SLICE 524288ll     // (131072: 2.0 ms instead of 1.2 for 960 k voxels -- 2048 chunks per launch leave the persistent producers unbalanced)
+size_t pv_pfn_fused_tensor_bytes(long long m, int t)
+{
+    const long long ms = m < P2_SLICE ? m : P2_SLICE;
+    return 256 + pv_pfn_rows_bytes(ms * t, ms, 1, nullptr, nullptr);
+}
+
 int pv_pfn_fused_tensor(const float *voxels, const int32_t *num_points, const int32_t *coors, int64_t m, int32_t t,
                         int32_t c, int32_t with_distance, float vx, float vy, float x_off, float y_off,
-                        const pv_pfn_layer *layers, float eps, unsigned int *counter, float *out, cudaStream_t st)
+                        const pv_pfn_layer *layers, float eps, void *workspace, float *out, cudaStream_t st)
 {
     P2Args a = {};
     a.mode = 0;
-    a.voxels = voxels; a.num = num_points; a.coors_in = coors; a.m = m;
+    a.voxels = voxels; a.num = num_points; a.coors_in = coors;
     a.t = t; a.c = c; a.with_distance = with_distance ? 1 : 0; a.c0 = c + 5 + a.with_distance;
     a.vx = vx; a.vy = vy; a.x_off = x_off; a.y_off = y_off; a.eps = eps;
-    a.counter = counter; a.out = out;
-    return pv_pfn_fused_launch(a, layers, 1, m, st);
+    a.counter = reinterpret_cast<unsigned int *>(workspace); a.out = out;
+    const long long ms_max = m < P2_SLICE ? m : P2_SLICE;
+    size_t desc_off = 0, ng_off = 0;
+    pv_pfn_rows_bytes(ms_max * t, ms_max, 1, &desc_off, &ng_off);
+    char *rows0 = reinterpret_cast<char *>(workspace) + 256;
+    a.drows_out = reinterpret_cast<float4 *>(rows0);
+    a.drow_stride = pv_pfn_rows_stride(ms_max * t);
+    a.desc_out = reinterpret_cast<uint4 *>(rows0 + desc_off);
+    a.ngroups_out = reinterpret_cast<uint32_t *>(rows0 + ng_off);
+    for (long long v0 = 0; v0 < m; v0 += P2_SLICE) {           // same stream: a slice's kernels finish before the next one reuses the scratch
+        a.v0 = v0;
+        a.m = m - v0 < P2_SLICE ? m - v0 : P2_SLICE;
+        const int rc = pv_pfn_fused_launch(a, layers, 1, a.m, st);
+        if (rc) return rc;
+    }
+    return PV_OK;
 }

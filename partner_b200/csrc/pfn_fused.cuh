@@ -5,7 +5,7 @@
 struct P2Args {
     int mode;
     // mode 0: padded tensor
-    const float *voxels; const int32_t *num; const int32_t *coors_in; long long m;
+    const float *voxels; const int32_t *num; const int32_t *coors_in; long long m, v0;   // voxels [v0, v0 + m) of the tensor (one slice)
     // mode 1: point lists of the list-based voxelizer
     const float *pts; int c_in, cart;
     const uint32_t *vox_cell, *vox_kg, *vox_c; uint32_t *kept;

@@ -572,7 +572,8 @@ struct P2Args;
 bool pv_pfn_fused_supported(const pv_pfn_layer *layers, int n_layers, int t, int c, int with_distance);
 int pv_pfn_fused_tensor(const float *voxels, const int32_t *num_points, const int32_t *coors, int64_t m, int32_t t,
                         int32_t c, int32_t with_distance, float vx, float vy, float x_off, float y_off,
-                        const pv_pfn_layer *layers, float eps, unsigned int *counter, float *out, cudaStream_t st);
+                        const pv_pfn_layer *layers, float eps, void *workspace, float *out, cudaStream_t st);
+size_t pv_pfn_fused_tensor_bytes(long long m, int t);     // scratch of the call above (queue words + decorated rows of one slice)
 
 static int pfn_tiled_supported(const pv_pfn_layer *layers, int n_layers, int t)
 {
@@ -659,7 +660,12 @@ static PfnWsLayout pfn_ws_layout(int64_t m, int32_t t)
     return L;
 }
 
-size_t pv_pfn_workspace_bytes(int64_t m, int32_t t) { return m > 0 && t > 0 ? pfn_ws_layout(m, t).total : 0; }
+size_t pv_pfn_workspace_bytes(int64_t m, int32_t t)
+{
+    if (m <= 0 || t <= 0) return 0;
+    const size_t tiled = pfn_ws_layout(m, t).total, fused = pv_pfn_fused_tensor_bytes(m, t);
+    return tiled > fused ? tiled : fused;
+}
 
 int pv_pfn_forward(const float *voxels, const int32_t *num_points, const int32_t *coors, int64_t m,
                    int32_t t, int32_t c, int32_t with_distance, float vx, float vy, float x_off,
@@ -675,13 +681,13 @@ int pv_pfn_forward(const float *voxels, const int32_t *num_points, const int32_t
             return PV_ERR_BAD_ARGUMENT;
     // two-layer nets (every PFN the reference's configs build): the warp-specialised kernel, second
     // layer on the tensor cores -- no environment switch, no global state
-    if (pv_pfn_fused_supported(layers, n_layers, t, c, with_distance) && workspace && workspace_bytes >= 256 &&
+    if (pv_pfn_fused_supported(layers, n_layers, t, c, with_distance) && workspace && workspace_bytes >= pv_pfn_fused_tensor_bytes(m, t) &&
         (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0 && (reinterpret_cast<uintptr_t>(coors) & 15u) == 0 &&
         (reinterpret_cast<uintptr_t>(out) & 15u) == 0)
     {
         const int rc = pv_pfn_fused_tensor(voxels, num_points, coors, m, t, c, with_distance, vx, vy, x_off, y_off, layers, eps,
-                                           reinterpret_cast<unsigned int *>(workspace), out, (cudaStream_t)stream);
-        if (rc != PV_ERR_UNSUPPORTED) return rc;             // (unsupported: this build's register budget, see pv_pfn_fused_launch)
+                                           workspace, out, (cudaStream_t)stream);
+        if (rc != PV_ERR_UNSUPPORTED) return rc;
     }
     if (pfn_tiled_supported(layers, n_layers, t) && c + 5 + (with_distance ? 1 : 0) <= PT_MAX_IN) {
         PtArgs q;
