@@ -283,3 +283,35 @@ def test_fused_pillar_front_end_row_widths(name, cartesian, c_in, with_distance,
     assert_close_fp32(got["features"], ref, "fused PFN features " + name)
     rc, _ = oracle.scatter(ref, coor, len(frames), [512, 512, 1])
     assert_close_fp32(got["canvas"], rc, "fused PFN canvas " + name)
+
+
+def test_static_pfn_slices_agree_with_one_slice_calls():
+    """The drop-in PillarFeatureNet on the padded tensor runs in slices of 524 288 voxels (pfn_fused.cu, P2_SLICE).
+    Size-independent property at 655 360 voxels (two slices, the second one partial): the rows of the big call are
+    bit-identical to the rows of calls on sub-ranges that fit one slice -- every voxel is evaluated on its own --,
+    and the first 120 000 rows match the oracle."""
+    import torch
+    from partner_b200 import PillarFeatureNet, synth
+    g = synth.GRIDS["NUSC-PILLAR"]
+    ref_gen = oracle.VoxelGenerator(g["voxel_size"], g["range"], g["max_points"], g["max_voxels"])
+    vox, coor, num = [], [], []
+    for b in range(2):
+        v, c, n = ref_gen.generate(oracle.transform_points(synth.nusc_frame(3400 + b)))[:3]
+        vox.append(v); num.append(n); coor.append(np.pad(c, ((0, 0), (1, 0)), constant_values=b))
+    vox, coor, num = np.concatenate(vox), np.concatenate(coor).astype(np.int32), np.concatenate(num)
+    m0 = vox.shape[0]
+    reps = -(-655360 // m0)
+    sel = (np.arange(reps * m0) * 7919 % m0)[:655360]            # a permuted tiling: slice boundaries fall inside frames
+    V, N, Cc = _cuda(vox[sel]), _cuda(num[sel]), _cuda(coor[sel])
+    net = _random_pfn_state(PillarFeatureNet(7, (64, 128), False, tuple(g["voxel_size"]), tuple(g["range"])), seed=5).cuda().eval()
+    big = net(V, N, Cc)
+    assert big.shape == (655360, 128)
+    for lo, hi in ((0, 300000), (300000, 655360), (524288 - 1000, 524288 + 1000)):
+        part = net(V[lo:hi].contiguous(), N[lo:hi].contiguous(), Cc[lo:hi].contiguous())
+        assert torch.equal(part, big[lo:hi]), "rows [%d, %d) differ between the sliced and the one-slice call" % (lo, hi)
+    layers = [dict(weight=L.linear.weight.detach().cpu().numpy(), mean=L.norm.running_mean.cpu().numpy(),
+                   var=L.norm.running_var.cpu().numpy(), gamma=L.norm.weight.detach().cpu().numpy(),
+                   beta=L.norm.bias.detach().cpu().numpy()) for L in net.pfn_layers]
+    k = 20000
+    ref = oracle.pfn_forward(vox[sel[:k]], num[sel[:k]], coor[sel[:k]], layers, g["voxel_size"], g["range"], with_distance=False, eps=1e-3)
+    assert_close_fp32(big[:k].cpu().numpy(), ref, "static PFN, sliced call")
