@@ -93,6 +93,7 @@ struct PvParams {
     float *voxels, *feats, *canvas;
     // dynamic voxelization (pv_dynamic_voxelize): coors = unq, num_points = unq_cnt, grid_ind = [N, 4]
     int32_t dyn;
+    int32_t any_order;        // list-based pipeline: the consumer does not need the lists sorted (pv_forward_pfn_canvas)
     const int32_t *gi_in;     // caller-provided (b, z, y, x) per point, or NULL = bin the points
     int32_t *unq_inv;         // [N] voxel row of every point, or NULL
 };

@@ -469,7 +469,9 @@ __global__ void __launch_bounds__(256) k_place(const __grid_constant__ PvParams 
     if (kg == PV_INF) return;                             // voxel beyond max_voxels: dropped
     const uint32_t c = (uint32_t)(m >> 32) & 0xFFFFu;
     uint32_t *list = p.ws.kept + kg;
-    if (c <= PV_SORT_MAX && c <= (uint32_t)p.T) { list[1u + (uint32_t)(m >> 48)] = i; return; }
+    // cells that keep all their points: arrival order through the cursor -- k_emit sorts up to PV_SORT_MAX of them,
+    // a consumer that takes maxima and a mean over the voxel (the PFN front end) does not care about the order at all
+    if (c <= (uint32_t)p.T && (c <= PV_SORT_MAX || p.any_order)) { list[1u + (uint32_t)(m >> 48)] = i; return; }
     const uint32_t L = min(c, (uint32_t)p.T);
     if (L < 2) return;
     // slots only ever decrease: a tail already below i can never admit i
@@ -744,7 +746,7 @@ static int fill_params(PvParams *p, PvF *f, const pv_config *cfg, const float *p
     p->num_tiles = (uint32_t)(n_total / SCAN_TILE + batch + 1);
     p->coors = p->num_points = p->voxel_counts = p->grid_ind = p->density = nullptr;
     p->voxels = p->feats = p->canvas = nullptr;
-    p->dyn = 0; p->gi_in = nullptr; p->unq_inv = nullptr;
+    p->dyn = 0; p->any_order = 0; p->gi_in = nullptr; p->unq_inv = nullptr;
     return PV_OK;
 }
 
@@ -1070,6 +1072,7 @@ int pv_forward_pfn_canvas(const pv_config *cfg, const float *points, const int32
     if (!pv_pfn_fused_supported(layers, n_layers, cfg->max_points, p.C, with_distance)) return PV_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     p.coors = coors; p.num_points = num_points; p.voxel_counts = voxel_counts;
+    p.any_order = 1;                                     // max / mean per voxel: no sorted lists needed
     rc = run_voxelize(p, f, st, nullptr, false);         // point lists only: no [M, T, C] tensor, no k_emit
     if (rc) return rc;
     P2Args a = {};
