@@ -352,8 +352,6 @@ __global__ void __launch_bounds__(P2_ROWS_THREADS, P2_ROWS_BLOCKS) k_pfn_rows(co
 template <int C0Q>          // float4s per decorated row (compile-time: the row registers are live across a hand-off)
 __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_constant__ P2Args a)
 {
-    constexpr int UH = P2_U0;
-    constexpr int uh = 0;
     extern __shared__ __align__(128) float smem[];
     const int N = a.n1;
     float *a_st = smem;                                    // [2 stages][hi | lo][128 x 64] canonical
@@ -495,11 +493,11 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                     const uint32_t span = lane >= dist ? (0xFFFFFFFFu >> (31 - lane)) & ~(0xFFFFFFFFu >> (31 - (lane - dist))) : 0xFFFFFFFFu;
                     if (row_ok && lane >= dist && (heads & span) == 0u) flags |= 1u << d;
                 }
-                float x0[UH];
+                float x0[P2_U0];
                 {
-                    unsigned long long acc[UH / 2];
+                    unsigned long long acc[P2_U0 / 2];
 #pragma unroll
-                    for (int u = 0; u < UH / 2; ++u) acc[u] = 0ull;
+                    for (int u = 0; u < P2_U0 / 2; ++u) acc[u] = 0ull;
 #pragma unroll
                     for (int k4 = 0; k4 < C0Q; ++k4) {
                         {
@@ -509,7 +507,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                                 const ulonglong2 *wr = reinterpret_cast<const ulonglong2 *>(w0t + (4 * k4 + kk) * P2_U0);
                                 const unsigned long long xin = p2_pack(in[kk], in[kk]);
 #pragma unroll
-                                for (int u4 = 0; u4 < UH / 4; ++u4) {
+                                for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
                                     const ulonglong2 w = wr[u4];
                                     acc[2 * u4] = p2_fma2(xin, w.x, acc[2 * u4]);
                                     acc[2 * u4 + 1] = p2_fma2(xin, w.y, acc[2 * u4 + 1]);
@@ -519,7 +517,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                     }
                     const ulonglong2 *bsc = reinterpret_cast<const ulonglong2 *>(bn0), *bsh = reinterpret_cast<const ulonglong2 *>(bn0 + P2_U0);
 #pragma unroll
-                    for (int u4 = 0; u4 < UH / 4; ++u4) {
+                    for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
                         const ulonglong2 sc2 = bsc[u4], sh2 = bsh[u4];
                         float y0, y1, y2, y3;
                         p2_unpack(p2_fma2(acc[2 * u4], sc2.x, sh2.x), y0, y1);
@@ -546,26 +544,24 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
                 // the x0 half of the operand row leaves BEFORE the per-voxel maximum is taken in the same registers:
                 // one live array of 32 values
 #pragma unroll
-                for (int u4 = 0; u4 < UH / 4; ++u4) {
+                for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
                     float4 hi, lo;
                     tc_split(x0[4 * u4], hi.x, lo.x); tc_split(x0[4 * u4 + 1], hi.y, lo.y); tc_split(x0[4 * u4 + 2], hi.z, lo.z); tc_split(x0[4 * u4 + 3], hi.w, lo.w);
-                    const uint32_t o = tc_canon(row, uh + 4 * u4, TC_M);
+                    const uint32_t o = tc_canon(row, 4 * u4, TC_M);
                     *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
                 }
-                p2_seg_max<UH>(x0, flags, nsteps);
+                p2_seg_max<P2_U0>(x0, flags, nsteps);
 #pragma unroll
-                for (int u = 0; u < UH; ++u) x0[u] = __shfl_sync(0xffffffffu, x0[u], last_lane & 31);
+                for (int u = 0; u < P2_U0; ++u) x0[u] = __shfl_sync(0xffffffffu, x0[u], last_lane & 31);
 #pragma unroll
-                for (int u4 = 0; u4 < UH / 4; ++u4) {
+                for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
                     float4 hi, lo;
                     tc_split(x0[4 * u4], hi.x, lo.x); tc_split(x0[4 * u4 + 1], hi.y, lo.y); tc_split(x0[4 * u4 + 2], hi.z, lo.z); tc_split(x0[4 * u4 + 3], hi.w, lo.w);
-                    const uint32_t o = tc_canon(row, P2_U0 + uh + 4 * u4, TC_M);
+                    const uint32_t o = tc_canon(row, P2_U0 + 4 * u4, TC_M);
                     *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
                 }
-                if (uh == 0) {                                  // the group's record is written by the pair's first warp
-                    const uint32_t lasts = __ballot_sync(0xffffffffu, seg_last);
-                    if (lane == 0) { mt->vid0 = (int)dsc.y; mt->lasts = lasts; mt->done = 0u; }
-                }
+                const uint32_t lasts = __ballot_sync(0xffffffffu, seg_last);
+                if (lane == 0) { mt->vid0 = (int)dsc.y; mt->lasts = lasts; mt->done = 0u; }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) p2_mbar_arrive(bar_full);
