@@ -37,16 +37,18 @@
 #include "tc_common.cuh"
 #include "pfn_fused.cuh"
 
-// warps 0-7 producers (two sets of four: set = operand stage, one warp per group of 32 rows) | warps 8-23
-// epilogue in two TEAMS of eight (team = round parity; TMEM quarter = warp & 3, row half = bit 2) | warp 24 issuer.
-// Four TMEM accumulator stages (acc = 2 * (round & 1) + set) against two operand stages in shared memory:
-// an operand stage is free again when its MMAs retire, an accumulator stage only when an epilogue team has
-// drained it -- and a lone warp retires an instruction every ~8 cycles, so a tile's epilogue takes ~3 us.
-// With two accumulator stages that time was on the critical path of every tile (traced: issue 1.4 us ->
-// MMA + wake-up 2.0 us -> epilogue 3.0 us -> next issue); with four, two teams drain two tiles at once.
+// warps 0-15 producers (two sets of eight: set = operand stage; TWO warps per group of 32 rows, each computing 16 of
+// layer 0's 32 units for the group's rows) | warps 16-27 epilogue in three TEAMS of four (team = tile index mod 3; a
+// warp = one TMEM quarter = 32 units, all four groups of the tile) | warp 28 issuer.
+// Four TMEM accumulator stages (acc = tile & 3, tile = 2 * round + set) against two operand stages in shared memory:
+// an operand stage is free again when its MMAs retire, an accumulator stage only when an epilogue team has drained it
+// -- and a lone warp retires an instruction every ~8 cycles, so draining a tile takes a team of four ~4 us.  With two
+// accumulator stages that time was on the critical path of every tile (traced: issue 1.4 us -> MMA + wake-up 2.0 us ->
+// epilogue 3.0 us -> next issue); with four stages three teams drain three tiles at once (1.3 us per tile), and two
+// warps per group halve the producers' serial instruction stream (the tile period was theirs: 2.8 us).
 #ifdef P2_TRACE          // development builds only: per-warp time stamps of block 0 (tools/pfn_trace.py)
 __device__ long long g_p2_trace[32 * 64 * 2 * 3];
-__device__ long long g_p2_trace2[16 * 64 * 2 * 4];
+__device__ long long g_p2_trace2[16 * 64 * 2 * 4];   // (unused by the three-team layout)
 #define P2_STAMP(round, s, k) do { if (blockIdx.x == 0 && lane == 0 && (round) < 64u) g_p2_trace[((warp * 64 + (round)) * 2 + (s)) * 3 + (k)] = clock64(); } while (0)
 #define P2_STAMP2(round, s, k) do { if (blockIdx.x == 0 && lane == 0 && (round) < 64u) g_p2_trace2[(((warp - P2_EPI_WARP0) * 64 + (round)) * 2 + (s)) * 4 + (k)] = clock64(); } while (0)
 extern "C" int pv_debug_p2_trace(void *dst, size_t bytes)
@@ -61,10 +63,10 @@ extern "C" int pv_debug_p2_trace2(void *dst, size_t bytes)
 #define P2_STAMP(round, s, k) do { } while (0)
 #define P2_STAMP2(round, s, k) do { } while (0)
 #endif
-#define P2_NPROD 8
-#define P2_EPI_WARP0 8
-#define P2_ISSUER_WARP 24
-#define P2_THREADS (25 * 32)
+#define P2_NPROD 16
+#define P2_EPI_WARP0 16
+#define P2_ISSUER_WARP 28
+#define P2_THREADS (29 * 32)
 // (measured: 4 epilogue warps and 128 registers per thread: 1.60 ms vs 1.26 ms)
 // (No setmaxnreg: it moves registers inside the pool the CTA was LAUNCHED with -- threads x the kernel's register
 // count -- and an .inc that pool cannot satisfy blocks for ever.  Every role fits the launch count since the
@@ -361,9 +363,9 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
     float *bn0 = w0t + P2_C0 * P2_U0;                      // mean, invstd, gamma, beta: 4 x 32
     float *bn1 = bn0 + 4 * P2_U0;                          // 4 x N
     P2Meta *meta = reinterpret_cast<P2Meta *>(bn1 + 4 * N);   // [2 sets][4 rounds in flight][4 groups]
-    uint4 *s_desc = reinterpret_cast<uint4 *>(meta + 32);      // [8 producer warps][64]: group descriptors of the warp's chunk
+    uint4 *s_desc = reinterpret_cast<uint4 *>(meta + 32);      // [8 producer pairs][2][64]: group descriptors of the pair's chunk
     __shared__ __align__(8) unsigned long long s_full[2], s_mma[2], s_acc[4], s_free[4], s_rec[4];
-    __shared__ uint32_t s_tmem, s_exit[2];
+    __shared__ uint32_t s_tmem, s_exit[2], s_chunk[8][2];
     __shared__ uint32_t s_abort;
     unsigned int *diag = a.counter + 2;     // diagnostic words of the watchdog (0 = healthy)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -376,13 +378,13 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
     }
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            tc_mbar_init(tc_smem_u32(&s_full[s]), 4);
+            tc_mbar_init(tc_smem_u32(&s_full[s]), 8);
             tc_mbar_init(tc_smem_u32(&s_mma[s]), 1);
-            s_exit[s] = 0u;
+            s_exit[s] = s == 0 ? 0u : 0xFFFFFFFFu;      // [0] producers: stop; [1] epilogue: first tile index that is not real
         }
         for (int q = 0; q < 4; ++q) {
             tc_mbar_init(tc_smem_u32(&s_acc[q]), 1);
-            tc_mbar_init(tc_smem_u32(&s_free[q]), 8);
+            tc_mbar_init(tc_smem_u32(&s_free[q]), 4);
             tc_mbar_init(tc_smem_u32(&s_rec[q]), 1);
         }
         s_abort = 0u;
@@ -420,265 +422,282 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
 
-    // register budget per role (warpgroups 0-1 = producers, 2-3 = epilogue, 4 = issuer): the kernel is
-    // launched at 96 registers per thread (17 warps allocate like 20); the epilogue and the issuer hand
-    // theirs back so that the producers can take 128 (1.26 -> 1.20 ms).  Tried on top of that and slower
-    // (1.51 ms): a software pipeline inside the producer warp (records of group k + 2, list entries and
-    // rows of group k + 1 in flight while group k is evaluated) -- the kernel is bound by issue slots
-    // (46 % busy with every role resident), not by the producers' load latency.
+    // (No setmaxnreg: it moves registers inside the pool the CTA was LAUNCHED with -- threads x the kernel's register
+    // count -- and an .inc that pool cannot satisfy blocks for ever.  Every role fits the launch count.)
     if (warp < P2_EPI_WARP0) {
         // =====================================================================================
-        // PRODUCER warp: set = stage, g = group inside the tile
+        // PRODUCER warp: set = operand stage, g = group inside the tile, uh = first of its 16 layer-0 units.
+        // The two warps of a pair walk the same groups (same chunk, same descriptors, same rows).
         // =====================================================================================
-        const int set = warp >> 2, g = warp & 3;
+        const int set = warp >> 3, g = (warp >> 1) & 3, pair = warp >> 1, uh = (warp & 1) * (P2_U0 / 2);
+        constexpr int UH = P2_U0 / 2;
         float *a_hi = a_st + (size_t)set * 2 * TC_M * P2_K, *a_lo = a_hi + TC_M * P2_K;
         const uint32_t bar_full = tc_smem_u32(&s_full[set]), bar_mma = tc_smem_u32(&s_mma[set]);
-        {
-            // ---------------------------------------------------------------------------------
-            // rows were gathered and decorated by k_pfn_rows: a group is a descriptor {first row in
-            // drows, first output row, head mask, total | scan steps << 8} and <= 32 consecutive
-            // 64-byte rows -- one coalesced load, no dependent gather left in this kernel
-            // ---------------------------------------------------------------------------------
-            uint4 *my_desc = s_desc + warp * P2_MC;           // descriptors of the warp's chunk
-            uint32_t ng = 0, gi = 0;
-            // the NEXT group's descriptor and rows: requested one group ahead, right after layer 0 of the current
-            // group has consumed the row registers, so that the loads travel while the warp waits for its operand
-            // stage and writes it (traced: 1-2 us of exposed load latency per group without this)
-            // (measured and rejected: ONE queue of groups instead of 64-voxel chunks per warp -- ticket, descriptor and
-            // rows become three dependent round trips per group: fused front end 1.674 vs 1.658 ms)
-            uint4 dsc_n = make_uint4(0, 0, 0, 0);
-            float4 in4[C0Q];
-            bool oow_n = false;
-            auto fetch_next = [&]() {
-                while (!oow_n && gi >= ng) {
+        uint4 *my_desc = s_desc + pair * 2 * P2_MC;       // descriptors of the pair's chunk (written by its first warp), double-buffered:
+                                                          // the first warp may stage chunk k + 1 while its partner still reads chunk k
+        uint32_t ng = 0, gi = 0, n_fetch = 0;
+        // the NEXT group's descriptor and rows: requested one group ahead, right after layer 0 of the current
+        // group has consumed the row registers, so that the loads travel while the warp waits for its operand
+        // stage and writes it (traced: 1-2 us of exposed load latency per group without this)
+        // (measured and rejected: ONE queue of groups instead of 64-voxel chunks per warp -- ticket, descriptor and
+        // rows become three dependent round trips per group: fused front end 1.674 vs 1.658 ms)
+        uint4 dsc_n = make_uint4(0, 0, 0, 0);
+        float4 in4[C0Q];
+        bool oow_n = false;
+        auto fetch_next = [&]() {
+            while (!oow_n && gi >= ng) {
+                // the pair's first warp takes the next chunk from the queue and stages its descriptors; a named
+                // barrier of the pair's 64 threads publishes them (slot parity: the partner may still read the old id)
+                const uint32_t slot = n_fetch & 1u;
+                ++n_fetch;
+                my_desc = s_desc + (pair * 2 + slot) * P2_MC;
+                if ((warp & 1) == 0) {
                     uint32_t id = 0;
                     if (lane == 0) id = atomicAdd(a.counter, 1u);
                     id = __shfl_sync(0xffffffffu, id, 0);
-                    if (id >= a.n_chunks) { oow_n = true; break; }
-                    ng = __ldcs(a.ngroups + id);
-                    __syncwarp();
-                    if ((uint32_t)lane < ng) my_desc[lane] = __ldcs(a.desc + (size_t)id * P2_MC + lane);       // (only what k_pfn_rows wrote)
-                    if (32u + lane < ng) my_desc[32 + lane] = __ldcs(a.desc + (size_t)id * P2_MC + 32 + lane);
-                    __syncwarp();
-                    gi = 0;
+                    uint32_t cnt = 0;
+                    if (id < a.n_chunks) {
+                        cnt = __ldcs(a.ngroups + id);
+                        if ((uint32_t)lane < cnt) my_desc[lane] = __ldcs(a.desc + (size_t)id * P2_MC + lane);       // (only what k_pfn_rows wrote)
+                        if (32u + lane < cnt) my_desc[32 + lane] = __ldcs(a.desc + (size_t)id * P2_MC + 32 + lane);
+                    } else cnt = 0xFFFFFFFFu;               // the queue is empty
+                    if (lane == 0) s_chunk[pair][slot] = cnt;
                 }
-                dsc_n = make_uint4(0, 0, 0, 0);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+                const uint32_t cnt = *reinterpret_cast<volatile uint32_t *>(&s_chunk[pair][slot]);
+                if (cnt == 0xFFFFFFFFu) { oow_n = true; break; }
+                ng = cnt;
+                gi = 0;
+            }
+            dsc_n = make_uint4(0, 0, 0, 0);
 #pragma unroll
-                for (int k4 = 0; k4 < C0Q; ++k4) in4[k4] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (!oow_n) {
-                    dsc_n = my_desc[gi];
-                    ++gi;
-                    if ((uint32_t)lane < (dsc_n.w & 0xffu)) {
-                        const float4 *src4 = a.drows + (size_t)dsc_n.x + lane;
+            for (int k4 = 0; k4 < C0Q; ++k4) in4[k4] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (!oow_n) {
+                dsc_n = my_desc[gi];
+                ++gi;
+                if ((uint32_t)lane < (dsc_n.w & 0xffu)) {
+                    const float4 *src4 = a.drows + (size_t)dsc_n.x + lane;
 #pragma unroll
-                        for (int k4 = 0; k4 < C0Q; ++k4) in4[k4] = __ldcs(src4 + (size_t)k4 * a.drow_stride);
-                    }
+                    for (int k4 = 0; k4 < C0Q; ++k4) in4[k4] = __ldg(src4 + (size_t)k4 * a.drow_stride);   // (the partner reads the same rows)
                 }
-            };
-            fetch_next();
-            for (uint32_t round = 0;; ++round) {
-                const uint4 dsc = dsc_n;
-                const bool out_of_work = oow_n;
-                // ---- everything that does not touch the operand stage comes BEFORE the wait for it: the group's
-                // segment structure and layer 0 (Linear as packed FFMA2 pairs -> folded BatchNorm -> ReLU) ----
-                const uint32_t heads = dsc.z, total = dsc.w & 0xffu, nsteps = (dsc.w >> 8) & 0xffu;
-                const bool row_ok = (uint32_t)lane < total;
-                const uint32_t above = lane < 31 ? heads & (0xFFFFFFFEu << lane) : 0u;   // heads in lanes > lane
-                const int last_lane = (above ? __ffs(above) - 1 : (int)total) - 1;
-                const bool seg_last = row_ok && lane == last_lane;
-                uint32_t flags = 0;
+            }
+        };
+        fetch_next();
+        for (uint32_t round = 0;; ++round) {
+            const uint4 dsc = dsc_n;
+            const bool out_of_work = oow_n;
+            // ---- everything that does not touch the operand stage comes BEFORE the wait for it: the group's
+            // segment structure and this warp's half of layer 0 (Linear as packed FFMA2 pairs -> folded BatchNorm -> ReLU) ----
+            const uint32_t heads = dsc.z, total = dsc.w & 0xffu, nsteps = (dsc.w >> 8) & 0xffu;
+            const bool row_ok = (uint32_t)lane < total;
+            const uint32_t above = lane < 31 ? heads & (0xFFFFFFFEu << lane) : 0u;   // heads in lanes > lane
+            const int last_lane = (above ? __ffs(above) - 1 : (int)total) - 1;
+            const bool seg_last = row_ok && lane == last_lane;
+            uint32_t flags = 0;
 #pragma unroll
-                for (int d = 0; d < 5; ++d) {
-                    const int dist = 1 << d;
-                    const uint32_t span = lane >= dist ? (0xFFFFFFFFu >> (31 - lane)) & ~(0xFFFFFFFFu >> (31 - (lane - dist))) : 0xFFFFFFFFu;
-                    if (row_ok && lane >= dist && (heads & span) == 0u) flags |= 1u << d;
-                }
-                float x0[P2_U0];
-                {
-                    unsigned long long acc[P2_U0 / 2];
+            for (int d = 0; d < 5; ++d) {
+                const int dist = 1 << d;
+                const uint32_t span = lane >= dist ? (0xFFFFFFFFu >> (31 - lane)) & ~(0xFFFFFFFFu >> (31 - (lane - dist))) : 0xFFFFFFFFu;
+                if (row_ok && lane >= dist && (heads & span) == 0u) flags |= 1u << d;
+            }
+            float x0[UH];
+            {
+                unsigned long long acc[UH / 2];
 #pragma unroll
-                    for (int u = 0; u < P2_U0 / 2; ++u) acc[u] = 0ull;
+                for (int u = 0; u < UH / 2; ++u) acc[u] = 0ull;
 #pragma unroll
-                    for (int k4 = 0; k4 < C0Q; ++k4) {
-                        {
-                            const float in[4] = {in4[k4].x, in4[k4].y, in4[k4].z, in4[k4].w};
+                for (int k4 = 0; k4 < C0Q; ++k4) {
+                    const float in[4] = {in4[k4].x, in4[k4].y, in4[k4].z, in4[k4].w};
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                const ulonglong2 *wr = reinterpret_cast<const ulonglong2 *>(w0t + (4 * k4 + kk) * P2_U0);
-                                const unsigned long long xin = p2_pack(in[kk], in[kk]);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const ulonglong2 *wr = reinterpret_cast<const ulonglong2 *>(w0t + (4 * k4 + kk) * P2_U0 + uh);
+                        const unsigned long long xin = p2_pack(in[kk], in[kk]);
 #pragma unroll
-                                for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
-                                    const ulonglong2 w = wr[u4];
-                                    acc[2 * u4] = p2_fma2(xin, w.x, acc[2 * u4]);
-                                    acc[2 * u4 + 1] = p2_fma2(xin, w.y, acc[2 * u4 + 1]);
-                                }
-                            }
+                        for (int u4 = 0; u4 < UH / 4; ++u4) {
+                            const ulonglong2 w = wr[u4];
+                            acc[2 * u4] = p2_fma2(xin, w.x, acc[2 * u4]);
+                            acc[2 * u4 + 1] = p2_fma2(xin, w.y, acc[2 * u4 + 1]);
                         }
                     }
-                    const ulonglong2 *bsc = reinterpret_cast<const ulonglong2 *>(bn0), *bsh = reinterpret_cast<const ulonglong2 *>(bn0 + P2_U0);
+                }
+                const ulonglong2 *bsc = reinterpret_cast<const ulonglong2 *>(bn0 + uh), *bsh = reinterpret_cast<const ulonglong2 *>(bn0 + P2_U0 + uh);
 #pragma unroll
-                    for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
-                        const ulonglong2 sc2 = bsc[u4], sh2 = bsh[u4];
-                        float y0, y1, y2, y3;
-                        p2_unpack(p2_fma2(acc[2 * u4], sc2.x, sh2.x), y0, y1);
-                        p2_unpack(p2_fma2(acc[2 * u4 + 1], sc2.y, sh2.y), y2, y3);
-                        x0[4 * u4] = row_ok ? fmaxf(y0, 0.0f) : 0.0f; x0[4 * u4 + 1] = row_ok ? fmaxf(y1, 0.0f) : 0.0f;
-                        x0[4 * u4 + 2] = row_ok ? fmaxf(y2, 0.0f) : 0.0f; x0[4 * u4 + 3] = row_ok ? fmaxf(y3, 0.0f) : 0.0f;
-                    }
+                for (int u4 = 0; u4 < UH / 4; ++u4) {
+                    const ulonglong2 sc2 = bsc[u4], sh2 = bsh[u4];
+                    float y0, y1, y2, y3;
+                    p2_unpack(p2_fma2(acc[2 * u4], sc2.x, sh2.x), y0, y1);
+                    p2_unpack(p2_fma2(acc[2 * u4 + 1], sc2.y, sh2.y), y2, y3);
+                    x0[4 * u4] = row_ok ? fmaxf(y0, 0.0f) : 0.0f; x0[4 * u4 + 1] = row_ok ? fmaxf(y1, 0.0f) : 0.0f;
+                    x0[4 * u4 + 2] = row_ok ? fmaxf(y2, 0.0f) : 0.0f; x0[4 * u4 + 3] = row_ok ? fmaxf(y3, 0.0f) : 0.0f;
                 }
-                if (!out_of_work) fetch_next();                  // the row registers are free again
-                P2_STAMP(round, 0, 0);
-                if (round > 0) {
-                    if (!p2_mbar_wait(bar_mma, (round - 1) & 1u, &s_abort, diag, 0x100u | (set << 4) | g | (round << 16))) break;   // the stage's previous tile has been consumed
-                    if (*reinterpret_cast<volatile uint32_t *>(&s_exit[set])) break;
-                }
-                P2_STAMP(round, 0, 1);
-                P2Meta *mt = meta + ((set * 4 + (round & 3u)) * 4 + g);
-                if (out_of_work) {
-                    if (lane == 0) mt->done = 1u;
-                    __syncwarp();
-                    if (lane == 0) p2_mbar_arrive(bar_full);
-                    continue;
-                }
-                const int row = g * 32 + lane;
-                // the x0 half of the operand row leaves BEFORE the per-voxel maximum is taken in the same registers:
-                // one live array of 32 values
-#pragma unroll
-                for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
-                    float4 hi, lo;
-                    tc_split(x0[4 * u4], hi.x, lo.x); tc_split(x0[4 * u4 + 1], hi.y, lo.y); tc_split(x0[4 * u4 + 2], hi.z, lo.z); tc_split(x0[4 * u4 + 3], hi.w, lo.w);
-                    const uint32_t o = tc_canon(row, 4 * u4, TC_M);
-                    *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
-                }
-                p2_seg_max<P2_U0>(x0, flags, nsteps);
-#pragma unroll
-                for (int u = 0; u < P2_U0; ++u) x0[u] = __shfl_sync(0xffffffffu, x0[u], last_lane & 31);
-#pragma unroll
-                for (int u4 = 0; u4 < P2_U0 / 4; ++u4) {
-                    float4 hi, lo;
-                    tc_split(x0[4 * u4], hi.x, lo.x); tc_split(x0[4 * u4 + 1], hi.y, lo.y); tc_split(x0[4 * u4 + 2], hi.z, lo.z); tc_split(x0[4 * u4 + 3], hi.w, lo.w);
-                    const uint32_t o = tc_canon(row, P2_U0 + 4 * u4, TC_M);
-                    *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
-                }
-                const uint32_t lasts = __ballot_sync(0xffffffffu, seg_last);
-                if (lane == 0) { mt->vid0 = (int)dsc.y; mt->lasts = lasts; mt->done = 0u; }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> the tensor core's async proxy
+            }
+            if (!out_of_work) fetch_next();                  // the row registers are free again
+            P2_STAMP(round, 0, 0);
+            if (round > 0) {
+                if (!p2_mbar_wait(bar_mma, (round - 1) & 1u, &s_abort, diag, 0x100u | (set << 4) | g | (round << 16))) break;   // the stage's previous tile has been consumed
+                if (*reinterpret_cast<volatile uint32_t *>(&s_exit[0])) break;
+            }
+            P2_STAMP(round, 0, 1);
+            P2Meta *mt = meta + ((set * 4 + (round & 3u)) * 4 + g);
+            if (out_of_work) {
+                if (lane == 0 && uh == 0) mt->done = 1u;
                 __syncwarp();
                 if (lane == 0) p2_mbar_arrive(bar_full);
-                P2_STAMP(round, 0, 2);
+                continue;
             }
+            const int row = g * 32 + lane;
+            // the x0 part of the operand row leaves BEFORE the per-voxel maximum is taken in the same registers
+#pragma unroll
+            for (int u4 = 0; u4 < UH / 4; ++u4) {
+                float4 hi, lo;
+                tc_split(x0[4 * u4], hi.x, lo.x); tc_split(x0[4 * u4 + 1], hi.y, lo.y); tc_split(x0[4 * u4 + 2], hi.z, lo.z); tc_split(x0[4 * u4 + 3], hi.w, lo.w);
+                const uint32_t o = tc_canon(row, uh + 4 * u4, TC_M);
+                *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
+            }
+            p2_seg_max<UH>(x0, flags, nsteps);
+#pragma unroll
+            for (int u = 0; u < UH; ++u) x0[u] = __shfl_sync(0xffffffffu, x0[u], last_lane & 31);
+#pragma unroll
+            for (int u4 = 0; u4 < UH / 4; ++u4) {
+                float4 hi, lo;
+                tc_split(x0[4 * u4], hi.x, lo.x); tc_split(x0[4 * u4 + 1], hi.y, lo.y); tc_split(x0[4 * u4 + 2], hi.z, lo.z); tc_split(x0[4 * u4 + 3], hi.w, lo.w);
+                const uint32_t o = tc_canon(row, P2_U0 + uh + 4 * u4, TC_M);
+                *reinterpret_cast<float4 *>(a_hi + o) = hi; *reinterpret_cast<float4 *>(a_lo + o) = lo;
+            }
+            if (uh == 0) {                                   // the group's record is written by the pair's first warp
+                const uint32_t lasts = __ballot_sync(0xffffffffu, seg_last);
+                if (lane == 0) { mt->vid0 = (int)dsc.y; mt->lasts = lasts; mt->done = 0u; }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) p2_mbar_arrive(bar_full);
+            P2_STAMP(round, 0, 2);
         }
     } else if (warp == P2_ISSUER_WARP) {
         // =====================================================================================
-        // ISSUER: the whole warp walks the pipeline (barrier waits are warp-wide, the warp stays
-        // converged for the block barrier and the TMEM release at the end); lane 0 issues
+        // ISSUER: the whole warp walks the tiles in order (tile = 2 * round + set; barrier waits are warp-wide, the warp
+        // stays converged for the block barrier and the TMEM release at the end); lane 0 issues.  A set whose producers
+        // are out of work keeps handing in empty tiles (all four records "done"), which are passed on unissued, so
+        // every tile index is released in order until BOTH sets are empty in the same round.
         // =====================================================================================
         const uint32_t idesc = tc_idesc_tf32(TC_M, TC_M);     // D[unit (M = 128, padded), row (N = 128)]
         const uint32_t a_k = (TC_M / 8) * 128, mn = 128;
-        bool fin[2] = {false, false};
-        for (uint32_t round = 0; !(fin[0] && fin[1]); ++round) {
-            for (int s = 0; s < 2; ++s) {
-                if (fin[s]) continue;
-                const uint32_t acc = ((round & 1u) << 1) | (uint32_t)s;       // accumulator stage of tile (round, s)
-                if (!p2_mbar_wait(tc_smem_u32(&s_full[s]), round & 1u, &s_abort, diag, 0x200u | (s << 4) | (round << 16))) { fin[0] = fin[1] = true; break; }
-                P2_STAMP(round, s, 0);
-                const P2Meta *mt = meta + (s * 4 + (round & 3u)) * 4;
-                const uint32_t all_done = *reinterpret_cast<const volatile uint32_t *>(&mt[0].done) &
-                                          *reinterpret_cast<const volatile uint32_t *>(&mt[1].done) &
-                                          *reinterpret_cast<const volatile uint32_t *>(&mt[2].done) &
-                                          *reinterpret_cast<const volatile uint32_t *>(&mt[3].done);
-                // the accumulator stage has been drained by its team (tile (round - 2, s)).  A parity wait tells
-                // two phases apart, so no barrier may run two phases ahead of its slowest waiter: every arrival
-                // on s_acc / s_rec [acc] below comes after this wait
-                if (round >= 2 && !p2_mbar_wait(tc_smem_u32(&s_free[acc]), ((round >> 1) - 1u) & 1u, &s_abort, diag, 0x300u | (acc << 4) | (round << 16))) { fin[0] = fin[1] = true; break; }
-                P2_STAMP(round, s, 1);
-                if (all_done) {                                             // every producer of the set is out of work
-                    fin[s] = true;
-                    // the OTHER team must have finished the set's last real tile (round - 1) before the exit flag
-                    // goes up (it reads the flag after its waits), and before its barriers see one more phase
-                    const uint32_t acc2 = acc ^ 2u;
-                    if (round >= 1 && !p2_mbar_wait(tc_smem_u32(&s_free[acc2]), (((round + 1u) >> 1) - 1u) & 1u, &s_abort, diag, 0x600u | (acc2 << 4) | (round << 16))) { fin[0] = fin[1] = true; break; }
-                    if (lane == 0) {
-                        *reinterpret_cast<volatile uint32_t *>(&s_exit[s]) = 1u;
-                        __threadfence_block();
-                        p2_mbar_arrive(tc_smem_u32(&s_rec[acc]));  p2_mbar_arrive(tc_smem_u32(&s_acc[acc]));    // team of this round
-                        p2_mbar_arrive(tc_smem_u32(&s_rec[acc2])); p2_mbar_arrive(tc_smem_u32(&s_acc[acc2]));   // team of the next round
-                        p2_mbar_arrive(tc_smem_u32(&s_mma[s]));                                                  // the set's producers
-                    }
-                    __syncwarp();
-                    continue;
-                }
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    // hands the producers' group records (acquired with the full barrier) on to the epilogue:
-                    // a plain release / acquire chain, independent of the tensor core's commit
-                    p2_mbar_arrive(tc_smem_u32(&s_rec[acc]));
-                    const float *a_hi = a_st + (size_t)s * 2 * TC_M * P2_K, *a_lo = a_hi + TC_M * P2_K;
-                    const uint32_t d_tmem = tmem + acc * (uint32_t)TC_M;
-#pragma unroll 1
-                    for (int ks = 0; ks < P2_K / 8; ++ks) {
-                        const uint32_t off = ks * 2 * a_k;
-                        const unsigned long long dxh = tc_desc(tc_smem_u32(a_hi) + off, a_k, mn), dxl = tc_desc(tc_smem_u32(a_lo) + off, a_k, mn);
-                        const unsigned long long dwh = tc_desc(tc_smem_u32(b_hi) + off, a_k, mn), dwl = tc_desc(tc_smem_u32(b_lo) + off, a_k, mn);
-                        tc_mma_tf32(d_tmem, dwl, dxh, idesc, ks > 0 ? 1u : 0u);     // small terms first
-                        tc_mma_tf32(d_tmem, dwh, dxl, idesc, 1u);
-                        tc_mma_tf32(d_tmem, dwh, dxh, idesc, 1u);
-                    }
-                    tc_commit(tc_smem_u32(&s_mma[s]));      // operand stage free (producers) ...
-                    tc_commit(tc_smem_u32(&s_acc[acc]));    // ... and accumulator ready (epilogue team), when the MMAs retire
-                }
-                __syncwarp();
-                P2_STAMP(round, s, 2);
+        // shared-memory descriptors of k-step 0, built once: a k-step advances the 14-bit start-address field by
+        // 2 * a_k bytes >> 4 (no carry: shared memory ends below 256 KB).  The issuing thread is one serial instruction
+        // stream (~8 cycles per instruction next to 28 other warps): rebuilding four descriptors per k-step cost
+        // ~400 instructions = 1.9 us per tile, more than the tensor pipe needs for the tile (traced)
+        const unsigned long long d_wh = tc_desc(tc_smem_u32(b_hi), a_k, mn), d_wl = tc_desc(tc_smem_u32(b_lo), a_k, mn);
+        const unsigned long long d_xh0 = tc_desc(tc_smem_u32(a_st), a_k, mn), d_xl0 = tc_desc(tc_smem_u32(a_st + TC_M * P2_K), a_k, mn);
+        const unsigned long long d_set = (unsigned long long)((2u * TC_M * P2_K * 4u) >> 4), d_ks = (unsigned long long)((2u * a_k) >> 4);
+        uint32_t empty0 = 0;
+        bool pending0 = false;                                 // set 0 handed in an empty tile this round: its producers are released
+                                                               // together with the decision of tile (round, 1) -- go on, or stop
+        for (uint32_t tile = 0;; ++tile) {
+            const uint32_t s = tile & 1u, round = tile >> 1, acc = tile & 3u;
+            if (!p2_mbar_wait(tc_smem_u32(&s_full[s]), round & 1u, &s_abort, diag, 0x200u | (s << 4) | (round << 16))) break;
+            P2_STAMP(round, s, 0);
+            const P2Meta *mt = meta + (s * 4 + (round & 3u)) * 4;
+            const uint32_t all_done = *reinterpret_cast<const volatile uint32_t *>(&mt[0].done) &
+                                      *reinterpret_cast<const volatile uint32_t *>(&mt[1].done) &
+                                      *reinterpret_cast<const volatile uint32_t *>(&mt[2].done) &
+                                      *reinterpret_cast<const volatile uint32_t *>(&mt[3].done);
+            // the accumulator stage has been drained by its team (tile - 4).  A parity wait tells two phases apart, so no
+            // barrier may run two phases ahead of its slowest waiter: every arrival on s_acc / s_rec [acc] below comes
+            // after this wait
+            if (tile >= 4 && !p2_mbar_wait(tc_smem_u32(&s_free[acc]), ((tile >> 2) - 1u) & 1u, &s_abort, diag, 0x300u | (acc << 4) | (round << 16))) break;
+            P2_STAMP(round, s, 1);
+            if (s == 0) empty0 = all_done;
+            const bool finish = s == 1 && all_done && empty0;          // both sets handed in an empty tile this round
+            if (finish && lane == 0) {
+                *reinterpret_cast<volatile uint32_t *>(&s_exit[1]) = tile;   // teams: tiles from here on are not real
+                *reinterpret_cast<volatile uint32_t *>(&s_exit[0]) = 1u;     // producers: stop after this round's s_mma
+                __threadfence_block();
             }
+            __syncwarp();
+            if (s == 1 && pending0) {                                   // set 0's empty tile of this round: release its producers now
+                if (lane == 0) p2_mbar_arrive(tc_smem_u32(&s_mma[0]));
+                pending0 = false;
+            }
+            if (all_done) {                                             // an empty tile: nothing to issue, the team skips it
+                if (lane == 0) {
+                    p2_mbar_arrive(tc_smem_u32(&s_rec[acc]));
+                    p2_mbar_arrive(tc_smem_u32(&s_acc[acc]));
+                    if (s == 1) p2_mbar_arrive(tc_smem_u32(&s_mma[1]));   // set 1: go on handing in empty tiles, or (finish) stop
+                }
+                if (s == 0) pending0 = true;
+                __syncwarp();
+                if (!finish) continue;
+                // ---- the end: the two other teams wait for the next two tile indices (both sets' producers have been
+                // released above and stop when they see the flag) ----
+                bool ok = true;
+                for (uint32_t tt = tile + 1; tt <= tile + 2 && ok; ++tt) {
+                    const uint32_t a2 = tt & 3u;
+                    if (tt >= 4) ok = p2_mbar_wait(tc_smem_u32(&s_free[a2]), ((tt >> 2) - 1u) & 1u, &s_abort, diag, 0x600u | (a2 << 4) | (round << 16));
+                    if (ok && lane == 0) { p2_mbar_arrive(tc_smem_u32(&s_rec[a2])); p2_mbar_arrive(tc_smem_u32(&s_acc[a2])); }
+                    __syncwarp();
+                }
+                break;
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                // hands the producers' group records (acquired with the full barrier) on to the epilogue:
+                // a plain release / acquire chain, independent of the tensor core's commit
+                p2_mbar_arrive(tc_smem_u32(&s_rec[acc]));
+                const uint32_t d_tmem = tmem + acc * (uint32_t)TC_M;
+                const unsigned long long dxh = d_xh0 + s * d_set, dxl = d_xl0 + s * d_set;
+#pragma unroll
+                for (int ks = 0; ks < P2_K / 8; ++ks) {
+                    tc_mma_tf32(d_tmem, d_wl + ks * d_ks, dxh + ks * d_ks, idesc, ks > 0 ? 1u : 0u);     // small terms first
+                    tc_mma_tf32(d_tmem, d_wh + ks * d_ks, dxl + ks * d_ks, idesc, 1u);
+                    tc_mma_tf32(d_tmem, d_wh + ks * d_ks, dxh + ks * d_ks, idesc, 1u);
+                }
+                tc_commit(tc_smem_u32(&s_mma[s]));      // operand stage free (producers) ...
+                tc_commit(tc_smem_u32(&s_acc[acc]));    // ... and accumulator ready (epilogue team), when the MMAs retire
+            }
+            __syncwarp();
+            P2_STAMP(round, s, 2);
         }
     } else {
         // =====================================================================================
-        // EPILOGUE warp: team = round parity it serves, e = TMEM quarter (lanes [32 e, 32 e + 32) = 32 units),
-        // half = which two groups of the tile
+        // EPILOGUE warp: team = tile index mod 3 it serves, e = TMEM quarter (lanes [32 e, 32 e + 32) = 32 units),
+        // all four groups of the tile
         // =====================================================================================
-        const int ew = warp - P2_EPI_WARP0, team = ew >> 3, e = warp & 3, half = (ew >> 2) & 1;
+        const int ew = warp - P2_EPI_WARP0, team = ew >> 2, e = warp & 3;
         const int unit = e * 32 + lane;
         const bool has_units = e * 32 < N;                                   // warp-uniform
         const float sc = unit < N ? bn1[2 * unit] : 0.0f, sh = unit < N ? bn1[2 * unit + 1] : 0.0f;
         const float neutral = __int_as_float(0xff800000);                    // -inf: sc >= 0 here, so the maximum of the raw accumulator decides
-        bool fin[2] = {false, false};
-        for (uint32_t round = (uint32_t)team; !(fin[0] && fin[1]); round += 2) {
-            for (int s = 0; s < 2; ++s) {
-                if (fin[s]) continue;
-                const uint32_t acc = ((round & 1u) << 1) | (uint32_t)s, par = (round >> 1) & 1u;
-                if (!p2_mbar_wait(tc_smem_u32(&s_rec[acc]), par, &s_abort, diag, 0x500u | (acc << 4) | (ew & 7) | (round << 16))) { fin[0] = fin[1] = true; break; }
-                if (!p2_mbar_wait(tc_smem_u32(&s_acc[acc]), par, &s_abort, diag, 0x400u | (acc << 4) | (ew & 7) | (round << 16))) { fin[0] = fin[1] = true; break; }
-                if (*reinterpret_cast<volatile uint32_t *>(&s_exit[s])) { fin[s] = true; continue; }
-                P2_STAMP(round, s, 0);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int gg = 2 * half; gg < 2 * half + 2 && has_units; ++gg) {
-                    const P2Meta *mt = meta + ((s * 4 + (round & 3u)) * 4 + gg);
-                    if (*reinterpret_cast<const volatile uint32_t *>(&mt->done)) continue;
-                    const uint32_t lasts = mt->lasts;
-                    float v[32];
-                    tc_ld_32x32(tmem + ((uint32_t)(e * 32) << 16) + acc * (uint32_t)TC_M + (uint32_t)(gg * 32), v);
-                    P2_STAMP2(round, s, 2 * (gg & 1));
-                    // branch-free: the voxels of a group take consecutive output rows (first one = vid0), so the
-                    // store address just advances at every voxel end; BatchNorm + ReLU are evaluated for every
-                    // column (two instructions) instead of branching 32 times, the store is predicated
-                    float run = neutral;
-                    float *const dst = a.out + (size_t)mt->vid0 * N + unit;   // units are a multiple of 32: every lane of the warp owns one
-                    uint32_t off = 0;                                        // 32-bit element offset: advances by N at every voxel end
+        for (uint32_t tile = (uint32_t)team;; tile += 3) {
+            const uint32_t s = tile & 1u, round = tile >> 1, acc = tile & 3u, par = (tile >> 2) & 1u;
+            if (!p2_mbar_wait(tc_smem_u32(&s_rec[acc]), par, &s_abort, diag, 0x500u | (acc << 4) | (ew & 3) | (round << 16))) break;
+            if (!p2_mbar_wait(tc_smem_u32(&s_acc[acc]), par, &s_abort, diag, 0x400u | (acc << 4) | (ew & 3) | (round << 16))) break;
+            if (tile >= *reinterpret_cast<volatile uint32_t *>(&s_exit[1])) break;
+            P2_STAMP(round, s, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int gg = 0; gg < 4 && has_units; ++gg) {
+                const P2Meta *mt = meta + ((s * 4 + (round & 3u)) * 4 + gg);
+                if (*reinterpret_cast<const volatile uint32_t *>(&mt->done)) continue;
+                const uint32_t lasts = mt->lasts;
+                float v[32];
+                tc_ld_32x32(tmem + ((uint32_t)(e * 32) << 16) + acc * (uint32_t)TC_M + (uint32_t)(gg * 32), v);
+                // the voxels of a group take consecutive output rows (first one = vid0): the store offset advances
+                // by one row at every voxel end
+                float run = neutral;
+                float *const dst = a.out + (size_t)mt->vid0 * N + unit;   // units are a multiple of 32: every lane of the warp owns one
+                uint32_t off = 0;
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) {
-                        const bool last = (lasts >> k) & 1u;                 // warp-uniform: the voxel ends at row k
-                        run = fmaxf(run, v[k]);
-                        if (last) __stcs(dst + off, fmaxf(__fmaf_rn(run, sc, sh), 0.0f));
-                        off += last ? (uint32_t)N : 0u;
-                        run = last ? neutral : run;
-                    }
-                    P2_STAMP2(round, s, 2 * (gg & 1) + 1);
+                for (int k = 0; k < 32; ++k) {
+                    const bool last = (lasts >> k) & 1u;                 // warp-uniform: the voxel ends at row k
+                    run = fmaxf(run, v[k]);
+                    if (last) __stcs(dst + off, fmaxf(__fmaf_rn(run, sc, sh), 0.0f));
+                    off += last ? (uint32_t)N : 0u;
+                    run = last ? neutral : run;
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) p2_mbar_arrive(tc_smem_u32(&s_free[acc]));
-                P2_STAMP(round, s, 1);
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) p2_mbar_arrive(tc_smem_u32(&s_free[acc]));
+            P2_STAMP(round, s, 1);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -705,7 +724,7 @@ bool pv_pfn_fused_supported(const pv_pfn_layer *layers, int n_layers, int t, int
 size_t pv_pfn_fused_smem(int n1)
 {
     return sizeof(float) * (2 * 2 * (size_t)TC_M * P2_K + 2 * (size_t)TC_M * P2_K + P2_C0 * P2_U0 + 4 * P2_U0 + 4 * (size_t)n1) +
-           sizeof(P2Meta) * 32 + 8 * P2_MC * sizeof(uint4) + 128;
+           sizeof(P2Meta) * 32 + 16 * P2_MC * sizeof(uint4) + 128;
 }
 
 // counter: 64 words (256 bytes) of device scratch, zeroed before every launch: [0] the dynamic mini-chunk queue,

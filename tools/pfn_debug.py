@@ -25,8 +25,8 @@ out = F.pfn_forward(torch.from_numpy(vox).cuda(), torch.from_numpy(num).cuda(), 
                     vs[0], vs[1], vs[0] / 2 + rg[0], vs[1] / 2 + rg[1], False, 1e-3)
 torch.cuda.synchronize()
 ws = [w for k, w in F._workspaces.items() if k[-1] == "pfn"][0]
-words = ws[:96].view(torch.int32).cpu().numpy()
-print("counter %d  status %d  watchdog 0x%x block %d" % (int(words[0]), int(words[1]), int(words[2]) & 0xffffffff, int(words[3])), " ".join("w%d:%x" % (k, int(words[4 + k]) & 0xffffffff) for k in range(25)))
+words = ws[:256].view(torch.int32).cpu().numpy()
+print("counter %d  status %d  watchdog 0x%x block %d" % (int(words[0]), int(words[1]), int(words[2]) & 0xffffffff, int(words[3])), " ".join("w%d:%x" % (k, int(words[4 + k]) & 0xffffffff) for k in range(29)))
 ref = oracle.pfn_forward(vox, num, coors, layers, vs, rg, with_distance=False, eps=1e-3)
 o = out.cpu().numpy()
 err = np.abs(o - ref)

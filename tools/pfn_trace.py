@@ -34,8 +34,8 @@ lib = _lib.load()
 lib.pv_debug_p2_trace.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
 buf = np.zeros((32, 64, 2, 3), np.int64)
 print("rc", lib.pv_debug_p2_trace(buf.ctypes.data, buf.nbytes))
-nprod = int(os.environ.get("NPROD", "8"))
-NEPI = 16
+nprod = int(os.environ.get("NPROD", "16"))
+NEPI = 12
 t0 = buf[buf > 0].min()
 mhz = 1.9
 def us(x): return (x - t0) / mhz / 1e3
@@ -49,12 +49,6 @@ print("issuer: round s: full seen / free seen / committed")
 for r in R:
     for s in (0, 1):
         print("  r%d s%d  %.2f %.2f %.2f" % (r, s, us(buf[nprod + NEPI, r, s, 0]), us(buf[nprod + NEPI, r, s, 1]), us(buf[nprod + NEPI, r, s, 2])))
-print("epilogue warp 0 and 4: round s: mma done seen / freed   (work)")
-for w in (nprod, nprod + 8):
-    for r in R:
-        if (r & 1) != ((w - nprod) >> 3): continue
-        for s in (0, 1):
-            print("  w%d r%d s%d  %.2f %.2f   work %.2f" % (w, r, s, us(buf[w, r, s, 0]), us(buf[w, r, s, 1]), (buf[w, r, s, 1] - buf[w, r, s, 0]) / mhz / 1e3))
 # per-producer compute time statistics
 comp = (buf[:nprod, 8:48, 0, 2] - buf[:nprod, 8:48, 0, 1]) / mhz / 1e3
 wait = (buf[:nprod, 8:48, 0, 1] - buf[:nprod, 8:48, 0, 0]) / mhz / 1e3
@@ -62,9 +56,13 @@ print("producer compute us: mean %.2f  (per warp %s)" % (comp.mean(), np.round(c
 print("producer wait-for-stage us: mean %.2f" % wait.mean())
 pre = (buf[:nprod, 9:48, 0, 0] - buf[:nprod, 8:47, 0, 2]) / mhz / 1e3
 print("producer fetch + layer 0 (before the wait) us: mean %.2f" % pre.mean())
-ew0 = (buf[nprod:nprod + 8, 8:48:2, :, 1] - buf[nprod:nprod + 8, 8:48:2, :, 0]) / mhz / 1e3
-ew1 = (buf[nprod + 8:nprod + 16, 9:48:2, :, 1] - buf[nprod + 8:nprod + 16, 9:48:2, :, 0]) / mhz / 1e3
-print("epilogue work us: team0 %.2f team1 %.2f" % (ew0.mean(), ew1.mean()))
+ew = []
+for w in range(NEPI):                       # team = w >> 2 serves tiles = team (mod 3); tile = 2 * round + s
+    for r in range(8, 48):
+        for s_ in (0, 1):
+            if (2 * r + s_) % 3 == (w >> 2) and buf[nprod + w, r, s_, 1] > 0:
+                ew.append((buf[nprod + w, r, s_, 1] - buf[nprod + w, r, s_, 0]) / mhz / 1e3)
+print("epilogue work per tile and warp us: mean %.2f" % np.mean(ew))
 iss = buf[nprod + NEPI, 8:48, :, :]
 print("issuer: wait full->free %.2f  issue %.2f   period per tile %.2f" % (((iss[:, :, 1] - iss[:, :, 0]) / mhz / 1e3).mean(), ((iss[:, :, 2] - iss[:, :, 1]) / mhz / 1e3).mean(),
       (iss[-1, 1, 2] - iss[0, 0, 2]) / mhz / 1e3 / (2 * 40 - 1)))
