@@ -671,6 +671,9 @@ __global__ void __launch_bounds__(P2_THREADS, 1) k_pfn_fused(const __grid_consta
             const uint32_t s = tile & 1u, round = tile >> 1, acc = tile & 3u, par = (tile >> 2) & 1u;
             if (!p2_mbar_wait(tc_smem_u32(&s_rec[acc]), par, &s_abort, diag, 0x500u | (acc << 4) | (ew & 3) | (round << 16))) break;
             if (!p2_mbar_wait(tc_smem_u32(&s_acc[acc]), par, &s_abort, diag, 0x400u | (acc << 4) | (ew & 3) | (round << 16))) break;
+            // (compute-sanitizer racecheck reports this read against the issuer's write of s_exit[1]: benign by design -- a real
+            // tile is below the final value and below the initial 0xFFFFFFFF alike; a tile at or past the end is only
+            // released, through the barriers above, after the write)
             if (tile >= *reinterpret_cast<volatile uint32_t *>(&s_exit[1])) break;
             P2_STAMP(round, s, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
