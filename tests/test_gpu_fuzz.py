@@ -206,3 +206,66 @@ def test_random_static_readers_vs_oracle(seed):
     rc, rb = oracle.scatter(ref, coors, B, [nx, ny, 1])
     assert np.array_equal(bev.cpu().numpy(), rb)
     assert_close_fp32(canvas.cpu().numpy(), rc, "canvas")
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_random_fused_pillar_front_end_vs_oracle(seed):
+    """pv_forward_pfn_canvas (gather pre-pass + tensor-core kernel + scatter) on random batches: 1-6 frames of
+    0 ... 40 000 points (empty and single-point frames, batches where only one producer set finds work, batches
+    that end in partial tiles), random caps (T down to 1, V binding or not), polar 3- to 7-channel or Cartesian
+    4- / 5-channel input, with and without the distance channel, output widths 32-128.  Integers bit-exact,
+    features / canvas within the 1e-5 gate; exercises the exit paths of the kernel's tile protocol."""
+    import torch
+    from partner_b200 import PillarFeatureNet, PillarFrontEnd
+    rng = np.random.default_rng(1000 + seed)
+    nx, ny = int(rng.choice([64, 128, 256])), int(rng.choice([64, 128, 512]))
+    lo = np.array([0.3, -3.1488, -5.0], np.float32)
+    vs = [float(rng.uniform(0.08, 0.4)), 2 * 3.1488 / ny, 8.0]
+    rg = [float(lo[0]), float(lo[1]), -5.0, float(lo[0] + vs[0] * nx), float(lo[1] + vs[1] * ny), 3.0]
+    T = int(rng.choice([1, 3, 20, 32]))
+    V = int(rng.choice([50, 2000, 60000]))
+    cartesian = bool(rng.random() < 0.5)
+    c_in = int(rng.choice([4, 5])) if cartesian else int(rng.choice([3, 4, 5, 7]))
+    with_distance = bool(rng.random() < 0.4)
+    units = int(rng.choice([32, 64, 96, 128]))
+    B = int(rng.integers(1, 7))
+    sizes = [int(rng.choice([0, 1, 40, 700, int(rng.integers(1000, 40000))])) for _ in range(B)]
+    frames, polar = [], []
+    for n in sizes:
+        rho = lo[0] + rng.random(n) * vs[0] * nx * float(rng.choice([0.05, 0.5, 1.05]))
+        phi = rng.uniform(-3.2, 3.2, n)
+        z = rng.uniform(-5.5, 3.5, n)
+        extra = rng.normal(0, 5, (n, 4))
+        if cartesian:
+            f = np.column_stack([rho * np.cos(phi), rho * np.sin(phi), z, extra])[:, :c_in].astype(np.float32)
+            frames.append(np.ascontiguousarray(f)); polar.append(oracle.transform_points(frames[-1]))
+        else:
+            f = np.column_stack([rho, phi, z, extra])[:, :c_in].astype(np.float32)
+            frames.append(np.ascontiguousarray(f)); polar.append(frames[-1])
+    C = polar[0].shape[1]
+    if C + 5 + (1 if with_distance else 0) > 16:
+        with_distance = False
+    torch.manual_seed(seed)
+    net = PillarFeatureNet(C, (64, units), with_distance, tuple(vs), tuple(rg)).cuda().eval()
+    g = torch.Generator().manual_seed(seed)
+    for L in net.pfn_layers:
+        u = L.norm.num_features
+        L.norm.running_mean.copy_(torch.randn(u, generator=g)); L.norm.running_var.copy_(torch.rand(u, generator=g) * 1.5 + 0.5)
+        L.norm.weight.data.copy_(torch.randn(u, generator=g)); L.norm.bias.data.copy_(torch.randn(u, generator=g))
+    fe = PillarFrontEnd(vs, rg, T, V, net, cartesian=cartesian)
+    got = fe(frames)
+    ref_gen = oracle.VoxelGenerator(vs, rg, T, V)
+    vox, coor, num, nv = oracle.collate([ref_gen.generate(p)[:3] for p in polar])
+    assert np.array_equal(got["num_voxels"], nv)
+    assert np.array_equal(got["coordinates"], coor)
+    assert np.array_equal(got["num_points"], num)
+    if coor.shape[0] == 0:
+        assert got["features"].shape[0] == 0 and not got["canvas"].any()
+        return
+    layers = [dict(weight=L.linear.weight.detach().cpu().numpy(), mean=L.norm.running_mean.cpu().numpy(),
+                   var=L.norm.running_var.cpu().numpy(), gamma=L.norm.weight.detach().cpu().numpy(),
+                   beta=L.norm.bias.detach().cpu().numpy()) for L in net.pfn_layers]
+    ref = oracle.pfn_forward(vox, num, coor, layers, vs, rg, with_distance=with_distance, eps=1e-3)
+    assert_close_fp32(got["features"], ref, "fused PFN features, random case %d" % seed)
+    rc, _ = oracle.scatter(ref, coor, len(frames), [nx, ny, 1])
+    assert_close_fp32(got["canvas"], rc, "fused PFN canvas, random case %d" % seed)
