@@ -707,6 +707,9 @@ def main():
     copy_ms = timed(copies, e2e_steps, n_streams) / e2e_steps
     h2d_ms = timed(lambda k: copies(k, True, False), e2e_steps, n_streams) / e2e_steps
     d2h_ms = timed(lambda k: copies(k, False, True), e2e_steps, n_streams) / e2e_steps
+    # copy floor with fewer copies in flight per rank (when many ranks share one host, 64 concurrent DMA streams can
+    # cost more than they hide): reported so that the stream count of the e2e loop can be chosen from data
+    copy_probe = {str(ns): timed(copies, e2e_steps, ns) / e2e_steps for ns in (1, 2) if ns < n_streams}
     # fully synchronous variant (one step at a time, slices copied after reading the counts)
     t0 = time.perf_counter()
     for k in range(8):
@@ -808,7 +811,8 @@ def main():
                                        "the part of e2e.ms_per_step that belongs to the host link, not to this code",
                     "h2d_only_ms_per_step": h2d_ms, "d2h_only_ms_per_step": d2h_ms,
                     "h2d_GBps_per_rank": (h2d // e2e_steps) / (h2d_ms * 1e-3) / 1e9,
-                    "d2h_GBps_per_rank": (d2h // e2e_steps) / (d2h_ms * 1e-3) / 1e9},
+                    "d2h_GBps_per_rank": (d2h // e2e_steps) / (d2h_ms * 1e-3) / 1e9,
+                    "copy_floor_ms_per_step_by_streams": copy_probe},
             "gpu_launches": LAUNCHES_PER_STEP[pipeline] * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": (ach / peak) if ach else None, "traffic": traffic, "traffic_source": traffic_src,
