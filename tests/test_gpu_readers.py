@@ -315,3 +315,21 @@ def test_static_pfn_slices_agree_with_one_slice_calls():
     k = 20000
     ref = oracle.pfn_forward(vox[sel[:k]], num[sel[:k]], coor[sel[:k]], layers, g["voxel_size"], g["range"], with_distance=False, eps=1e-3)
     assert_close_fp32(big[:k].cpu().numpy(), ref, "static PFN, sliced call")
+
+
+def test_fused_pillar_front_end_without_points():
+    """pv_forward_pfn_canvas on batches that contain no voxel at all (no points; only out-of-range points): the
+    tensor-core kernel's tile protocol ends in its first round, nothing is written but the zero canvas."""
+    from partner_b200 import PillarFeatureNet, PillarFrontEnd, synth
+    g = synth.GRIDS["NUSC-PILLAR"]
+    net = _random_pfn_state(PillarFeatureNet(7, (64, 128), False, tuple(g["voxel_size"]), tuple(g["range"])), seed=3).cuda().eval()
+    fe = PillarFrontEnd(g["voxel_size"], g["range"], g["max_points"], g["max_voxels"], net, cartesian=True)
+    far = np.zeros((500, 5), np.float32)
+    far[:, 0] = 500.0                                          # rho beyond the grid
+    for frames in ([np.zeros((0, 5), np.float32)], [np.zeros((0, 5), np.float32), far, np.zeros((0, 5), np.float32)]):
+        got = fe(frames)
+        assert got["features"].shape == (0, 128) and got["coordinates"].shape == (0, 4)
+        assert np.array_equal(got["num_voxels"], np.zeros(len(frames), np.int64))
+        assert got["canvas"].shape == (len(frames), 128, 512, 512) and not got["canvas"].any()
+    one = fe([synth.nusc_frame(3500, nsweeps=1)[:300]])       # and the next call on the same workspaces is a normal one
+    assert one["features"].shape[0] == int(one["num_voxels"].sum()) > 0 and np.isfinite(one["features"]).all()
