@@ -20,6 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--filters", default="64,128")
+ap.add_argument("--streams", type=int, default=1, help="replay the fused front end round-robin on this many streams (independent batches overlap)")
 ap.add_argument("--fused-only", action="store_true", help="skip the three-call path (for ncu launch lists of the fused front end)")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -86,9 +87,20 @@ for gr in graphs:
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 reps = 4 * args.iters
+streams = [torch.cuda.Stream(dev) for _ in range(args.streams)] if args.streams > 1 else None
 e0.record()
-for it in range(reps):
-    graphs[it % n_sets].replay()
+if streams is None:
+    for it in range(reps):
+        graphs[it % n_sets].replay()
+else:
+    cur = torch.cuda.current_stream(dev)
+    for st in streams:
+        st.wait_stream(cur)
+    for it in range(reps):
+        with torch.cuda.stream(streams[it % args.streams]):
+            graphs[it % n_sets].replay()
+    for st in streams:
+        cur.wait_stream(st)
 e1.record()
 torch.cuda.synchronize()
 fused_ms = e0.elapsed_time(e1) / reps
